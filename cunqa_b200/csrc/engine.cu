@@ -1,0 +1,379 @@
+// engine.cu -- State implementation: device memory, op queue, tile-pass launches, measurement.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "measure_kernels.cuh"
+#include "tile_kernel.cuh"
+
+namespace cb200 {
+
+static int env_int(const char *name, int dflt)
+{
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+State::State(int n_qubits, int prec, int dev, int nbatch)
+    : n(n_qubits), precision(prec), device(dev), batch(nbatch), queue(std::max(1, n_qubits), std::max(1, nbatch), PlanOptions())
+{
+    if (n < 1 || n > 40) throw InvalidArg("n_qubits must be in [1,40]");
+    if (precision != 64 && precision != 32) throw InvalidArg("precision must be 64 or 32");
+    if (batch < 1) throw InvalidArg("batch must be >= 1");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw CudaError(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                        "); cunqa_b200 has no CPU fallback");
+    if (device < 0 || device >= count) throw InvalidArg("device index out of range");
+    CB200_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CB200_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) throw CudaError("cunqa_b200 kernels are built for sm_100a only (found sm_" +
+                                         std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    num_sms_ = prop.multiProcessorCount;
+    n_local_ = n;
+    amp_bytes_ = precision == 64 ? 16 : 8;
+    state_bytes_ = amp_bytes_ * ((size_t)batch << n);
+    opt.tile_bits = env_int("CB200_TILE_BITS", precision == 64 ? 12 : 13);
+    opt.min_run_bits = env_int("CB200_MIN_RUN_BITS", precision == 64 ? 4 : 5);
+    opt.max_pass_cost = env_int("CB200_MAX_PASS_COST", 0);
+    opt.max_diag_qubits = env_int("CB200_MAX_DIAG_QUBITS", 10);
+    opt.fuse = env_int("CB200_FUSE", 1) != 0;
+    ctas_per_sm_ = env_int("CB200_CTAS_PER_SM", 0);
+    queue = OpQueue(n, batch, opt);
+    CB200_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CB200_CUDA(cudaMalloc(&d_state_, state_bytes_));
+    CB200_CUDA(cudaMalloc(&d_small_, sizeof(double) * 4 * batch));
+    CB200_CUDA(cudaMalloc(&d_outcome_, sizeof(int) * batch));
+    CB200_CUDA(cudaMalloc(&d_counters_, sizeof(uint64_t) * batch));
+    CB200_CUDA(cudaMalloc(&d_forced_, sizeof(int8_t) * batch));
+    reset();
+}
+
+State::~State()
+{
+    cudaSetDevice(device);
+    if (stream_) cudaStreamSynchronize(stream_);
+    cudaFree(d_state_); cudaFree(d_diag_); cudaFree(d_flags_); cudaFree(d_partial_); cudaFree(d_small_);
+    cudaFree(d_outcome_); cudaFree(d_counters_); cudaFree(d_forced_); cudaFree(d_lvl1_); cudaFree(d_lvl2_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+void State::reset()
+{
+    CB200_CUDA(cudaSetDevice(device));
+    queue.reset();
+    const uint64_t total = (uint64_t)batch << n;
+    const int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)num_sms_ * 16);
+    if (precision == 64) init_zero_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_, 1ull << n, total);
+    else init_zero_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, 1ull << n, total);
+    CB200_CUDA(cudaGetLastError());
+    stats.launches++;
+}
+
+// ---- queueing (forwarded to the host-only OpQueue) ------------------------------------------------
+void State::apply_matrix(const int *qubits, int k, const int *ctrls, int nc, const cplx *mat, const uint8_t *flags)
+{
+    queue.apply_matrix(qubits, k, ctrls, nc, mat, flags);
+    maybe_flush();
+}
+void State::apply_diagonal(const int *qubits, int k, const cplx *diag, const uint8_t *flags)
+{
+    queue.apply_diagonal(qubits, k, diag, flags);
+    maybe_flush();
+}
+void State::global_phase(double theta, const uint8_t *flags)
+{
+    queue.global_phase(theta, flags);
+    maybe_flush();
+}
+void State::apply_named(const std::string &name, const int *qubits, int nq, const double *params, int np,
+                        const uint8_t *flags)
+{
+    queue.apply_named(name, qubits, nq, params, np, flags);
+    maybe_flush();
+}
+
+// ---- flush: plan + launch -----------------------------------------------------------------------
+template <typename T>
+void State::flush_t()
+{
+    using V = typename Vec2<T>::type;
+    std::vector<HostOp> &ops = queue.ops();
+    if (ops.empty()) return;
+    CB200_CUDA(cudaSetDevice(device));
+    const std::vector<Pass> passes = schedule_passes(ops, n_local_, opt);
+    std::vector<cplx> diag_host;
+    std::vector<PassParams<T>> params(passes.size());
+    std::string err;
+    for (size_t i = 0; i < passes.size(); i++)
+        if (!encode_pass<T>(passes[i], ops, n_local_, batch, params[i], diag_host, err)) throw Unsupported(err);
+    // diagonal tables
+    if (!diag_host.empty()) {
+        if (diag_host.size() > diag_cap_) {
+            CB200_CUDA(cudaStreamSynchronize(stream_));
+            cudaFree(d_diag_);
+            diag_cap_ = std::max<size_t>(diag_host.size() * 2, 4096);
+            CB200_CUDA(cudaMalloc(&d_diag_, diag_cap_ * sizeof(V)));
+        }
+        std::vector<V> tmp(diag_host.size());
+        for (size_t i = 0; i < diag_host.size(); i++) { tmp[i].x = (T)diag_host[i].real(); tmp[i].y = (T)diag_host[i].imag(); }
+        CB200_CUDA(cudaMemcpyAsync(d_diag_, tmp.data(), tmp.size() * sizeof(V), cudaMemcpyHostToDevice, stream_));
+        CB200_CUDA(cudaStreamSynchronize(stream_));  // tmp is pageable and dies here
+    }
+    if (!queue.mask_rows.empty()) {
+        const size_t need = queue.mask_rows.size() * (size_t)batch;
+        if (need > flags_cap_) {
+            CB200_CUDA(cudaStreamSynchronize(stream_));
+            cudaFree(d_flags_);
+            flags_cap_ = need * 2;
+            CB200_CUDA(cudaMalloc(&d_flags_, flags_cap_));
+        }
+        std::vector<uint8_t> tmp(need);
+        for (size_t r = 0; r < queue.mask_rows.size(); r++) std::memcpy(tmp.data() + r * batch, queue.mask_rows[r].data(), batch);
+        CB200_CUDA(cudaMemcpyAsync(d_flags_, tmp.data(), need, cudaMemcpyHostToDevice, stream_));
+        CB200_CUDA(cudaStreamSynchronize(stream_));
+    }
+    auto kern = tile_pass_kernel<T>;
+    static thread_local int occ_cache[2] = {0, 0};
+    for (size_t i = 0; i < passes.size(); i++) {
+        const PassParams<T> &p = params[i];
+        const size_t smem = sizeof(V) * ((size_t)1 << p.t) + sizeof(uint64_t) * ((size_t)1 << (p.t - p.L));
+        CB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = ctas_per_sm_;
+        if (occ <= 0) {
+            CB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTileThreads, smem));
+            if (occ < 1) occ = 1;
+        }
+        (void)occ_cache;
+        const uint64_t total_tiles = p.tiles_per_state * (uint64_t)batch;
+        const unsigned grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_ * occ);
+        kern<<<grid, kTileThreads, smem, stream_>>>(p, (V *)d_state_, (const V *)d_diag_, d_flags_);
+        CB200_CUDA(cudaGetLastError());
+        stats.passes++;
+        stats.launches++;
+        stats.bytes += 2ull * state_bytes_;
+        stats.fused_ops += (uint64_t)p.n_ops;
+    }
+    queue.clear_pending();
+}
+
+void State::flush()
+{
+    if (precision == 64) flush_t<double>();
+    else flush_t<float>();
+}
+
+void State::sync()
+{
+    flush();
+    CB200_CUDA(cudaSetDevice(device));
+    CB200_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// ---- measurement --------------------------------------------------------------------------------
+void State::ensure_scratch(size_t partial_doubles)
+{
+    if (partial_doubles > partial_cap_) {
+        CB200_CUDA(cudaStreamSynchronize(stream_));
+        cudaFree(d_partial_);
+        partial_cap_ = partial_doubles;
+        CB200_CUDA(cudaMalloc(&d_partial_, partial_cap_ * sizeof(double)));
+    }
+}
+
+// d_all[b] = sum |a|^2 ; d_sel[b] = sum over (index & sel_mask)==sel_mask   (either may be null)
+template <typename T>
+void State::reduce2_t(uint64_t sel_mask, double *d_all, double *d_sel)
+{
+    using V = typename Vec2<T>::type;
+    const uint64_t amps = 1ull << n_local_;
+    int nblk = (int)std::min<uint64_t>((amps + kRedThreads * 8 - 1) / (kRedThreads * 8),
+                                       std::max<uint64_t>(1, (uint64_t)num_sms_ * 8 / batch));
+    if (nblk < 1) nblk = 1;
+    ensure_scratch((size_t)nblk * batch);
+    dim3 grid(nblk, batch);
+    if (d_all) {
+        prob_partial_kernel<V><<<grid, kRedThreads, 0, stream_>>>((const V *)d_state_, amps, 0ull, d_partial_);
+        sum_partials_kernel<<<batch, kRedThreads, 0, stream_>>>(d_partial_, nblk, d_all);
+        stats.launches += 2;
+    }
+    if (d_sel) {
+        prob_partial_kernel<V><<<grid, kRedThreads, 0, stream_>>>((const V *)d_state_, amps, sel_mask, d_partial_);
+        sum_partials_kernel<<<batch, kRedThreads, 0, stream_>>>(d_partial_, nblk, d_sel);
+        stats.launches += 2;
+    }
+    CB200_CUDA(cudaGetLastError());
+}
+
+void State::norm(double *out)
+{
+    flush();
+    if (precision == 64) reduce2_t<double>(0, d_small_, nullptr); else reduce2_t<float>(0, d_small_, nullptr);
+    CB200_CUDA(cudaMemcpyAsync(out, d_small_, sizeof(double) * batch, cudaMemcpyDeviceToHost, stream_));
+    CB200_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void State::prob1(int qubit, double *out)
+{
+    if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
+    flush();
+    const uint64_t sel = 1ull << queue.l2p[qubit];
+    if (precision == 64) reduce2_t<double>(sel, nullptr, d_small_ + batch); else reduce2_t<float>(sel, nullptr, d_small_ + batch);
+    CB200_CUDA(cudaMemcpyAsync(out, d_small_ + batch, sizeof(double) * batch, cudaMemcpyDeviceToHost, stream_));
+    CB200_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void State::measure(int qubit, uint64_t seed, const uint64_t *counters, const int8_t *forced, int *bits_out, bool reset_after)
+{
+    if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
+    flush();
+    const int pq = queue.l2p[qubit];
+    const uint64_t sel = 1ull << pq;
+    if (precision == 64) reduce2_t<double>(sel, d_small_, d_small_ + batch); else reduce2_t<float>(sel, d_small_, d_small_ + batch);
+    std::vector<uint64_t> zero_ctr;
+    if (!counters) { zero_ctr.assign(batch, 0); counters = zero_ctr.data(); }
+    CB200_CUDA(cudaMemcpyAsync(d_counters_, counters, sizeof(uint64_t) * batch, cudaMemcpyHostToDevice, stream_));
+    if (forced) CB200_CUDA(cudaMemcpyAsync(d_forced_, forced, sizeof(int8_t) * batch, cudaMemcpyHostToDevice, stream_));
+    measure_decide_kernel<<<(batch + 127) / 128, 128, 0, stream_>>>(d_small_, d_small_ + batch, batch, seed, d_counters_,
+                                                                     forced ? d_forced_ : nullptr, d_outcome_, d_small_ + 2 * batch);
+    const uint64_t work = ((uint64_t)batch << n_local_) >> 1;
+    const int blocks = (int)std::min<uint64_t>((work + 255) / 256, (uint64_t)num_sms_ * 16);
+    if (precision == 64)
+        collapse_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_, n_local_, pq, batch, d_outcome_, d_small_ + 2 * batch, reset_after ? 1 : 0);
+    else
+        collapse_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, n_local_, pq, batch, d_outcome_, d_small_ + 2 * batch, reset_after ? 1 : 0);
+    CB200_CUDA(cudaGetLastError());
+    stats.launches += 2;
+    stats.bytes += 2ull * state_bytes_ + 2ull * state_bytes_;  // two reductions (1*S each) + collapse (2*S)
+    std::vector<int> tmp;
+    int *dst = bits_out;
+    if (!dst) { tmp.resize(batch); dst = tmp.data(); }
+    CB200_CUDA(cudaMemcpyAsync(dst, d_outcome_, sizeof(int) * batch, cudaMemcpyDeviceToHost, stream_));
+    CB200_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out)
+{
+    if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
+    flush();
+    const int nl = n_local_;
+    const int bits0 = std::min(nl, kChunkBits);
+    const int bits1 = std::min(nl - bits0, kChunkBits);
+    const uint64_t n1 = 1ull << (nl - bits0);           // level-1 entries (chunk sums)
+    const uint64_t n2 = 1ull << (nl - bits0 - bits1);   // level-2 entries
+    if (n1 > lvl1_cap_) { CB200_CUDA(cudaStreamSynchronize(stream_)); cudaFree(d_lvl1_); lvl1_cap_ = n1; CB200_CUDA(cudaMalloc(&d_lvl1_, n1 * sizeof(double))); }
+    if (n2 > lvl2_cap_) { CB200_CUDA(cudaStreamSynchronize(stream_)); cudaFree(d_lvl2_); lvl2_cap_ = n2; CB200_CUDA(cudaMalloc(&d_lvl2_, n2 * sizeof(double))); }
+    const int g1 = (int)std::min<uint64_t>(n1, (uint64_t)num_sms_ * 16);
+    const int g2 = (int)std::min<uint64_t>(n2, (uint64_t)num_sms_ * 16);
+    uint64_t *d_out = nullptr;
+    CB200_CUDA(cudaMalloc(&d_out, sizeof(uint64_t) * std::max<uint64_t>(shots, 1)));
+    const int sblocks = (int)std::min<uint64_t>((shots * 32 + kRedThreads - 1) / kRedThreads, (uint64_t)num_sms_ * 8);
+    if (precision == 64) {
+        const double2 *st = (const double2 *)d_state_ + ((size_t)b << nl);
+        chunk_sums_amp_kernel<double2><<<g1, kRedThreads, 0, stream_>>>(st, bits0, n1, d_lvl1_);
+        chunk_sums_f64_kernel<<<g2, kRedThreads, 0, stream_>>>(d_lvl1_, bits1, n2, d_lvl2_);
+        top_prefix_kernel<<<1, 32, 0, stream_>>>(d_lvl2_, n2);
+        if (shots) sample_kernel<double2><<<std::max(sblocks, 1), kRedThreads, 0, stream_>>>(st, nl, bits0, bits1, d_lvl1_, d_lvl2_, n2, shots, seed, d_out);
+    } else {
+        const float2 *st = (const float2 *)d_state_ + ((size_t)b << nl);
+        chunk_sums_amp_kernel<float2><<<g1, kRedThreads, 0, stream_>>>(st, bits0, n1, d_lvl1_);
+        chunk_sums_f64_kernel<<<g2, kRedThreads, 0, stream_>>>(d_lvl1_, bits1, n2, d_lvl2_);
+        top_prefix_kernel<<<1, 32, 0, stream_>>>(d_lvl2_, n2);
+        if (shots) sample_kernel<float2><<<std::max(sblocks, 1), kRedThreads, 0, stream_>>>(st, nl, bits0, bits1, d_lvl1_, d_lvl2_, n2, shots, seed, d_out);
+    }
+    cudaError_t e = cudaGetLastError();
+    stats.launches += 4;
+    stats.bytes += state_bytes_ / batch;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(uint64_t) * shots, cudaMemcpyDeviceToHost, stream_);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    cudaFree(d_out);
+    if (e != cudaSuccess) throw CudaError(std::string("sampling failed: ") + cudaGetErrorString(e));
+    if (!queue.identity_perm())
+        for (uint64_t s = 0; s < shots; s++) out[s] = queue.logical_index(out[s]);
+}
+
+void State::get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out)
+{
+    if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
+    flush();
+    if (cnt == 0) return;
+    std::vector<uint64_t> phys(cnt);
+    const uint64_t dim = 1ull << n;
+    for (uint64_t i = 0; i < cnt; i++) {
+        if (idx[i] >= dim) throw InvalidArg("amplitude index out of range");
+        phys[i] = queue.phys_index(idx[i]);
+    }
+    uint64_t *d_idx = nullptr; double2 *d_out = nullptr;
+    CB200_CUDA(cudaMalloc(&d_idx, cnt * sizeof(uint64_t)));
+    cudaError_t e = cudaMalloc(&d_out, cnt * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, phys.data(), cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, stream_);
+    if (e == cudaSuccess) {
+        const int blocks = (int)((cnt + 255) / 256);
+        if (precision == 64) gather_amps_kernel<double2><<<blocks, 256, 0, stream_>>>((const double2 *)d_state_ + ((size_t)b << n_local_), d_idx, cnt, d_out);
+        else gather_amps_kernel<float2><<<blocks, 256, 0, stream_>>>((const float2 *)d_state_ + ((size_t)b << n_local_), d_idx, cnt, d_out);
+        e = cudaGetLastError();
+        stats.launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, cnt * sizeof(double2), cudaMemcpyDeviceToHost, stream_);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    cudaFree(d_idx); cudaFree(d_out);
+    if (e != cudaSuccess) throw CudaError(std::string("get_amplitudes failed: ") + cudaGetErrorString(e));
+}
+
+void State::set_amplitudes(int b, const double *in)
+{
+    if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
+    flush();
+    CB200_CUDA(cudaStreamSynchronize(stream_));
+    const uint64_t dim = 1ull << n;
+    // logical -> physical layout on the host, then one upload
+    std::vector<double2> host(dim);
+    for (uint64_t i = 0; i < dim; i++) host[queue.phys_index(i)] = make_double2(in[2 * i], in[2 * i + 1]);
+    double2 *d_in = nullptr;
+    CB200_CUDA(cudaMalloc(&d_in, dim * sizeof(double2)));
+    cudaError_t e = cudaMemcpyAsync(d_in, host.data(), dim * sizeof(double2), cudaMemcpyHostToDevice, stream_);
+    if (e == cudaSuccess) {
+        const int blocks = (int)std::min<uint64_t>((dim + 255) / 256, (uint64_t)num_sms_ * 16);
+        if (precision == 64) scatter_amps_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_ + ((size_t)b << n_local_), d_in, dim);
+        else scatter_amps_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_ + ((size_t)b << n_local_), d_in, dim);
+        e = cudaGetLastError();
+        stats.launches++;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    cudaFree(d_in);
+    if (e != cudaSuccess) throw CudaError(std::string("set_amplitudes failed: ") + cudaGetErrorString(e));
+}
+
+void State::probabilities(int b, const int *qubits, int k, double *out)
+{
+    if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
+    if (k < 1 || k > 20) throw InvalidArg("marginal over 1..20 qubits");
+    flush();
+    std::vector<int> pq(k);
+    for (int i = 0; i < k; i++) if (qubits[i] < 0 || qubits[i] >= n) throw InvalidArg("qubit out of range");
+    for (int i = 0; i < k; i++) pq[i] = queue.l2p[qubits[i]];
+    int *d_q = nullptr; double *d_o = nullptr;
+    CB200_CUDA(cudaMalloc(&d_q, k * sizeof(int)));
+    cudaError_t e = cudaMalloc(&d_o, sizeof(double) << k);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, pq.data(), k * sizeof(int), cudaMemcpyHostToDevice, stream_);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_o, 0, sizeof(double) << k, stream_);
+    if (e == cudaSuccess) {
+        const uint64_t amps = 1ull << n_local_;
+        const int blocks = (int)std::min<uint64_t>((amps + 255) / 256, (uint64_t)num_sms_ * 16);
+        if (precision == 64) marginal_kernel<double2><<<blocks, 256, 0, stream_>>>((const double2 *)d_state_ + ((size_t)b << n_local_), amps, d_q, k, d_o);
+        else marginal_kernel<float2><<<blocks, 256, 0, stream_>>>((const float2 *)d_state_ + ((size_t)b << n_local_), amps, d_q, k, d_o);
+        e = cudaGetLastError();
+        stats.launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, sizeof(double) << k, cudaMemcpyDeviceToHost, stream_);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    cudaFree(d_q); cudaFree(d_o);
+    if (e != cudaSuccess) throw CudaError(std::string("probabilities failed: ") + cudaGetErrorString(e));
+}
+
+}  // namespace cb200

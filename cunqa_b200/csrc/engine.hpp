@@ -1,0 +1,93 @@
+// engine.hpp -- device state + op queue of the B200 state-vector engine.
+//
+// A State is what the reference gets from AER::AerState (configure/allocate_qubits/initialize/
+// apply_*/apply_measure/clear, aer_simulator_adapter.cpp:185-533,887-892,937-952): a register of
+// n qubits, here x `batch` independent copies so that many shots / many small vQPUs advance in one
+// kernel launch.  Gates are queued, fused and scheduled into tile passes at flush time.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "opqueue.hpp"
+
+namespace cb200 {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define CB200_CUDA(call)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            throw cb200::CudaError(std::string(#call) + " failed: " + cudaGetErrorString(e_));        \
+    } while (0)
+
+struct Stats {
+    uint64_t passes = 0, gates = 0, fused_ops = 0, bytes = 0, launches = 0;
+    uint64_t relabelled_swaps = 0;
+};
+
+struct DistContext;  // dist.cu
+
+class State {
+public:
+    State(int n_qubits, int precision, int device, int batch);
+    ~State();
+    State(const State &) = delete;
+    State &operator=(const State &) = delete;
+
+    void reset();
+    // ---- queueing (logical qubits; `flags` = per-state condition for batched feed-forward)
+    void apply_matrix(const int *qubits, int k, const int *ctrls, int nc, const cplx *mat, const uint8_t *flags = nullptr);
+    void apply_diagonal(const int *qubits, int k, const cplx *diag, const uint8_t *flags = nullptr);
+    void apply_named(const std::string &name, const int *qubits, int nq, const double *params, int np,
+                     const uint8_t *flags = nullptr);
+    void global_phase(double theta, const uint8_t *flags = nullptr);
+    void flush();
+    void sync();
+
+    // ---- measurement
+    void norm(double *out);
+    void prob1(int qubit, double *out);
+    void probabilities(int b, const int *qubits, int k, double *out);
+    void measure(int qubit, uint64_t seed, const uint64_t *counters, const int8_t *forced, int *bits_out, bool reset_after);
+    void sample(int b, uint64_t shots, uint64_t seed, uint64_t *out);
+    void get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out);
+    void set_amplitudes(int b, const double *in);
+
+    int n, precision, device, batch;
+    PlanOptions opt;
+    Stats stats;
+    OpQueue queue;  // pending ops + logical->physical qubit map
+    DistContext *dist = nullptr;
+    int n_local() const { return n_local_; }
+    void *device_ptr() { return d_state_; }
+    size_t state_bytes() const { return state_bytes_; }
+    cudaStream_t stream() const { return stream_; }
+
+private:
+    template <typename T> void flush_t();
+    template <typename T> void reduce2_t(uint64_t sel_mask, double *d_all, double *d_sel);
+    void ensure_scratch(size_t partial_doubles);
+    void maybe_flush() { if (queue.pending() >= 4096) flush(); }
+
+    int n_local_;
+    size_t amp_bytes_, state_bytes_;
+    void *d_state_ = nullptr;
+    cudaStream_t stream_ = nullptr;
+    int num_sms_ = 148;
+    int ctas_per_sm_ = 0;  // 0 = occupancy query
+    // device scratch
+    void *d_diag_ = nullptr; size_t diag_cap_ = 0;       // diagonal tables (elements of V)
+    uint8_t *d_flags_ = nullptr; size_t flags_cap_ = 0;  // mask rows
+    double *d_partial_ = nullptr; size_t partial_cap_ = 0;
+    double *d_small_ = nullptr;   // [4*batch]: norm, p1, scale, (spare)
+    int *d_outcome_ = nullptr;    // [batch]
+    uint64_t *d_counters_ = nullptr; int8_t *d_forced_ = nullptr;
+    double *d_lvl1_ = nullptr, *d_lvl2_ = nullptr; size_t lvl1_cap_ = 0, lvl2_cap_ = 0;
+};
+
+}  // namespace cb200

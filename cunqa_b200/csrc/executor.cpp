@@ -1,0 +1,774 @@
+// executor.cpp -- whole-task execution (see executor.hpp).
+#include "executor.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <map>
+#include <random>
+#include <set>
+
+namespace cb200 {
+
+namespace {
+
+struct Inst {
+    std::string name;
+    std::vector<int> qubits, clbits, l_clbits, r_clbits;
+    std::vector<double> params;
+    std::vector<cplx> matrix;  // unitary / cunitary (row-major) or diagonal entries
+    int matrix_dim = 0;
+    std::vector<std::string> qpus;
+    std::vector<Inst> sub;
+    std::string operation = "and";
+    int condition = 1;
+};
+
+std::vector<int> int_list(const Json &j)
+{
+    std::vector<int> out;
+    for (const Json &v : j.arr) out.push_back((int)v.as_int());
+    return out;
+}
+
+Inst parse_inst(const Json &j);
+
+std::vector<Inst> parse_insts(const Json &arr)
+{
+    if (!arr.is_array()) throw std::runtime_error("'instructions' must be an array");
+    std::vector<Inst> out;
+    for (const Json &j : arr.arr) out.push_back(parse_inst(j));
+    return out;
+}
+
+// field layout per instruction family: /root/reference/src/utils/constants.hpp.in:570-916
+Inst parse_inst(const Json &j)
+{
+    Inst in;
+    in.name = j.at("name").as_string();
+    if (const Json *q = j.find("qubits")) in.qubits = int_list(*q);
+    if (const Json *c = j.find("clbits")) in.clbits = int_list(*c);
+    if (const Json *c = j.find("l_clbits")) in.l_clbits = int_list(*c);
+    if (const Json *c = j.find("r_clbits")) in.r_clbits = int_list(*c);
+    if (const Json *p = j.find("params"))
+        for (const Json &v : p->arr) in.params.push_back(v.as_double());
+    if (const Json *q = j.find("qpus"))
+        for (const Json &v : q->arr) in.qpus.push_back(v.as_string());
+    if (const Json *s = j.find("instructions")) in.sub = parse_insts(*s);
+    if (const Json *o = j.find("operation")) in.operation = o->as_string();
+    if (const Json *c = j.find("condition")) in.condition = (int)c->as_int();
+    if (const Json *m = j.find("matrix")) {
+        // unitary: [[ [ [re,im], ... ], ... ]]   diagonal: [[ [re,im], ... ]]   (one extra list level)
+        const Json &inner = m->at(0);
+        if (in.name == "diagonal") {
+            for (const Json &z : inner.arr) in.matrix.emplace_back(z.at(0).as_double(), z.at(1).as_double());
+            in.matrix_dim = (int)in.matrix.size();
+        } else {
+            in.matrix_dim = (int)inner.size();
+            for (const Json &row : inner.arr) {
+                if ((int)row.size() != in.matrix_dim) throw std::runtime_error("matrix of '" + in.name + "' is not square");
+                for (const Json &z : row.arr) in.matrix.emplace_back(z.at(0).as_double(), z.at(1).as_double());
+            }
+        }
+    }
+    return in;
+}
+
+int log2_exact(int v)
+{
+    int k = 0;
+    while ((1 << k) < v) k++;
+    if ((1 << k) != v) throw std::runtime_error("matrix dimension is not a power of two");
+    return k;
+}
+
+bool is_classical_or_remote(const std::string &n)
+{
+    static const std::set<std::string> S = {"measure", "reset", "cif", "copy", "send", "recv", "qsend", "qrecv", "expose", "rcontrol"};
+    return S.count(n) != 0;
+}
+
+// queue one unitary instruction.  qmap maps instruction qubit -> register qubit.
+template <typename Q, typename MapF>
+void queue_gate(Q &q, const Inst &in, MapF qmap, const uint8_t *flags, bool reverse_unitary_qubits)
+{
+    std::vector<int> qs;
+    for (int x : in.qubits) qs.push_back(qmap(x));
+    if (in.name == "unitary") {
+        const int k = log2_exact(in.matrix_dim);
+        if ((int)qs.size() != k) throw std::runtime_error("unitary: matrix size does not match the qubit list");
+        if (reverse_unitary_qubits) std::reverse(qs.begin(), qs.end());
+        q.apply_matrix(qs.data(), k, nullptr, 0, in.matrix.data(), flags);
+    } else if (in.name == "cunitary") {
+        const int k = log2_exact(in.matrix_dim);
+        const int nc = (int)qs.size() - k;
+        if (nc < 1) throw std::runtime_error("cunitary: needs control qubit(s)");
+        q.apply_matrix(qs.data() + nc, k, qs.data(), nc, in.matrix.data(), flags);
+    } else if (in.name == "diagonal") {
+        const int k = log2_exact(in.matrix_dim);
+        if ((int)qs.size() != k) throw std::runtime_error("diagonal: size does not match the qubit list");
+        q.apply_diagonal(qs.data(), k, in.matrix.data(), flags);
+    } else {
+        q.apply_named(in.name, qs.data(), (int)qs.size(), in.params.data(), (int)in.params.size(), flags);
+    }
+}
+
+struct TaskCfg {
+    std::string id;
+    int num_qubits = 0, num_clbits = 0;
+    uint64_t shots = 1024;
+    bool has_seed = false;
+    uint64_t seed = 0;
+    int precision = 64;
+    bool is_dynamic = false;
+    std::vector<std::string> sending_to;
+    std::vector<Inst> insts;
+    int n_comm = -1;
+    bool bugcompat_unitary_order = false;
+    bool bugcompat_teledata = false;
+    int max_batch = 0;
+};
+
+// config keys honoured (cf. quantum_task_to_AER, aer_helpers.hpp:93-140)
+TaskCfg parse_task(const Json &t)
+{
+    TaskCfg c;
+    c.id = t.contains("id") ? t.at("id").as_string() : std::string("task");
+    const Json &cfg = t.at("config");
+    c.num_qubits = (int)cfg.at("num_qubits").as_int();
+    c.num_clbits = cfg.contains("num_clbits") ? (int)cfg.at("num_clbits").as_int() : c.num_qubits;
+    if (cfg.contains("shots")) c.shots = (uint64_t)cfg.at("shots").as_int();
+    if (cfg.contains("seed")) { c.has_seed = true; c.seed = (uint64_t)cfg.at("seed").as_int(); }
+    if (cfg.contains("precision")) {
+        const std::string p = cfg.at("precision").as_string();
+        if (p == "single") c.precision = 32;
+        else if (p == "double") c.precision = 64;
+        else throw std::runtime_error("precision must be 'single' or 'double'");
+    }
+    if (cfg.contains("method")) {
+        const std::string m = cfg.at("method").as_string();
+        if (m != "automatic" && m != "statevector")
+            throw std::runtime_error("method '" + m + "' is not supported by the B200 backend (statevector only)");
+    }
+    if (cfg.contains("n_communication_qubits")) c.n_comm = (int)cfg.at("n_communication_qubits").as_int();
+    if (cfg.contains("b200_bugcompat_unitary_order")) c.bugcompat_unitary_order = cfg.at("b200_bugcompat_unitary_order").as_bool();
+    if (cfg.contains("b200_bugcompat_teledata")) c.bugcompat_teledata = cfg.at("b200_bugcompat_teledata").as_bool();
+    if (cfg.contains("b200_max_batch")) c.max_batch = (int)cfg.at("b200_max_batch").as_int();
+    c.is_dynamic = t.contains("is_dynamic") ? t.at("is_dynamic").as_bool() : false;
+    if (const Json *s = t.find("sending_to"))
+        for (const Json &v : s->arr) c.sending_to.push_back(v.as_string());
+    c.insts = parse_insts(t.at("instructions"));
+    if (c.num_qubits < 1) throw std::runtime_error("num_qubits must be >= 1");
+    return c;
+}
+
+uint64_t fresh_seed()
+{
+    std::random_device rd;
+    return ((uint64_t)rd() << 32) ^ rd();
+}
+
+std::string bits_to_string(const std::vector<uint8_t> &creg, int zero, int ncl)
+{
+    // clbit c at string index ncl-1-c (aer_simulator_adapter.cpp:780-789; aer_helpers.hpp:175-179)
+    std::string s((size_t)ncl, '0');
+    for (int c = 0; c < ncl; c++)
+        if (creg[zero + c]) s[ncl - 1 - c] = '1';
+    return s;
+}
+
+Json counts_json(const std::map<std::string, uint64_t> &counts)
+{
+    Json j = Json::object();
+    for (auto &kv : counts) j.set(kv.first, Json::integer((long long)kv.second));
+    return j;
+}
+
+bool cif_op(const std::string &op, bool a, bool b)
+{
+    if (op == "and") return a & b;
+    if (op == "or") return a | b;
+    if (op == "xor") return a ^ b;
+    if (op == "andn") return a & !b;
+    if (op == "orn") return a | !b;
+    if (op == "xorn") return a ^ !b;
+    throw std::runtime_error("unknown cif operation '" + op + "'");
+}
+
+}  // namespace
+
+State &Backend::get_state(int n, int precision, int batch)
+{
+    if (state_ && state_->n == n && state_->precision == precision && state_->batch == batch) {
+        state_->reset();
+        return *state_;
+    }
+    state_.reset();
+    state_.reset(new State(n, precision, device_, batch));
+    return *state_;
+}
+
+std::string Backend::execute(const std::string &tasks_json)
+{
+    try {
+        const Json msg = Json::parse(tasks_json);
+        return run(msg).dump();
+    } catch (const std::exception &e) {
+        // same contract as the reference adapters (aer_simulator_adapter.cpp:836-840)
+        Json err = Json::object();
+        err.set("ERROR", Json::string(e.what()));
+        return err.dump();
+    }
+}
+
+// {"params":[...],"shots":N}: rewrite the cached task in circuit order by gate arity
+// (/root/reference/src/quantum_task.cpp:39-108)
+static void update_params(Json &task, const Json &msg)
+{
+    const Json &params = msg.at("params");
+    size_t counter = 0;
+    Json *insts = task.find("instructions");
+    if (!insts || insts->arr.empty()) throw std::runtime_error("Circuit not sent before updating parameters.");
+    for (Json &inst : insts->arr) {
+        const std::string name = inst.at("name").as_string();
+        int ar = update_param_arity(name);
+        if (ar == 0) continue;
+        Json *p = inst.find("params");
+        if (!p) throw std::runtime_error("Error updating parameters: instruction '" + name + "' has no params");
+        if ((name == "u" || name == "cu") && p->arr.size() < 4) ar = (int)p->arr.size();  // builder emits 3-parameter u
+        for (int k = 0; k < ar; k++) {
+            if (counter >= params.size()) throw std::runtime_error("Error updating parameters: too few parameters (check correct size).");
+            if ((size_t)k >= p->arr.size()) p->arr.push_back(Json::number(0));
+            p->arr[k] = Json::number(params.at(counter++).as_double());
+        }
+    }
+    Json *cfg = task.find("config");
+    if (cfg && msg.contains("shots")) cfg->set("shots", Json::integer(msg.at("shots").as_int()));
+}
+
+Json Backend::run(const Json &msg)
+{
+    if (msg.is_array()) {
+        std::vector<Json> tasks(msg.arr.begin(), msg.arr.end());
+        if (tasks.empty()) throw std::runtime_error("empty task list");
+        return run_dynamic(tasks);
+    }
+    if (!msg.is_object()) throw std::runtime_error("quantum task must be a JSON object");
+    if (msg.contains("instructions") && msg.contains("config")) {
+        cached_ = msg;
+        has_cached_ = true;
+    } else if (msg.contains("params")) {
+        if (!has_cached_) throw std::runtime_error("Circuit not sent before updating parameters.");
+        update_params(cached_, msg);
+    } else {
+        throw std::runtime_error("message has neither instructions+config nor params");
+    }
+    const Json &task = cached_;
+    // static vs dynamic (aer_simple_simulator.cpp:8-22): the flag decides; a "static" task that
+    // measures mid-circuit is also sent down the per-shot path, as Aer does internally.
+    bool dynamic = task.contains("is_dynamic") && task.at("is_dynamic").as_bool();
+    if (!dynamic) {
+        const Json &insts = task.at("instructions");
+        uint64_t measured = 0;
+        for (const Json &j : insts.arr) {
+            const std::string name = j.at("name").as_string();
+            if (name == "measure") {
+                for (const Json &q : j.at("qubits").arr) measured |= 1ull << q.as_int();
+            } else if (is_classical_or_remote(name)) {
+                dynamic = true;
+            } else if (const Json *qs = j.find("qubits")) {
+                for (const Json &q : qs->arr)
+                    if (q.as_int() >= 0 && ((measured >> q.as_int()) & 1ull)) dynamic = true;
+            }
+        }
+    }
+    if (dynamic) {
+        Json r = run_dynamic({task});
+        Json out = Json::object();
+        const std::string id = task.contains("id") ? task.at("id").as_string() : std::string("task");
+        out.set("counts", r.at("id_counts").at(id));
+        out.set("time_taken", r.at("time_taken"));
+        return out;
+    }
+    return run_static(task);
+}
+
+Json Backend::run_static(const Json &task)
+{
+    const TaskCfg c = parse_task(task);
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    State &st = get_state(c.num_qubits, c.precision, 1);
+    const Stats before = st.stats;
+    const uint64_t gates_before = st.queue.gates;
+    std::vector<std::pair<int, int>> meas;  // (qubit, clbit)
+    bool save_state = false;
+    for (const Inst &in : c.insts) {
+        if (in.name == "measure") {
+            if (in.qubits.size() != in.clbits.size()) throw std::runtime_error("measure: qubits/clbits size mismatch");
+            for (size_t i = 0; i < in.qubits.size(); i++) {
+                if (in.qubits[i] < 0 || in.qubits[i] >= c.num_qubits) throw std::runtime_error("measure: qubit out of range");
+                if (in.clbits[i] < 0 || in.clbits[i] >= c.num_clbits) throw std::runtime_error("measure: clbit out of range");
+                meas.emplace_back(in.qubits[i], in.clbits[i]);
+            }
+        } else if (in.name == "save_state") {
+            save_state = true;
+        } else {
+            queue_gate(st, in, [](int q) { return q; }, nullptr, false);
+        }
+    }
+    const uint64_t seed = c.has_seed ? c.seed : fresh_seed();
+    std::vector<uint64_t> samples(c.shots);
+    st.sample(0, c.shots, seed, samples.data());
+    std::map<std::string, uint64_t> counts;
+    std::string key((size_t)c.num_clbits, '0');
+    for (uint64_t s : samples) {
+        std::fill(key.begin(), key.end(), '0');
+        for (auto &qc : meas)
+            key[c.num_clbits - 1 - qc.second] = ((s >> qc.first) & 1ull) ? '1' : '0';
+        counts[key]++;
+    }
+    Json out = Json::object();
+    out.set("counts", counts_json(counts));
+    if (save_state) {
+        if (c.num_qubits > 20) throw std::runtime_error("save_state: statevector return is limited to 20 qubits");
+        const uint64_t dim = 1ull << c.num_qubits;
+        std::vector<uint64_t> idx(dim);
+        for (uint64_t i = 0; i < dim; i++) idx[i] = i;
+        std::vector<double> amps(2 * dim);
+        st.get_amplitudes(0, idx.data(), dim, amps.data());
+        Json sv = Json::array();
+        for (uint64_t i = 0; i < dim; i++) {
+            Json z = Json::array();
+            z.arr.push_back(Json::number(amps[2 * i]));
+            z.arr.push_back(Json::number(amps[2 * i + 1]));
+            sv.arr.push_back(std::move(z));
+        }
+        out.set("statevector", std::move(sv));
+    }
+    const auto t1 = std::chrono::high_resolution_clock::now();
+    out.set("time_taken", Json::number(std::chrono::duration<double>(t1 - t0).count()));
+    last_stats = st.stats;
+    last_stats.passes -= before.passes;
+    last_stats.launches -= before.launches;
+    last_stats.bytes -= before.bytes;
+    last_stats.fused_ops -= before.fused_ops;
+    last_stats.gates = st.queue.gates - gates_before;
+    return out;
+}
+
+// ---- dynamic path: per-shot interpreter, shots batched on the device ---------------------------
+namespace {
+
+struct CommPair {
+    int q0, q1;
+    bool idle = true;
+    std::string sendr, recvr, proto;
+    int label = 0;
+};
+
+struct TaskRt {
+    const TaskCfg *cfg;
+    int zq = 0, zc = 0;
+    size_t pc = 0;
+    bool finished = false, b_td = false, b_tg = false, b_cc = false, cat = false;
+};
+
+using Bits = std::vector<uint8_t>;
+
+}  // namespace
+
+Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
+{
+    std::vector<TaskCfg> cfgs;
+    for (const Json &t : tasks_json) cfgs.push_back(parse_task(t));
+    const bool multi = cfgs.size() > 1;
+    const TaskCfg &c0 = cfgs[0];
+    // joint register: sum of task widths + communication pairs (aer_simulator_adapter.cpp:855-874)
+    int n_comm = 0;
+    if (multi) {
+        n_comm = c0.n_comm >= 0 ? c0.n_comm : 2;
+        if (n_comm % 2) n_comm++;
+    }
+    int n_total = n_comm, ncl_total = 0;
+    for (const TaskCfg &c : cfgs) { n_total += c.num_qubits; ncl_total += c.num_clbits; }
+    const uint64_t shots = c0.shots;
+    const uint64_t seed = c0.has_seed ? c0.seed : fresh_seed();
+    const int precision = 64;  // the reference forces double on this path (:946)
+
+    // does any task talk to another process?  then shots run one by one, in the reference's order
+    bool external_cc = false;
+    if (!multi)
+        for (const Inst &in : c0.insts)
+            if (in.name == "send" || in.name == "recv") external_cc = true;
+    if (external_cc && (!send_ || !recv_)) throw std::runtime_error("send/recv used but no classical channel is attached");
+
+    // batch size: as many shots as fit a memory budget
+    uint64_t B = shots;
+    {
+        const double state_bytes = 16.0 * std::ldexp(1.0, n_total);
+        const double budget = 48.0 * 1073741824.0;
+        uint64_t cap = (uint64_t)std::max(1.0, std::floor(budget / state_bytes));
+        cap = std::min<uint64_t>(cap, 4096);
+        if (c0.max_batch > 0) cap = std::min<uint64_t>(cap, (uint64_t)c0.max_batch);
+        B = std::max<uint64_t>(1, std::min(B, cap));
+        if (external_cc) B = 1;
+    }
+
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    std::map<std::string, std::map<std::string, uint64_t>> counters;
+    for (const TaskCfg &c : cfgs) counters[c.id];
+    Stats acc;
+    if (shots == 0) B = 1;
+    State *stp = shots ? &get_state(n_total, precision, (int)B) : nullptr;
+    const Stats before = stp ? stp->stats : Stats();
+    const uint64_t gates_before = stp ? stp->queue.gates : 0;
+
+    for (uint64_t shot0 = 0; shot0 < shots; shot0 += B) {
+        State &st = *stp;
+        if (shot0 > 0) st.reset();
+        const int nb = (int)B;  // the last batch may carry surplus states; their results are dropped
+        const uint64_t live = std::min<uint64_t>(B, shots - shot0);
+        std::vector<TaskRt> T(cfgs.size());
+        std::map<std::string, size_t> by_id;
+        {
+            int zq = 0, zc = 0;
+            for (size_t i = 0; i < cfgs.size(); i++) {
+                T[i].cfg = &cfgs[i];
+                T[i].zq = zq;
+                T[i].zc = zc;
+                zq += cfgs[i].num_qubits;
+                zc += cfgs[i].num_clbits;
+                by_id[cfgs[i].id] = i;
+            }
+        }
+        std::vector<CommPair> pairs;
+        for (int i = 0; i < n_comm; i += 2) pairs.push_back(CommPair{n_total - n_comm + i, n_total - n_comm + i + 1});
+        std::vector<Bits> creg((size_t)ncl_total, Bits(nb, 0));
+        std::map<std::string, std::deque<Bits>> q_td, q_tg;
+        std::map<std::pair<std::string, std::string>, std::deque<Bits>> q_cc;
+        std::vector<uint64_t> ordinal(nb, 0), ctr(nb);
+
+        auto peer = [&](const std::string &id) -> TaskRt & {
+            auto it = by_id.find(id);
+            if (it == by_id.end()) throw std::runtime_error("remote instruction refers to unknown task '" + id + "'");
+            return T[it->second];
+        };
+        // measure (optionally conditioned by `flags`) every state; returns the outcome bits
+        auto measure = [&](int q, bool reset_after, const uint8_t *flags) -> Bits {
+            std::vector<int8_t> forced;
+            for (int b = 0; b < nb; b++) ctr[b] = ((shot0 + b + 1) << 20) + ordinal[b];
+            if (flags) {
+                forced.assign(nb, -1);
+                for (int b = 0; b < nb; b++) if (!flags[b]) forced[b] = -2;
+            }
+            std::vector<int> out(nb);
+            st.measure(q, seed, ctr.data(), flags ? forced.data() : nullptr, out.data(), reset_after);
+            Bits bits(nb, 0);
+            for (int b = 0; b < nb; b++) {
+                if (out[b] >= 0) { bits[b] = (uint8_t)out[b]; ordinal[b]++; }
+            }
+            return bits;
+        };
+        auto any = [&](const Bits &f) { return std::any_of(f.begin(), f.end(), [](uint8_t v) { return v != 0; }); };
+        auto all = [&](const Bits &f) { return std::all_of(f.begin(), f.end(), [](uint8_t v) { return v != 0; }); };
+        auto named = [&](const char *name, std::vector<int> qs, const Bits *flags) {
+            if (flags && !any(*flags)) return;
+            const uint8_t *fp = (flags && !all(*flags)) ? flags->data() : nullptr;
+            st.apply_named(name, qs.data(), (int)qs.size(), nullptr, 0, fp);
+        };
+        auto gen_ent = [&](size_t npairs) {
+            std::vector<int> idx;
+            for (size_t i = 0; i < pairs.size() && idx.size() < npairs; i++) if (pairs[i].idle) idx.push_back((int)i);
+            if (idx.size() < npairs) return std::vector<int>();
+            for (int i : idx) {
+                pairs[i].idle = false;
+                measure(pairs[i].q1, true, nullptr);
+                measure(pairs[i].q0, true, nullptr);
+                named("h", {pairs[i].q0}, nullptr);
+                named("cx", {pairs[i].q0, pairs[i].q1}, nullptr);
+            }
+            return idx;
+        };
+        auto my_pairs = [&](const std::string &s, const std::string &r, const std::string &proto, size_t npairs) {
+            std::vector<int> out;
+            for (size_t i = 0; i < pairs.size(); i++) {
+                if (npairs && out.size() == npairs) break;
+                if (!pairs[i].idle && pairs[i].sendr == s && pairs[i].recvr == r && pairs[i].proto == proto) out.push_back((int)i);
+            }
+            return out;
+        };
+
+        // one instruction of task t (cond = per-state condition from enclosing cif, may be null)
+        std::function<void(TaskRt &, const Inst &, const std::vector<int> &, const Bits *)> step =
+            [&](TaskRt &t, const Inst &in, const std::vector<int> &comm_idx, const Bits *cond) {
+                const TaskCfg &c = *t.cfg;
+                auto qmap = [&](int q) {
+                    if (q < 0) {
+                        for (int i : comm_idx)
+                            if (!pairs[i].idle && pairs[i].label == q) return pairs[i].q1;
+                        throw std::runtime_error("unresolved remote control qubit");
+                    }
+                    if (q >= c.num_qubits) throw std::runtime_error("qubit index out of range in task '" + c.id + "'");
+                    return q + t.zq;
+                };
+                auto clb = [&](int cl) -> Bits & {
+                    if (cl < 0 || cl >= c.num_clbits) throw std::runtime_error("clbit index out of range in task '" + c.id + "'");
+                    return creg[(size_t)(cl + t.zc)];
+                };
+                auto assign = [&](Bits &dst, const Bits &src) {
+                    for (int b = 0; b < nb; b++) if (!cond || (*cond)[b]) dst[b] = src[b];
+                };
+                const std::string &name = in.name;
+                if (name == "measure") {
+                    assign(clb(in.clbits.at(0)), measure(qmap(in.qubits.at(0)), false, cond ? cond->data() : nullptr));
+                } else if (name == "copy") {
+                    if (in.l_clbits.size() != in.r_clbits.size())
+                        throw std::runtime_error("The number of copied clbits and the number of clbits copied on does not match.");
+                    for (size_t i = 0; i < in.l_clbits.size(); i++) { const Bits src = clb(in.r_clbits[i]); assign(clb(in.l_clbits[i]), src); }
+                } else if (name == "reset") {
+                    measure(qmap(in.qubits.at(0)), true, cond ? cond->data() : nullptr);
+                } else if (name == "send") {
+                    if (multi) {
+                        for (int cl : in.clbits) q_cc[{c.id, in.qpus.at(0)}].push_back(clb(cl));
+                    } else {
+                        for (int cl : in.clbits) send_(user_, clb(cl)[0], in.qpus.at(0).c_str());
+                    }
+                } else if (name == "recv") {
+                    if (multi) {
+                        auto &qq = q_cc[{in.qpus.at(0), c.id}];
+                        if (qq.size() >= in.clbits.size()) {
+                            for (int cl : in.clbits) { assign(clb(cl), qq.front()); qq.pop_front(); }
+                            t.b_cc = false;
+                        } else {
+                            t.b_cc = true;
+                        }
+                    } else {
+                        st.sync();  // drain the stream before blocking on the network (cf. flush_ops, :574)
+                        for (int cl : in.clbits) {
+                            Bits v(nb, (uint8_t)(recv_(user_, in.qpus.at(0).c_str()) == 1));
+                            assign(clb(cl), v);
+                        }
+                    }
+                } else if (name == "cif") {
+                    // fold the clbits with cif_ops (:582-600)
+                    const bool cnd = in.condition != 0;
+                    Bits res(nb, 0);
+                    for (int b = 0; b < nb; b++) {
+                        bool accb = cnd ? clb(in.clbits.at(0))[b] != 0 : clb(in.clbits.at(0))[b] == 0;
+                        for (size_t k = 1; k < in.clbits.size(); k++) accb = cif_op(in.operation, accb, clb(in.clbits[k])[b] != 0);
+                        const bool r = cnd ? accb : !accb;
+                        res[b] = (uint8_t)((cnd == r) && (!cond || (*cond)[b]));
+                    }
+                    if (any(res))
+                        for (const Inst &sub : in.sub) step(t, sub, {}, &res);
+                } else if (name == "qsend") {
+                    const std::vector<int> idx = gen_ent(1);
+                    if (idx.empty()) { t.b_td = true; return; }
+                    t.b_td = false;
+                    CommPair &p = pairs[idx[0]];
+                    p.proto = "teledata";
+                    const int q = qmap(in.qubits.at(0));
+                    named("cx", {q, p.q0}, nullptr);
+                    named("h", {q}, nullptr);
+                    q_td[c.id].push_back(measure(q, true, nullptr));  // measure + "reset if 1" (:618-624)
+                    q_td[c.id].push_back(measure(p.q0, false, nullptr));
+                    peer(in.qpus.at(0)).b_td = false;
+                    p.sendr = c.id;
+                    p.recvr = in.qpus.at(0);
+                } else if (name == "qrecv") {
+                    auto &qq = q_td[in.qpus.at(0)];
+                    if (qq.empty()) { t.b_td = true; return; }
+                    if (t.b_td) return;
+                    const Bits m1 = qq.front(); qq.pop_front();
+                    const Bits m2 = qq.front(); qq.pop_front();
+                    const std::vector<int> mine = my_pairs(in.qpus.at(0), c.id, "teledata", 1);
+                    if (mine.empty()) throw std::runtime_error("qrecv without an entangled pair");
+                    CommPair &p = pairs[mine[0]];
+                    // m1 = outcome of the sent qubit, m2 = outcome of the sender's comm qubit.  The documented
+                    // protocol (docs/source/_static/teledata.png) is X <- m2, Z <- m1; the reference code
+                    // (:653-658) has them swapped, which does not teleport -- mirrored only under bugcompat.
+                    const bool lit = cfgs[0].bugcompat_teledata;
+                    named("x", {p.q1}, lit ? &m1 : &m2);
+                    named("z", {p.q1}, lit ? &m2 : &m1);
+                    named("swap", {p.q1, qmap(in.qubits.at(0))}, nullptr);
+                    p.idle = true;
+                } else if (name == "expose") {
+                    if (!t.cat) {
+                        const std::vector<int> idx = gen_ent(in.qubits.size());
+                        if (idx.empty()) { t.b_tg = true; return; }
+                        int qid = 0;
+                        for (int i : idx) {
+                            CommPair &p = pairs[i];
+                            p.proto = "telegate";
+                            p.label = -(qid + 1);
+                            named("cx", {qmap(in.qubits[qid]), p.q0}, nullptr);
+                            q_tg[c.id].push_back(measure(p.q0, false, nullptr));
+                            t.cat = true;
+                            t.b_tg = true;
+                            peer(in.qpus.at(0)).b_tg = false;
+                            p.sendr = c.id;
+                            p.recvr = in.qpus.at(0);
+                            qid++;
+                        }
+                        return;
+                    }
+                    auto &qq = q_tg[in.qpus.at(0)];
+                    for (size_t i = 0; i < in.qubits.size(); i++) {
+                        if (qq.empty()) throw std::runtime_error("expose: missing telegate measurement");
+                        const Bits m = qq.front(); qq.pop_front();
+                        named("z", {qmap(in.qubits[i])}, &m);
+                    }
+                    t.cat = false;
+                    for (int i : my_pairs(c.id, in.qpus.at(0), "telegate", in.qubits.size())) pairs[i].idle = true;
+                } else if (name == "rcontrol") {
+                    auto &qq = q_tg[in.qpus.at(0)];
+                    if (qq.empty()) { t.b_tg = true; return; }
+                    if (t.b_tg) return;
+                    const std::vector<int> idx = my_pairs(in.qpus.at(0), c.id, "telegate", 0);
+                    for (int i : idx) {
+                        const Bits m = qq.front(); qq.pop_front();
+                        named("x", {pairs[i].q1}, &m);
+                    }
+                    for (const Inst &sub : in.sub) step(t, sub, idx, cond);
+                    for (int i : idx) {
+                        named("h", {pairs[i].q1}, nullptr);
+                        q_tg[c.id].push_back(measure(pairs[i].q1, false, nullptr));
+                    }
+                    peer(in.qpus.at(0)).b_tg = false;
+                    t.b_tg = false;
+                } else {
+                    if (cond && !any(*cond)) return;
+                    const uint8_t *fp = (cond && !all(*cond)) ? cond->data() : nullptr;
+                    queue_gate(st, in, qmap, fp, c.bugcompat_unitary_order);
+                }
+            };
+
+        // round-robin scheduler (aer_simulator_adapter.cpp:755-778)
+        bool ended = false;
+        uint64_t guard = 0;
+        while (!ended) {
+            ended = true;
+            bool progressed = false;
+            for (TaskRt &t : T) {
+                if (t.finished) continue;
+                const std::vector<Inst> &ins = t.cfg->insts;
+                if (t.pc >= ins.size()) { t.finished = true; continue; }
+                if (t.b_td || t.b_tg || t.b_cc) {
+                    ended = false;
+                    if (!t.b_cc) continue;
+                    // a task blocked on a local RECV re-polls its queue (the reference would spin forever here)
+                }
+                const size_t pc0 = t.pc;
+                const bool was_blocked = t.b_td || t.b_tg || t.b_cc;
+                step(t, ins[t.pc], {}, nullptr);
+                if (!(t.b_td || t.b_tg || t.b_cc)) t.pc++;
+                if (t.pc != pc0 || !was_blocked) progressed = true;
+                if (t.pc != ins.size()) ended = false;
+                else t.finished = true;
+            }
+            if (!ended && !progressed && ++guard > 1000)
+                throw std::runtime_error("dynamic circuit deadlock: every task is blocked on communication");
+            if (progressed) guard = 0;
+        }
+        st.sync();
+        for (const TaskRt &t : T)
+            for (uint64_t b = 0; b < live; b++) {
+                std::vector<uint8_t> bits((size_t)ncl_total);
+                for (int cl = 0; cl < ncl_total; cl++) bits[cl] = creg[cl][b];
+                counters[t.cfg->id][bits_to_string(bits, t.zc, t.cfg->num_clbits)]++;
+            }
+    }
+    const auto t1 = std::chrono::high_resolution_clock::now();
+    Json idc = Json::object();
+    for (auto &kv : counters) idc.set(kv.first, counts_json(kv.second));
+    Json out = Json::object();
+    out.set("id_counts", std::move(idc));
+    out.set("time_taken", Json::number(std::chrono::duration<double>(t1 - t0).count()));
+    if (stp) {
+        last_stats = stp->stats;
+        last_stats.passes -= before.passes;
+        last_stats.launches -= before.launches;
+        last_stats.bytes -= before.bytes;
+        last_stats.fused_ops -= before.fused_ops;
+        last_stats.gates = stp->queue.gates - gates_before;
+    }
+    (void)acc;
+    return out;
+}
+
+// ---- planning without a device -------------------------------------------------------------------
+std::string plan_task_json(const std::string &task_json, const std::string &options_json)
+{
+    const Json task = Json::parse(task_json);
+    const TaskCfg c = parse_task(task);
+    PlanOptions opt;
+    opt.tile_bits = c.precision == 64 ? 12 : 13;
+    opt.min_run_bits = c.precision == 64 ? 4 : 5;
+    if (!options_json.empty()) {
+        const Json o = Json::parse(options_json);
+        if (o.contains("tile_bits")) opt.tile_bits = (int)o.at("tile_bits").as_int();
+        if (o.contains("min_run_bits")) opt.min_run_bits = (int)o.at("min_run_bits").as_int();
+        if (o.contains("max_diag_qubits")) opt.max_diag_qubits = (int)o.at("max_diag_qubits").as_int();
+        if (o.contains("max_pass_cost")) opt.max_pass_cost = (int)o.at("max_pass_cost").as_int();
+        if (o.contains("fuse")) opt.fuse = o.at("fuse").as_bool();
+    }
+    OpQueue q(c.num_qubits, 1, opt);
+    for (const Inst &in : c.insts) {
+        if (is_classical_or_remote(in.name)) continue;
+        queue_gate(q, in, [](int x) { return x; }, nullptr, false);
+    }
+    const std::vector<Pass> passes = schedule_passes(q.ops(), c.num_qubits, opt);
+    auto cplx_arr = [](const std::vector<cplx> &v) {
+        Json a = Json::array();
+        for (const cplx &z : v) {
+            Json e = Json::array();
+            e.arr.push_back(Json::number(z.real()));
+            e.arr.push_back(Json::number(z.imag()));
+            a.arr.push_back(std::move(e));
+        }
+        return a;
+    };
+    auto int_arr = [](const std::vector<int> &v) {
+        Json a = Json::array();
+        for (int x : v) a.arr.push_back(Json::integer(x));
+        return a;
+    };
+    Json out = Json::object();
+    out.set("num_qubits", Json::integer(c.num_qubits));
+    out.set("gates", Json::integer((long long)q.gates));
+    out.set("relabelled_swaps", Json::integer((long long)q.relabelled_swaps));
+    out.set("l2p", int_arr(q.l2p));
+    Json jops = Json::array();
+    static const char *kinds[] = {"dense", "diag", "permx", "swap"};
+    for (const HostOp &op : q.ops()) {
+        Json o = Json::object();
+        o.set("kind", Json::string(kinds[(int)op.kind]));
+        o.set("q", int_arr(op.q));
+        o.set("ctrl", int_arr(op.ctrl));
+        o.set("m", cplx_arr(op.m));
+        o.set("n_orig", Json::integer(op.n_orig));
+        jops.arr.push_back(std::move(o));
+    }
+    out.set("ops", std::move(jops));
+    Json jp = Json::array();
+    for (const Pass &p : passes) {
+        Json o = Json::object();
+        o.set("tile_q", int_arr(p.tile_q));
+        o.set("L", Json::integer(p.L));
+        o.set("ops", int_arr(p.op_idx));
+        // encode to make sure the pass is launchable, and report the kernel-parameter footprint
+        PassParams<double> pp;
+        std::vector<cplx> diag;
+        std::string err;
+        if (!encode_pass<double>(p, q.ops(), c.num_qubits, 1, pp, diag, err)) throw std::runtime_error(err);
+        o.set("diag_entries", Json::integer((long long)diag.size()));
+        jp.arr.push_back(std::move(o));
+    }
+    out.set("passes", std::move(jp));
+    return out.dump();
+}
+
+}  // namespace cb200

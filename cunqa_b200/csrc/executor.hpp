@@ -1,0 +1,46 @@
+// executor.hpp -- whole-task execution behind cb200_backend_execute.
+//
+// Static tasks:  AerSimulatorAdapter::simulate(const Backend*)           (aer_simulator_adapter.cpp:806-842)
+// Dynamic tasks: AerSimulatorAdapter::simulate(ClassicalChannel*, bool)  (:845-935) + execute_shot_ (:120-792)
+// with shots batched on the device (B independent states advance per launch) instead of the
+// reference's one-state-per-shot loop / OpenMP team (:877-925).
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+
+#include "engine.hpp"
+#include "json_min.hpp"
+
+namespace cb200 {
+
+typedef void (*send_fn)(void *user, int bit, const char *target);
+typedef int (*recv_fn)(void *user, const char *origin);
+
+class Backend {
+public:
+    explicit Backend(int device) : device_(device) {}
+    // returns the result JSON text (never throws: failures become {"ERROR": "..."} )
+    std::string execute(const std::string &tasks_json);
+    void set_channel(send_fn s, recv_fn r, void *user) { send_ = s; recv_ = r; user_ = user; }
+    Stats last_stats;
+
+private:
+    Json run(const Json &msg);
+    Json run_static(const Json &task);
+    Json run_dynamic(const std::vector<Json> &tasks);
+    State &get_state(int n, int precision, int batch);
+
+    int device_;
+    std::unique_ptr<State> state_;
+    Json cached_;          // last full task message (for {"params":...} updates)
+    bool has_cached_ = false;
+    send_fn send_ = nullptr;
+    recv_fn recv_ = nullptr;
+    void *user_ = nullptr;
+};
+
+// plan a task without a device: fused ops + tile passes as JSON (cb200_plan_json)
+std::string plan_task_json(const std::string &task_json, const std::string &options_json);
+
+}  // namespace cb200

@@ -1,0 +1,60 @@
+// pass_types.hpp -- POD descriptors shared by the host planner and the sm_100a tile-pass kernel.
+//
+// A *tile pass* is one in-place sweep over the whole state (2*S algorithmic bytes): the state is
+// cut into tiles of 2^t amplitudes spanned by a chosen set of t "tile qubits" (the low L of them
+// are always physical qubits 0..L-1, so that every tile is made of contiguous runs of 2^L
+// amplitudes = 128-bit coalesced segments); each CTA stages a tile in shared memory, applies the
+// pass's whole op list to it, and writes it back.
+#pragma once
+#include <cstdint>
+
+namespace cb200 {
+
+constexpr int kMaxTileBits = 13;  // 2^13 complex128 = 128 KiB of shared memory
+constexpr int kMaxOps = 48;       // ops per pass
+constexpr int kMaxDenseK = 5;     // dense block width (qubits)
+constexpr int kMaxDiagK = 12;     // diagonal table width (qubits)
+constexpr int kMaxFix = 12;       // targets + in-tile controls of one op
+constexpr int kMatScalars = 2560; // scalars (re/im) of dense-matrix storage per pass (kernel params)
+
+enum OpKind : uint8_t {
+    OP_DENSE = 0,  // dense 2^k x 2^k on in-tile targets, optional controls
+    OP_DIAG = 1,   // diagonal table over k qubits anywhere (in-tile or not)
+    OP_PERMX = 2,  // X on tbit[0] (controls optional): pure pair swap, no flops
+    OP_SWAP = 3,   // swap tbit[0] <-> tbit[1] (controls optional)
+};
+
+struct DevOp {
+    uint8_t kind;
+    uint8_t k;       // DENSE: #targets; DIAG: #qubits of the table
+    uint8_t nfix;    // DENSE/PERM: number of entries in fixpos (targets + in-tile controls)
+    uint8_t has_mask;
+    uint8_t tbit[8];        // DENSE/PERM: tile-bit position of target m
+    uint8_t fixpos[kMaxFix]; // ascending tile-bit positions where a bit is inserted into the group index
+    uint8_t dsrc[kMaxDiagK]; // DIAG: source of table-index bit m: <64 tile bit, >=64 physical qubit (v-64) outside the tile
+    uint32_t ctrl_in;   // in-tile control bits (OR-ed into the tile index; those bits are in fixpos)
+    uint32_t mat_off;   // DENSE: scalar offset into PassParams::mats; DIAG: element offset into the diag-table buffer
+    uint64_t ctrl_out;  // physical-qubit mask of controls outside the tile (tested on the tile base)
+    int32_t mask_row;   // row of the per-state flag matrix (batched feed-forward) when has_mask
+    int32_t pad_;
+};
+static_assert(sizeof(DevOp) == 64, "DevOp layout");
+
+template <typename T>
+struct PassParams {
+    int32_t n;        // qubits per state
+    int32_t t;        // tile bits
+    int32_t L;        // low tile bits that are physical qubits 0..L-1 (contiguous run = 2^L amps)
+    int32_t n_ops;
+    int32_t batch;    // independent states
+    int32_t pad_;
+    uint64_t tiles_per_state;
+    uint8_t tile_q[16]; // physical qubit of tile bit j (ascending)
+    DevOp ops[kMaxOps];
+    T mats[kMatScalars];
+};
+
+// dim3 / smem sizing helpers shared with the host
+constexpr int kTileThreads = 256;
+
+}  // namespace cb200

@@ -1,0 +1,308 @@
+// planner.cpp -- gate fusion + tile-pass scheduling (host only; see planner.hpp).
+#include "planner.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace cb200 {
+
+uint64_t HostOp::qmask() const
+{
+    uint64_t m = 0;
+    for (int x : q) m |= 1ull << x;
+    for (int x : ctrl) m |= 1ull << x;
+    return m;
+}
+uint64_t HostOp::xmask() const
+{
+    if (kind == DIAG) return 0;
+    uint64_t m = 0;
+    for (int x : q) m |= 1ull << x;
+    return m;
+}
+
+static int popcount64(uint64_t v) { return __builtin_popcountll(v); }
+
+static std::vector<int> mask_to_list(uint64_t m)
+{
+    std::vector<int> out;
+    for (int i = 0; i < 64; i++) if ((m >> i) & 1ull) out.push_back(i);
+    return out;
+}
+
+// full dense matrix of `op` over the qubit list uq (index bit m <-> uq[m]); uq must cover op's qubits
+std::vector<cplx> embed_dense(const HostOp &op, const std::vector<int> &uq)
+{
+    const int K = (int)uq.size();
+    const int D = 1 << K;
+    auto pos = [&](int qubit) {
+        for (int i = 0; i < K; i++) if (uq[i] == qubit) return i;
+        return -1;
+    };
+    std::vector<int> tp, cp;
+    for (int x : op.q) tp.push_back(pos(x));
+    for (int x : op.ctrl) cp.push_back(pos(x));
+    const int k = (int)op.q.size();
+    std::vector<cplx> M((size_t)D * D, cplx(0, 0));
+    for (int c = 0; c < D; c++) {
+        bool on = true;
+        for (int p : cp) if (!((c >> p) & 1)) on = false;
+        if (!on) { M[(size_t)c * D + c] = 1; continue; }
+        int j = 0;  // sub-index over op.q
+        for (int m = 0; m < k; m++) j |= ((c >> tp[m]) & 1) << m;
+        int rest = c;
+        for (int m = 0; m < k; m++) rest &= ~(1 << tp[m]);
+        auto row_of = [&](int jj) {
+            int r = rest;
+            for (int m = 0; m < k; m++) if ((jj >> m) & 1) r |= 1 << tp[m];
+            return r;
+        };
+        switch (op.kind) {
+        case HostOp::DENSE:
+            for (int jj = 0; jj < (1 << k); jj++) M[(size_t)row_of(jj) * D + c] = op.m[(size_t)jj * (1 << k) + j];
+            break;
+        case HostOp::DIAG: M[(size_t)c * D + c] = op.m[j]; break;
+        case HostOp::PERMX: M[(size_t)row_of(j ^ 1) * D + c] = 1; break;
+        case HostOp::SWAP: {
+            const int jj = ((j & 1) << 1) | ((j >> 1) & 1);
+            M[(size_t)row_of(jj) * D + c] = 1;
+            break;
+        }
+        }
+    }
+    return M;
+}
+
+std::vector<cplx> matmul(const std::vector<cplx> &b, const std::vector<cplx> &a, int dim)
+{
+    std::vector<cplx> out((size_t)dim * dim, cplx(0, 0));
+    for (int r = 0; r < dim; r++)
+        for (int k = 0; k < dim; k++) {
+            const cplx v = b[(size_t)r * dim + k];
+            if (v == cplx(0, 0)) continue;
+            for (int c = 0; c < dim; c++) out[(size_t)r * dim + c] += v * a[(size_t)k * dim + c];
+        }
+    return out;
+}
+
+HostOp expand_controls(const HostOp &op)
+{
+    if (op.ctrl.empty() && op.kind == HostOp::DENSE) return op;
+    HostOp out;
+    out.kind = HostOp::DENSE;
+    out.q = op.q;
+    out.q.insert(out.q.end(), op.ctrl.begin(), op.ctrl.end());
+    out.m = embed_dense(op, out.q);
+    out.mask_row = op.mask_row;
+    out.n_orig = op.n_orig;
+    return out;
+}
+
+bool Fuser::try_merge(HostOp &prev, const HostOp &nw)
+{
+    const uint64_t P = prev.qmask(), N = nw.qmask(), U = P | N;
+    const int nu = popcount64(U);
+    if (prev.kind == HostOp::DIAG && nw.kind == HostOp::DIAG) {
+        if (nu > opt.max_diag_qubits) return false;
+        const std::vector<int> uq = mask_to_list(U);
+        std::vector<cplx> tab((size_t)1 << nu);
+        auto sub = [&](const HostOp &o, int idx) {
+            int j = 0;
+            for (size_t m = 0; m < o.q.size(); m++) {
+                const int p = (int)(std::find(uq.begin(), uq.end(), o.q[m]) - uq.begin());
+                j |= ((idx >> p) & 1) << m;
+            }
+            return o.m[j];
+        };
+        for (int idx = 0; idx < (1 << nu); idx++) tab[idx] = sub(prev, idx) * sub(nw, idx);
+        prev.q = uq;
+        prev.m = std::move(tab);
+        prev.n_orig += nw.n_orig;
+        return true;
+    }
+    // dense absorb: one op's qubit set contains the other's
+    if (U != P && U != N) return false;
+    if (nu > opt.max_dense_qubits) return false;
+    const HostOp &big = (U == P) ? prev : nw;
+    const bool big_plain_dense = big.kind == HostOp::DENSE && big.ctrl.empty();
+    if (nu > 2 && !big_plain_dense) return false;
+    // keep the qubit order of the containing op so that a plain dense block keeps its matrix layout
+    std::vector<int> uq = big.q;
+    for (int c : big.ctrl) uq.push_back(c);
+    const std::vector<cplx> A = embed_dense(prev, uq), B = embed_dense(nw, uq);
+    HostOp merged;
+    merged.kind = HostOp::DENSE;
+    merged.q = uq;
+    merged.m = matmul(B, A, 1 << nu);
+    merged.n_orig = prev.n_orig + nw.n_orig;
+    // a product that is diagonal goes back to the (tile-free) diagonal form
+    if (is_diagonal(merged.m, 1 << nu)) {
+        std::vector<cplx> d((size_t)1 << nu);
+        for (int i = 0; i < (1 << nu); i++) d[i] = merged.m[(size_t)i * (1 << nu) + i];
+        merged.kind = HostOp::DIAG;
+        merged.m = std::move(d);
+    }
+    prev = std::move(merged);
+    return true;
+}
+
+void Fuser::push(HostOp op)
+{
+    if (!opt.fuse || op.mask_row >= 0) { ops.push_back(std::move(op)); return; }
+    const uint64_t qm = op.qmask(), xm = op.xmask();
+    int steps = 0;
+    for (int i = (int)ops.size() - 1; i >= 0 && steps < 64; --i, ++steps) {
+        HostOp &prev = ops[i];
+        const uint64_t pm = prev.qmask();
+        if (!(pm & qm)) continue;      // disjoint: commutes
+        if (prev.mask_row >= 0) break; // conditioned op: ordering barrier
+        if (try_merge(prev, op)) return;
+        const bool commute = ((prev.xmask() & qm) == 0) && ((xm & pm) == 0);
+        if (commute) continue;         // both act diagonally on the shared qubits
+        break;
+    }
+    ops.push_back(std::move(op));
+}
+
+static int dense_cost(const HostOp &op)
+{
+    switch (op.kind) {
+    case HostOp::DENSE: return 1 << op.q.size();
+    case HostOp::DIAG: return 1;
+    default: return 1;
+    }
+}
+
+std::vector<Pass> schedule_passes(const std::vector<HostOp> &ops, int n, const PlanOptions &opt)
+{
+    std::vector<Pass> passes;
+    const int t = std::min(n, std::min(opt.tile_bits, kMaxTileBits));
+    const int lmin = std::min(t, std::max(0, opt.min_run_bits));
+    std::vector<char> done(ops.size(), 0);
+    size_t first = 0, remaining = ops.size();
+    const uint64_t all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+    while (remaining > 0) {
+        while (first < ops.size() && done[first]) first++;
+        uint64_t Q = (lmin >= 64) ? ~0ull : ((1ull << lmin) - 1ull);
+        // the first pending op always goes in; if it does not fit beside the forced low qubits,
+        // shrink the forced set (its targets still span >= 1 run of the lowest qubits)
+        {
+            const uint64_t need = ops[first].xmask();
+            int forced = lmin;
+            while (forced > 0 && popcount64((((1ull << forced) - 1ull)) | need) > t) forced--;
+            Q = (forced > 0 ? ((1ull << forced) - 1ull) : 0ull);
+        }
+        uint64_t blockedX = 0, blockedZ = 0;
+        Pass pass;
+        int cost = 0, mat_scalars = 0;
+        for (size_t i = first; i < ops.size(); i++) {
+            if (done[i]) continue;
+            const HostOp &op = ops[i];
+            const uint64_t qx = op.xmask();
+            const uint64_t qz = op.qmask() & ~qx;
+            bool can = !(qx & (blockedX | blockedZ)) && !(qz & blockedX);
+            if (can) {
+                const uint64_t newQ = Q | qx;
+                const int c = dense_cost(op);
+                const int ms = op.kind == HostOp::DENSE ? 2 * (1 << (2 * op.q.size())) : 0;
+                bool fits = popcount64(newQ) <= t && (int)pass.op_idx.size() < kMaxOps &&
+                            mat_scalars + ms <= kMatScalars;
+                if (fits && opt.max_pass_cost > 0 && !pass.op_idx.empty() && cost + c > opt.max_pass_cost) fits = false;
+                if (fits) {
+                    Q = newQ;
+                    cost += c;
+                    mat_scalars += ms;
+                    pass.op_idx.push_back((int)i);
+                    continue;
+                }
+            }
+            blockedX |= qx;
+            blockedZ |= qz;
+            if ((blockedX & all) == all) break;
+        }
+        // pad the tile with the lowest unused physical qubits (longer contiguous runs)
+        for (int qb = 0; qb < n && popcount64(Q) < t; qb++) Q |= 1ull << qb;
+        pass.tile_q = mask_to_list(Q);
+        pass.L = 0;
+        while (pass.L < (int)pass.tile_q.size() && pass.tile_q[pass.L] == pass.L) pass.L++;
+        for (int i : pass.op_idx) { done[i] = 1; remaining--; }
+        passes.push_back(std::move(pass));
+    }
+    return passes;
+}
+
+template <typename T>
+bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int batch, PassParams<T> &out,
+                 std::vector<cplx> &diag_host, std::string &err)
+{
+    std::memset(&out, 0, sizeof(out));
+    const int t = (int)pass.tile_q.size();
+    out.n = n;
+    out.t = t;
+    out.L = pass.L;
+    out.batch = batch;
+    out.tiles_per_state = 1ull << (n - t);
+    for (int j = 0; j < t; j++) out.tile_q[j] = (uint8_t)pass.tile_q[j];
+    auto tile_pos = [&](int qubit) {
+        for (int j = 0; j < t; j++) if (pass.tile_q[j] == qubit) return j;
+        return -1;
+    };
+    int nops = 0, mat_used = 0;
+    for (int oi : pass.op_idx) {
+        const HostOp &op = ops[oi];
+        if (nops >= kMaxOps) { err = "too many ops in one pass"; return false; }
+        DevOp &d = out.ops[nops++];
+        d.has_mask = op.mask_row >= 0;
+        d.mask_row = op.mask_row;
+        if (op.kind == HostOp::DIAG) {
+            d.kind = OP_DIAG;
+            d.k = (uint8_t)op.q.size();
+            if (d.k > kMaxDiagK) { err = "diagonal table too wide"; return false; }
+            for (int m = 0; m < d.k; m++) {
+                const int p = tile_pos(op.q[m]);
+                d.dsrc[m] = (uint8_t)(p >= 0 ? p : 64 + op.q[m]);
+            }
+            d.mat_off = (uint32_t)diag_host.size();
+            diag_host.insert(diag_host.end(), op.m.begin(), op.m.end());
+            continue;
+        }
+        d.kind = op.kind == HostOp::DENSE ? OP_DENSE : (op.kind == HostOp::PERMX ? OP_PERMX : OP_SWAP);
+        d.k = (uint8_t)op.q.size();
+        if (op.kind == HostOp::DENSE && d.k > kMaxDenseK) { err = "dense block wider than 5 qubits"; return false; }
+        std::vector<int> fix;
+        for (int m = 0; m < d.k; m++) {
+            const int p = tile_pos(op.q[m]);
+            if (p < 0) { err = "internal: target outside tile"; return false; }
+            d.tbit[m] = (uint8_t)p;
+            fix.push_back(p);
+        }
+        for (int c : op.ctrl) {
+            const int p = tile_pos(c);
+            if (p >= 0) { d.ctrl_in |= 1u << p; fix.push_back(p); }
+            else d.ctrl_out |= 1ull << c;
+        }
+        std::sort(fix.begin(), fix.end());
+        if ((int)fix.size() > kMaxFix) { err = "too many in-tile controls"; return false; }
+        d.nfix = (uint8_t)fix.size();
+        for (size_t f = 0; f < fix.size(); f++) d.fixpos[f] = (uint8_t)fix[f];
+        if (op.kind == HostOp::DENSE) {
+            const int sc = 2 * (1 << (2 * d.k));
+            if (mat_used + sc > kMatScalars) { err = "pass matrix storage exhausted"; return false; }
+            d.mat_off = (uint32_t)mat_used;
+            for (size_t e = 0; e < op.m.size(); e++) {
+                out.mats[mat_used + 2 * e] = (T)op.m[e].real();
+                out.mats[mat_used + 2 * e + 1] = (T)op.m[e].imag();
+            }
+            mat_used += sc;
+        }
+    }
+    out.n_ops = nops;
+    return true;
+}
+
+template bool encode_pass<double>(const Pass &, const std::vector<HostOp> &, int, int, PassParams<double> &,
+                                  std::vector<cplx> &, std::string &);
+template bool encode_pass<float>(const Pass &, const std::vector<HostOp> &, int, int, PassParams<float> &,
+                                 std::vector<cplx> &, std::string &);
+
+}  // namespace cb200

@@ -1,0 +1,72 @@
+// planner.hpp -- host side of the hot path (H1 of SURVEY 8a): gate fusion and tile-pass scheduling.
+//
+// Plays the role of Aer's fusion pass + op buffer on the reference's CPU path (the work behind
+// controller_execute / flush_ops at aer_simulator_adapter.cpp:829,564), but plans for the B200
+// memory system: ops are grouped into *tile passes* (one HBM round trip each, see pass_types.hpp)
+// instead of one 2^n sweep per fused gate.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "gates.hpp"
+#include "pass_types.hpp"
+
+namespace cb200 {
+
+struct HostOp {
+    enum Kind { DENSE, DIAG, PERMX, SWAP } kind = DENSE;
+    std::vector<int> q;     // DENSE/PERMX/SWAP: target qubits; DIAG: table qubits (bit m of the table index <-> q[m])
+    std::vector<int> ctrl;  // control qubits (must all be 1); always empty for DIAG (folded into the table)
+    std::vector<cplx> m;    // DENSE: 2^k x 2^k row-major; DIAG: 2^k entries
+    int mask_row = -1;      // per-state flag row (batched feed-forward), -1 = unconditional
+    int n_orig = 1;         // original circuit gates folded into this op
+
+    uint64_t qmask() const;   // all qubits touched
+    uint64_t xmask() const;   // qubits acted on non-diagonally
+};
+
+struct PlanOptions {
+    int tile_bits = 12;        // t: 2^t amplitudes staged per tile
+    int min_run_bits = 4;      // L_min: low physical qubits forced into every tile (coalescing)
+    int max_diag_qubits = 10;  // width of a merged diagonal table
+    int max_dense_qubits = 5;  // widest dense block the kernel accepts
+    int max_pass_cost = 0;     // cap on sum over dense ops of 2^k per pass (0 = unlimited)
+    bool fuse = true;
+};
+
+struct Pass {
+    std::vector<int> tile_q;       // ascending physical qubits spanning the tile
+    int L = 0;                     // leading run bits
+    std::vector<int> op_idx;       // indices into the fused op list, program order
+};
+
+// Fuser: feeds ops one at a time and merges them into the pending list.
+class Fuser {
+public:
+    explicit Fuser(const PlanOptions &o) : opt(o) {}
+    void push(HostOp op);
+    std::vector<HostOp> ops;
+    PlanOptions opt;
+
+private:
+    bool try_merge(HostOp &prev, const HostOp &nw);
+};
+
+// expand controls into a dense matrix over (targets..., ctrls...) ; index bit order = [q..., ctrl...]
+HostOp expand_controls(const HostOp &op);
+// dense product on the union qubit set `uq` (bit m <-> uq[m]):  result = B_embedded * A_embedded (A first)
+std::vector<cplx> embed_dense(const HostOp &op, const std::vector<int> &uq);
+std::vector<cplx> matmul(const std::vector<cplx> &b, const std::vector<cplx> &a, int dim);
+
+// group the fused ops into tile passes for an n-qubit register
+std::vector<Pass> schedule_passes(const std::vector<HostOp> &ops, int n, const PlanOptions &opt);
+
+// build the kernel parameter block of one pass.  diag tables are appended to `diag_host`
+// (element units) and referenced by offset.  Returns false + err if the pass cannot be encoded.
+template <typename T>
+bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int batch, PassParams<T> &out,
+                 std::vector<cplx> &diag_host, std::string &err);
+
+}  // namespace cb200

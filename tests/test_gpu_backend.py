@@ -1,0 +1,172 @@
+"""GPU (-m gpu): whole-task execution through cb200_backend_execute -- the call the CUNQA plugin
+makes -- against the oracle's interpreter (static sample path and per-shot dynamic path)."""
+import math
+
+import numpy as np
+import pytest
+
+import cunqa_b200 as cb
+from cunqa_b200 import circuits as C
+from oracle import oracle_np as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def backend(lib_built):
+    be = cb.Backend(0)
+    yield be
+    be.close()
+
+
+def test_ghz20_config1(backend):
+    """BASELINE config 1: GHZ-20, 1024 shots, seed 1234"""
+    n, shots = 20, 1024
+    res = backend.execute(C.task(C.ghz(n), n, shots=shots, seed=1234))
+    assert "ERROR" not in res, res
+    counts = res["counts"]
+    assert set(counts) <= {"0" * n, "1" * n} and sum(counts.values()) == shots
+    assert abs(counts["0" * n] / shots - 0.5) <= 4 * math.sqrt(0.25 / shots)
+    assert res["time_taken"] > 0
+    _, want = O.run_static(C.ghz(n), n, shots=shots, seed=1234, backend="c")
+    assert counts == want  # shared RNG stream
+
+
+def test_static_counts_equal_oracle(backend):
+    n = 9
+    ins = C.quantum_volume(n, depth=5, seed=4)
+    # measure a subset into shuffled clbits: clbit c is character ncl-1-c
+    ins += [{"name": "measure", "qubits": [q], "clbits": [c]} for q, c in [(0, 3), (4, 0), (8, 1)]]
+    res = backend.execute(C.task(ins, n, num_clbits=5, shots=3000, seed=21))
+    _, want = O.run_static(ins, n, n_clbits=5, shots=3000, seed=21, backend="c")
+    assert res["counts"] == want
+    assert all(len(k) == 5 for k in res["counts"])
+
+
+def test_precision_single(backend):
+    n = 12
+    ins = C.hea_ansatz(n, 3)
+    res = backend.execute(C.task(ins, n, shots=4000, seed=3, precision="single"))
+    _, want = O.run_static(ins, n, shots=4000, seed=3, backend="c")
+    assert O.tvd(res["counts"], want) < 0.01  # rounding can move a handful of shots
+
+
+def test_save_state(backend):
+    n = 5
+    ins = C.quantum_volume(n, depth=3, seed=2) + [{"name": "save_state", "qubits": list(range(n))}]
+    res = backend.execute(C.task(ins, n, shots=10, seed=1))
+    sv = np.array([complex(*z) for z in res["statevector"]])
+    ref, _ = O.run_static(ins, n, backend="numpy")
+    assert np.abs(sv - ref.amplitudes()).max() < 1e-12
+
+
+def test_errors_become_error_json(backend):
+    res = backend.execute(C.task([{"name": "hz2", "qubits": [0]}], 2))
+    assert "ERROR" in res and "unsupported" in res["ERROR"]
+    res = backend.execute({"params": [0.1], "shots": 5}) if False else res
+    res = backend.execute(C.task([{"name": "h", "qubits": [0]}], 2, method="stabilizer"))
+    assert "ERROR" in res and "statevector only" in res["ERROR"]
+    res = backend.execute("{not json")
+    assert "ERROR" in res
+
+
+def test_upgrade_parameters_path(lib_built):
+    """{"params":[...],"shots":N} re-runs the cached circuit with new angles (quantum_task.cpp:39-108)"""
+    be = cb.Backend(0)
+    n = 6
+    p0 = np.linspace(0.1, 2.0, 2 * n * 2)
+    p1 = p0[::-1].copy()
+    res = be.execute({"params": list(p1), "shots": 10})
+    assert "ERROR" in res and "Circuit not sent" in res["ERROR"]
+    be.execute(C.task(C.hea_ansatz(n, 2, params=p0), n, shots=100, seed=5))
+    res = be.execute({"params": list(p1), "shots": 2500})
+    _, want = O.run_static(C.hea_ansatz(n, 2, params=p1), n, shots=2500, seed=5, backend="numpy")
+    assert res["counts"] == want
+    be.close()
+
+
+def dyn_task(ins, n, ncl, shots, seed, **cfg):
+    return C.task(ins, n, num_clbits=ncl, shots=shots, seed=seed, is_dynamic=True, **cfg)
+
+
+def test_mid_circuit_measure_and_cif(backend):
+    ins = [{"name": "h", "qubits": [0]}, {"name": "ry", "qubits": [2], "params": [0.9]},
+           {"name": "measure", "qubits": [0], "clbits": [0]},
+           {"name": "cif", "clbits": [0], "operation": "and", "condition": 1,
+            "instructions": [{"name": "x", "qubits": [1]}, {"name": "rx", "qubits": [2], "params": [1.3]}]},
+           {"name": "cif", "clbits": [0], "operation": "and", "condition": 0,
+            "instructions": [{"name": "h", "qubits": [1]}]},
+           {"name": "measure", "qubits": [1], "clbits": [1]}, {"name": "measure", "qubits": [2], "clbits": [2]},
+           {"name": "reset", "qubits": [0]}, {"name": "measure", "qubits": [0], "clbits": [3]}]
+    shots = 600
+    res = backend.execute(dyn_task(ins, 3, 4, shots, 17))
+    assert "ERROR" not in res, res
+    want = O.run_dynamic([{"id": "task", "num_qubits": 3, "num_clbits": 4, "instructions": ins}], shots, seed=17)["task"]
+    assert res["counts"] == want  # same per-shot RNG counters => identical shots
+    assert all(k[0] == "0" for k in res["counts"])  # clbit 3 (leftmost) holds the reset qubit
+
+
+@pytest.mark.parametrize("op,cond", [("and", 1), ("or", 1), ("xor", 1), ("andn", 0), ("orn", 1), ("xorn", 0)])
+def test_cif_operations(backend, op, cond):
+    ins = [{"name": "h", "qubits": [0]}, {"name": "h", "qubits": [1]},
+           {"name": "measure", "qubits": [0], "clbits": [0]}, {"name": "measure", "qubits": [1], "clbits": [1]},
+           {"name": "cif", "clbits": [0, 1], "operation": op, "condition": cond, "instructions": [{"name": "x", "qubits": [2]}]},
+           {"name": "measure", "qubits": [2], "clbits": [2]}]
+    res = backend.execute(dyn_task(ins, 3, 3, 300, 2))
+    want = O.run_dynamic([{"id": "task", "num_qubits": 3, "num_clbits": 3, "instructions": ins}], 300, seed=2)["task"]
+    assert res["counts"] == want
+
+
+def test_batching_does_not_change_results(backend):
+    ins = C.hea_ansatz(5, 2, measure=False) + [{"name": "measure", "qubits": [2], "clbits": [0]},
+                                               {"name": "cif", "clbits": [0], "operation": "and", "condition": 1,
+                                                "instructions": [{"name": "y", "qubits": [4]}]}] + C.measure_all(5)
+    a = backend.execute(dyn_task(ins, 5, 5, 257, 9))
+    b = backend.execute(dyn_task(ins, 5, 5, 257, 9, b200_max_batch=1))
+    c = backend.execute(dyn_task(ins, 5, 5, 257, 9, b200_max_batch=100))
+    assert a["counts"] == b["counts"] == c["counts"] and sum(a["counts"].values()) == 257
+
+
+@pytest.mark.parametrize("maker", [C.hea_teledata_pair, C.hea_telegate_pair])
+def test_quantum_communication_joint_register(backend, maker):
+    """executor-style call: several tasks, one joint register + comm pair (aer_simulator_adapter.cpp:131-159)"""
+    tasks = maker(4)
+    shots = 400
+    msg = [C.task(t["instructions"], t["num_qubits"], shots=shots, seed=33, task_id=t["id"], is_dynamic=True) for t in tasks]
+    res = backend.execute(msg)
+    assert "ERROR" not in res, res
+    want = O.run_dynamic(tasks, shots, seed=33)
+    assert res["id_counts"] == want
+
+
+def test_teledata_teleports(backend):
+    theta = 1.1
+    a = [{"name": "ry", "qubits": [0], "params": [theta]}, {"name": "qsend", "qubits": [0], "qpus": ["B"]}]
+    b = [{"name": "qrecv", "qubits": [0], "qpus": ["A"]}, {"name": "measure", "qubits": [0], "clbits": [0]}]
+    shots = 4000
+    msg = [C.task(a, 1, shots=shots, seed=1, task_id="A", is_dynamic=True), C.task(b, 1, shots=shots, seed=1, task_id="B", is_dynamic=True)]
+    res = backend.execute(msg)
+    p1 = res["id_counts"]["B"].get("1", 0) / shots
+    assert abs(p1 - math.sin(theta / 2) ** 2) < 4 * math.sqrt(0.25 / shots)
+    # the literal reference code (X/Z corrections swapped, quirk Q6) only under the bugcompat switch
+    msg[0]["config"]["b200_bugcompat_teledata"] = True
+    lit = backend.execute(msg)
+    want = O.run_dynamic([{"id": "A", "num_qubits": 1, "num_clbits": 1, "instructions": a},
+                          {"id": "B", "num_qubits": 1, "num_clbits": 1, "instructions": b}], shots, seed=1, teledata_literal=True)
+    assert lit["id_counts"] == want
+
+
+def test_classical_send_recv_between_processes(lib_built):
+    """SEND/RECV through the channel hooks (ClassicalChannel::send_measure / recv_measure)"""
+    be = cb.Backend(0)
+    sent, inbox = [], [1, 0, 1, 1, 0, 0, 1, 0]
+    be.set_channel(lambda bit, tgt: sent.append((bit, tgt)), lambda org: inbox.pop(0))
+    ins = [{"name": "x", "qubits": [0]}, {"name": "measure", "qubits": [0], "clbits": [0]},
+           {"name": "send", "clbits": [0], "qpus": ["peer"]}, {"name": "recv", "clbits": [1], "qpus": ["peer"]},
+           {"name": "cif", "clbits": [1], "operation": "and", "condition": 1, "instructions": [{"name": "x", "qubits": [1]}]},
+           {"name": "measure", "qubits": [1], "clbits": [1]}]
+    res = be.execute(C.task(ins, 2, shots=8, seed=0, is_dynamic=True, sending_to=["peer"]))
+    assert "ERROR" not in res, res
+    assert sent == [(1, "peer")] * 8
+    assert res["counts"] == {"11": 4, "01": 4}
+    be.close()

@@ -1,0 +1,182 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Tolerances are BASELINE.json's: max-abs amplitude error <= 1e-10 (fp64) / 1e-5 (fp32),
+fidelity >= 1 - 1e-9 (fp64); histograms: exact agreement where oracle and engine share the RNG
+stream, TVD within the shot-noise bound otherwise.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import cunqa_b200 as cb
+from cunqa_b200 import circuits as C
+from oracle import oracle_np as O
+from conftest import random_circuit
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"double": 1e-10, "single": 1e-5}
+
+
+def fidelity(a, b):
+    return abs(np.vdot(a, b)) ** 2 / (np.vdot(a, a).real * np.vdot(b, b).real)
+
+
+def run_gpu(ins, n, precision="double", batch=1):
+    with cb.StateVector(n, precision, batch=batch) as sv:
+        sv.run(ins)
+        return sv.amplitudes(), sv.stats()
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+@pytest.mark.parametrize("seed", range(10))
+def test_random_circuits_match_oracle(lib_built, seed, precision):
+    n = 2 + seed
+    ins = random_circuit(n, 150, seed, max_unitary=min(n, 5))
+    ref, _ = O.run_static(ins, n, backend="numpy")
+    got, _ = run_gpu(ins, n, precision)
+    assert np.abs(got - ref.amplitudes()).max() < TOL[precision]
+    if precision == "double":
+        assert fidelity(got, ref.amplitudes()) >= 1 - 1e-9
+
+
+@pytest.mark.parametrize("tile_bits,run_bits", [(4, 0), (5, 2), (6, 3), (8, 4), (10, 5), (13, 4)])
+def test_many_tiles_and_strided_runs(lib_built, monkeypatch, tile_bits, run_bits):
+    """small tiles force every addressing path: out-of-tile controls, diagonal bits taken from the
+    tile base, high tile qubits with strided runs"""
+    monkeypatch.setenv("CB200_TILE_BITS", str(tile_bits))
+    monkeypatch.setenv("CB200_MIN_RUN_BITS", str(run_bits))
+    n = 14
+    ins = random_circuit(n, 200, 100 + tile_bits, max_unitary=min(4, tile_bits))
+    ref, _ = O.run_static(ins, n, backend="c")
+    got, stats = run_gpu(ins, n)
+    assert np.abs(got - ref.amplitudes()).max() < 1e-10
+    assert stats["passes"] >= 1 and stats["gates"] == sum(1 for i in ins if i["name"] != "id")
+
+
+@pytest.mark.parametrize("fuse", ["0", "1"])
+def test_fusion_on_off_same_result(lib_built, monkeypatch, fuse):
+    monkeypatch.setenv("CB200_FUSE", fuse)
+    n = 12
+    ins = C.hea_ansatz(n, layers=4, measure=False) + random_circuit(n, 60, 5)
+    ref, _ = O.run_static(ins, n, backend="numpy")
+    got, _ = run_gpu(ins, n)
+    assert np.abs(got - ref.amplitudes()).max() < 1e-10
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 12, 13, 20, 24])
+def test_qft_closed_form(lib_built, n):
+    x = C.qft_x(n, seed=7)
+    with cb.StateVector(n) as sv:
+        sv.run(C.qft(n, x))
+        rng = np.random.default_rng(0)
+        idx = np.arange(1 << n) if n <= 16 else rng.integers(0, 1 << n, size=1 << 16).astype(np.uint64)
+        got = sv.amplitudes(idx)
+        assert np.abs(got - O.qft_amplitudes(n, x, idx)).max() < 1e-10
+        assert abs(sv.norm()[0] - 1) < 1e-10
+        assert sv.stats()["relabelled_swaps"] == n // 2
+
+
+@pytest.mark.parametrize("n,precision", [(16, "double"), (20, "double"), (22, "double"), (20, "single")])
+def test_quantum_volume_vs_oracle(lib_built, n, precision):
+    ins = C.quantum_volume(n, seed=2024)
+    ref, _ = O.run_static(ins, n, backend="c")
+    got, stats = run_gpu(ins, n, precision)
+    assert np.abs(got - ref.amplitudes()).max() < TOL[precision]
+    if precision == "double":
+        assert fidelity(got, ref.amplitudes()) >= 1 - 1e-9
+    assert stats["passes"] < len(ins)  # several blocks per HBM round trip
+
+
+def test_quantum_volume_inverse_roundtrip_26(lib_built):
+    """size-independent property at a size the oracle would need minutes for: U^dagger U |0> = |0>"""
+    n = 26
+    ins = C.quantum_volume(n, depth=8, seed=1)
+    with cb.StateVector(n) as sv:
+        sv.run(ins + C.inverse(ins))
+        a0 = sv.amplitudes([0, 1, 12345, (1 << n) - 1])
+        assert abs(a0[0] - 1) < 1e-10 and np.abs(a0[1:]).max() < 1e-10
+        assert abs(sv.norm()[0] - 1) < 1e-10
+
+
+def test_dense_blocks_up_to_five_qubits(lib_built):
+    n = 9
+    rng = np.random.default_rng(3)
+    ins = []
+    for k in (1, 2, 3, 4, 5, 5, 4, 3):
+        q = list(map(int, rng.permutation(n)[:k]))
+        ins.append(C.unitary_inst(C.haar_unitary(rng, 1 << k), q))
+    ref, _ = O.run_static(ins, n, backend="numpy")
+    for precision in ("double", "single"):
+        got, _ = run_gpu(ins, n, precision)
+        assert np.abs(got - ref.amplitudes()).max() < TOL[precision]
+
+
+def test_set_get_amplitudes_and_probabilities(lib_built):
+    n = 7
+    rng = np.random.default_rng(1)
+    v = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    v /= np.linalg.norm(v)
+    with cb.StateVector(n) as sv:
+        sv.apply_gate("swap", [0, 5])  # non-trivial qubit relabelling must be transparent
+        sv.set_amplitudes(v)
+        assert np.abs(sv.amplitudes() - v).max() < 1e-15
+        p = sv.probabilities([1, 4, 6])
+        i = np.arange(1 << n)
+        j = ((i >> 1) & 1) | (((i >> 4) & 1) << 1) | (((i >> 6) & 1) << 2)
+        ref = np.bincount(j, weights=np.abs(v) ** 2, minlength=8)
+        assert np.abs(p - ref).max() < 1e-13
+        assert abs(sv.prob1(4)[0] - ref.reshape(2, 2, 2)[:, 1, :].sum()) < 1e-13
+
+
+def test_sampling_matches_oracle_stream(lib_built):
+    """same splitmix64 stream + same inverse-CDF rule => the same shots, not just the same histogram"""
+    for n in (3, 10, 14, 21):
+        ins = C.quantum_volume(n, depth=5, seed=n)
+        ref, _ = O.run_static(ins, n, backend="c")
+        want = ref.sample(4000, 77)
+        with cb.StateVector(n) as sv:
+            sv.run(ins)
+            got = sv.sample(4000, 77)
+        # a shot can differ only if u falls within rounding distance of a CDF step
+        assert np.count_nonzero(got != want) <= 2
+
+
+def test_measure_collapse_matches_oracle(lib_built):
+    n = 10
+    ins = C.quantum_volume(n, depth=4, seed=8)
+    ref, _ = O.run_static(ins, n, backend="c")
+    with cb.StateVector(n) as sv:
+        sv.run(ins)
+        for step, q in enumerate([3, 0, 9, 3]):
+            want = ref.measure(q, 5, step)
+            got = sv.measure(q, seed=5, counters=[step])[0]
+            assert got == want
+            assert np.abs(sv.amplitudes() - ref.amplitudes()).max() < 1e-10
+        sv.measure(7, seed=5, counters=[99], reset=True)
+        assert sv.prob1(7)[0] < 1e-14 and abs(sv.norm()[0] - 1) < 1e-10
+
+
+def test_batched_states_and_masked_gates(lib_built):
+    n, B = 6, 5
+    flags = np.array([1, 0, 1, 1, 0], dtype=np.uint8)
+    with cb.StateVector(n, batch=B) as sv:
+        sv.apply_gate("h", [0])
+        sv.apply_gate("x", [3], flags=flags)          # feed-forward: only flagged states
+        sv.apply_gate("cry", [0, 3], [0.8], flags=1 - flags)
+        sv.apply_gate("cx", [0, 5])
+        for b in range(B):
+            st = O.NumpyState(n)
+            O.apply_gate(st, {"name": "h", "qubits": [0]})
+            if flags[b]:
+                O.apply_gate(st, {"name": "x", "qubits": [3]})
+            else:
+                O.apply_gate(st, {"name": "cry", "qubits": [0, 3], "params": [0.8]})
+            O.apply_gate(st, {"name": "cx", "qubits": [0, 5]})
+            assert np.abs(sv.amplitudes(b=b) - st.amplitudes()).max() < 1e-12
+        # forced outcomes: deterministic test mode
+        bits = sv.measure(0, forced=[1, 0, 1, 0, 1])
+        assert list(bits) == [1, 0, 1, 0, 1]
+        assert np.allclose(sv.norm(), 1.0, atol=1e-12)
+        assert np.allclose(sv.prob1(5), [1, 0, 1, 0, 1], atol=1e-12)

@@ -1,0 +1,116 @@
+"""CPU: pin the oracle (C restatement + numpy twin) against analytic known answers and each other.
+
+The reference holds no numeric fixtures for this path (parity unpinned), so the
+anchors are closed forms: GHZ, QFT|x>, U^dagger U = 1, teleportation fidelity.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from cunqa_b200 import circuits as C
+from oracle import oracle_np as O
+from conftest import random_circuit
+
+
+@pytest.mark.parametrize("backend", ["numpy", "c"])
+@pytest.mark.parametrize("n", [1, 2, 5, 11])
+def test_qft_closed_form(lib_built, backend, n):
+    x = C.qft_x(n, seed=n)
+    st, _ = O.run_static(C.qft(n, x), n, backend=backend)
+    ref = O.qft_amplitudes(n, x, np.arange(1 << n))
+    assert np.abs(st.amplitudes() - ref).max() < 1e-13
+
+
+@pytest.mark.parametrize("backend", ["numpy", "c"])
+def test_ghz(lib_built, backend):
+    n = 9
+    st, counts = O.run_static(C.ghz(n), n, shots=2000, seed=11, backend=backend)
+    a = st.amplitudes()
+    assert abs(a[0] - 1 / math.sqrt(2)) < 1e-14 and abs(a[-1] - 1 / math.sqrt(2)) < 1e-14
+    assert np.abs(a[1:-1]).max() < 1e-15
+    assert set(counts) <= {"0" * n, "1" * n}
+    assert abs(counts["0" * n] / 2000 - 0.5) < 4 * math.sqrt(0.25 / 2000)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_numpy_twin_equals_c(lib_built, seed):
+    n = 3 + seed
+    ins = random_circuit(n, 120, seed)
+    a, _ = O.run_static(ins, n, backend="numpy")
+    b, _ = O.run_static(ins, n, backend="c")
+    assert np.abs(a.amplitudes() - b.amplitudes()).max() < 1e-13
+    assert abs(a.norm() - 1) < 1e-12
+
+
+def test_inverse_roundtrip(lib_built):
+    n = 10
+    ins = C.quantum_volume(n, depth=6, seed=5)
+    st, _ = O.run_static(ins + C.inverse(ins), n, backend="c")
+    a = st.amplitudes()
+    assert abs(a[0] - 1) < 1e-12 and np.abs(a[1:]).max() < 1e-12
+
+
+def test_sampling_same_stream_both_backends(lib_built):
+    n = 8
+    ins = C.quantum_volume(n, depth=4, seed=1, measure=True)
+    a, ca = O.run_static(ins, n, shots=500, seed=42, backend="numpy")
+    b, cb = O.run_static(ins, n, shots=500, seed=42, backend="c")
+    assert ca == cb  # same splitmix stream, same inverse-CDF rule
+    p = np.abs(a.amplitudes()) ** 2
+    emp = np.zeros(1 << n)
+    for k, v in ca.items():
+        emp[int(k, 2)] = v / 500
+    assert 0.5 * np.abs(emp - p).sum() < 0.5 * math.sqrt((1 << n) / 500) + 0.05
+
+
+def test_measure_collapse(lib_built):
+    for backend in ("numpy", "c"):
+        st = O.make_state(3, backend)
+        st.apply_matrix([0], O._FIXED_1Q["h"])
+        st.apply_matrix([1], O._FIXED_1Q["x"], [0])
+        out = st.measure(0, seed=3, counter=0)
+        a = st.amplitudes()
+        assert abs(abs(a[3 if out else 0]) - 1) < 1e-14 and abs(st.norm() - 1) < 1e-14
+
+
+def test_bit_order_clbit0_rightmost():
+    # aer_helpers.hpp:175-179: clbit 0 is the rightmost character
+    assert O.bits_to_string({0: 1}, 3) == "001"
+    assert O.bits_to_string({2: 1}, 3) == "100"
+
+
+def test_teledata_moves_the_state(lib_built):
+    """QSEND/QRECV restatement: B's qubit 0 must end up in the state A prepared (any outcome bits)."""
+    theta = 1.1
+    a = [{"name": "ry", "qubits": [0], "params": [theta]}, {"name": "qsend", "qubits": [0], "qpus": ["B"]}]
+    b = [{"name": "qrecv", "qubits": [0], "qpus": ["A"]}, {"name": "measure", "qubits": [0], "clbits": [0]}]
+    tasks = [{"id": "A", "num_qubits": 1, "num_clbits": 1, "instructions": a},
+             {"id": "B", "num_qubits": 1, "num_clbits": 1, "instructions": b}]
+    shots = 4000
+    res = O.run_dynamic(tasks, shots, seed=9)
+    p1 = res["B"].get("1", 0) / shots
+    assert abs(p1 - math.sin(theta / 2) ** 2) < 4 * math.sqrt(0.25 / shots)
+
+
+def test_telegate_is_a_remote_cx(lib_built):
+    """EXPOSE/RCONTROL restatement: remote cx from A's |+> onto B's |0> gives a Bell pair."""
+    a = [{"name": "h", "qubits": [0]}, {"name": "expose", "qubits": [0], "qpus": ["B"]},
+         {"name": "measure", "qubits": [0], "clbits": [0]}]
+    b = [{"name": "rcontrol", "qpus": ["A"], "instructions": [{"name": "cx", "qubits": [-1, 0]}]},
+         {"name": "measure", "qubits": [0], "clbits": [0]}]
+    tasks = [{"id": "A", "num_qubits": 1, "num_clbits": 1, "instructions": a},
+             {"id": "B", "num_qubits": 1, "num_clbits": 1, "instructions": b}]
+    # joint outcomes must be perfectly correlated: run shot by shot with the same seed and compare
+    for shot_seed in range(40):
+        r = O.run_dynamic(tasks, 1, seed=shot_seed)
+        assert list(r["A"]) == list(r["B"])
+
+
+def test_cif_feed_forward(lib_built):
+    ins = [{"name": "h", "qubits": [0]}, {"name": "measure", "qubits": [0], "clbits": [0]},
+           {"name": "cif", "clbits": [0], "operation": "and", "condition": 1,
+            "instructions": [{"name": "x", "qubits": [1]}]},
+           {"name": "measure", "qubits": [1], "clbits": [1]}]
+    res = O.run_dynamic([{"id": "t", "num_qubits": 2, "num_clbits": 2, "instructions": ins}], 200, seed=4)
+    assert set(res["t"]) <= {"00", "11"} and len(res["t"]) == 2

@@ -1,0 +1,107 @@
+"""CPU: the host fuser + tile-pass scheduler (H1) must be an exact re-arrangement of the circuit.
+
+The plan is obtained through the C ABI (cb200_plan_json, no GPU needed) and replayed with the
+numpy oracle; the result must equal the gate-by-gate oracle run of the original circuit.
+"""
+import numpy as np
+import pytest
+
+import cunqa_b200 as cb
+from cunqa_b200 import circuits as C
+from oracle import oracle_np as O
+from conftest import random_circuit
+
+X = np.array([[0, 1], [1, 0]], dtype=complex)
+
+
+def replay_plan(plan, n):
+    st = O.make_state(n, "numpy" if n <= 12 else "c")
+    executed = []
+    for ps in plan["passes"]:
+        tile = set(ps["tile_q"])
+        assert len(ps["tile_q"]) == len(tile) <= 13
+        assert ps["tile_q"] == sorted(ps["tile_q"]) and ps["tile_q"][:ps["L"]] == list(range(ps["L"]))
+        for oi in ps["ops"]:
+            op = plan["ops"][oi]
+            executed.append(oi)
+            m = np.array([complex(*z) for z in op["m"]])
+            if op["kind"] == "dense":
+                assert set(op["q"]) <= tile, "dense targets must be staged in the tile"
+                d = 1 << len(op["q"])
+                st.apply_matrix(op["q"], m.reshape(d, d), op["ctrl"])
+            elif op["kind"] == "diag":
+                st.apply_diagonal(op["q"], m)
+            elif op["kind"] == "permx":
+                assert set(op["q"]) <= tile
+                st.apply_matrix(op["q"], X, op["ctrl"])
+            else:
+                assert set(op["q"]) <= tile
+                st.apply_swap(op["q"][0], op["q"][1], op["ctrl"])
+    assert sorted(executed) == list(range(len(plan["ops"]))), "every fused op runs exactly once"
+    phys = st.amplitudes()
+    l2p = plan["l2p"]
+    idx = np.arange(1 << n)
+    pidx = np.zeros_like(idx)
+    for q in range(n):
+        pidx |= ((idx >> q) & 1) << l2p[q]
+    return phys[pidx]
+
+
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("opts", [None, {"tile_bits": 5, "min_run_bits": 2}, {"tile_bits": 7, "min_run_bits": 3, "max_pass_cost": 6},
+                                  {"fuse": False, "tile_bits": 6, "min_run_bits": 0}])
+def test_plan_equals_circuit(lib_built, seed, opts):
+    n = 4 + seed % 6
+    ins = random_circuit(n, 90, seed)
+    plan = cb.plan(C.task(ins, n), opts)
+    ref, _ = O.run_static(ins, n, backend="numpy")
+    got = replay_plan(plan, n)
+    assert np.abs(got - ref.amplitudes()).max() < 1e-12
+    assert plan["gates"] == sum(1 for i in ins if i["name"] not in ("id",))
+
+
+def test_qft_plan_is_few_passes(lib_built):
+    n = 30
+    plan = cb.plan(C.task(C.qft(n, 0), n))
+    assert plan["relabelled_swaps"] == n // 2       # uncontrolled swaps cost no pass
+    assert len(plan["passes"]) <= 6                  # vs 480 per-gate sweeps
+    # all cp gates were folded into diagonal tables of <= 10 qubits
+    assert all(len(o["q"]) <= 10 for o in plan["ops"] if o["kind"] == "diag")
+
+
+def test_qft_plan_small_exact(lib_built):
+    n = 11
+    x = 1234
+    plan = cb.plan(C.task(C.qft(n, x), n), {"tile_bits": 6, "min_run_bits": 2})
+    got = replay_plan(plan, n)
+    assert np.abs(got - O.qft_amplitudes(n, x, np.arange(1 << n))).max() < 1e-12
+
+
+def test_qv_plan(lib_built):
+    n = 14
+    ins = C.quantum_volume(n, seed=3)
+    plan = cb.plan(C.task(ins, n), {"tile_bits": 8, "min_run_bits": 3})
+    ref, _ = O.run_static(ins, n, backend="c")
+    assert np.abs(replay_plan(plan, n) - ref.amplitudes()).max() < 1e-12
+    # the point of tile passes: several 2-qubit blocks per HBM round trip
+    assert len(plan["passes"]) < len(ins) / 2
+
+
+def test_hea_fuses_single_qubit_gates(lib_built):
+    n = 10
+    ins = C.hea_ansatz(n, layers=3, measure=False)
+    plan = cb.plan(C.task(ins, n))
+    # ry/rz are absorbed into the neighbouring cx blocks
+    assert len(plan["ops"]) <= 3 * (n - 1) + n
+    ref, _ = O.run_static(ins, n, backend="numpy")
+    assert np.abs(replay_plan(plan, n) - ref.amplitudes()).max() < 1e-12
+
+
+def test_bad_instruction_reports_error(lib_built):
+    from cunqa_b200.binding import B200Error
+    with pytest.raises(B200Error, match="unsupported instruction"):
+        cb.plan(C.task([{"name": "hz2", "qubits": [0]}], 2))
+    with pytest.raises(B200Error, match="out of range"):
+        cb.plan(C.task([{"name": "h", "qubits": [5]}], 2))
+    with pytest.raises(B200Error, match="duplicate"):
+        cb.plan(C.task([{"name": "cx", "qubits": [1, 1]}], 2))
