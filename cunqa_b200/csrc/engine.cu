@@ -35,6 +35,7 @@ State::State(int n_qubits, int prec, int dev, int nbatch)
     if (prop.major < 10) throw CudaError("cunqa_b200 kernels are built for sm_100a only (found sm_" +
                                          std::to_string(prop.major) + std::to_string(prop.minor) + ")");
     num_sms_ = prop.multiProcessorCount;
+    max_smem_ = prop.sharedMemPerBlockOptin;
     n_local_ = n;
     amp_bytes_ = precision == 64 ? 16 : 8;
     state_bytes_ = amp_bytes_ * ((size_t)batch << n);
@@ -44,6 +45,7 @@ State::State(int n_qubits, int prec, int dev, int nbatch)
     opt.max_diag_qubits = env_int("CB200_MAX_DIAG_QUBITS", 10);
     opt.fuse = env_int("CB200_FUSE", 1) != 0;
     ctas_per_sm_ = env_int("CB200_CTAS_PER_SM", 0);
+    use_tma_ = env_int("CB200_USE_TMA", 1) != 0;
     queue = OpQueue(n, batch, opt);
     CB200_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CB200_CUDA(cudaMalloc(&d_state_, state_bytes_));
@@ -98,6 +100,49 @@ void State::apply_named(const std::string &name, const int *qubits, int nq, cons
     maybe_flush();
 }
 
+// ---- TMA tensor maps ------------------------------------------------------------------------------
+// The state is described to the TMA unit as a 3-D tensor of scalars: [128-byte row][2^20 rows][rest],
+// box = {one row wide, 2^(Lb - amps-per-row-shift) rows, 1} = one contiguous run of 2^Lb amplitudes,
+// hardware 128-byte swizzle on the shared-memory side (matches swz<T>() in tile_kernel.cuh).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CB200_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !ptr) throw CudaError("cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+const CUtensorMap *State::tensor_map(int Lb)
+{
+    if (Lb < 0 || Lb >= 16) throw InvalidArg("bad TMA box size");
+    if (tmap_ready_[Lb]) return &tmaps_[Lb];
+    const int aprs = precision == 64 ? 3 : 4;  // log2(amplitudes per 128-byte row)
+    const uint64_t nrows = state_bytes_ >> 7;
+    const uint64_t d1 = std::min<uint64_t>(nrows, 1ull << kRowShift);
+    const uint64_t d2 = std::max<uint64_t>(1, nrows >> kRowShift);
+    const cuuint32_t inner = precision == 64 ? 16 : 32;
+    const cuuint64_t gdim[3] = {inner, d1, d2};
+    const cuuint64_t gstride[2] = {128, 128ull << kRowShift};
+    const cuuint32_t box[3] = {inner, 1u << (Lb - aprs), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode_tiled_fn()(&tmaps_[Lb], precision == 64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                         3, d_state_, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    tmap_ready_[Lb] = true;
+    return &tmaps_[Lb];
+}
+
 // ---- flush: plan + launch -----------------------------------------------------------------------
 template <typename T>
 void State::flush_t()
@@ -139,20 +184,32 @@ void State::flush_t()
         CB200_CUDA(cudaStreamSynchronize(stream_));
     }
     auto kern = tile_pass_kernel<T>;
-    static thread_local int occ_cache[2] = {0, 0};
+    auto kern_tma = tile_pass_tma_kernel<T>;
+    const int aprs = sizeof(V) == 16 ? 3 : 4;
     for (size_t i = 0; i < passes.size(); i++) {
         const PassParams<T> &p = params[i];
-        const size_t smem = sizeof(V) * ((size_t)1 << p.t) + sizeof(uint64_t) * ((size_t)1 << (p.t - p.L));
-        CB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = ctas_per_sm_;
-        if (occ <= 0) {
-            CB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTileThreads, smem));
-            if (occ < 1) occ = 1;
-        }
-        (void)occ_cache;
         const uint64_t total_tiles = p.tiles_per_state * (uint64_t)batch;
-        const unsigned grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_ * occ);
-        kern<<<grid, kTileThreads, smem, stream_>>>(p, (V *)d_state_, (const V *)d_diag_, d_flags_);
+        const int Lb = std::min(p.L, aprs + 8);
+        // TMA path: runs of >= 2 rows (256 B), at most one TMA op per thread and direction
+        const uint32_t buf_stride = (uint32_t)std::max<size_t>(1024, sizeof(V) << p.t);
+        const size_t smem_tma = (size_t)kStages * buf_stride + sizeof(uint64_t) * (((size_t)1 << (p.t - Lb)) + 2 * kStages) + 1024;
+        const bool tma = use_tma_ && p.L >= aprs + 1 && (p.t - Lb) <= 9 && state_bytes_ >= 128 && smem_tma <= max_smem_;
+        if (tma) {
+            const size_t smem = smem_tma;
+            CB200_CUDA(cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_);
+            kern_tma<<<grid, kTmaThreads, smem, stream_>>>(p, *tensor_map(Lb), (const V *)d_diag_, d_flags_, Lb, buf_stride);
+        } else {
+            const size_t smem = sizeof(V) * ((size_t)1 << p.t) + sizeof(uint64_t) * ((size_t)1 << (p.t - p.L));
+            CB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = ctas_per_sm_;
+            if (occ <= 0) {
+                CB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTileThreads, smem));
+                if (occ < 1) occ = 1;
+            }
+            const unsigned grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_ * occ);
+            kern<<<grid, kTileThreads, smem, stream_>>>(p, (V *)d_state_, (const V *)d_diag_, d_flags_);
+        }
         CB200_CUDA(cudaGetLastError());
         stats.passes++;
         stats.launches++;

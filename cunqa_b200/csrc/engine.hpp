@@ -5,6 +5,7 @@
 // n qubits, here x `batch` independent copies so that many shots / many small vQPUs advance in one
 // kernel launch.  Gates are queued, fused and scheduled into tile passes at flush time.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -79,7 +80,12 @@ private:
     void *d_state_ = nullptr;
     cudaStream_t stream_ = nullptr;
     int num_sms_ = 148;
-    int ctas_per_sm_ = 0;  // 0 = occupancy query
+    size_t max_smem_ = 232448;
+    int ctas_per_sm_ = 0;  // 0 = occupancy query (generic kernel only)
+    bool use_tma_ = true;
+    const CUtensorMap *tensor_map(int Lb);  // 3-D map over the state, box = one run of 2^Lb amplitudes
+    CUtensorMap tmaps_[16];
+    bool tmap_ready_[16] = {};
     // device scratch
     void *d_diag_ = nullptr; size_t diag_cap_ = 0;       // diagonal tables (elements of V)
     uint8_t *d_flags_ = nullptr; size_t flags_cap_ = 0;  // mask rows

@@ -49,6 +49,7 @@ struct PassParams {
     int32_t batch;    // independent states
     int32_t pad_;
     uint64_t tiles_per_state;
+    uint64_t cond_mask; // ops whose activity depends on the tile (controls outside the tile / per-state mask)
     uint8_t tile_q[16]; // physical qubit of tile bit j (ascending)
     DevOp ops[kMaxOps];
     T mats[kMatScalars];

@@ -297,6 +297,9 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
         }
     }
     out.n_ops = nops;
+    out.cond_mask = 0;
+    for (int o = 0; o < nops; o++)
+        if (out.ops[o].ctrl_out != 0 || out.ops[o].has_mask) out.cond_mask |= 1ull << o;
     return true;
 }
 

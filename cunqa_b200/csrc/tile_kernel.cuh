@@ -6,6 +6,7 @@
 // list (dense k-qubit blocks, diagonal tables, X/SWAP permutations, all optionally controlled and
 // optionally masked per state) before writing it back.  Algorithmic bytes per pass = 2*S.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "pass_types.hpp"
@@ -16,16 +17,19 @@ template <typename T> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
 
-// shared-memory slot swizzle: XOR-fold the higher index bits into the bits that select the
-// 16-byte bank group, so that sweeps whose lanes differ only in higher tile bits stay conflict free.
+// shared-memory slot swizzle = the TMA hardware's 128-byte swizzle (CU_TENSOR_MAP_SWIZZLE_128B):
+// the 16-byte chunk index inside a 128-byte row (byte-address bits 4..6) is XOR-ed with the row
+// index mod 8 (byte-address bits 7..9).  Tile buffers are 1024-byte aligned, so the pattern is a
+// pure function of the tile index; sweeps whose lanes differ in tile bits 3..5 (fp64) stay
+// bank-conflict free.  Both kernels (TMA-staged and generic) use the same layout.
 template <typename T> __device__ __forceinline__ uint32_t swz(uint32_t i);
-template <> __device__ __forceinline__ uint32_t swz<double>(uint32_t i)
+template <> __device__ __forceinline__ uint32_t swz<double>(uint32_t i)   // 16-byte amplitudes
 {
-    return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9) ^ (i >> 12)) & 7u);
+    return i ^ ((i >> 3) & 7u);
 }
-template <> __device__ __forceinline__ uint32_t swz<float>(uint32_t i)
+template <> __device__ __forceinline__ uint32_t swz<float>(uint32_t i)    // 8-byte amplitudes
 {
-    return i ^ (((i >> 4) ^ (i >> 8) ^ (i >> 12)) & 15u);
+    return i ^ (((i >> 4) & 7u) << 1);
 }
 
 __device__ __forceinline__ uint32_t insert0(uint32_t g, uint32_t pos)
@@ -59,7 +63,7 @@ __device__ __forceinline__ void cfma(V &acc, const T mr, const T mi, const V a)
 // ---- dense k-qubit block on the tile -----------------------------------------------------------
 // K <= 2: the matrix is hoisted into registers (constant-bank loads, no shared-memory traffic);
 // K >= 3: matrix elements stream from the constant bank inside the row loop.
-template <typename T, int K>
+template <typename T, int K, int NT>
 __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
                                          const int t, const int tid)
 {
@@ -80,7 +84,7 @@ __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const Dev
         T mr[D * D], mi[D * D];
 #pragma unroll
         for (int e = 0; e < D * D; e++) { mr[e] = mat[2 * e]; mi[e] = mat[2 * e + 1]; }
-        for (uint32_t g = tid; g < ngroups; g += kTileThreads) {
+        for (uint32_t g = tid; g < ngroups; g += NT) {
             uint32_t idx = g;
             for (int f = 0; f < nfix; f++) idx = insert0(idx, op.fixpos[f]);
             idx |= op.ctrl_in;
@@ -96,7 +100,7 @@ __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const Dev
             }
         }
     } else {
-        for (uint32_t g = tid; g < ngroups; g += kTileThreads) {
+        for (uint32_t g = tid; g < ngroups; g += NT) {
             uint32_t idx = g;
             for (int f = 0; f < nfix; f++) idx = insert0(idx, op.fixpos[f]);
             idx |= op.ctrl_in;
@@ -120,7 +124,7 @@ __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const Dev
 }
 
 // ---- X / SWAP permutations (optionally controlled): pure data movement ------------------------
-template <typename T>
+template <typename T, int NT>
 __device__ __forceinline__ void op_perm(typename Vec2<T>::type *tile, const DevOp &op, const int t, const int tid)
 {
     using V = typename Vec2<T>::type;
@@ -129,7 +133,7 @@ __device__ __forceinline__ void op_perm(typename Vec2<T>::type *tile, const DevO
     uint32_t oa, ob;
     if (op.kind == OP_PERMX) { oa = 0; ob = 1u << op.tbit[0]; }
     else { oa = 1u << op.tbit[0]; ob = 1u << op.tbit[1]; }
-    for (uint32_t g = tid; g < ngroups; g += kTileThreads) {
+    for (uint32_t g = tid; g < ngroups; g += NT) {
         uint32_t idx = g;
         for (int f = 0; f < nfix; f++) idx = insert0(idx, op.fixpos[f]);
         idx |= op.ctrl_in;
@@ -138,6 +142,75 @@ __device__ __forceinline__ void op_perm(typename Vec2<T>::type *tile, const DevO
         tile[sa] = b;
         tile[sb] = a;
     }
+}
+
+// which ops of the pass act on the tile at `base` of state `b`: unconditional ops always do; ops with
+// controls outside the tile or a per-state mask (rare; listed in cond_mask) are tested individually
+template <typename T>
+__device__ __forceinline__ uint64_t active_ops(const PassParams<T> &p, const uint8_t *__restrict__ flags,
+                                               const uint64_t b, const uint64_t base)
+{
+    const uint64_t all = p.n_ops >= 64 ? ~0ull : ((1ull << p.n_ops) - 1ull);
+    uint64_t active = all & ~p.cond_mask;
+    for (uint64_t m = p.cond_mask; m != 0; m &= m - 1) {
+        const int o = __ffsll((long long)m) - 1;
+        const DevOp &op = p.ops[o];
+        bool on = (base & op.ctrl_out) == op.ctrl_out;
+        if (on && op.has_mask) on = flags[(size_t)op.mask_row * p.batch + b] != 0;
+        if (on) active |= 1ull << o;
+    }
+    return active;
+}
+
+// ---- apply the pass's op list to one staged tile (block-wide; ends with a barrier) -------------
+template <typename T, int NT>
+__device__ __forceinline__ void apply_ops(const PassParams<T> &p, typename Vec2<T>::type *tile,
+                                          const typename Vec2<T>::type *__restrict__ diag_tabs,
+                                          const uint64_t active, const uint64_t base, const int t, const int tid)
+{
+    using V = typename Vec2<T>::type;
+    const uint32_t tile_amps = 1u << t;
+    for (int o = 0; o < p.n_ops; o++) {
+            if (!((active >> o) & 1ull)) continue;
+            const DevOp &op = p.ops[o];
+            if (op.kind == OP_DENSE) {
+                const T *mat = p.mats + op.mat_off;
+                switch (op.k) {
+                case 1: op_dense<T, 1, NT>(tile, op, mat, t, tid); break;
+                case 2: op_dense<T, 2, NT>(tile, op, mat, t, tid); break;
+                case 3: op_dense<T, 3, NT>(tile, op, mat, t, tid); break;
+                case 4: op_dense<T, 4, NT>(tile, op, mat, t, tid); break;
+                default: op_dense<T, 5, NT>(tile, op, mat, t, tid); break;
+                }
+                __syncthreads();
+            } else if (op.kind == OP_DIAG) {
+                // a run of consecutive diagonal ops is applied in ONE sweep of the tile
+                int oe = o;
+                while (oe + 1 < p.n_ops && p.ops[oe + 1].kind == OP_DIAG) oe++;
+                for (uint32_t i = tid; i < tile_amps; i += NT) {
+                    const uint32_t s = swz<T>(i);
+                    V v = tile[s];
+                    for (int q = o; q <= oe; q++) {
+                        if (!((active >> q) & 1ull)) continue;
+                        const DevOp &d = p.ops[q];
+                        uint32_t ti = 0;
+                        for (int m = 0; m < d.k; m++) {
+                            const uint32_t src = d.dsrc[m];
+                            const uint32_t bit = src < 64 ? ((i >> src) & 1u) : (uint32_t)((base >> (src - 64)) & 1ull);
+                            ti |= bit << m;
+                        }
+                        const V ph = diag_tabs[d.mat_off + ti];
+                        v = cmul<V, T>(ph.x, ph.y, v);
+                    }
+                    tile[s] = v;
+                }
+                o = oe;
+                __syncthreads();
+            } else {
+                op_perm<T, NT>(tile, op, t, tid);
+                __syncthreads();
+            }
+        }
 }
 
 // ---- the pass kernel ---------------------------------------------------------------------------
@@ -149,7 +222,8 @@ tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type
                  const typename Vec2<T>::type *__restrict__ diag_tabs, const uint8_t *__restrict__ flags)
 {
     using V = typename Vec2<T>::type;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    unsigned char *smem_raw = smem_dyn;
     V *tile = reinterpret_cast<V *>(smem_raw);
     const int t = p.t, L = p.L, n = p.n;
     const uint32_t tile_amps = 1u << t;
@@ -177,13 +251,7 @@ tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type
         base <<= L;  // tile qubits 0..L-1 are the L lowest physical qubits
 
         // which ops act on this tile (controls outside the tile, per-state masks)
-        uint64_t active = 0;
-        for (int o = 0; o < p.n_ops; o++) {
-            const DevOp &op = p.ops[o];
-            bool on = (base & op.ctrl_out) == op.ctrl_out;
-            if (on && op.has_mask) on = flags[(size_t)op.mask_row * p.batch + b] != 0;
-            if (on) active |= 1ull << o;
-        }
+        const uint64_t active = active_ops(p, flags, b, base);
         if (active == 0) continue;  // untouched tile: no traffic at all
 
         V *gbase = state + (b << n) + base;
@@ -193,47 +261,7 @@ tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type
             tile[swz<T>(i)] = gbase[run_off[i >> L] + (i & run_mask)];
         __syncthreads();
 
-        for (int o = 0; o < p.n_ops; o++) {
-            if (!((active >> o) & 1ull)) continue;
-            const DevOp &op = p.ops[o];
-            if (op.kind == OP_DENSE) {
-                const T *mat = p.mats + op.mat_off;
-                switch (op.k) {
-                case 1: op_dense<T, 1>(tile, op, mat, t, tid); break;
-                case 2: op_dense<T, 2>(tile, op, mat, t, tid); break;
-                case 3: op_dense<T, 3>(tile, op, mat, t, tid); break;
-                case 4: op_dense<T, 4>(tile, op, mat, t, tid); break;
-                default: op_dense<T, 5>(tile, op, mat, t, tid); break;
-                }
-                __syncthreads();
-            } else if (op.kind == OP_DIAG) {
-                // a run of consecutive diagonal ops is applied in ONE sweep of the tile
-                int oe = o;
-                while (oe + 1 < p.n_ops && p.ops[oe + 1].kind == OP_DIAG) oe++;
-                for (uint32_t i = tid; i < tile_amps; i += kTileThreads) {
-                    const uint32_t s = swz<T>(i);
-                    V v = tile[s];
-                    for (int q = o; q <= oe; q++) {
-                        if (!((active >> q) & 1ull)) continue;
-                        const DevOp &d = p.ops[q];
-                        uint32_t ti = 0;
-                        for (int m = 0; m < d.k; m++) {
-                            const uint32_t src = d.dsrc[m];
-                            const uint32_t bit = src < 64 ? ((i >> src) & 1u) : (uint32_t)((base >> (src - 64)) & 1ull);
-                            ti |= bit << m;
-                        }
-                        const V ph = diag_tabs[d.mat_off + ti];
-                        v = cmul<V, T>(ph.x, ph.y, v);
-                    }
-                    tile[s] = v;
-                }
-                o = oe;
-                __syncthreads();
-            } else {
-                op_perm<T>(tile, op, t, tid);
-                __syncthreads();
-            }
-        }
+        apply_ops<T, kTileThreads>(p, tile, diag_tabs, active, base, t, tid);
 
         // ---- stage out
 #pragma unroll 4
@@ -241,6 +269,162 @@ tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type
             gbase[run_off[i >> L] + (i & run_mask)] = tile[swz<T>(i)];
         __syncthreads();
     }
+}
+
+// =================================================================================================
+// TMA-staged, software-pipelined pass kernel (the production path for every pass whose tiles are
+// made of >= 256-byte runs).
+//
+//   * one persistent CTA per SM, kTmaThreads threads, kStages tile buffers in shared memory;
+//   * tiles move HBM -> smem and smem -> HBM with cp.async.bulk.tensor (TMA) through a 3-D tensor
+//     map over the state ([128-byte row][2^20 rows][rest]) with the hardware 128-byte swizzle, one
+//     TMA op per contiguous run (box = 2^Lb amplitudes); no register staging, no LSU issue slots;
+//   * loads complete on an mbarrier (complete_tx), stores are tracked with bulk async-groups;
+//   * while tile k is being computed, tile k+1 is landing and tile k-1 is draining.
+// =================================================================================================
+constexpr int kTmaThreads = 512;
+constexpr int kStages = 3;
+constexpr int kRowShift = 20;  // rows per dim-1 of the tensor map
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_constant__ CUtensorMap tmap,
+                     const typename Vec2<T>::type *__restrict__ diag_tabs, const uint8_t *__restrict__ flags,
+                     const int Lb, const uint32_t buf_stride)
+{
+    using V = typename Vec2<T>::type;
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    // tile buffers must sit on 1024-byte boundaries for the 128-byte swizzle pattern
+    unsigned char *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    const int t = p.t, L = p.L, n = p.n;
+    const int tid = threadIdx.x;
+    const uint32_t nbox = 1u << (t - Lb);          // TMA ops per tile per direction
+    const uint32_t tile_bytes = (uint32_t)sizeof(V) << t;
+    constexpr int kAmpsPerRowShift = sizeof(V) == 16 ? 3 : 4;  // amplitudes per 128-byte row
+    uint64_t *box_off = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * buf_stride);
+    uint64_t *full = box_off + nbox;
+    uint64_t *slot_tile = full + kStages;  // tile number staged in each slot (~0 = none)
+
+    // amplitude offset of box r inside a tile: the low (L-Lb) bits of r continue the contiguous run,
+    // the rest are deposited at the high tile qubits
+    for (uint32_t r = tid; r < nbox; r += kTmaThreads) {
+        uint64_t o = (uint64_t)(r & ((1u << (L - Lb)) - 1u)) << Lb;
+        const uint32_t hi = r >> (L - Lb);
+        for (int j = L; j < t; j++)
+            if ((hi >> (j - L)) & 1u) o |= 1ull << p.tile_q[j];
+        box_off[r] = o;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); slot_tile[s] = ~0ull; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint64_t total_tiles = p.tiles_per_state * (uint64_t)p.batch;
+    // tile -> (state, base amplitude, active-op mask); all threads evaluate it identically
+    auto decode = [&](uint64_t tileno, uint64_t &b, uint64_t &base) -> uint64_t {
+        b = tileno / p.tiles_per_state;
+        uint64_t x = tileno - b * p.tiles_per_state;
+        for (int j = L; j < t; j++) x = insert0_64(x, p.tile_q[j] - L);
+        base = x << L;
+        return active_ops(p, flags, b, base);
+    };
+    // next tile of this CTA (stride gridDim.x) that some op acts on
+    auto next_active = [&](uint64_t from) -> uint64_t {
+        uint64_t b, base;
+        for (uint64_t x = from; x < total_tiles; x += gridDim.x)
+            if (decode(x, b, base) != 0) return x;
+        return ~0ull;
+    };
+    auto issue_load = [&](int s, uint64_t tileno) {
+        uint64_t b, base;
+        decode(tileno, b, base);
+        if (tid == 0) mbar_arrive_expect_tx(&full[s], tile_bytes);
+        if ((uint32_t)tid < nbox) {
+            const uint64_t row = ((b << n) + base + box_off[tid]) >> kAmpsPerRowShift;
+            tma_load_3d(smem_raw + (size_t)s * buf_stride + ((size_t)tid << Lb) * sizeof(V), &tmap, &full[s], 0,
+                        (int)(row & ((1ull << kRowShift) - 1ull)), (int)(row >> kRowShift));
+        }
+    };
+
+    uint64_t cursor = next_active(blockIdx.x);
+    for (int s = 0; s < kStages - 1; s++) {
+        if (cursor == ~0ull) break;
+        if (tid == 0) slot_tile[s] = cursor;
+        issue_load(s, cursor);
+        cursor = next_active(cursor + gridDim.x);
+    }
+    __syncthreads();
+
+    for (uint32_t k = 0;; k++) {
+        const int s = (int)(k % kStages);
+        const uint64_t tileno = slot_tile[s];
+        if (tileno == ~0ull) break;
+        uint64_t b, base;
+        const uint64_t active = decode(tileno, b, base);
+        V *tile = reinterpret_cast<V *>(smem_raw + (size_t)s * buf_stride);
+        mbar_wait(&full[s], (k / kStages) & 1u);
+
+        apply_ops<T, kTmaThreads>(p, tile, diag_tabs, active, base, t, tid);  // ends with __syncthreads
+
+        // generic-proxy writes -> visible to the async proxy, then drain this tile with TMA stores
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if ((uint32_t)tid < nbox) {
+            const uint64_t row = ((b << n) + base + box_off[tid]) >> kAmpsPerRowShift;
+            tma_store_3d(&tmap, smem_raw + (size_t)s * buf_stride + ((size_t)tid << Lb) * sizeof(V), 0,
+                         (int)(row & ((1ull << kRowShift) - 1ull)), (int)(row >> kRowShift));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the slot refilled below held tile k-1: its store must have finished READING shared memory
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        __syncthreads();
+        const int s2 = (int)((k + kStages - 1) % kStages);
+        if (tid == 0) slot_tile[s2] = cursor;
+        if (cursor != ~0ull) {
+            issue_load(s2, cursor);
+            cursor = next_active(cursor + gridDim.x);
+        }
+        __syncthreads();
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 }  // namespace cb200

@@ -255,20 +255,24 @@ class NumpyState:
 _LIB = None
 
 
-def build_c_oracle(force=False):
-    """compile oracle/sv_oracle.c -> oracle/libsv_oracle.so (gcc -O3 -fopenmp)."""
-    so = os.path.join(_HERE, "libsv_oracle.so")
+def build_c_oracle(force=False, native=False):
+    """compile oracle/sv_oracle.c -> oracle/libsv_oracle.so (gcc -O3 -fopenmp).
+
+    The default build targets x86-64-v3 so that the .so built in the dev container also runs on the
+    GPU box's host CPU; native=True (bench.py's CPU-baseline legs) rebuilds with -march=native on
+    the machine that times it."""
+    so = os.path.join(_HERE, "libsv_oracle_native.so" if native else "libsv_oracle.so")
     src = os.path.join(_HERE, "sv_oracle.c")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared",
-                               "-o", so, src, "-lm"])
+        subprocess.check_call(["gcc", "-O3", "-march=native" if native else "-march=x86-64-v3", "-fopenmp",
+                               "-fPIC", "-shared", "-o", so, src, "-lm"])
     return so
 
 
-def c_oracle():
+def c_oracle(native=False):
     global _LIB
     if _LIB is None:
-        lib = ctypes.CDLL(build_c_oracle())
+        lib = ctypes.CDLL(build_c_oracle(force=native, native=native))
         dp = ctypes.POINTER(ctypes.c_double)
         ip = ctypes.POINTER(ctypes.c_int)
         lib.orc_init_zero.argtypes = [dp, ctypes.c_int]
