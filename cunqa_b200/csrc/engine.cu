@@ -36,14 +36,17 @@ State::State(int n_qubits, int prec, int dev, int nbatch)
                                          std::to_string(prop.major) + std::to_string(prop.minor) + ")");
     num_sms_ = prop.multiProcessorCount;
     max_smem_ = prop.sharedMemPerBlockOptin;
+    max_smem_sm_ = prop.sharedMemPerMultiprocessor;
+    tma_threads_ = env_int("CB200_TMA_THREADS", 0);
     n_local_ = n;
     amp_bytes_ = precision == 64 ? 16 : 8;
     state_bytes_ = amp_bytes_ * ((size_t)batch << n);
-    opt.tile_bits = env_int("CB200_TILE_BITS", precision == 64 ? 12 : 13);
+    opt.tile_bits = env_int("CB200_TILE_BITS", precision == 64 ? 11 : 12);
     opt.min_run_bits = env_int("CB200_MIN_RUN_BITS", precision == 64 ? 4 : 5);
     opt.max_pass_cost = env_int("CB200_MAX_PASS_COST", 0);
     opt.max_diag_qubits = env_int("CB200_MAX_DIAG_QUBITS", 10);
     opt.fuse = env_int("CB200_FUSE", 1) != 0;
+    opt.pair_ops = env_int("CB200_PAIR_OPS", 1) != 0;
     ctas_per_sm_ = env_int("CB200_CTAS_PER_SM", 0);
     use_tma_ = env_int("CB200_USE_TMA", 1) != 0;
     queue = OpQueue(n, batch, opt);
@@ -156,7 +159,7 @@ void State::flush_t()
     std::vector<PassParams<T>> params(passes.size());
     std::string err;
     for (size_t i = 0; i < passes.size(); i++)
-        if (!encode_pass<T>(passes[i], ops, n_local_, batch, params[i], diag_host, err)) throw Unsupported(err);
+        if (!encode_pass<T>(passes[i], ops, n_local_, batch, params[i], diag_host, err, opt.pair_ops)) throw Unsupported(err);
     // diagonal tables
     if (!diag_host.empty()) {
         if (diag_host.size() > diag_cap_) {
@@ -184,21 +187,27 @@ void State::flush_t()
         CB200_CUDA(cudaStreamSynchronize(stream_));
     }
     auto kern = tile_pass_kernel<T>;
-    auto kern_tma = tile_pass_tma_kernel<T>;
     const int aprs = sizeof(V) == 16 ? 3 : 4;
     for (size_t i = 0; i < passes.size(); i++) {
         const PassParams<T> &p = params[i];
         const uint64_t total_tiles = p.tiles_per_state * (uint64_t)batch;
         const int Lb = std::min(p.L, aprs + 8);
-        // TMA path: runs of >= 2 rows (256 B), at most one TMA op per thread and direction
+        // TMA path: runs of >= 2 rows (256 B)
         const uint32_t buf_stride = (uint32_t)std::max<size_t>(1024, sizeof(V) << p.t);
-        const size_t smem_tma = (size_t)kStages * buf_stride + sizeof(uint64_t) * (((size_t)1 << (p.t - Lb)) + 2 * kStages) + 1024;
-        const bool tma = use_tma_ && p.L >= aprs + 1 && (p.t - Lb) <= 9 && state_bytes_ >= 128 && smem_tma <= max_smem_;
+        const size_t smem_tma = (size_t)kStages * buf_stride + sizeof(uint64_t) * (((size_t)1 << (p.t - Lb)) + kStages) + 1024;
+        int nt = 1 << std::max(6, std::min(8, p.t - kAmpsPerThreadShift));  // 64 / 128 / 256 threads
+        if (tma_threads_ > 0) nt = tma_threads_;
+        const int ctas = 256 / nt;
+        const bool tma = use_tma_ && p.L >= aprs + 1 && state_bytes_ >= 128 && smem_tma * ctas <= max_smem_sm_ && smem_tma <= max_smem_;
         if (tma) {
-            const size_t smem = smem_tma;
-            CB200_CUDA(cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const unsigned grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_);
-            kern_tma<<<grid, kTmaThreads, smem, stream_>>>(p, *tensor_map(Lb), (const V *)d_diag_, d_flags_, Lb, buf_stride);
+            const unsigned grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_ * ctas);
+            auto launch = [&](auto kern_tma) {
+                CB200_CUDA(cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+                kern_tma<<<grid, nt, smem_tma, stream_>>>(p, *tensor_map(Lb), (const V *)d_diag_, d_flags_, Lb, buf_stride);
+            };
+            if (nt == 256) launch(tile_pass_tma_kernel<T, 256>);
+            else if (nt == 128) launch(tile_pass_tma_kernel<T, 128>);
+            else launch(tile_pass_tma_kernel<T, 64>);
         } else {
             const size_t smem = sizeof(V) * ((size_t)1 << p.t) + sizeof(uint64_t) * ((size_t)1 << (p.t - p.L));
             CB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -80,7 +80,8 @@ private:
     void *d_state_ = nullptr;
     cudaStream_t stream_ = nullptr;
     int num_sms_ = 148;
-    size_t max_smem_ = 232448;
+    size_t max_smem_ = 232448, max_smem_sm_ = 233472;
+    int tma_threads_ = 0;
     int ctas_per_sm_ = 0;  // 0 = occupancy query (generic kernel only)
     bool use_tma_ = true;
     const CUtensorMap *tensor_map(int Lb);  // 3-D map over the state, box = one run of 2^Lb amplitudes

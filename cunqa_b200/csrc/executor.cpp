@@ -705,7 +705,7 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
     const Json task = Json::parse(task_json);
     const TaskCfg c = parse_task(task);
     PlanOptions opt;
-    opt.tile_bits = c.precision == 64 ? 12 : 13;
+    opt.tile_bits = c.precision == 64 ? 11 : 12;
     opt.min_run_bits = c.precision == 64 ? 4 : 5;
     if (!options_json.empty()) {
         const Json o = Json::parse(options_json);

@@ -22,12 +22,14 @@ enum OpKind : uint8_t {
     OP_DIAG = 1,   // diagonal table over k qubits anywhere (in-tile or not)
     OP_PERMX = 2,  // X on tbit[0] (controls optional): pure pair swap, no flops
     OP_SWAP = 3,   // swap tbit[0] <-> tbit[1] (controls optional)
+    OP_PAIR = 4,   // register block: two dense gates A (k qubits, local bits [0,k)) and B (k2 qubits, local
+                   // bits [s,s+k2)) applied back to back to the 2^R amplitudes a thread holds in registers
 };
 
 struct DevOp {
     uint8_t kind;
-    uint8_t k;       // DENSE: #targets; DIAG: #qubits of the table
-    uint8_t nfix;    // DENSE/PERM: number of entries in fixpos (targets + in-tile controls)
+    uint8_t k;       // DENSE: #targets; DIAG: #qubits of the table; PAIR: #targets of gate A
+    uint8_t nfix;    // DENSE/PERM/PAIR: number of entries in fixpos (targets + in-tile controls)
     uint8_t has_mask;
     uint8_t tbit[8];        // DENSE/PERM: tile-bit position of target m
     uint8_t fixpos[kMaxFix]; // ascending tile-bit positions where a bit is inserted into the group index
@@ -36,7 +38,8 @@ struct DevOp {
     uint32_t mat_off;   // DENSE: scalar offset into PassParams::mats; DIAG: element offset into the diag-table buffer
     uint64_t ctrl_out;  // physical-qubit mask of controls outside the tile (tested on the tile base)
     int32_t mask_row;   // row of the per-state flag matrix (batched feed-forward) when has_mask
-    int32_t pad_;
+    uint8_t k2, s;      // PAIR: #targets of gate B and its first local bit; B's matrix follows A's in mats
+    uint8_t pad_[2];
 };
 static_assert(sizeof(DevOp) == 64, "DevOp layout");
 

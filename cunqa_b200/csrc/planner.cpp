@@ -233,7 +233,7 @@ std::vector<Pass> schedule_passes(const std::vector<HostOp> &ops, int n, const P
 
 template <typename T>
 bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int batch, PassParams<T> &out,
-                 std::vector<cplx> &diag_host, std::string &err)
+                 std::vector<cplx> &diag_host, std::string &err, bool pair_ops)
 {
     std::memset(&out, 0, sizeof(out));
     const int t = (int)pass.tile_q.size();
@@ -248,12 +248,52 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
         return -1;
     };
     int nops = 0, mat_used = 0;
-    for (int oi : pass.op_idx) {
+    auto pairable = [&](const HostOp &o) {
+        return o.kind == HostOp::DENSE && o.q.size() <= 2 && o.ctrl.empty() && o.mask_row < 0;
+    };
+    for (size_t pi = 0; pi < pass.op_idx.size(); pi++) {
+        const int oi = pass.op_idx[pi];
         const HostOp &op = ops[oi];
         if (nops >= kMaxOps) { err = "too many ops in one pass"; return false; }
         DevOp &d = out.ops[nops++];
         d.has_mask = op.mask_row >= 0;
         d.mask_row = op.mask_row;
+        // register block: this dense gate and the next one share one shared-memory round trip
+        if (pair_ops && pairable(op) && pi + 1 < pass.op_idx.size() && pairable(ops[pass.op_idx[pi + 1]])) {
+            const HostOp &A = op, &B = ops[pass.op_idx[pi + 1]];
+            std::vector<int> a_only, shared, b_only;
+            for (int x : A.q) (std::find(B.q.begin(), B.q.end(), x) == B.q.end() ? a_only : shared).push_back(x);
+            for (int x : B.q) if (std::find(A.q.begin(), A.q.end(), x) == A.q.end()) b_only.push_back(x);
+            std::vector<int> la = a_only, lb = shared, local = a_only;
+            la.insert(la.end(), shared.begin(), shared.end());
+            lb.insert(lb.end(), b_only.begin(), b_only.end());
+            local.insert(local.end(), shared.begin(), shared.end());
+            local.insert(local.end(), b_only.begin(), b_only.end());
+            const int K1 = (int)A.q.size(), K2 = (int)B.q.size(), S = K1 - (int)shared.size(), R = (int)local.size();
+            const int sc = 2 * ((1 << (2 * K1)) + (1 << (2 * K2)));
+            if (R <= 4 && mat_used + sc <= kMatScalars) {
+                d.kind = OP_PAIR;
+                d.k = (uint8_t)K1;
+                d.k2 = (uint8_t)K2;
+                d.s = (uint8_t)S;
+                std::vector<int> fix;
+                for (int m = 0; m < R; m++) {
+                    const int p = tile_pos(local[m]);
+                    if (p < 0) { err = "internal: target outside tile"; return false; }
+                    d.tbit[m] = (uint8_t)p;
+                    fix.push_back(p);
+                }
+                std::sort(fix.begin(), fix.end());
+                d.nfix = (uint8_t)R;
+                for (int f = 0; f < R; f++) d.fixpos[f] = (uint8_t)fix[f];
+                d.mat_off = (uint32_t)mat_used;
+                const std::vector<cplx> MA = embed_dense(A, la), MB = embed_dense(B, lb);
+                for (const std::vector<cplx> *M : {&MA, &MB})
+                    for (const cplx &z : *M) { out.mats[mat_used++] = (T)z.real(); out.mats[mat_used++] = (T)z.imag(); }
+                pi++;  // B consumed
+                continue;
+            }
+        }
         if (op.kind == HostOp::DIAG) {
             d.kind = OP_DIAG;
             d.k = (uint8_t)op.q.size();
@@ -304,8 +344,8 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
 }
 
 template bool encode_pass<double>(const Pass &, const std::vector<HostOp> &, int, int, PassParams<double> &,
-                                  std::vector<cplx> &, std::string &);
+                                  std::vector<cplx> &, std::string &, bool);
 template bool encode_pass<float>(const Pass &, const std::vector<HostOp> &, int, int, PassParams<float> &,
-                                 std::vector<cplx> &, std::string &);
+                                 std::vector<cplx> &, std::string &, bool);
 
 }  // namespace cb200

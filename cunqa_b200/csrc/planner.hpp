@@ -34,6 +34,7 @@ struct PlanOptions {
     int max_dense_qubits = 5;  // widest dense block the kernel accepts
     int max_pass_cost = 0;     // cap on sum over dense ops of 2^k per pass (0 = unlimited)
     bool fuse = true;
+    bool pair_ops = true;      // register-block adjacent dense gates (two gates per shared-memory round trip)
 };
 
 struct Pass {
@@ -67,6 +68,6 @@ std::vector<Pass> schedule_passes(const std::vector<HostOp> &ops, int n, const P
 // (element units) and referenced by offset.  Returns false + err if the pass cannot be encoded.
 template <typename T>
 bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int batch, PassParams<T> &out,
-                 std::vector<cplx> &diag_host, std::string &err);
+                 std::vector<cplx> &diag_host, std::string &err, bool pair_ops = true);
 
 }  // namespace cb200

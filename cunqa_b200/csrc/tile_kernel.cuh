@@ -123,6 +123,87 @@ __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const Dev
     }
 }
 
+// ---- register block: two dense gates per shared-memory round trip ---------------------------------
+// The thread holds the 2^R amplitudes spanned by the block's R local bits in registers; gate A acts on
+// local bits [0,K1), gate B on local bits [S,S+K2).  All register indices are compile-time.
+template <typename T, int R, int K, int S>
+__device__ __forceinline__ void block_gate(typename Vec2<T>::type (&a)[1 << R], const T *mat)
+{
+    using V = typename Vec2<T>::type;
+    constexpr int D = 1 << K;
+    T mr[D * D], mi[D * D];
+#pragma unroll
+    for (int e = 0; e < D * D; e++) { mr[e] = mat[2 * e]; mi[e] = mat[2 * e + 1]; }
+#pragma unroll
+    for (int rest = 0; rest < (1 << (R - K)); rest++) {
+        const int lo = rest & ((1 << S) - 1), hi = rest >> S;
+        const int base = (hi << (S + K)) | lo;
+        V in[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) in[j] = a[base | (j << S)];
+#pragma unroll
+        for (int r = 0; r < D; r++) {
+            V acc = cmul<V, T>(mr[r * D], mi[r * D], in[0]);
+#pragma unroll
+            for (int c = 1; c < D; c++) cfma<V, T>(acc, mr[r * D + c], mi[r * D + c], in[c]);
+            a[base | (r << S)] = acc;
+        }
+    }
+}
+
+template <typename T, int K1, int K2, int S, int NT>
+__device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
+                                        const int t, const int tid)
+{
+    using V = typename Vec2<T>::type;
+    constexpr int R = (K1 > S + K2) ? K1 : (S + K2);
+    constexpr int D = 1 << R;
+    // the swizzle is XOR-linear and the block bits are disjoint from the group bits, so
+    // swz(idx | off_j) = swz(idx) ^ swz(off_j): one XOR per amplitude instead of re-swizzling
+    uint32_t sb[R], fp[R];
+#pragma unroll
+    for (int m = 0; m < R; m++) { sb[m] = swz<T>(1u << op.tbit[m]); fp[m] = op.fixpos[m]; }
+    uint32_t soff[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int m = 0; m < R; m++) if ((j >> m) & 1) o ^= sb[m];
+        soff[j] = o;
+    }
+    const uint32_t ngroups = 1u << (t - R);
+    for (uint32_t g = tid; g < ngroups; g += NT) {
+        uint32_t idx = g;
+#pragma unroll
+        for (int f = 0; f < R; f++) idx = insert0(idx, fp[f]);
+        const uint32_t sidx = swz<T>(idx);
+        V a[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) a[j] = tile[sidx ^ soff[j]];
+        block_gate<T, R, K1, 0>(a, mat);
+        block_gate<T, R, K2, S>(a, mat + 2 * (1 << (2 * K1)));
+#pragma unroll
+        for (int j = 0; j < D; j++) tile[sidx ^ soff[j]] = a[j];
+    }
+}
+
+template <typename T, int NT>
+__device__ __forceinline__ void op_pair_dispatch(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
+                                                 const int t, const int tid)
+{
+    switch ((op.k << 4) | (op.k2 << 2) | op.s) {
+    case (1 << 4) | (1 << 2) | 1: op_pair<T, 1, 1, 1, NT>(tile, op, mat, t, tid); break;
+    case (1 << 4) | (1 << 2) | 0: op_pair<T, 1, 1, 0, NT>(tile, op, mat, t, tid); break;
+    case (1 << 4) | (2 << 2) | 1: op_pair<T, 1, 2, 1, NT>(tile, op, mat, t, tid); break;
+    case (1 << 4) | (2 << 2) | 0: op_pair<T, 1, 2, 0, NT>(tile, op, mat, t, tid); break;
+    case (2 << 4) | (1 << 2) | 2: op_pair<T, 2, 1, 2, NT>(tile, op, mat, t, tid); break;
+    case (2 << 4) | (1 << 2) | 1: op_pair<T, 2, 1, 1, NT>(tile, op, mat, t, tid); break;
+    case (2 << 4) | (2 << 2) | 2: op_pair<T, 2, 2, 2, NT>(tile, op, mat, t, tid); break;
+    case (2 << 4) | (2 << 2) | 1: op_pair<T, 2, 2, 1, NT>(tile, op, mat, t, tid); break;
+    default: op_pair<T, 2, 2, 0, NT>(tile, op, mat, t, tid); break;
+    }
+}
+
 // ---- X / SWAP permutations (optionally controlled): pure data movement ------------------------
 template <typename T, int NT>
 __device__ __forceinline__ void op_perm(typename Vec2<T>::type *tile, const DevOp &op, const int t, const int tid)
@@ -163,7 +244,9 @@ __device__ __forceinline__ uint64_t active_ops(const PassParams<T> &p, const uin
 }
 
 // ---- apply the pass's op list to one staged tile (block-wide; ends with a barrier) -------------
-template <typename T, int NT>
+// COND = false: no op of the pass depends on the tile (no outside controls, no per-state masks), so the
+// whole op loop is driven by kernel parameters only and stays on the uniform datapath.
+template <typename T, int NT, bool COND>
 __device__ __forceinline__ void apply_ops(const PassParams<T> &p, typename Vec2<T>::type *tile,
                                           const typename Vec2<T>::type *__restrict__ diag_tabs,
                                           const uint64_t active, const uint64_t base, const int t, const int tid)
@@ -171,7 +254,7 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, typename Vec2<
     using V = typename Vec2<T>::type;
     const uint32_t tile_amps = 1u << t;
     for (int o = 0; o < p.n_ops; o++) {
-            if (!((active >> o) & 1ull)) continue;
+            if (COND && !((active >> o) & 1ull)) continue;
             const DevOp &op = p.ops[o];
             if (op.kind == OP_DENSE) {
                 const T *mat = p.mats + op.mat_off;
@@ -183,6 +266,9 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, typename Vec2<
                 default: op_dense<T, 5, NT>(tile, op, mat, t, tid); break;
                 }
                 __syncthreads();
+            } else if (op.kind == OP_PAIR) {
+                op_pair_dispatch<T, NT>(tile, op, p.mats + op.mat_off, t, tid);
+                __syncthreads();
             } else if (op.kind == OP_DIAG) {
                 // a run of consecutive diagonal ops is applied in ONE sweep of the tile
                 int oe = o;
@@ -191,7 +277,7 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, typename Vec2<
                     const uint32_t s = swz<T>(i);
                     V v = tile[s];
                     for (int q = o; q <= oe; q++) {
-                        if (!((active >> q) & 1ull)) continue;
+                        if (COND && !((active >> q) & 1ull)) continue;
                         const DevOp &d = p.ops[q];
                         uint32_t ti = 0;
                         for (int m = 0; m < d.k; m++) {
@@ -261,7 +347,7 @@ tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type
             tile[swz<T>(i)] = gbase[run_off[i >> L] + (i & run_mask)];
         __syncthreads();
 
-        apply_ops<T, kTileThreads>(p, tile, diag_tabs, active, base, t, tid);
+        apply_ops<T, kTileThreads, true>(p, tile, diag_tabs, active, base, t, tid);
 
         // ---- stage out
 #pragma unroll 4
@@ -275,15 +361,15 @@ tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type
 // TMA-staged, software-pipelined pass kernel (the production path for every pass whose tiles are
 // made of >= 256-byte runs).
 //
-//   * one persistent CTA per SM, kTmaThreads threads, kStages tile buffers in shared memory;
+//   * one persistent CTA per SM, NT threads, kStages tile buffers in shared memory;
 //   * tiles move HBM -> smem and smem -> HBM with cp.async.bulk.tensor (TMA) through a 3-D tensor
 //     map over the state ([128-byte row][2^20 rows][rest]) with the hardware 128-byte swizzle, one
 //     TMA op per contiguous run (box = 2^Lb amplitudes); no register staging, no LSU issue slots;
 //   * loads complete on an mbarrier (complete_tx), stores are tracked with bulk async-groups;
 //   * while tile k is being computed, tile k+1 is landing and tile k-1 is draining.
 // =================================================================================================
-constexpr int kTmaThreads = 512;
 constexpr int kStages = 3;
+constexpr int kAmpsPerThreadShift = 4;  // a thread owns 2^4 amplitudes of the tile (one 4-bit register block)
 constexpr int kRowShift = 20;  // rows per dim-1 of the tensor map
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -322,8 +408,10 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void 
                  : "memory");
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kTmaThreads, 1)
+// NT threads per CTA = 2^(t-4); 256/NT CTAs are resident per SM, each running its own pipeline on its own
+// tiles, so the load / math / store / barrier phases of different CTAs interleave on an SM.
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT, 256 / NT)
 tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_constant__ CUtensorMap tmap,
                      const typename Vec2<T>::type *__restrict__ diag_tabs, const uint8_t *__restrict__ flags,
                      const int Lb, const uint32_t buf_stride)
@@ -339,11 +427,10 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     constexpr int kAmpsPerRowShift = sizeof(V) == 16 ? 3 : 4;  // amplitudes per 128-byte row
     uint64_t *box_off = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * buf_stride);
     uint64_t *full = box_off + nbox;
-    uint64_t *slot_tile = full + kStages;  // tile number staged in each slot (~0 = none)
 
     // amplitude offset of box r inside a tile: the low (L-Lb) bits of r continue the contiguous run,
     // the rest are deposited at the high tile qubits
-    for (uint32_t r = tid; r < nbox; r += kTmaThreads) {
+    for (uint32_t r = tid; r < nbox; r += NT) {
         uint64_t o = (uint64_t)(r & ((1u << (L - Lb)) - 1u)) << Lb;
         const uint32_t hi = r >> (L - Lb);
         for (int j = L; j < t; j++)
@@ -351,78 +438,82 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         box_off[r] = o;
     }
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); slot_tile[s] = ~0ull; }
+        for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
     const uint64_t total_tiles = p.tiles_per_state * (uint64_t)p.batch;
-    // tile -> (state, base amplitude, active-op mask); all threads evaluate it identically
-    auto decode = [&](uint64_t tileno, uint64_t &b, uint64_t &base) -> uint64_t {
-        b = tileno / p.tiles_per_state;
-        uint64_t x = tileno - b * p.tiles_per_state;
+    const int tps_shift = n - t;  // tiles_per_state = 2^(n-t)
+    const bool cond = p.cond_mask != 0;
+    // tile number -> amplitude offset of the tile inside the whole buffer (state b, base within the state)
+    auto tile_base = [&](uint64_t tileno, uint64_t &b) -> uint64_t {
+        b = tileno >> tps_shift;
+        uint64_t x = tileno & (p.tiles_per_state - 1ull);
         for (int j = L; j < t; j++) x = insert0_64(x, p.tile_q[j] - L);
-        base = x << L;
-        return active_ops(p, flags, b, base);
+        return x << L;
     };
-    // next tile of this CTA (stride gridDim.x) that some op acts on
+    // next tile of this CTA (stride gridDim.x) that some op acts on; ~0 = none.  Evaluated identically by
+    // every thread, so the tile sequence lives in registers and needs no shared bookkeeping.
     auto next_active = [&](uint64_t from) -> uint64_t {
-        uint64_t b, base;
-        for (uint64_t x = from; x < total_tiles; x += gridDim.x)
-            if (decode(x, b, base) != 0) return x;
+        if (!cond) return from < total_tiles ? from : ~0ull;
+        for (uint64_t x = from; x < total_tiles; x += gridDim.x) {
+            uint64_t b;
+            const uint64_t base = tile_base(x, b);
+            if (active_ops(p, flags, b, base) != 0) return x;
+        }
         return ~0ull;
     };
     auto issue_load = [&](int s, uint64_t tileno) {
-        uint64_t b, base;
-        decode(tileno, b, base);
+        uint64_t b;
+        const uint64_t base = tile_base(tileno, b);
         if (tid == 0) mbar_arrive_expect_tx(&full[s], tile_bytes);
-        if ((uint32_t)tid < nbox) {
-            const uint64_t row = ((b << n) + base + box_off[tid]) >> kAmpsPerRowShift;
-            tma_load_3d(smem_raw + (size_t)s * buf_stride + ((size_t)tid << Lb) * sizeof(V), &tmap, &full[s], 0,
+        for (uint32_t r = tid; r < nbox; r += NT) {
+            const uint64_t row = ((b << n) + base + box_off[r]) >> kAmpsPerRowShift;
+            tma_load_3d(smem_raw + (size_t)s * buf_stride + ((size_t)r << Lb) * sizeof(V), &tmap, &full[s], 0,
                         (int)(row & ((1ull << kRowShift) - 1ull)), (int)(row >> kRowShift));
         }
     };
 
-    uint64_t cursor = next_active(blockIdx.x);
-    for (int s = 0; s < kStages - 1; s++) {
-        if (cursor == ~0ull) break;
-        if (tid == 0) slot_tile[s] = cursor;
-        issue_load(s, cursor);
-        cursor = next_active(cursor + gridDim.x);
-    }
-    __syncthreads();
+    // t0 = tile computed in this iteration, t1 = tile already loading, t2 = tile to be loaded next
+    uint64_t t0 = next_active(blockIdx.x);
+    uint64_t t1 = t0 == ~0ull ? ~0ull : next_active(t0 + gridDim.x);
+    uint64_t t2 = t1 == ~0ull ? ~0ull : next_active(t1 + gridDim.x);
+    if (t0 != ~0ull) issue_load(0, t0);
+    if (t1 != ~0ull) issue_load(1, t1);
 
-    for (uint32_t k = 0;; k++) {
-        const int s = (int)(k % kStages);
-        const uint64_t tileno = slot_tile[s];
-        if (tileno == ~0ull) break;
-        uint64_t b, base;
-        const uint64_t active = decode(tileno, b, base);
+    int s = 0;            // slot of t0
+    uint32_t parity = 0;  // flips every time s wraps
+    while (t0 != ~0ull) {
+        uint64_t b;
+        const uint64_t base = tile_base(t0, b);
         V *tile = reinterpret_cast<V *>(smem_raw + (size_t)s * buf_stride);
-        mbar_wait(&full[s], (k / kStages) & 1u);
+        mbar_wait(&full[s], parity);
 
-        apply_ops<T, kTmaThreads>(p, tile, diag_tabs, active, base, t, tid);  // ends with __syncthreads
+        if (!cond) apply_ops<T, NT, false>(p, tile, diag_tabs, ~0ull, base, t, tid);
+        else apply_ops<T, NT, true>(p, tile, diag_tabs, active_ops(p, flags, b, base), base, t, tid);
 
-        // generic-proxy writes -> visible to the async proxy, then drain this tile with TMA stores
+        // every thread's generic-proxy writes -> visible to the async proxy; then drain the tile with TMA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        const int s2 = s == 0 ? kStages - 1 : s - 1;  // slot that held the previous tile; receives t2
         if ((uint32_t)tid < nbox) {
-            const uint64_t row = ((b << n) + base + box_off[tid]) >> kAmpsPerRowShift;
-            tma_store_3d(&tmap, smem_raw + (size_t)s * buf_stride + ((size_t)tid << Lb) * sizeof(V), 0,
-                         (int)(row & ((1ull << kRowShift) - 1ull)), (int)(row >> kRowShift));
+            for (uint32_t r = tid; r < nbox; r += NT) {
+                const uint64_t row = ((b << n) + base + box_off[r]) >> kAmpsPerRowShift;
+                tma_store_3d(&tmap, smem_raw + (size_t)s * buf_stride + ((size_t)r << Lb) * sizeof(V), 0,
+                             (int)(row & ((1ull << kRowShift) - 1ull)), (int)(row >> kRowShift));
+            }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            // the slot refilled below held tile k-1: its store must have finished READING shared memory
+            // Thread r refills exactly the boxes it drained one iteration ago, so it only has to wait for
+            // ITS OWN previous store to have finished reading shared memory -- no block barrier here.
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
-        __syncthreads();
-        const int s2 = (int)((k + kStages - 1) % kStages);
-        if (tid == 0) slot_tile[s2] = cursor;
-        if (cursor != ~0ull) {
-            issue_load(s2, cursor);
-            cursor = next_active(cursor + gridDim.x);
-        }
-        __syncthreads();
+        if (t2 != ~0ull) issue_load(s2, t2);
+        t0 = t1;
+        t1 = t2;
+        t2 = t2 == ~0ull ? ~0ull : next_active(t2 + gridDim.x);
+        if (++s == kStages) { s = 0; parity ^= 1u; }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
