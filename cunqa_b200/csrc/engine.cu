@@ -38,6 +38,7 @@ State::State(int n_qubits, int prec, int dev, int nbatch)
     max_smem_ = prop.sharedMemPerBlockOptin;
     max_smem_sm_ = prop.sharedMemPerMultiprocessor;
     tma_threads_ = env_int("CB200_TMA_THREADS", 0);
+    tma_fold_dims_ = env_int("CB200_TMA_FOLD", 1) != 0;
     n_local_ = n;
     amp_bytes_ = precision == 64 ? 16 : 8;
     state_bytes_ = amp_bytes_ * ((size_t)batch << n);
@@ -124,26 +125,30 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-const CUtensorMap *State::tensor_map(int Lb)
+// {128-byte row, row index in the whole buffer, qa, qb, qc}: box = one run of 2^run_bits amplitudes (<= 256
+// rows) times the three high tile qubits qa/qb/qc (size-2 dimensions with stride 2^q amplitudes; unused
+// ones are passed as -1).  Hardware 128-byte swizzle on the shared-memory side (= swz<T>() in the kernel).
+void State::make_tensor_map(CUtensorMap *out, int run_bits, const int hi_qubits[3])
 {
-    if (Lb < 0 || Lb >= 16) throw InvalidArg("bad TMA box size");
-    if (tmap_ready_[Lb]) return &tmaps_[Lb];
     const int aprs = precision == 64 ? 3 : 4;  // log2(amplitudes per 128-byte row)
     const uint64_t nrows = state_bytes_ >> 7;
-    const uint64_t d1 = std::min<uint64_t>(nrows, 1ull << kRowShift);
-    const uint64_t d2 = std::max<uint64_t>(1, nrows >> kRowShift);
+    if (nrows >= (1ull << 31)) throw Unsupported("state too large for one tensor map");
     const cuuint32_t inner = precision == 64 ? 16 : 32;
-    const cuuint64_t gdim[3] = {inner, d1, d2};
-    const cuuint64_t gstride[2] = {128, 128ull << kRowShift};
-    const cuuint32_t box[3] = {inner, 1u << (Lb - aprs), 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = encode_tiled_fn()(&tmaps_[Lb], precision == 64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                                         3, d_state_, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t gdim[5] = {inner, nrows, 1, 1, 1};
+    cuuint64_t gstride[4] = {128, 128, 128, 128};
+    cuuint32_t box[5] = {inner, 1u << (run_bits - aprs), 1, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    for (int d = 0; d < 3; d++) {
+        if (hi_qubits[d] < 0) continue;
+        gdim[2 + d] = 2;
+        box[2 + d] = 2;
+        gstride[1 + d] = (cuuint64_t)amp_bytes_ << hi_qubits[d];
+    }
+    const CUresult r = encode_tiled_fn()(out, precision == 64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                         5, d_state_, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
-    tmap_ready_[Lb] = true;
-    return &tmaps_[Lb];
 }
 
 // ---- flush: plan + launch -----------------------------------------------------------------------
@@ -191,19 +196,25 @@ void State::flush_t()
     for (size_t i = 0; i < passes.size(); i++) {
         const PassParams<T> &p = params[i];
         const uint64_t total_tiles = p.tiles_per_state * (uint64_t)batch;
-        const int Lb = std::min(p.L, aprs + 8);
-        // TMA path: runs of >= 2 rows (256 B)
+        // TMA box: the contiguous run (at most 256 rows of it) plus up to three high tile qubits
+        const int run_bits = std::min(p.L, aprs + 8);
+        int hi_q[3] = {-1, -1, -1};
+        int box_bits = run_bits;
+        if (run_bits == p.L && tma_fold_dims_)
+            for (int d = 0; d < 3 && p.L + d < p.t; d++) { hi_q[d] = p.tile_q[p.L + d]; box_bits++; }
         const uint32_t buf_stride = (uint32_t)std::max<size_t>(1024, sizeof(V) << p.t);
-        const size_t smem_tma = (size_t)kStages * buf_stride + sizeof(uint64_t) * (((size_t)1 << (p.t - Lb)) + kStages) + 1024;
+        const size_t smem_tma = (size_t)kStages * buf_stride + sizeof(uint64_t) * (((size_t)1 << (p.t - box_bits)) + kStages) + 1024;
         int nt = 1 << std::max(6, std::min(8, p.t - kAmpsPerThreadShift));  // 64 / 128 / 256 threads
         if (tma_threads_ > 0) nt = tma_threads_;
         const int ctas = 256 / nt;
         const bool tma = use_tma_ && p.L >= aprs + 1 && state_bytes_ >= 128 && smem_tma * ctas <= max_smem_sm_ && smem_tma <= max_smem_;
         if (tma) {
+            CUtensorMap tmap;
+            make_tensor_map(&tmap, run_bits, hi_q);
             const unsigned grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_ * ctas);
             auto launch = [&](auto kern_tma) {
                 CB200_CUDA(cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
-                kern_tma<<<grid, nt, smem_tma, stream_>>>(p, *tensor_map(Lb), (const V *)d_diag_, d_flags_, Lb, buf_stride);
+                kern_tma<<<grid, nt, smem_tma, stream_>>>(p, tmap, (const V *)d_diag_, d_flags_, box_bits, buf_stride);
             };
             if (nt == 256) launch(tile_pass_tma_kernel<T, 256>);
             else if (nt == 128) launch(tile_pass_tma_kernel<T, 128>);

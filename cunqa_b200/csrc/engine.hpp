@@ -84,9 +84,8 @@ private:
     int tma_threads_ = 0;
     int ctas_per_sm_ = 0;  // 0 = occupancy query (generic kernel only)
     bool use_tma_ = true;
-    const CUtensorMap *tensor_map(int Lb);  // 3-D map over the state, box = one run of 2^Lb amplitudes
-    CUtensorMap tmaps_[16];
-    bool tmap_ready_[16] = {};
+    void make_tensor_map(CUtensorMap *out, int run_bits, const int hi_qubits[3]);
+    bool tma_fold_dims_ = true;
     // device scratch
     void *d_diag_ = nullptr; size_t diag_cap_ = 0;       // diagonal tables (elements of V)
     uint8_t *d_flags_ = nullptr; size_t flags_cap_ = 0;  // mask rows

@@ -370,7 +370,6 @@ tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type
 // =================================================================================================
 constexpr int kStages = 3;
 constexpr int kAmpsPerThreadShift = 4;  // a thread owns 2^4 amplitudes of the tile (one 4-bit register block)
-constexpr int kRowShift = 20;  // rows per dim-1 of the tensor map
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
@@ -394,17 +393,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
+// 5-D tensor map of a pass: {128-byte row, row index in the whole buffer, tile qubit a, b, c}; the box is
+// {row, 2^(L-rowshift) rows, 2, 2, 2}: one TMA op moves the 8 runs spanned by three high tile qubits.
+__device__ __forceinline__ void tma_load_row(void *dst, const CUtensorMap *map, uint64_t *bar, int row)
 {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %3, %3, %3}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(0), "r"(row)
         : "memory");
 }
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2)
+__device__ __forceinline__ void tma_store_row(const CUtensorMap *map, const void *src, int row)
 {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %2, %2, %2}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(0), "r"(row)
                  : "memory");
 }
 
@@ -414,7 +415,7 @@ template <typename T, int NT>
 __global__ void __launch_bounds__(NT, 256 / NT)
 tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_constant__ CUtensorMap tmap,
                      const typename Vec2<T>::type *__restrict__ diag_tabs, const uint8_t *__restrict__ flags,
-                     const int Lb, const uint32_t buf_stride)
+                     const int box_bits, const uint32_t buf_stride)
 {
     using V = typename Vec2<T>::type;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -422,19 +423,21 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     unsigned char *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int t = p.t, L = p.L, n = p.n;
     const int tid = threadIdx.x;
-    const uint32_t nbox = 1u << (t - Lb);          // TMA ops per tile per direction
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    // one TMA box covers tile bits [0, box_bits): the contiguous run (or a 256-row piece of it when the run
+    // is longer) plus up to three high tile qubits folded into the tensor map
+    const uint32_t nbox = 1u << (t - box_bits);    // TMA ops per tile per direction
     const uint32_t tile_bytes = (uint32_t)sizeof(V) << t;
     constexpr int kAmpsPerRowShift = sizeof(V) == 16 ? 3 : 4;  // amplitudes per 128-byte row
     uint64_t *box_off = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * buf_stride);
     uint64_t *full = box_off + nbox;
 
-    // amplitude offset of box r inside a tile: the low (L-Lb) bits of r continue the contiguous run,
-    // the rest are deposited at the high tile qubits
+    // amplitude offset of box r inside a tile: tile-index bit j >= box_bits of the box number is deposited at
+    // physical qubit tile_q[j] (which is j itself while j < L: the box is then a piece of the run)
     for (uint32_t r = tid; r < nbox; r += NT) {
-        uint64_t o = (uint64_t)(r & ((1u << (L - Lb)) - 1u)) << Lb;
-        const uint32_t hi = r >> (L - Lb);
-        for (int j = L; j < t; j++)
-            if ((hi >> (j - L)) & 1u) o |= 1ull << p.tile_q[j];
+        uint64_t o = 0;
+        for (int j = box_bits; j < t; j++)
+            if ((r >> (j - box_bits)) & 1u) o |= 1ull << p.tile_q[j];
         box_off[r] = o;
     }
     if (tid == 0) {
@@ -469,10 +472,12 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         uint64_t b;
         const uint64_t base = tile_base(tileno, b);
         if (tid == 0) mbar_arrive_expect_tx(&full[s], tile_bytes);
-        for (uint32_t r = tid; r < nbox; r += NT) {
-            const uint64_t row = ((b << n) + base + box_off[r]) >> kAmpsPerRowShift;
-            tma_load_3d(smem_raw + (size_t)s * buf_stride + ((size_t)r << Lb) * sizeof(V), &tmap, &full[s], 0,
-                        (int)(row & ((1ull << kRowShift) - 1ull)), (int)(row >> kRowShift));
+        // TMA instructions take warp-uniform operands: lane 0 of warp w issues boxes w, w+nwarps, ...
+        if (lane == 0) {
+            for (uint32_t r = warp; r < nbox; r += NT / 32) {
+                const uint64_t row = ((b << n) + base + box_off[r]) >> kAmpsPerRowShift;
+                tma_load_row(smem_raw + (size_t)s * buf_stride + ((size_t)r << box_bits) * sizeof(V), &tmap, &full[s], (int)row);
+            }
         }
     };
 
@@ -498,15 +503,14 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         const int s2 = s == 0 ? kStages - 1 : s - 1;  // slot that held the previous tile; receives t2
-        if ((uint32_t)tid < nbox) {
-            for (uint32_t r = tid; r < nbox; r += NT) {
+        if (lane == 0) {
+            for (uint32_t r = warp; r < nbox; r += NT / 32) {
                 const uint64_t row = ((b << n) + base + box_off[r]) >> kAmpsPerRowShift;
-                tma_store_3d(&tmap, smem_raw + (size_t)s * buf_stride + ((size_t)r << Lb) * sizeof(V), 0,
-                             (int)(row & ((1ull << kRowShift) - 1ull)), (int)(row >> kRowShift));
+                tma_store_row(&tmap, smem_raw + (size_t)s * buf_stride + ((size_t)r << box_bits) * sizeof(V), (int)row);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            // Thread r refills exactly the boxes it drained one iteration ago, so it only has to wait for
-            // ITS OWN previous store to have finished reading shared memory -- no block barrier here.
+            // The issuing lane refills exactly the boxes it drained one iteration ago, so it only has to wait
+            // for ITS OWN previous store to have finished reading shared memory -- no block barrier here.
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
         if (t2 != ~0ull) issue_load(s2, t2);
