@@ -39,6 +39,7 @@ State::State(int n_qubits, int prec, int dev, int nbatch)
     max_smem_sm_ = prop.sharedMemPerMultiprocessor;
     tma_threads_ = env_int("CB200_TMA_THREADS", 0);
     tma_fold_dims_ = env_int("CB200_TMA_FOLD", 1) != 0;
+    tma_stages_ = env_int("CB200_TMA_STAGES", 2) == 3 ? 3 : 2;
     n_local_ = n;
     amp_bytes_ = precision == 64 ? 16 : 8;
     state_bytes_ = amp_bytes_ * ((size_t)batch << n);
@@ -203,10 +204,12 @@ void State::flush_t()
         if (run_bits == p.L && tma_fold_dims_)
             for (int d = 0; d < 3 && p.L + d < p.t; d++) { hi_q[d] = p.tile_q[p.L + d]; box_bits++; }
         const uint32_t buf_stride = (uint32_t)std::max<size_t>(1024, sizeof(V) << p.t);
-        const size_t smem_tma = (size_t)kStages * buf_stride + sizeof(uint64_t) * (((size_t)1 << (p.t - box_bits)) + kStages) + 1024;
+        const int stages = tma_stages_;
+        const size_t smem_tma = (size_t)stages * buf_stride + sizeof(uint64_t) * (((size_t)1 << (p.t - box_bits)) + stages + 1) +
+                                sizeof(T) * (size_t)((p.n_mat + 1) & ~1) + 1024;
         int nt = 1 << std::max(6, std::min(8, p.t - kAmpsPerThreadShift));  // 64 / 128 / 256 threads
         if (tma_threads_ > 0) nt = tma_threads_;
-        const int ctas = 256 / nt;
+        const int ctas = std::max(1, (stages == 3 ? 256 : 384) / nt);
         const bool tma = use_tma_ && p.L >= aprs + 1 && state_bytes_ >= 128 && smem_tma * ctas <= max_smem_sm_ && smem_tma <= max_smem_;
         if (tma) {
             CUtensorMap tmap;
@@ -216,9 +219,22 @@ void State::flush_t()
                 CB200_CUDA(cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
                 kern_tma<<<grid, nt, smem_tma, stream_>>>(p, tmap, (const V *)d_diag_, d_flags_, box_bits, buf_stride);
             };
-            if (nt == 256) launch(tile_pass_tma_kernel<T, 256>);
-            else if (nt == 128) launch(tile_pass_tma_kernel<T, 128>);
-            else launch(tile_pass_tma_kernel<T, 64>);
+            const bool cnd = p.cond_mask != 0, full = p.needs_full != 0;
+            auto pick = [&](auto nt_tag) {
+                constexpr int N = decltype(nt_tag)::value;
+                if (stages == 3) {
+                    if (!cnd && !full) launch(tile_pass_tma_kernel<T, N, false, false, 3>);
+                    else if (!cnd) launch(tile_pass_tma_kernel<T, N, false, true, 3>);
+                    else launch(tile_pass_tma_kernel<T, N, true, true, 3>);
+                } else {
+                    if (!cnd && !full) launch(tile_pass_tma_kernel<T, N, false, false, 2>);
+                    else if (!cnd) launch(tile_pass_tma_kernel<T, N, false, true, 2>);
+                    else launch(tile_pass_tma_kernel<T, N, true, true, 2>);
+                }
+            };
+            if (nt == 256) pick(std::integral_constant<int, 256>());
+            else if (nt == 128) pick(std::integral_constant<int, 128>());
+            else pick(std::integral_constant<int, 64>());
         } else {
             const size_t smem = sizeof(V) * ((size_t)1 << p.t) + sizeof(uint64_t) * ((size_t)1 << (p.t - p.L));
             CB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

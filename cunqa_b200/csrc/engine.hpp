@@ -86,6 +86,7 @@ private:
     bool use_tma_ = true;
     void make_tensor_map(CUtensorMap *out, int run_bits, const int hi_qubits[3]);
     bool tma_fold_dims_ = true;
+    int tma_stages_ = 2;
     // device scratch
     void *d_diag_ = nullptr; size_t diag_cap_ = 0;       // diagonal tables (elements of V)
     uint8_t *d_flags_ = nullptr; size_t flags_cap_ = 0;  // mask rows

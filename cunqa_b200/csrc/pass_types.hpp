@@ -33,7 +33,10 @@ struct DevOp {
     uint8_t has_mask;
     uint8_t tbit[8];        // DENSE/PERM: tile-bit position of target m
     uint8_t fixpos[kMaxFix]; // ascending tile-bit positions where a bit is inserted into the group index
-    uint8_t dsrc[kMaxDiagK]; // DIAG: source of table-index bit m: <64 tile bit, >=64 physical qubit (v-64) outside the tile
+    union {
+        uint8_t dsrc[kMaxDiagK]; // DIAG: source of table-index bit m: <64 tile bit, >=64 physical qubit (v-64) outside the tile
+        uint16_t seg[6];         // PAIR: group index -> tile index deposit, idx = sum_k (g & seg[k]) << k  (k <= nfix)
+    };
     uint32_t ctrl_in;   // in-tile control bits (OR-ed into the tile index; those bits are in fixpos)
     uint32_t mat_off;   // DENSE: scalar offset into PassParams::mats; DIAG: element offset into the diag-table buffer
     uint64_t ctrl_out;  // physical-qubit mask of controls outside the tile (tested on the tile base)
@@ -53,6 +56,8 @@ struct PassParams {
     int32_t pad_;
     uint64_t tiles_per_state;
     uint64_t cond_mask; // ops whose activity depends on the tile (controls outside the tile / per-state mask)
+    int32_t n_mat;      // scalars used in mats (staged into shared memory once per CTA)
+    int32_t needs_full; // 1: some op needs the FULL kernel variant (dense k>=3, unusual register blocks)
     uint8_t tile_q[16]; // physical qubit of tile bit j (ascending)
     DevOp ops[kMaxOps];
     T mats[kMatScalars];

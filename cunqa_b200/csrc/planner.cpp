@@ -286,6 +286,12 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
                 std::sort(fix.begin(), fix.end());
                 d.nfix = (uint8_t)R;
                 for (int f = 0; f < R; f++) d.fixpos[f] = (uint8_t)fix[f];
+                // segment masks of the group index: bits between consecutive fixed positions move up together
+                for (int k = 0; k <= R; k++) {
+                    const int lo = k == 0 ? 0 : fix[k - 1] - (k - 1);
+                    const int hi = k == R ? 16 : fix[k] - k;
+                    d.seg[k] = (uint16_t)(hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u);
+                }
                 d.mat_off = (uint32_t)mat_used;
                 const std::vector<cplx> MA = embed_dense(A, la), MB = embed_dense(B, lb);
                 for (const std::vector<cplx> *M : {&MA, &MB})
@@ -337,6 +343,17 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
         }
     }
     out.n_ops = nops;
+    out.n_mat = mat_used;
+    out.needs_full = 0;
+    for (int o = 0; o < nops; o++) {
+        const DevOp &d = out.ops[o];
+        if (d.kind == OP_DENSE && d.k >= 3) out.needs_full = 1;
+        if (d.kind == OP_PAIR) {
+            const int code = (d.k << 4) | (d.k2 << 2) | d.s;
+            if (code != ((2 << 4) | (2 << 2) | 2) && code != ((2 << 4) | (2 << 2) | 1) && code != ((1 << 4) | (1 << 2) | 1))
+                out.needs_full = 1;
+        }
+    }
     out.cond_mask = 0;
     for (int o = 0; o < nops; o++)
         if (out.ops[o].ctrl_out != 0 || out.ops[o].has_mask) out.cond_mask |= 1ull << o;

@@ -160,9 +160,11 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
     constexpr int D = 1 << R;
     // the swizzle is XOR-linear and the block bits are disjoint from the group bits, so
     // swz(idx | off_j) = swz(idx) ^ swz(off_j): one XOR per amplitude instead of re-swizzling
-    uint32_t sb[R], fp[R];
+    uint32_t sb[R], seg[R + 1];
 #pragma unroll
-    for (int m = 0; m < R; m++) { sb[m] = swz<T>(1u << op.tbit[m]); fp[m] = op.fixpos[m]; }
+    for (int m = 0; m < R; m++) sb[m] = swz<T>(1u << op.tbit[m]);
+#pragma unroll
+    for (int m = 0; m <= R; m++) seg[m] = op.seg[m];
     uint32_t soff[D];
 #pragma unroll
     for (int j = 0; j < D; j++) {
@@ -173,9 +175,9 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
     }
     const uint32_t ngroups = 1u << (t - R);
     for (uint32_t g = tid; g < ngroups; g += NT) {
-        uint32_t idx = g;
+        uint32_t idx = 0;
 #pragma unroll
-        for (int f = 0; f < R; f++) idx = insert0(idx, fp[f]);
+        for (int m = 0; m <= R; m++) idx |= (g & seg[m]) << m;
         const uint32_t sidx = swz<T>(idx);
         V a[D];
 #pragma unroll
@@ -187,20 +189,25 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
     }
 }
 
-template <typename T, int NT>
+// FULL = false keeps only the register blocks the headline circuits produce (keeps the hot kernel small
+// enough for the instruction cache); the planner sets PassParams::needs_full for anything else.
+template <typename T, int NT, bool FULL>
 __device__ __forceinline__ void op_pair_dispatch(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
                                                  const int t, const int tid)
 {
-    switch ((op.k << 4) | (op.k2 << 2) | op.s) {
-    case (1 << 4) | (1 << 2) | 1: op_pair<T, 1, 1, 1, NT>(tile, op, mat, t, tid); break;
-    case (1 << 4) | (1 << 2) | 0: op_pair<T, 1, 1, 0, NT>(tile, op, mat, t, tid); break;
-    case (1 << 4) | (2 << 2) | 1: op_pair<T, 1, 2, 1, NT>(tile, op, mat, t, tid); break;
-    case (1 << 4) | (2 << 2) | 0: op_pair<T, 1, 2, 0, NT>(tile, op, mat, t, tid); break;
-    case (2 << 4) | (1 << 2) | 2: op_pair<T, 2, 1, 2, NT>(tile, op, mat, t, tid); break;
-    case (2 << 4) | (1 << 2) | 1: op_pair<T, 2, 1, 1, NT>(tile, op, mat, t, tid); break;
-    case (2 << 4) | (2 << 2) | 2: op_pair<T, 2, 2, 2, NT>(tile, op, mat, t, tid); break;
-    case (2 << 4) | (2 << 2) | 1: op_pair<T, 2, 2, 1, NT>(tile, op, mat, t, tid); break;
-    default: op_pair<T, 2, 2, 0, NT>(tile, op, mat, t, tid); break;
+    const int code = (op.k << 4) | (op.k2 << 2) | op.s;
+    if (code == ((2 << 4) | (2 << 2) | 2)) { op_pair<T, 2, 2, 2, NT>(tile, op, mat, t, tid); return; }
+    if (code == ((2 << 4) | (2 << 2) | 1)) { op_pair<T, 2, 2, 1, NT>(tile, op, mat, t, tid); return; }
+    if (code == ((1 << 4) | (1 << 2) | 1)) { op_pair<T, 1, 1, 1, NT>(tile, op, mat, t, tid); return; }
+    if constexpr (FULL) {
+        switch (code) {
+        case (1 << 4) | (1 << 2) | 0: op_pair<T, 1, 1, 0, NT>(tile, op, mat, t, tid); break;
+        case (1 << 4) | (2 << 2) | 1: op_pair<T, 1, 2, 1, NT>(tile, op, mat, t, tid); break;
+        case (1 << 4) | (2 << 2) | 0: op_pair<T, 1, 2, 0, NT>(tile, op, mat, t, tid); break;
+        case (2 << 4) | (1 << 2) | 2: op_pair<T, 2, 1, 2, NT>(tile, op, mat, t, tid); break;
+        case (2 << 4) | (1 << 2) | 1: op_pair<T, 2, 1, 1, NT>(tile, op, mat, t, tid); break;
+        default: op_pair<T, 2, 2, 0, NT>(tile, op, mat, t, tid); break;
+        }
     }
 }
 
@@ -246,8 +253,8 @@ __device__ __forceinline__ uint64_t active_ops(const PassParams<T> &p, const uin
 // ---- apply the pass's op list to one staged tile (block-wide; ends with a barrier) -------------
 // COND = false: no op of the pass depends on the tile (no outside controls, no per-state masks), so the
 // whole op loop is driven by kernel parameters only and stays on the uniform datapath.
-template <typename T, int NT, bool COND>
-__device__ __forceinline__ void apply_ops(const PassParams<T> &p, typename Vec2<T>::type *tile,
+template <typename T, int NT, bool COND, bool FULL>
+__device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats, typename Vec2<T>::type *tile,
                                           const typename Vec2<T>::type *__restrict__ diag_tabs,
                                           const uint64_t active, const uint64_t base, const int t, const int tid)
 {
@@ -257,17 +264,17 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, typename Vec2<
             if (COND && !((active >> o) & 1ull)) continue;
             const DevOp &op = p.ops[o];
             if (op.kind == OP_DENSE) {
-                const T *mat = p.mats + op.mat_off;
-                switch (op.k) {
-                case 1: op_dense<T, 1, NT>(tile, op, mat, t, tid); break;
-                case 2: op_dense<T, 2, NT>(tile, op, mat, t, tid); break;
-                case 3: op_dense<T, 3, NT>(tile, op, mat, t, tid); break;
-                case 4: op_dense<T, 4, NT>(tile, op, mat, t, tid); break;
-                default: op_dense<T, 5, NT>(tile, op, mat, t, tid); break;
+                const T *mat = mats + op.mat_off;
+                if (op.k == 1) op_dense<T, 1, NT>(tile, op, mat, t, tid);
+                else if (op.k == 2) op_dense<T, 2, NT>(tile, op, mat, t, tid);
+                else if constexpr (FULL) {
+                    if (op.k == 3) op_dense<T, 3, NT>(tile, op, mat, t, tid);
+                    else if (op.k == 4) op_dense<T, 4, NT>(tile, op, mat, t, tid);
+                    else op_dense<T, 5, NT>(tile, op, mat, t, tid);
                 }
                 __syncthreads();
             } else if (op.kind == OP_PAIR) {
-                op_pair_dispatch<T, NT>(tile, op, p.mats + op.mat_off, t, tid);
+                op_pair_dispatch<T, NT, FULL>(tile, op, mats + op.mat_off, t, tid);
                 __syncthreads();
             } else if (op.kind == OP_DIAG) {
                 // a run of consecutive diagonal ops is applied in ONE sweep of the tile
@@ -347,7 +354,7 @@ tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type
             tile[swz<T>(i)] = gbase[run_off[i >> L] + (i & run_mask)];
         __syncthreads();
 
-        apply_ops<T, kTileThreads, true>(p, tile, diag_tabs, active, base, t, tid);
+        apply_ops<T, kTileThreads, true, true>(p, p.mats, tile, diag_tabs, active, base, t, tid);
 
         // ---- stage out
 #pragma unroll 4
@@ -368,7 +375,6 @@ tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type
 //   * loads complete on an mbarrier (complete_tx), stores are tracked with bulk async-groups;
 //   * while tile k is being computed, tile k+1 is landing and tile k-1 is draining.
 // =================================================================================================
-constexpr int kStages = 3;
 constexpr int kAmpsPerThreadShift = 4;  // a thread owns 2^4 amplitudes of the tile (one 4-bit register block)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -411,8 +417,10 @@ __device__ __forceinline__ void tma_store_row(const CUtensorMap *map, const void
 
 // NT threads per CTA = 2^(t-4); 256/NT CTAs are resident per SM, each running its own pipeline on its own
 // tiles, so the load / math / store / barrier phases of different CTAs interleave on an SM.
-template <typename T, int NT>
-__global__ void __launch_bounds__(NT, 256 / NT)
+// kStages tile buffers per CTA: 3 = the CTA overlaps its own load / math / store; 2 = one more CTA fits per
+// SM and the overlap comes from the other resident CTAs.
+template <typename T, int NT, bool COND, bool FULL, int kStages>
+__global__ void __launch_bounds__(NT, (kStages == 3 ? 256 : 384) / NT)
 tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_constant__ CUtensorMap tmap,
                      const typename Vec2<T>::type *__restrict__ diag_tabs, const uint8_t *__restrict__ flags,
                      const int box_bits, const uint32_t buf_stride)
@@ -431,6 +439,9 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     constexpr int kAmpsPerRowShift = sizeof(V) == 16 ? 3 : 4;  // amplitudes per 128-byte row
     uint64_t *box_off = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * buf_stride);
     uint64_t *full = box_off + nbox;
+    // the pass's dense matrices, staged once: broadcast shared-memory loads instead of constant-bank loads
+    T *mats_s = reinterpret_cast<T *>(full + kStages + 1);
+    for (int e = tid; e < p.n_mat; e += NT) mats_s[e] = p.mats[e];
 
     // amplitude offset of box r inside a tile: tile-index bit j >= box_bits of the box number is deposited at
     // physical qubit tile_q[j] (which is j itself while j < L: the box is then a piece of the run)
@@ -449,7 +460,7 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
 
     const uint64_t total_tiles = p.tiles_per_state * (uint64_t)p.batch;
     const int tps_shift = n - t;  // tiles_per_state = 2^(n-t)
-    const bool cond = p.cond_mask != 0;
+    constexpr bool cond = COND;
     // tile number -> amplitude offset of the tile inside the whole buffer (state b, base within the state)
     auto tile_base = [&](uint64_t tileno, uint64_t &b) -> uint64_t {
         b = tileno >> tps_shift;
@@ -481,28 +492,30 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         }
     };
 
-    // t0 = tile computed in this iteration, t1 = tile already loading, t2 = tile to be loaded next
-    uint64_t t0 = next_active(blockIdx.x);
-    uint64_t t1 = t0 == ~0ull ? ~0ull : next_active(t0 + gridDim.x);
-    uint64_t t2 = t1 == ~0ull ? ~0ull : next_active(t1 + gridDim.x);
-    if (t0 != ~0ull) issue_load(0, t0);
-    if (t1 != ~0ull) issue_load(1, t1);
+    // tq[0] = tile computed in this iteration, tq[1..kStages-2] = tiles already loading,
+    // tq[kStages-1] = tile to be loaded next (all register-resident, statically indexed)
+    uint64_t tq[kStages];
+    tq[0] = next_active(blockIdx.x);
+#pragma unroll
+    for (int i = 1; i < kStages; i++) tq[i] = tq[i - 1] == ~0ull ? ~0ull : next_active(tq[i - 1] + gridDim.x);
+#pragma unroll
+    for (int i = 0; i < kStages - 1; i++)
+        if (tq[i] != ~0ull) issue_load(i, tq[i]);
 
-    int s = 0;            // slot of t0
+    int s = 0;            // slot of tq[0]
     uint32_t parity = 0;  // flips every time s wraps
-    while (t0 != ~0ull) {
+    while (tq[0] != ~0ull) {
         uint64_t b;
-        const uint64_t base = tile_base(t0, b);
+        const uint64_t base = tile_base(tq[0], b);
         V *tile = reinterpret_cast<V *>(smem_raw + (size_t)s * buf_stride);
         mbar_wait(&full[s], parity);
 
-        if (!cond) apply_ops<T, NT, false>(p, tile, diag_tabs, ~0ull, base, t, tid);
-        else apply_ops<T, NT, true>(p, tile, diag_tabs, active_ops(p, flags, b, base), base, t, tid);
+        apply_ops<T, NT, COND, FULL>(p, mats_s, tile, diag_tabs, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid);
 
         // every thread's generic-proxy writes -> visible to the async proxy; then drain the tile with TMA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        const int s2 = s == 0 ? kStages - 1 : s - 1;  // slot that held the previous tile; receives t2
+        const int s2 = s == 0 ? kStages - 1 : s - 1;  // slot that held the previous tile; receives tq[kStages-1]
         if (lane == 0) {
             for (uint32_t r = warp; r < nbox; r += NT / 32) {
                 const uint64_t row = ((b << n) + base + box_off[r]) >> kAmpsPerRowShift;
@@ -513,10 +526,10 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
             // for ITS OWN previous store to have finished reading shared memory -- no block barrier here.
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
-        if (t2 != ~0ull) issue_load(s2, t2);
-        t0 = t1;
-        t1 = t2;
-        t2 = t2 == ~0ull ? ~0ull : next_active(t2 + gridDim.x);
+        if (tq[kStages - 1] != ~0ull) issue_load(s2, tq[kStages - 1]);
+#pragma unroll
+        for (int i = 0; i < kStages - 1; i++) tq[i] = tq[i + 1];
+        tq[kStages - 1] = tq[kStages - 1] == ~0ull ? ~0ull : next_active(tq[kStages - 1] + gridDim.x);
         if (++s == kStages) { s = 0; parity ^= 1u; }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

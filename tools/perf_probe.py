@@ -31,6 +31,8 @@ if __name__ == "__main__":
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 30
     if which in ("qv", "all"):
         probe("qv", C.quantum_volume(n, depth=min(n, 10)), n)
+    if which == "qvfull":
+        probe("qv_full", C.quantum_volume(n), n)
     if which in ("qft", "all"):
         probe("qft", C.qft(n, C.qft_x(n)), n)
     if which in ("h", "all"):
