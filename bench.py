@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the CUNQA B200 state-vector backend.
+
+Workload (BASELINE.json config 3, the one `metric` is quoted on and the largest that fits one
+GPU): 33-qubit random quantum-volume circuit, depth 33 (528 Haar SU(4) `unitary` gates), complex128,
+128 GiB state updated in place.  One *step* = one complete pass of the hot path over that circuit
+(state reset + all gates).  `value` = original circuit gates per second, whole job.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+* our arm: device-timed with CUDA events recorded on the engine's own stream; the state lives in HBM
+  for the whole run.  `e2e` re-runs the same circuit through cb200_backend_execute (the call the CUNQA
+  plugin makes): wire-JSON task in host memory -> plan -> kernel parameters H2D -> simulate ->
+  1024 shots sampled -> D2H -> counts JSON.
+* `roofline`: the tile-pass kernel; algorithmic bytes per launch = 2*S (every amplitude read once and
+  written once), duration = average launch time over the timed region.
+* `cpu_baseline` / `--impl reference`: the reference's CPU path for this workload is Aer's statevector
+  simulator, which cannot be installed here (no network, un-vendored); the arm times oracle/sv_oracle.c
+  (gate-by-gate restatement, OpenMP over all host cores) on a bounded sample and scales it to the
+  33-qubit state (amplitude updates per second / 2^33).
+* N > 1 (torchrun): every rank simulates its own 33-qubit state on its own GPU (the "many independent
+  vQPUs" regime of SURVEY 8e: no data-path collective), weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+QV_QUBITS = 33
+SEED = 2024
+SHOTS = 1024
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)"""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx = max(mx, float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(target_seconds=12.0, max_qubits=28):
+    """time the CPU oracle (gate-by-gate, OpenMP) on a bounded QV sample; -> dict for `cpu_baseline`"""
+    import numpy as np
+    from cunqa_b200 import circuits as C
+    from oracle import oracle_np as O
+    lib = O.c_oracle(native=True)
+    cores = lib.orc_num_threads()
+    try:
+        avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
+    except (ValueError, OSError):
+        avail_gb = 8.0
+    n = max_qubits
+    while n > 20 and 16 * 2 ** n / 2 ** 30 > 0.4 * avail_gb:
+        n -= 1
+    ins = C.quantum_volume(n, depth=QV_QUBITS, seed=SEED)
+    st = O.COracleState(n)
+    done, t0 = 0, time.perf_counter()
+    for inst in ins:
+        O.apply_gate(st, inst)
+        done += 1
+        if done >= n // 2 and time.perf_counter() - t0 > target_seconds:
+            break
+    dt = time.perf_counter() - t0
+    value = done * 2.0 ** n / 2.0 ** QV_QUBITS / dt
+    return {"value": value, "unit": "gates/s", "cores": cores, "kind": "port",
+            "sample": f"first {done} gates of the same seeded QV circuit at {n} qubits ({16 * 2 ** n / 2 ** 30:.0f} GiB state) in {dt:.1f} s, "
+                      f"scaled by 2^{n}/2^{QV_QUBITS} to the 33-qubit state; oracle/sv_oracle.c, unfused, OpenMP x{cores} "
+                      f"(CPU restatement of the Aer statevector algorithm, not Aer)"}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # W warm-up + K timed samples
+    per_step = max(3.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_sample(per_step)
+    vals, times, info = [], [], None
+    for _ in range(args.steps):
+        info, dt = cpu_sample(per_step)
+        vals.append(info["value"])
+        times.append(dt)
+    value = sum(vals) / len(vals)
+    info["value"] = value
+    line = {"impl": "reference", "metric": "gates_per_second", "value": value, "unit": "gates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"QV-{QV_QUBITS} depth {QV_QUBITS} fp64 (528 Haar SU(4) gates), CPU sample scaled to 33 qubits",
+                       "seed": SEED},
+            "cpu_baseline": info,
+            "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--qubits", type=int, default=0, help="override the workload width (debugging only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import cunqa_b200 as cb
+    from cunqa_b200 import circuits as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: cunqa_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.qubits or QV_QUBITS
+    free_b, _total_b = torch.cuda.mem_get_info()
+    workload_note = ""
+    while 16 * 2 ** n > 0.92 * free_b and n > 20:
+        n -= 1
+        workload_note = f" (reduced to {n} qubits: only {free_b / 2 ** 30:.0f} GiB free on this GPU)"
+    depth = QV_QUBITS if n == QV_QUBITS else n
+    ins = C.quantum_volume(n, depth=depth, seed=SEED)
+    gates = C.n_gates(ins)
+    S = 16 * 2 ** n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sv = cb.StateVector(n, "double", device=local_rank)
+    stream = torch.cuda.ExternalStream(sv.stream(), device=torch.device("cuda", local_rank))
+
+    def step():
+        sv.reset()
+        sv.run(ins)
+        sv.flush()
+
+    for _ in range(args.warmup):
+        step()
+    sv.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    s0 = sv.stats()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record(stream)
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record(stream)
+    sv.sync()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    s1 = sv.stats()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    # the last state is still resident: a cheap sanity check that the timed work was real
+    norm = float(sv.norm()[0])
+    if abs(norm - 1.0) > 1e-9:
+        raise SystemExit(f"state norm {norm} after the timed region: result invalid")
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    passes = (s1["passes"] - s0["passes"]) / args.steps
+    launches = s1["launches"] - s0["launches"]
+    sv.close()
+    del sv
+    torch.cuda.empty_cache()
+
+    # ---- end-to-end through the plugin-facing call: wire JSON (host) -> counts (host)
+    task_text = json.dumps(C.task(ins + C.measure_all(n), n, shots=SHOTS, seed=SEED, device=local_rank))
+    be = cb.Backend(local_rank)
+    res = be.execute(task_text)  # warm-up (allocates the state)
+    if "ERROR" in res:
+        raise SystemExit("e2e run failed: " + res["ERROR"])
+    barrier()
+    e2e_steps = max(1, min(2, args.steps))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = be.execute(task_text)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    est = be.stats()
+    assert sum(res["counts"].values()) == SHOTS
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    be.close()
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = gates * world / (ms_per_step / 1e3)
+        peak, peak_src = load_peaks()
+        achieved = 2.0 * S * passes / (ms_per_step / 1e3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(f"qv{n}_bytes_per_launch")
+        line = {
+            "metric": "gates_per_second", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"QV-{n} depth {depth} fp64, {gates} Haar SU(4) unitary gates, "
+                                   f"{S / 2 ** 30:.0f} GiB state in place per GPU" + workload_note,
+                       "seed": SEED, "tile_passes_per_step": passes, "l2": "inputs larger than L2 (no flush needed)",
+                       "parallelism": "1 state per GPU, no collective" if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "tile_pass_tma_kernel<double>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": 2 * S},
+            "e2e": {"value": gates * world / e2e_s, "unit": "gates/s", "h2d_bytes_per_step": est["h2d_bytes"] + len(task_text),
+                    "d2h_bytes_per_step": est["d2h_bytes"], "ms_per_step": e2e_s * 1e3, "shots": SHOTS,
+                    "api": "cb200_backend_execute (wire-JSON task in host memory -> counts JSON)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            info, _ = cpu_sample()
+            line["cpu_baseline"] = info
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

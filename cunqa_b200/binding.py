@@ -66,6 +66,8 @@ SIGNATURES = {
     "cb200_sample": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, _c_u64_p]),
     "cb200_get_amplitudes": (ctypes.c_int, [_vp, ctypes.c_int, _c_u64_p, ctypes.c_uint64, _c_dbl_p]),
     "cb200_set_amplitudes": (ctypes.c_int, [_vp, ctypes.c_int, _c_dbl_p]),
+    "cb200_state_stream": (_vp, [_vp]),
+    "cb200_backend_stream": (_vp, [_vp]),
     "cb200_stats": (ctypes.c_int, [_vp, _c_u64_p]),
     "cb200_plan_json": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "cb200_gate_matrix": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, _c_dbl_p, ctypes.c_int, _c_dbl_p]),
@@ -83,6 +85,9 @@ for _name, (_res, _args) in SIGNATURES.items():
     _f = getattr(lib, _name)
     _f.restype = _res
     _f.argtypes = _args
+
+
+STAT_KEYS = ("passes", "gates", "fused_ops", "bytes", "launches", "relabelled_swaps", "h2d_bytes", "d2h_bytes")
 
 
 def _check(status):
@@ -255,8 +260,11 @@ class StateVector:
     def stats(self):
         out = np.zeros(8, dtype=np.uint64)
         _check(lib.cb200_stats(self._h, out.ctypes.data_as(_c_u64_p)))
-        keys = ("passes", "gates", "fused_ops", "bytes", "launches", "relabelled_swaps")
-        return {k: int(v) for k, v in zip(keys, out)}
+        return {k: int(v) for k, v in zip(STAT_KEYS, out)}
+
+    def stream(self):
+        """cudaStream_t (as int) all kernels of this state run on"""
+        return int(lib.cb200_state_stream(self._h) or 0)
 
 
 class Backend:
@@ -291,5 +299,7 @@ class Backend:
     def stats(self):
         out = np.zeros(8, dtype=np.uint64)
         _check(lib.cb200_backend_stats(self._h, out.ctypes.data_as(_c_u64_p)))
-        keys = ("passes", "gates", "fused_ops", "bytes", "launches", "relabelled_swaps")
-        return {k: int(v) for k, v in zip(keys, out)}
+        return {k: int(v) for k, v in zip(STAT_KEYS, out)}
+
+    def stream(self):
+        return int(lib.cb200_backend_stream(self._h) or 0)

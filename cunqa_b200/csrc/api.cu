@@ -38,7 +38,7 @@ char *dup_string(const std::string &s)
 void fill_stats(const Stats &st, uint64_t gates, uint64_t relabelled, uint64_t out[8])
 {
     out[0] = st.passes; out[1] = gates; out[2] = st.fused_ops; out[3] = st.bytes; out[4] = st.launches;
-    out[5] = relabelled; out[6] = 0; out[7] = 0;
+    out[5] = relabelled; out[6] = st.h2d_bytes; out[7] = st.d2h_bytes;
 }
 }  // namespace
 
@@ -132,6 +132,9 @@ int cb200_set_amplitudes(cb200_state *s, int b, const double *in)
     NEED(s);
     return guard([&] { s->impl->set_amplitudes(b, in); });
 }
+
+void *cb200_state_stream(cb200_state *s) { return (s && s->impl) ? (void *)s->impl->stream() : nullptr; }
+void *cb200_backend_stream(cb200_backend *b) { return (b && b->impl) ? b->impl->stream_ptr() : nullptr; }
 
 int cb200_stats(const cb200_state *s, uint64_t stats[8])
 {

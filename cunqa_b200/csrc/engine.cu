@@ -177,6 +177,7 @@ void State::flush_t()
         std::vector<V> tmp(diag_host.size());
         for (size_t i = 0; i < diag_host.size(); i++) { tmp[i].x = (T)diag_host[i].real(); tmp[i].y = (T)diag_host[i].imag(); }
         CB200_CUDA(cudaMemcpyAsync(d_diag_, tmp.data(), tmp.size() * sizeof(V), cudaMemcpyHostToDevice, stream_));
+        stats.h2d_bytes += tmp.size() * sizeof(V);
         CB200_CUDA(cudaStreamSynchronize(stream_));  // tmp is pageable and dies here
     }
     if (!queue.mask_rows.empty()) {
@@ -190,6 +191,7 @@ void State::flush_t()
         std::vector<uint8_t> tmp(need);
         for (size_t r = 0; r < queue.mask_rows.size(); r++) std::memcpy(tmp.data() + r * batch, queue.mask_rows[r].data(), batch);
         CB200_CUDA(cudaMemcpyAsync(d_flags_, tmp.data(), need, cudaMemcpyHostToDevice, stream_));
+        stats.h2d_bytes += need;
         CB200_CUDA(cudaStreamSynchronize(stream_));
     }
     auto kern = tile_pass_kernel<T>;
@@ -249,6 +251,7 @@ void State::flush_t()
         CB200_CUDA(cudaGetLastError());
         stats.passes++;
         stats.launches++;
+        stats.h2d_bytes += sizeof(PassParams<T>) + (tma ? sizeof(CUtensorMap) : 0);
         stats.bytes += 2ull * state_bytes_;
         stats.fused_ops += (uint64_t)p.n_ops;
     }
@@ -309,6 +312,7 @@ void State::norm(double *out)
     if (precision == 64) reduce2_t<double>(0, d_small_, nullptr); else reduce2_t<float>(0, d_small_, nullptr);
     CB200_CUDA(cudaMemcpyAsync(out, d_small_, sizeof(double) * batch, cudaMemcpyDeviceToHost, stream_));
     CB200_CUDA(cudaStreamSynchronize(stream_));
+    stats.d2h_bytes += sizeof(double) * batch;
 }
 
 void State::prob1(int qubit, double *out)
@@ -348,6 +352,8 @@ void State::measure(int qubit, uint64_t seed, const uint64_t *counters, const in
     if (!dst) { tmp.resize(batch); dst = tmp.data(); }
     CB200_CUDA(cudaMemcpyAsync(dst, d_outcome_, sizeof(int) * batch, cudaMemcpyDeviceToHost, stream_));
     CB200_CUDA(cudaStreamSynchronize(stream_));
+    stats.h2d_bytes += (sizeof(uint64_t) + (forced ? 1 : 0)) * (size_t)batch;
+    stats.d2h_bytes += sizeof(int) * batch;
 }
 
 void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out)
@@ -386,6 +392,7 @@ void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out)
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
     cudaFree(d_out);
     if (e != cudaSuccess) throw CudaError(std::string("sampling failed: ") + cudaGetErrorString(e));
+    stats.d2h_bytes += sizeof(uint64_t) * shots;
     if (!queue.identity_perm())
         for (uint64_t s = 0; s < shots; s++) out[s] = queue.logical_index(out[s]);
 }
@@ -416,6 +423,8 @@ void State::get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
     cudaFree(d_idx); cudaFree(d_out);
     if (e != cudaSuccess) throw CudaError(std::string("get_amplitudes failed: ") + cudaGetErrorString(e));
+    stats.h2d_bytes += cnt * sizeof(uint64_t);
+    stats.d2h_bytes += cnt * sizeof(double2);
 }
 
 void State::set_amplitudes(int b, const double *in)
@@ -440,6 +449,7 @@ void State::set_amplitudes(int b, const double *in)
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
     cudaFree(d_in);
     if (e != cudaSuccess) throw CudaError(std::string("set_amplitudes failed: ") + cudaGetErrorString(e));
+    stats.h2d_bytes += dim * sizeof(double2);
 }
 
 void State::probabilities(int b, const int *qubits, int k, double *out)

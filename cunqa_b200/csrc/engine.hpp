@@ -28,7 +28,7 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 
 struct Stats {
     uint64_t passes = 0, gates = 0, fused_ops = 0, bytes = 0, launches = 0;
-    uint64_t relabelled_swaps = 0;
+    uint64_t relabelled_swaps = 0, h2d_bytes = 0, d2h_bytes = 0;
 };
 
 struct DistContext;  // dist.cu

@@ -355,7 +355,10 @@ Json Backend::run_static(const Json &task)
     last_stats.launches -= before.launches;
     last_stats.bytes -= before.bytes;
     last_stats.fused_ops -= before.fused_ops;
+    last_stats.h2d_bytes -= before.h2d_bytes;
+    last_stats.d2h_bytes -= before.d2h_bytes;
     last_stats.gates = st.queue.gates - gates_before;
+    last_stats.relabelled_swaps = st.queue.relabelled_swaps;
     return out;
 }
 
@@ -693,6 +696,8 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
         last_stats.launches -= before.launches;
         last_stats.bytes -= before.bytes;
         last_stats.fused_ops -= before.fused_ops;
+        last_stats.h2d_bytes -= before.h2d_bytes;
+        last_stats.d2h_bytes -= before.d2h_bytes;
         last_stats.gates = stp->queue.gates - gates_before;
     }
     (void)acc;

@@ -92,10 +92,15 @@ int cb200_get_amplitudes(cb200_state *s, int b, const uint64_t *idx, uint64_t n,
 /* upload a full state vector (2^n (re,im) doubles) into state `b` (tests / save_state round trips) */
 int cb200_set_amplitudes(cb200_state *s, int b, const double *in_reim);
 
+/* the CUDA stream (cudaStream_t) every kernel of this state is launched on, for timing with CUDA events */
+void *cb200_state_stream(cb200_state *s);
+
 /* ---- planner introspection (host only, no device needed) ------------------------------------- */
-/* kernel statistics of everything flushed so far on this state:
+/* counters of everything flushed so far on this state:
  * stats[0]=tile passes launched, [1]=gates queued (original), [2]=fused ops executed,
- * [3]=algorithmic bytes moved by passes (2*S each), [4]=kernel launches (all kinds) */
+ * [3]=algorithmic bytes moved by passes (2*S each), [4]=kernel launches (all kinds),
+ * [5]=swaps done by relabelling, [6]=host->device bytes (kernel parameters, tables, flags, uploads),
+ * [7]=device->host bytes (outcomes, samples, amplitudes) */
 int cb200_stats(const cb200_state *s, uint64_t stats[8]);
 /* plan a wire-format task without executing it; returns a JSON description of the fused ops and
  * tile passes (used by the CPU tests to prove the plan is equivalent to the circuit). */
@@ -123,8 +128,10 @@ int cb200_backend_set_channel(cb200_backend *b, cb200_send_fn send, cb200_recv_f
  * `{"id_counts":{id:{...}},"time_taken":s}` for several; `{"ERROR":"..."}` on failure
  * (status stays CB200_OK so that the plugin can forward the message, cf. :836-840). */
 int cb200_backend_execute(cb200_backend *b, const char *tasks_json, char **result_json_out);
-/* cumulative counters of the backend's last execute: same layout as cb200_stats */
+/* counters of the backend's last execute: same layout as cb200_stats */
 int cb200_backend_stats(const cb200_backend *b, uint64_t stats[8]);
+/* stream of the backend's current state (NULL before the first execute) */
+void *cb200_backend_stream(cb200_backend *b);
 
 /* ---- sharded state across the GPUs of one box (no reference analogue) -------------
  * One process per GPU.  The top log2(world) qubits are global (index bits select the rank).
