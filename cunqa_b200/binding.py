@@ -70,6 +70,7 @@ SIGNATURES = {
     "cb200_backend_stream": (_vp, [_vp]),
     "cb200_stats": (ctypes.c_int, [_vp, _c_u64_p]),
     "cb200_plan_json": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "cb200_update_task_json": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "cb200_gate_matrix": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, _c_dbl_p, ctypes.c_int, _c_dbl_p]),
     "cb200_backend_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int]),
     "cb200_backend_destroy": (ctypes.c_int, [_vp]),
@@ -134,6 +135,13 @@ def plan(task, options=None):
     opts = json.dumps(options).encode() if options else None
     out = _vp()
     _check(lib.cb200_plan_json(text.encode(), opts, ctypes.byref(out)))
+    return json.loads(_take_string(out))
+
+
+def update_task(task, update):
+    """apply a {"params":[...],"shots":N} message to a task the way the backend does; host only."""
+    out = _vp()
+    _check(lib.cb200_update_task_json(json.dumps(task).encode(), json.dumps(update).encode(), ctypes.byref(out)))
     return json.loads(_take_string(out))
 
 

@@ -148,6 +148,12 @@ int cb200_plan_json(const char *task_json, const char *options_json, char **plan
     *plan_json_out = nullptr;
     return guard([&] { *plan_json_out = dup_string(plan_task_json(task_json, options_json ? options_json : "")); });
 }
+int cb200_update_task_json(const char *task_json, const char *update_json, char **out)
+{
+    if (!task_json || !update_json || !out) { g_err = "null argument"; return CB200_ERR_INVALID; }
+    *out = nullptr;
+    return guard([&] { *out = dup_string(update_task_json(task_json, update_json)); });
+}
 int cb200_gate_matrix(const char *name, int nq, const double *params, int np, double *out_reim)
 {
     if (!name || !out_reim || nq < 1 || nq > 6) { g_err = "bad argument"; return CB200_ERR_INVALID; }

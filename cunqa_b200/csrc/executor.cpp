@@ -704,6 +704,13 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
     return out;
 }
 
+std::string update_task_json(const std::string &task_json, const std::string &update_json)
+{
+    Json task = Json::parse(task_json);
+    update_params(task, Json::parse(update_json));
+    return task.dump();
+}
+
 // ---- planning without a device -------------------------------------------------------------------
 std::string plan_task_json(const std::string &task_json, const std::string &options_json)
 {

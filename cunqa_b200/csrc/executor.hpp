@@ -41,6 +41,9 @@ private:
     void *user_ = nullptr;
 };
 
+// apply a {"params":..,"shots":..} message to a task (host only; cb200_update_task_json)
+std::string update_task_json(const std::string &task_json, const std::string &update_json);
+
 // plan a task without a device: fused ops + tile passes as JSON (cb200_plan_json)
 std::string plan_task_json(const std::string &task_json, const std::string &options_json);
 

@@ -105,6 +105,10 @@ int cb200_stats(const cb200_state *s, uint64_t stats[8]);
 /* plan a wire-format task without executing it; returns a JSON description of the fused ops and
  * tile passes (used by the CPU tests to prove the plan is equivalent to the circuit). */
 int cb200_plan_json(const char *task_json, const char *options_json, char **plan_json_out);
+/* apply a `{"params":[...],"shots":N}` update message to a wire-format task exactly as the backend does
+ * between two executes (replaces QuantumTask::update_params_, /root/reference/src/quantum_task.cpp:39-108);
+ * returns the updated task as JSON text.  Host only. */
+int cb200_update_task_json(const char *task_json, const char *update_json, char **task_json_out);
 /* matrix of a named gate exactly as the engine builds it: out = 2^nq x 2^nq row-major (re,im),
  * controls expanded.  nq <= 6. */
 int cb200_gate_matrix(const char *name, int nq, const double *params, int np, double *out_reim);

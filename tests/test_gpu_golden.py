@@ -1,0 +1,62 @@
+"""GPU (-m gpu): the engine, through the C ABI, on the committed golden fixtures (wire JSON built by the
+reference's own Python front end; expected numbers from the oracle, analytic where available)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cunqa_b200 as cb
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    with open(os.path.join(GOLD, name + ".json")) as f:
+        return json.load(f)
+
+
+def sv(rec, key="oracle_statevector"):
+    a = np.asarray(rec[key], dtype=float)
+    return a[:, 0] + 1j * a[:, 1]
+
+
+@pytest.fixture(scope="module")
+def backend(lib_built):
+    be = cb.Backend(0)
+    yield be
+    be.close()
+
+
+@pytest.mark.parametrize("name", ["ghz8", "qft7", "vocab5", "hea6"])
+@pytest.mark.parametrize("precision,tol", [("double", 1e-10), ("single", 1e-5)])
+def test_static_amplitudes(lib_built, name, precision, tol):
+    rec = load(name)
+    n = rec["task"]["config"]["num_qubits"]
+    with cb.StateVector(n, precision) as s:
+        s.run(rec["task"]["instructions"])
+        assert np.abs(s.amplitudes() - sv(rec)).max() < tol
+
+
+@pytest.mark.parametrize("name", ["ghz8", "qft7", "vocab5", "hea6", "dyn3"])
+def test_counts_equal_oracle(backend, name):
+    rec = load(name)
+    res = backend.execute(rec["task"])
+    assert "ERROR" not in res, res
+    assert res["counts"] == rec["oracle_counts"]
+
+
+def test_parameter_update_roundtrip(backend):
+    rec = load("hea6")
+    backend.execute(rec["task"])
+    res = backend.execute(rec["update"])
+    assert "ERROR" not in res and sum(res["counts"].values()) == rec["update"]["shots"]
+
+
+@pytest.mark.parametrize("name", ["teledata", "telegate"])
+def test_quantum_communication_families(backend, name):
+    rec = load(name)
+    res = backend.execute(rec["tasks"])
+    assert "ERROR" not in res, res
+    assert res["id_counts"] == rec["oracle_id_counts"]
