@@ -9,7 +9,7 @@ import importlib
 
 from . import circuits  # noqa: F401
 
-_LAZY = ("StateVector", "Backend", "B200Error", "plan", "gate_matrix", "version", "device_count", "update_task")
+_LAZY = ("StateVector", "ShardedStateVector", "Backend", "B200Error", "plan", "gate_matrix", "version", "device_count", "update_task")
 
 
 def __getattr__(name):

@@ -81,6 +81,7 @@ SIGNATURES = {
     "cb200_state_create_dist": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_u8_p]),
     "cb200_dist_export_handle": (ctypes.c_int, [_vp, _c_u8_p]),
     "cb200_dist_import_handles": (ctypes.c_int, [_vp, _c_u8_p]),
+    "cb200_dist_stats": (ctypes.c_int, [_vp, _c_u64_p]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _f = getattr(lib, _name)
@@ -273,6 +274,45 @@ class StateVector:
     def stream(self):
         """cudaStream_t (as int) all kernels of this state run on"""
         return int(lib.cb200_state_stream(self._h) or 0)
+
+
+class ShardedStateVector(StateVector):
+    """One state sharded over the GPUs of a box: one process per GPU, top log2(world) qubits global.
+
+    Rendezvous uses an initialised torch.distributed process group (NCCL or gloo): rank 0's NCCL id is
+    broadcast, every rank's CUDA IPC handle is all-gathered, then the engine talks NCCL / peer memory itself.
+    """
+
+    def __init__(self, n_qubits_total, precision="double", device=0, group=None):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        prec = {"double": 64, "single": 32, 64: 64, 32: 32}[precision]
+        dev = torch.device("cuda", device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_uint8 * 128)()
+            _check(lib.cb200_dist_unique_id(buf))
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        ident = ident.to(dev)
+        dist.broadcast(ident, 0, group=group)
+        idbuf = (ctypes.c_uint8 * 128)(*ident.cpu().tolist())
+        self._h = _vp()
+        _check(lib.cb200_state_create_dist(ctypes.byref(self._h), n_qubits_total, prec, device, rank, world, idbuf))
+        self.n, self.batch, self.precision = n_qubits_total, 1, prec
+        self.rank, self.world = rank, world
+        hbuf = (ctypes.c_uint8 * 64)()
+        _check(lib.cb200_dist_export_handle(self._h, hbuf))
+        mine = torch.tensor(list(hbuf), dtype=torch.uint8).to(dev)
+        allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(allh, mine, group=group)
+        flat = (ctypes.c_uint8 * (64 * world))(*[int(v) for h in allh for v in h.cpu().tolist()])
+        _check(lib.cb200_dist_import_handles(self._h, flat))
+
+    def dist_stats(self):
+        out = np.zeros(4, dtype=np.uint64)
+        _check(lib.cb200_dist_stats(self._h, out.ctypes.data_as(_c_u64_p)))
+        return {"rank": int(out[0]), "world": int(out[1]), "swaps": int(out[2]), "swap_bytes_sent": int(out[3])}
 
 
 class Backend:

@@ -13,8 +13,9 @@ using namespace cb200;
 struct cb200_state { State *impl; };
 struct cb200_backend { Backend *impl; };
 
+thread_local std::string g_cb200_err;
+#define g_err g_cb200_err
 namespace {
-thread_local std::string g_err;
 
 template <typename F>
 int guard(F f)

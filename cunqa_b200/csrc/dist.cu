@@ -1,9 +1,254 @@
-// dist.cu -- sharded state across the GPUs of one box (placeholder until the single-GPU path is green)
+// dist.cu -- one state sharded over the GPUs of a box (BASELINE config 4).
+//
+// One process per GPU.  Rank r owns the amplitudes whose top log2(world) physical index bits equal r.
+//   * diagonal gates and controls on global qubits: resolved per rank on the host (dist_plan.cpp), no traffic;
+//   * a non-diagonal gate on a global qubit: global<->local QUBIT SWAP.  Every rank exchanges half of its shard
+//     with rank ^ (1 << gbit).  The exchange is ONE kernel per rank that reads and writes the partner's HBM
+//     directly over NVLink/NVSwitch (peer pointers from CUDA IPC), swapping in place -- no staging buffer,
+//     which a 128 GiB shard on a 180 GB GPU could not afford.  Each rank moves half of the pair's elements,
+//     so both directions of the link are busy.  Stream-ordered NCCL all-reduces fence the kernel on both sides;
+//   * norms / probabilities / sampled shots / amplitude reads: local kernels + ncclAllReduce.
+// NCCL is resolved with dlopen so that a process which already loaded one (PyTorch) shares it.
 #include "../../include/cunqa_b200.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
 #include <string>
-extern "C" {
-int cb200_dist_unique_id(uint8_t *) { return CB200_ERR_UNSUPPORTED; }
-int cb200_state_create_dist(cb200_state **, int, int, int, int, int, const uint8_t *) { return CB200_ERR_UNSUPPORTED; }
-int cb200_dist_export_handle(cb200_state *, uint8_t *) { return CB200_ERR_UNSUPPORTED; }
-int cb200_dist_import_handles(cb200_state *, const uint8_t *) { return CB200_ERR_UNSUPPORTED; }
+#include <vector>
+
+#include "dist_plan.hpp"
+#include "engine.hpp"
+#include "tile_kernel.cuh"
+
+namespace cb200 {
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi &nccl()
+{
+    static NcclApi api;
+    if (!api.lib) {
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) throw CudaError(std::string("cannot load NCCL: ") + dlerror());
+        auto sym = [&](const char *n) {
+            void *p = dlsym(api.lib, n);
+            if (!p) throw CudaError(std::string("NCCL symbol missing: ") + n);
+            return p;
+        };
+        api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    }
+    return api;
 }
+
+#define CB200_NCCL(call)                                                                                  \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess) throw CudaError(std::string(#call) + " failed: " + nccl().GetErrorString(r_)); \
+    } while (0)
+
+struct DistContext {
+    int rank = 0, world = 1, gbits = 0;
+    ncclComm_t comm = nullptr;
+    std::vector<void *> peers;  // shard base pointer of every rank (own entry = local pointer)
+    int *d_fence = nullptr;
+    uint64_t swaps = 0, swap_bytes = 0;
+};
+
+// A = the rank whose global bit is 0.  Pair element g (bit lbit removed): A's amplitude insert0(g)|1<<lbit
+// is exchanged with B's amplitude insert0(g).  This rank handles g in [lo, hi).
+template <typename V>
+__global__ void __launch_bounds__(256) qubit_swap_kernel(V *__restrict__ mine, V *__restrict__ peer, int lbit,
+                                                         uint64_t lo, uint64_t hi, int mybit)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t bit = 1ull << lbit;
+    for (uint64_t g = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < hi; g += stride) {
+        const uint64_t i0 = insert0_64(g, (uint32_t)lbit);
+        const uint64_t mi = mybit ? i0 : (i0 | bit);
+        const uint64_t pi = mybit ? (i0 | bit) : i0;
+        const V a = mine[mi];
+        const V b = peer[pi];
+        mine[mi] = b;
+        peer[pi] = a;
+    }
+}
+
+void State::dist_fence()
+{
+    CB200_NCCL(nccl().AllReduce(dist->d_fence, dist->d_fence, 1, ncclInt, ncclSum, dist->comm, stream_));
+    stats.launches++;
+}
+
+void State::dist_swap(int gbit, int lbit)
+{
+    if ((int)dist->peers.size() != dist->world) throw InvalidArg("sharded state: peer handles were not imported");
+    const int partner = dist->rank ^ (1 << gbit);
+    const int mybit = (dist->rank >> gbit) & 1;
+    const uint64_t pairs = 1ull << (n_local_ - 1);
+    const uint64_t lo = mybit ? pairs / 2 : 0, hi = mybit ? pairs : pairs / 2;
+    dist_fence();  // both shards quiescent
+    const int blocks = (int)std::min<uint64_t>((hi - lo + 255) / 256, (uint64_t)num_sms_ * 16);
+    if (precision == 64)
+        qubit_swap_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_, (double2 *)dist->peers[partner], lbit, lo, hi, mybit);
+    else
+        qubit_swap_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, (float2 *)dist->peers[partner], lbit, lo, hi, mybit);
+    CB200_CUDA(cudaGetLastError());
+    dist_fence();  // the partner's writes into this shard have landed
+    stats.launches++;
+    dist->swaps++;
+    dist->swap_bytes += state_bytes_ / 2;  // sent (= received) per rank
+}
+
+template <typename T>
+void State::flush_dist_t()
+{
+    std::vector<HostOp> &ops = queue.ops();
+    if (ops.empty()) return;
+    CB200_CUDA(cudaSetDevice(device));
+    const DistPlan plan = plan_distributed(ops, n, n_local_, dist->rank);
+    for (const DistSegment &seg : plan.segments) {
+        if (seg.is_swap) dist_swap(seg.gbit, seg.lbit);
+        else {
+            std::vector<HostOp> local = seg.ops;
+            launch_ops_t<T>(local);
+        }
+    }
+    for (int &p : queue.l2p) p = plan.sigma[p];
+    queue.clear_pending();
+}
+template void State::flush_dist_t<double>();
+template void State::flush_dist_t<float>();
+
+void State::dist_allreduce_f64(double *d_buf, size_t count)
+{
+    CB200_NCCL(nccl().AllReduce(d_buf, d_buf, count, ncclDouble, ncclSum, dist->comm, stream_));
+    stats.launches++;
+}
+void State::dist_allreduce_u64(uint64_t *d_buf, size_t count)
+{
+    CB200_NCCL(nccl().AllReduce(d_buf, d_buf, count, ncclUint64, ncclSum, dist->comm, stream_));
+    stats.launches++;
+}
+
+void State::dist_init(int rank, int world, const uint8_t *id)
+{
+    dist = new DistContext();
+    dist->rank = rank;
+    dist->world = world;
+    while ((1 << dist->gbits) < world) dist->gbits++;
+    ncclUniqueId uid;
+    static_assert(sizeof(ncclUniqueId) == CB200_DIST_ID_BYTES, "ncclUniqueId size");
+    std::memcpy(&uid, id, sizeof(uid));
+    CB200_NCCL(nccl().CommInitRank(&dist->comm, world, uid, rank));
+    CB200_CUDA(cudaMalloc(&dist->d_fence, sizeof(int)));
+    CB200_CUDA(cudaMemset(dist->d_fence, 0, sizeof(int)));
+}
+
+void State::dist_destroy()
+{
+    if (!dist) return;
+    for (int r = 0; r < (int)dist->peers.size(); r++)
+        if (r != dist->rank && dist->peers[r]) cudaIpcCloseMemHandle(dist->peers[r]);
+    if (dist->comm) nccl().CommDestroy(dist->comm);
+    cudaFree(dist->d_fence);
+    delete dist;
+    dist = nullptr;
+}
+
+void State::dist_export(uint8_t *out)
+{
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(cudaIpcMemHandle_t) == CB200_IPC_HANDLE_BYTES, "IPC handle size");
+    CB200_CUDA(cudaIpcGetMemHandle(&h, d_state_));
+    std::memcpy(out, &h, sizeof(h));
+}
+
+void State::dist_import(const uint8_t *all)
+{
+    dist->peers.assign(dist->world, nullptr);
+    for (int r = 0; r < dist->world; r++) {
+        if (r == dist->rank) { dist->peers[r] = d_state_; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, all + (size_t)r * CB200_IPC_HANDLE_BYTES, sizeof(h));
+        CB200_CUDA(cudaIpcOpenMemHandle(&dist->peers[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+}
+
+int State::dist_rank() const { return dist ? dist->rank : 0; }
+int State::dist_world() const { return dist ? dist->world : 1; }
+uint64_t State::dist_swaps() const { return dist ? dist->swaps : 0; }
+uint64_t State::dist_swap_bytes() const { return dist ? dist->swap_bytes : 0; }
+
+}  // namespace cb200
+
+using namespace cb200;
+struct cb200_state { State *impl; };
+extern thread_local std::string g_cb200_err;
+
+extern "C" {
+
+int cb200_dist_unique_id(uint8_t *id_out)
+{
+    try {
+        ncclUniqueId uid;
+        CB200_NCCL(nccl().GetUniqueId(&uid));
+        std::memcpy(id_out, &uid, sizeof(uid));
+        return CB200_OK;
+    } catch (const std::exception &e) { g_cb200_err = e.what(); return CB200_ERR_NCCL; }
+}
+
+int cb200_state_create_dist(cb200_state **out, int n_qubits_total, int precision, int device, int rank, int world,
+                            const uint8_t *id)
+{
+    if (!out || !id) { g_cb200_err = "null argument"; return CB200_ERR_INVALID; }
+    *out = nullptr;
+    try {
+        if (world < 2 || (world & (world - 1)) || rank < 0 || rank >= world) throw InvalidArg("world must be a power of two >= 2 and 0 <= rank < world");
+        State *s = new State(n_qubits_total, precision, device, 1, rank, world, id);
+        *out = new cb200_state{s};
+        return CB200_OK;
+    } catch (const InvalidArg &e) { g_cb200_err = e.what(); return CB200_ERR_INVALID; }
+    catch (const std::exception &e) { g_cb200_err = e.what(); return CB200_ERR_CUDA; }
+}
+
+int cb200_dist_export_handle(cb200_state *s, uint8_t *handle_out)
+{
+    if (!s || !s->impl || !handle_out) { g_cb200_err = "null argument"; return CB200_ERR_INVALID; }
+    try { s->impl->dist_export(handle_out); return CB200_OK; }
+    catch (const std::exception &e) { g_cb200_err = e.what(); return CB200_ERR_CUDA; }
+}
+
+int cb200_dist_import_handles(cb200_state *s, const uint8_t *handles_all_ranks)
+{
+    if (!s || !s->impl || !handles_all_ranks || !s->impl->dist) { g_cb200_err = "not a sharded state"; return CB200_ERR_INVALID; }
+    try { s->impl->dist_import(handles_all_ranks); return CB200_OK; }
+    catch (const std::exception &e) { g_cb200_err = e.what(); return CB200_ERR_CUDA; }
+}
+
+int cb200_dist_stats(const cb200_state *s, uint64_t out[4])
+{
+    if (!s || !s->impl) { g_cb200_err = "null handle"; return CB200_ERR_INVALID; }
+    out[0] = (uint64_t)s->impl->dist_rank();
+    out[1] = (uint64_t)s->impl->dist_world();
+    out[2] = s->impl->dist_swaps();
+    out[3] = s->impl->dist_swap_bytes();
+    return CB200_OK;
+}
+
+}  // extern "C"

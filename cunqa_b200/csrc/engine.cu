@@ -20,7 +20,21 @@ static int env_int(const char *name, int dflt)
 State::State(int n_qubits, int prec, int dev, int nbatch)
     : n(n_qubits), precision(prec), device(dev), batch(nbatch), queue(std::max(1, n_qubits), std::max(1, nbatch), PlanOptions())
 {
-    if (n < 1 || n > 40) throw InvalidArg("n_qubits must be in [1,40]");
+    construct(0, 1, nullptr);
+}
+
+State::State(int n_qubits, int prec, int dev, int nbatch, int rank, int world, const uint8_t *nccl_id)
+    : n(n_qubits), precision(prec), device(dev), batch(nbatch), queue(std::max(1, n_qubits), std::max(1, nbatch), PlanOptions())
+{
+    construct(rank, world, nccl_id);
+}
+
+void State::construct(int rank, int world, const uint8_t *nccl_id)
+{
+    int gbits = 0;
+    while ((1 << gbits) < world) gbits++;
+    if (n < 1 || n - gbits > 40 || n > 62) throw InvalidArg("n_qubits out of range");
+    if (world > 1 && (n - gbits < 12 || batch != 1)) throw InvalidArg("sharded states need >= 12 local qubits and batch 1");
     if (precision != 64 && precision != 32) throw InvalidArg("precision must be 64 or 32");
     if (batch < 1) throw InvalidArg("batch must be >= 1");
     int count = 0;
@@ -40,24 +54,26 @@ State::State(int n_qubits, int prec, int dev, int nbatch)
     tma_threads_ = env_int("CB200_TMA_THREADS", 0);
     tma_fold_dims_ = env_int("CB200_TMA_FOLD", 1) != 0;
     tma_stages_ = env_int("CB200_TMA_STAGES", 2) == 3 ? 3 : 2;
-    n_local_ = n;
+    n_local_ = n - gbits;
     amp_bytes_ = precision == 64 ? 16 : 8;
-    state_bytes_ = amp_bytes_ * ((size_t)batch << n);
+    state_bytes_ = amp_bytes_ * ((size_t)batch << n_local_);
     opt.tile_bits = env_int("CB200_TILE_BITS", precision == 64 ? 11 : 12);
     opt.min_run_bits = env_int("CB200_MIN_RUN_BITS", precision == 64 ? 4 : 5);
     opt.max_pass_cost = env_int("CB200_MAX_PASS_COST", 0);
     opt.max_diag_qubits = env_int("CB200_MAX_DIAG_QUBITS", 10);
     opt.fuse = env_int("CB200_FUSE", 1) != 0;
     opt.pair_ops = env_int("CB200_PAIR_OPS", 1) != 0;
+    if (gbits) opt.global_mask = ((1ull << gbits) - 1ull) << n_local_;
     ctas_per_sm_ = env_int("CB200_CTAS_PER_SM", 0);
     use_tma_ = env_int("CB200_USE_TMA", 1) != 0;
     queue = OpQueue(n, batch, opt);
     CB200_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CB200_CUDA(cudaMalloc(&d_state_, state_bytes_));
-    CB200_CUDA(cudaMalloc(&d_small_, sizeof(double) * 4 * batch));
+    CB200_CUDA(cudaMalloc(&d_small_, sizeof(double) * (4 * batch + 64)));
     CB200_CUDA(cudaMalloc(&d_outcome_, sizeof(int) * batch));
     CB200_CUDA(cudaMalloc(&d_counters_, sizeof(uint64_t) * batch));
     CB200_CUDA(cudaMalloc(&d_forced_, sizeof(int8_t) * batch));
+    if (world > 1) dist_init(rank, world, nccl_id);
     reset();
 }
 
@@ -65,6 +81,7 @@ State::~State()
 {
     cudaSetDevice(device);
     if (stream_) cudaStreamSynchronize(stream_);
+    dist_destroy();
     cudaFree(d_state_); cudaFree(d_diag_); cudaFree(d_flags_); cudaFree(d_partial_); cudaFree(d_small_);
     cudaFree(d_outcome_); cudaFree(d_counters_); cudaFree(d_forced_); cudaFree(d_lvl1_); cudaFree(d_lvl2_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -74,10 +91,11 @@ void State::reset()
 {
     CB200_CUDA(cudaSetDevice(device));
     queue.reset();
-    const uint64_t total = (uint64_t)batch << n;
+    const uint64_t total = (uint64_t)batch << n_local_;
     const int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)num_sms_ * 16);
-    if (precision == 64) init_zero_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_, 1ull << n, total);
-    else init_zero_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, 1ull << n, total);
+    const int origin = dist_rank() == 0;  // |0...0> lives on rank 0
+    if (precision == 64) init_zero_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_, 1ull << n_local_, total, origin);
+    else init_zero_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, 1ull << n_local_, total, origin);
     CB200_CUDA(cudaGetLastError());
     stats.launches++;
 }
@@ -156,10 +174,19 @@ void State::make_tensor_map(CUtensorMap *out, int run_bits, const int hi_qubits[
 template <typename T>
 void State::flush_t()
 {
-    using V = typename Vec2<T>::type;
     std::vector<HostOp> &ops = queue.ops();
     if (ops.empty()) return;
     CB200_CUDA(cudaSetDevice(device));
+    launch_ops_t<T>(ops);
+    queue.clear_pending();
+}
+
+// plan `ops` (physical qubits < n_local) into tile passes and launch them on this shard
+template <typename T>
+void State::launch_ops_t(std::vector<HostOp> &ops)
+{
+    using V = typename Vec2<T>::type;
+    if (ops.empty()) return;
     const std::vector<Pass> passes = schedule_passes(ops, n_local_, opt);
     std::vector<cplx> diag_host;
     std::vector<PassParams<T>> params(passes.size());
@@ -208,7 +235,7 @@ void State::flush_t()
         const uint32_t buf_stride = (uint32_t)std::max<size_t>(1024, sizeof(V) << p.t);
         const int stages = tma_stages_;
         const size_t smem_tma = (size_t)stages * buf_stride + sizeof(uint64_t) * (((size_t)1 << (p.t - box_bits)) + stages + 1) +
-                                sizeof(T) * (size_t)((p.n_mat + 1) & ~1) + 1024;
+                                sizeof(T) * (size_t)((p.n_mat + 1) & ~1) + (size_t)p.n_diag * (4 + 2 * kDiagLut) + 16 + 1024;
         int nt = 1 << std::max(6, std::min(8, p.t - kAmpsPerThreadShift));  // 64 / 128 / 256 threads
         if (tma_threads_ > 0) nt = tma_threads_;
         const int ctas = std::max(1, (stages == 3 ? 256 : 384) / nt);
@@ -255,11 +282,17 @@ void State::flush_t()
         stats.bytes += 2ull * state_bytes_;
         stats.fused_ops += (uint64_t)p.n_ops;
     }
-    queue.clear_pending();
 }
+template void State::launch_ops_t<double>(std::vector<HostOp> &);
+template void State::launch_ops_t<float>(std::vector<HostOp> &);
 
 void State::flush()
 {
+    if (dist) {
+        if (precision == 64) flush_dist_t<double>();
+        else flush_dist_t<float>();
+        return;
+    }
     if (precision == 64) flush_t<double>();
     else flush_t<float>();
 }
@@ -310,6 +343,7 @@ void State::norm(double *out)
 {
     flush();
     if (precision == 64) reduce2_t<double>(0, d_small_, nullptr); else reduce2_t<float>(0, d_small_, nullptr);
+    if (dist) dist_allreduce_f64(d_small_, 1);
     CB200_CUDA(cudaMemcpyAsync(out, d_small_, sizeof(double) * batch, cudaMemcpyDeviceToHost, stream_));
     CB200_CUDA(cudaStreamSynchronize(stream_));
     stats.d2h_bytes += sizeof(double) * batch;
@@ -319,8 +353,16 @@ void State::prob1(int qubit, double *out)
 {
     if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
     flush();
-    const uint64_t sel = 1ull << queue.l2p[qubit];
+    const int pq1 = queue.l2p[qubit];
+    uint64_t sel = 1ull << pq1;
+    if (dist && pq1 >= n_local_) {
+        // global qubit: the whole shard counts, or none of it
+        if ((dist_rank() >> (pq1 - n_local_)) & 1) { if (precision == 64) reduce2_t<double>(0, d_small_ + batch, nullptr); else reduce2_t<float>(0, d_small_ + batch, nullptr); }
+        else CB200_CUDA(cudaMemsetAsync(d_small_ + batch, 0, sizeof(double), stream_));
+        sel = 0;
+    } else
     if (precision == 64) reduce2_t<double>(sel, nullptr, d_small_ + batch); else reduce2_t<float>(sel, nullptr, d_small_ + batch);
+    if (dist) dist_allreduce_f64(d_small_ + batch, 1);
     CB200_CUDA(cudaMemcpyAsync(out, d_small_ + batch, sizeof(double) * batch, cudaMemcpyDeviceToHost, stream_));
     CB200_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -328,6 +370,7 @@ void State::prob1(int qubit, double *out)
 void State::measure(int qubit, uint64_t seed, const uint64_t *counters, const int8_t *forced, int *bits_out, bool reset_after)
 {
     if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
+    if (dist) throw Unsupported("mid-circuit measurement of a sharded state is not implemented");
     flush();
     const int pq = queue.l2p[qubit];
     const uint64_t sel = 1ull << pq;
@@ -371,23 +414,44 @@ void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out)
     const int g2 = (int)std::min<uint64_t>(n2, (uint64_t)num_sms_ * 16);
     uint64_t *d_out = nullptr;
     CB200_CUDA(cudaMalloc(&d_out, sizeof(uint64_t) * std::max<uint64_t>(shots, 1)));
+    double total_all = -1.0, off_lo = 0.0, off_hi = 0.0;
+    uint64_t prefix = 0;
+    if (dist) {
+        // every rank learns all shard norms, then owns one interval of the global CDF
+        const int w = dist_world(), r = dist_rank();
+        if (precision == 64) reduce2_t<double>(0, d_small_, nullptr); else reduce2_t<float>(0, d_small_, nullptr);
+        double mine = 0.0;
+        CB200_CUDA(cudaMemcpyAsync(&mine, d_small_, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        CB200_CUDA(cudaStreamSynchronize(stream_));
+        std::vector<double> all(w, 0.0);
+        all[r] = mine;
+        CB200_CUDA(cudaMemcpyAsync(d_small_ + 8, all.data(), sizeof(double) * w, cudaMemcpyHostToDevice, stream_));
+        dist_allreduce_f64(d_small_ + 8, w);
+        CB200_CUDA(cudaMemcpyAsync(all.data(), d_small_ + 8, sizeof(double) * w, cudaMemcpyDeviceToHost, stream_));
+        CB200_CUDA(cudaStreamSynchronize(stream_));
+        total_all = 0.0;
+        for (int i = 0; i < w; i++) { if (i == r) off_lo = total_all; total_all += all[i]; }
+        off_hi = r == w - 1 ? 1e300 : off_lo + all[r];
+        prefix = (uint64_t)r << nl;
+    }
     const int sblocks = (int)std::min<uint64_t>((shots * 32 + kRedThreads - 1) / kRedThreads, (uint64_t)num_sms_ * 8);
     if (precision == 64) {
         const double2 *st = (const double2 *)d_state_ + ((size_t)b << nl);
         chunk_sums_amp_kernel<double2><<<g1, kRedThreads, 0, stream_>>>(st, bits0, n1, d_lvl1_);
         chunk_sums_f64_kernel<<<g2, kRedThreads, 0, stream_>>>(d_lvl1_, bits1, n2, d_lvl2_);
         top_prefix_kernel<<<1, 32, 0, stream_>>>(d_lvl2_, n2);
-        if (shots) sample_kernel<double2><<<std::max(sblocks, 1), kRedThreads, 0, stream_>>>(st, nl, bits0, bits1, d_lvl1_, d_lvl2_, n2, shots, seed, d_out);
+        if (shots) sample_kernel<double2><<<std::max(sblocks, 1), kRedThreads, 0, stream_>>>(st, nl, bits0, bits1, d_lvl1_, d_lvl2_, n2, shots, seed, d_out, total_all, off_lo, off_hi, prefix);
     } else {
         const float2 *st = (const float2 *)d_state_ + ((size_t)b << nl);
         chunk_sums_amp_kernel<float2><<<g1, kRedThreads, 0, stream_>>>(st, bits0, n1, d_lvl1_);
         chunk_sums_f64_kernel<<<g2, kRedThreads, 0, stream_>>>(d_lvl1_, bits1, n2, d_lvl2_);
         top_prefix_kernel<<<1, 32, 0, stream_>>>(d_lvl2_, n2);
-        if (shots) sample_kernel<float2><<<std::max(sblocks, 1), kRedThreads, 0, stream_>>>(st, nl, bits0, bits1, d_lvl1_, d_lvl2_, n2, shots, seed, d_out);
+        if (shots) sample_kernel<float2><<<std::max(sblocks, 1), kRedThreads, 0, stream_>>>(st, nl, bits0, bits1, d_lvl1_, d_lvl2_, n2, shots, seed, d_out, total_all, off_lo, off_hi, prefix);
     }
     cudaError_t e = cudaGetLastError();
     stats.launches += 4;
     stats.bytes += state_bytes_ / batch;
+    if (e == cudaSuccess && dist && shots) dist_allreduce_u64(d_out, shots);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(uint64_t) * shots, cudaMemcpyDeviceToHost, stream_);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
     cudaFree(d_out);
@@ -404,9 +468,15 @@ void State::get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out
     if (cnt == 0) return;
     std::vector<uint64_t> phys(cnt);
     const uint64_t dim = 1ull << n;
+    const uint64_t local_mask = (1ull << n_local_) - 1ull;
+    std::vector<uint8_t> owned(cnt, 1);
     for (uint64_t i = 0; i < cnt; i++) {
         if (idx[i] >= dim) throw InvalidArg("amplitude index out of range");
         phys[i] = queue.phys_index(idx[i]);
+        if (dist) {
+            owned[i] = (int)(phys[i] >> n_local_) == dist_rank();
+            phys[i] = owned[i] ? (phys[i] & local_mask) : 0;  // not owned: read any valid slot, zeroed below
+        }
     }
     uint64_t *d_idx = nullptr; double2 *d_out = nullptr;
     CB200_CUDA(cudaMalloc(&d_idx, cnt * sizeof(uint64_t)));
@@ -419,6 +489,16 @@ void State::get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out
         e = cudaGetLastError();
         stats.launches++;
     }
+    if (e == cudaSuccess && dist) {
+        // zero what this rank does not own, then sum over ranks
+        std::vector<double2> tmp(cnt);
+        e = cudaMemcpyAsync(tmp.data(), d_out, cnt * sizeof(double2), cudaMemcpyDeviceToHost, stream_);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+        for (uint64_t i = 0; i < cnt; i++) if (!owned[i]) tmp[i] = make_double2(0.0, 0.0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_out, tmp.data(), cnt * sizeof(double2), cudaMemcpyHostToDevice, stream_);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+        if (e == cudaSuccess) dist_allreduce_f64(reinterpret_cast<double *>(d_out), 2 * cnt);
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, cnt * sizeof(double2), cudaMemcpyDeviceToHost, stream_);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
     cudaFree(d_idx); cudaFree(d_out);
@@ -430,6 +510,7 @@ void State::get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out
 void State::set_amplitudes(int b, const double *in)
 {
     if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
+    if (dist) throw Unsupported("set_amplitudes on a sharded state is not implemented");
     flush();
     CB200_CUDA(cudaStreamSynchronize(stream_));
     const uint64_t dim = 1ull << n;
@@ -456,6 +537,7 @@ void State::probabilities(int b, const int *qubits, int k, double *out)
 {
     if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
     if (k < 1 || k > 20) throw InvalidArg("marginal over 1..20 qubits");
+    if (dist) throw Unsupported("marginals of a sharded state are not implemented");
     flush();
     std::vector<int> pq(k);
     for (int i = 0; i < k; i++) if (qubits[i] < 0 || qubits[i] >= n) throw InvalidArg("qubit out of range");

@@ -36,6 +36,8 @@ struct DistContext;  // dist.cu
 class State {
 public:
     State(int n_qubits, int precision, int device, int batch);
+    // sharded over `world` ranks (one process per GPU): n_qubits is the TOTAL width
+    State(int n_qubits, int precision, int device, int batch, int rank, int world, const uint8_t *nccl_id);
     ~State();
     State(const State &) = delete;
     State &operator=(const State &) = delete;
@@ -69,7 +71,24 @@ public:
     size_t state_bytes() const { return state_bytes_; }
     cudaStream_t stream() const { return stream_; }
 
+    // ---- sharded mode (dist.cu)
+    void dist_export(uint8_t *handle_out);
+    void dist_import(const uint8_t *handles_all_ranks);
+    int dist_rank() const;
+    int dist_world() const;
+    uint64_t dist_swaps() const;
+    uint64_t dist_swap_bytes() const;
+
 private:
+    void construct(int rank, int world, const uint8_t *nccl_id);
+    void dist_init(int rank, int world, const uint8_t *id);
+    void dist_destroy();
+    void dist_fence();
+    void dist_swap(int gbit, int lbit);
+    void dist_allreduce_f64(double *d_buf, size_t count);
+    void dist_allreduce_u64(uint64_t *d_buf, size_t count);
+    template <typename T> void flush_dist_t();
+    template <typename T> void launch_ops_t(std::vector<HostOp> &ops);
     template <typename T> void flush_t();
     template <typename T> void reduce2_t(uint64_t sel_mask, double *d_all, double *d_sel);
     void ensure_scratch(size_t partial_doubles);

@@ -1,5 +1,6 @@
 // executor.cpp -- whole-task execution (see executor.hpp).
 #include "executor.hpp"
+#include "dist_plan.hpp"
 
 #include <algorithm>
 #include <chrono>
@@ -717,6 +718,7 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
     const Json task = Json::parse(task_json);
     const TaskCfg c = parse_task(task);
     PlanOptions opt;
+    int world = 1, rank = 0;
     opt.tile_bits = c.precision == 64 ? 11 : 12;
     opt.min_run_bits = c.precision == 64 ? 4 : 5;
     if (!options_json.empty()) {
@@ -726,13 +728,19 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
         if (o.contains("max_diag_qubits")) opt.max_diag_qubits = (int)o.at("max_diag_qubits").as_int();
         if (o.contains("max_pass_cost")) opt.max_pass_cost = (int)o.at("max_pass_cost").as_int();
         if (o.contains("fuse")) opt.fuse = o.at("fuse").as_bool();
+        if (o.contains("world")) world = (int)o.at("world").as_int();
+        if (o.contains("rank")) rank = (int)o.at("rank").as_int();
     }
+    int gbits = 0;
+    while ((1 << gbits) < world) gbits++;
+    if ((1 << gbits) != world || gbits >= c.num_qubits) throw std::runtime_error("world must be a power of two smaller than 2^num_qubits");
+    const int n_local = c.num_qubits - gbits;
+    if (gbits) opt.global_mask = ((1ull << gbits) - 1ull) << n_local;
     OpQueue q(c.num_qubits, 1, opt);
     for (const Inst &in : c.insts) {
         if (is_classical_or_remote(in.name)) continue;
         queue_gate(q, in, [](int x) { return x; }, nullptr, false);
     }
-    const std::vector<Pass> passes = schedule_passes(q.ops(), c.num_qubits, opt);
     auto cplx_arr = [](const std::vector<cplx> &v) {
         Json a = Json::array();
         for (const cplx &z : v) {
@@ -748,37 +756,68 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
         for (int x : v) a.arr.push_back(Json::integer(x));
         return a;
     };
+    static const char *kinds[] = {"dense", "diag", "permx", "swap"};
+    auto ops_json = [&](const std::vector<HostOp> &ops) {
+        Json jops = Json::array();
+        for (const HostOp &op : ops) {
+            Json o = Json::object();
+            o.set("kind", Json::string(kinds[(int)op.kind]));
+            o.set("q", int_arr(op.q));
+            o.set("ctrl", int_arr(op.ctrl));
+            o.set("m", cplx_arr(op.m));
+            o.set("n_orig", Json::integer(op.n_orig));
+            jops.arr.push_back(std::move(o));
+        }
+        return jops;
+    };
+    auto passes_json = [&](const std::vector<HostOp> &ops, int nq) {
+        Json jp = Json::array();
+        for (const Pass &p : schedule_passes(ops, nq, opt)) {
+            Json o = Json::object();
+            o.set("tile_q", int_arr(p.tile_q));
+            o.set("L", Json::integer(p.L));
+            o.set("ops", int_arr(p.op_idx));
+            // encode to make sure the pass is launchable, and report the kernel-parameter footprint
+            PassParams<double> pp;
+            std::vector<cplx> diag;
+            std::string err;
+            if (!encode_pass<double>(p, ops, nq, 1, pp, diag, err)) throw std::runtime_error(err);
+            o.set("diag_entries", Json::integer((long long)diag.size()));
+            jp.arr.push_back(std::move(o));
+        }
+        return jp;
+    };
     Json out = Json::object();
     out.set("num_qubits", Json::integer(c.num_qubits));
     out.set("gates", Json::integer((long long)q.gates));
     out.set("relabelled_swaps", Json::integer((long long)q.relabelled_swaps));
+    if (world > 1) {
+        // sharded state: this rank's segments (local pass groups and global<->local qubit swaps)
+        const DistPlan dp = plan_distributed(q.ops(), c.num_qubits, n_local, rank);
+        std::vector<int> l2p(q.l2p);
+        for (int &p : l2p) p = dp.sigma[p];
+        out.set("l2p", int_arr(l2p));
+        out.set("n_local", Json::integer(n_local));
+        Json segs = Json::array();
+        for (const DistSegment &s : dp.segments) {
+            Json o = Json::object();
+            if (s.is_swap) {
+                Json sw = Json::array();
+                sw.arr.push_back(Json::integer(s.gbit));
+                sw.arr.push_back(Json::integer(s.lbit));
+                o.set("swap", std::move(sw));
+            } else {
+                o.set("ops", ops_json(s.ops));
+                o.set("passes", passes_json(s.ops, n_local));
+            }
+            segs.arr.push_back(std::move(o));
+        }
+        out.set("segments", std::move(segs));
+        return out.dump();
+    }
     out.set("l2p", int_arr(q.l2p));
-    Json jops = Json::array();
-    static const char *kinds[] = {"dense", "diag", "permx", "swap"};
-    for (const HostOp &op : q.ops()) {
-        Json o = Json::object();
-        o.set("kind", Json::string(kinds[(int)op.kind]));
-        o.set("q", int_arr(op.q));
-        o.set("ctrl", int_arr(op.ctrl));
-        o.set("m", cplx_arr(op.m));
-        o.set("n_orig", Json::integer(op.n_orig));
-        jops.arr.push_back(std::move(o));
-    }
-    out.set("ops", std::move(jops));
-    Json jp = Json::array();
-    for (const Pass &p : passes) {
-        Json o = Json::object();
-        o.set("tile_q", int_arr(p.tile_q));
-        o.set("L", Json::integer(p.L));
-        o.set("ops", int_arr(p.op_idx));
-        // encode to make sure the pass is launchable, and report the kernel-parameter footprint
-        PassParams<double> pp;
-        std::vector<cplx> diag;
-        std::string err;
-        if (!encode_pass<double>(p, q.ops(), c.num_qubits, 1, pp, diag, err)) throw std::runtime_error(err);
-        o.set("diag_entries", Json::integer((long long)diag.size()));
-        jp.arr.push_back(std::move(o));
-    }
+    out.set("ops", ops_json(q.ops()));
+    Json jp = passes_json(q.ops(), c.num_qubits);
     out.set("passes", std::move(jp));
     return out.dump();
 }

@@ -52,11 +52,11 @@ __device__ __forceinline__ double splitmix_uniform(uint64_t seed, uint64_t count
 
 // |0...0> for every state of the batch
 template <typename V>
-__global__ void init_zero_kernel(V *state, uint64_t amps_per_state, uint64_t total)
+__global__ void init_zero_kernel(V *state, uint64_t amps_per_state, uint64_t total, int has_origin)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        V v; v.x = ((i & (amps_per_state - 1)) == 0) ? 1 : 0; v.y = 0;
+        V v; v.x = (has_origin && (i & (amps_per_state - 1)) == 0) ? 1 : 0; v.y = 0;
         state[i] = v;
     }
 }
@@ -203,13 +203,20 @@ __device__ __forceinline__ uint64_t warp_search(F load, uint64_t len, double &u)
 template <typename V>
 __global__ void __launch_bounds__(kRedThreads)
 sample_kernel(const V *__restrict__ state, int n, int bits0, int bits1, const double *__restrict__ lvl1,
-              const double *__restrict__ lvl2_prefix, uint64_t n2, uint64_t shots, uint64_t seed, uint64_t *__restrict__ out)
+              const double *__restrict__ lvl2_prefix, uint64_t n2, uint64_t shots, uint64_t seed, uint64_t *__restrict__ out,
+              double total_all, double off_lo, double off_hi, uint64_t index_prefix)
 {
+    // sharded state: total_all = norm of the whole state, this shard owns the CDF interval [off_lo, off_hi) and
+    // writes 0 for shots that fall elsewhere (an all-reduce sums the ranks' answers); single GPU: total_all < 0
     const int lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t s = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); s < shots; s += warps) {
-        const double total = lvl2_prefix[n2 - 1];
+        const double total = total_all < 0.0 ? lvl2_prefix[n2 - 1] : total_all;
         double u = splitmix_uniform(seed, s) * total;
+        if (total_all >= 0.0) {
+            if (!(u >= off_lo && u < off_hi)) { if (lane == 0) out[s] = 0; continue; }
+            u -= off_lo;
+        }
         // top level: binary search on the inclusive prefix (first g with prefix[g] > u)
         uint64_t lo = 0, hi = n2;
         while (lo < hi) {
@@ -224,7 +231,7 @@ sample_kernel(const V *__restrict__ state, int n, int bits0, int bits1, const do
         const uint64_t c = warp_search([&](uint64_t j) { return l1[j]; }, len1, u);
         const V *a = state + ((g * len1 + c) << bits0);
         const uint64_t i = warp_search([&](uint64_t j) { return abs2(a[j]); }, len0, u);
-        if (lane == 0) out[s] = ((g * len1 + c) << bits0) + i;
+        if (lane == 0) out[s] = index_prefix | (((g * len1 + c) << bits0) + i);
     }
 }
 

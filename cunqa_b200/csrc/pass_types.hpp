@@ -16,6 +16,7 @@ constexpr int kMaxDenseK = 5;     // dense block width (qubits)
 constexpr int kMaxDiagK = 12;     // diagonal table width (qubits)
 constexpr int kMaxFix = 12;       // targets + in-tile controls of one op
 constexpr int kMatScalars = 2560; // scalars (re/im) of dense-matrix storage per pass (kernel params)
+constexpr int kDiagLut = 192;     // per diagonal op: 64 entries for tile bits 0..5 + 128 for tile bits 6..12
 
 enum OpKind : uint8_t {
     OP_DENSE = 0,  // dense 2^k x 2^k on in-tile targets, optional controls
@@ -42,6 +43,7 @@ struct DevOp {
     uint64_t ctrl_out;  // physical-qubit mask of controls outside the tile (tested on the tile base)
     int32_t mask_row;   // row of the per-state flag matrix (batched feed-forward) when has_mask
     uint8_t k2, s;      // PAIR: #targets of gate B and its first local bit; B's matrix follows A's in mats
+                        // DIAG: k2 = slot of this op among the pass's diagonal ops (index of its pext tables)
     uint8_t pad_[2];
 };
 static_assert(sizeof(DevOp) == 64, "DevOp layout");
@@ -58,6 +60,9 @@ struct PassParams {
     uint64_t cond_mask; // ops whose activity depends on the tile (controls outside the tile / per-state mask)
     int32_t n_mat;      // scalars used in mats (staged into shared memory once per CTA)
     int32_t needs_full; // 1: some op needs the FULL kernel variant (dense k>=3, unusual register blocks)
+    int32_t n_diag;     // number of OP_DIAG ops; diag_op[slot] = op index of the slot-th one
+    int32_t pad2_;
+    uint8_t diag_op[kMaxOps];
     uint8_t tile_q[16]; // physical qubit of tile bit j (ascending)
     DevOp ops[kMaxOps];
     T mats[kMatScalars];

@@ -122,6 +122,7 @@ bool Fuser::try_merge(HostOp &prev, const HostOp &nw)
     }
     // dense absorb: one op's qubit set contains the other's
     if (U != P && U != N) return false;
+    if (U & opt.global_mask) return false;  // keep controls / diagonals on global qubits communication-free
     if (nu > opt.max_dense_qubits) return false;
     const HostOp &big = (U == P) ? prev : nw;
     const bool big_plain_dense = big.kind == HostOp::DENSE && big.ctrl.empty();
@@ -301,15 +302,36 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
             }
         }
         if (op.kind == HostOp::DIAG) {
+            // table index layout chosen for the kernel: in-tile qubits first, in ascending tile-bit order (so that
+            // the in-tile part of the index is a bit-extract of the tile index), then the out-of-tile qubits
             d.kind = OP_DIAG;
-            d.k = (uint8_t)op.q.size();
-            if (d.k > kMaxDiagK) { err = "diagonal table too wide"; return false; }
-            for (int m = 0; m < d.k; m++) {
+            const int k = (int)op.q.size();
+            d.k = (uint8_t)k;
+            if (k > kMaxDiagK) { err = "diagonal table too wide"; return false; }
+            std::vector<std::pair<int, int>> in;  // (tile pos, op bit)
+            std::vector<int> outb;
+            for (int m = 0; m < k; m++) {
                 const int p = tile_pos(op.q[m]);
-                d.dsrc[m] = (uint8_t)(p >= 0 ? p : 64 + op.q[m]);
+                if (p >= 0) in.emplace_back(p, m);
+                else outb.push_back(m);
             }
+            std::sort(in.begin(), in.end());
+            std::vector<int> order;  // new index bit -> old index bit
+            uint32_t mask_in = 0;
+            for (auto &pm : in) { order.push_back(pm.second); mask_in |= 1u << pm.first; }
+            for (int m : outb) order.push_back(m);
+            for (int m = 0; m < k; m++)
+                d.dsrc[m] = (uint8_t)(m < (int)in.size() ? in[m].first : 64 + op.q[order[m]]);
+            d.nfix = (uint8_t)in.size();
+            d.ctrl_in = mask_in;  // DIAG: tile-bit mask of the in-tile table qubits
+            d.k2 = (uint8_t)out.n_diag;
+            out.diag_op[out.n_diag++] = (uint8_t)(nops - 1);
             d.mat_off = (uint32_t)diag_host.size();
-            diag_host.insert(diag_host.end(), op.m.begin(), op.m.end());
+            for (int idx = 0; idx < (1 << k); idx++) {
+                int old = 0;
+                for (int m = 0; m < k; m++) old |= ((idx >> m) & 1) << order[m];
+                diag_host.push_back(op.m[old]);
+            }
             continue;
         }
         d.kind = op.kind == HostOp::DENSE ? OP_DENSE : (op.kind == HostOp::PERMX ? OP_PERMX : OP_SWAP);

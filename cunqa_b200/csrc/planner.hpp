@@ -35,6 +35,7 @@ struct PlanOptions {
     int max_pass_cost = 0;     // cap on sum over dense ops of 2^k per pass (0 = unlimited)
     bool fuse = true;
     bool pair_ops = true;      // register-block adjacent dense gates (two gates per shared-memory round trip)
+    uint64_t global_mask = 0;  // sharded state: physical qubits that select the rank (never fused into dense blocks)
 };
 
 struct Pass {

@@ -253,10 +253,13 @@ __device__ __forceinline__ uint64_t active_ops(const PassParams<T> &p, const uin
 // ---- apply the pass's op list to one staged tile (block-wide; ends with a barrier) -------------
 // COND = false: no op of the pass depends on the tile (no outside controls, no per-state masks), so the
 // whole op loop is driven by kernel parameters only and stays on the uniform datapath.
+// lut/dhi: per-diagonal-op bit-extract tables (build_diag_luts) and per-tile high index parts; lut == nullptr
+// selects the slow per-bit gather (generic kernel).
 template <typename T, int NT, bool COND, bool FULL>
 __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats, typename Vec2<T>::type *tile,
                                           const typename Vec2<T>::type *__restrict__ diag_tabs,
-                                          const uint64_t active, const uint64_t base, const int t, const int tid)
+                                          const uint64_t active, const uint64_t base, const int t, const int tid,
+                                          const uint16_t *lut = nullptr, uint32_t *dhi = nullptr)
 {
     using V = typename Vec2<T>::type;
     const uint32_t tile_amps = 1u << t;
@@ -280,6 +283,29 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                 // a run of consecutive diagonal ops is applied in ONE sweep of the tile
                 int oe = o;
                 while (oe + 1 < p.n_ops && p.ops[oe + 1].kind == OP_DIAG) oe++;
+                if (lut != nullptr) {
+                    // table index = (bits taken from the tile base, once per tile) | pext(tile index, in-tile mask)
+                    const int s0 = op.k2, s1 = p.ops[oe].k2;
+                    for (int sl = s0 + tid; sl <= s1; sl += NT) {
+                        const DevOp &d = p.ops[p.diag_op[sl]];
+                        uint32_t hi = 0;
+                        for (int m = d.nfix; m < d.k; m++) hi |= (uint32_t)((base >> (d.dsrc[m] - 64)) & 1ull) << m;
+                        dhi[sl] = hi + d.mat_off;
+                    }
+                    __syncthreads();
+                    for (uint32_t i = tid; i < tile_amps; i += NT) {
+                        const uint32_t s = swz<T>(i);
+                        V v = tile[s];
+                        const uint16_t *l0 = lut + s0 * kDiagLut + (i & 63u);
+                        const uint16_t *l1 = lut + s0 * kDiagLut + 64 + (i >> 6);
+                        for (int sl = s0; sl <= s1; sl++, l0 += kDiagLut, l1 += kDiagLut) {
+                            if (COND && !((active >> p.diag_op[sl]) & 1ull)) continue;
+                            const V ph = diag_tabs[dhi[sl] + (uint32_t)(*l0 | *l1)];
+                            v = cmul<V, T>(ph.x, ph.y, v);
+                        }
+                        tile[s] = v;
+                    }
+                } else
                 for (uint32_t i = tid; i < tile_amps; i += NT) {
                     const uint32_t s = swz<T>(i);
                     V v = tile[s];
@@ -442,6 +468,19 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     // the pass's dense matrices, staged once: broadcast shared-memory loads instead of constant-bank loads
     T *mats_s = reinterpret_cast<T *>(full + kStages + 1);
     for (int e = tid; e < p.n_mat; e += NT) mats_s[e] = p.mats[e];
+    // per diagonal op: bit-extract tables of the in-tile index part (tile bits 0..5 and 6..12) + per-tile high part
+    uint32_t *dhi = reinterpret_cast<uint32_t *>(mats_s + ((p.n_mat + 1) & ~1));
+    uint16_t *lut = reinterpret_cast<uint16_t *>(dhi + p.n_diag);
+    for (int e = tid; e < p.n_diag * kDiagLut; e += NT) {
+        const int sl = e / kDiagLut, r = e - sl * kDiagLut;
+        const uint32_t mask = p.ops[p.diag_op[sl]].ctrl_in;
+        const uint32_t val = r < 64 ? (uint32_t)r : (uint32_t)(r - 64) << 6;
+        uint32_t out = 0, kbit = 0;
+        for (uint32_t m = r < 64 ? (mask & 63u) : (mask & ~63u); m != 0; m &= m - 1, kbit++)
+            out |= ((val >> (__ffs((int)m) - 1)) & 1u) << kbit;
+        if (r >= 64) out <<= __popc(mask & 63u);
+        lut[e] = (uint16_t)out;
+    }
 
     // amplitude offset of box r inside a tile: tile-index bit j >= box_bits of the box number is deposited at
     // physical qubit tile_q[j] (which is j itself while j < L: the box is then a piece of the run)
@@ -510,7 +549,7 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         V *tile = reinterpret_cast<V *>(smem_raw + (size_t)s * buf_stride);
         mbar_wait(&full[s], parity);
 
-        apply_ops<T, NT, COND, FULL>(p, mats_s, tile, diag_tabs, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid);
+        apply_ops<T, NT, COND, FULL>(p, mats_s, tile, diag_tabs, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid, lut, dhi);
 
         // every thread's generic-proxy writes -> visible to the async proxy; then drain the tile with TMA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
