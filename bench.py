@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--qubits", type=int, default=0, help="override the workload width (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N>1: skip the sharded QFT leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -255,6 +256,49 @@ def main():
     e2e_s = float(t.item())
     be.close()
 
+    # ---- N > 1: the other multi-GPU regime -- ONE state sharded over all ranks (BASELINE config 4):
+    # QFT on (n + log2 N) qubits, top log2 N qubits global, global<->local qubit swaps over NVLink peer memory
+    sharded = None
+    if world > 1 and (world & (world - 1)) == 0 and not args.no_sharded:
+        from oracle import oracle_np as O
+        import numpy as np
+        g = world.bit_length() - 1
+        nq = n + g
+        xq = C.qft_x(nq, seed=7)
+        qins = C.qft(nq, xq)
+        ssv = cb.ShardedStateVector(nq, "double", device=local_rank)
+        sstream = torch.cuda.ExternalStream(ssv.stream(), device=torch.device("cuda", local_rank))
+        times = []
+        for rep in range(3):
+            ssv.reset(); ssv.sync()
+            barrier()
+            a0, d0 = ssv.stats(), ssv.dist_stats()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record(sstream)
+            ssv.run(qins); ssv.flush()
+            q1.record(sstream)
+            ssv.sync()
+            barrier()
+            tt = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            times.append(float(tt.item()))
+        a1, d1 = ssv.stats(), ssv.dist_stats()
+        idx = np.random.default_rng(2).integers(0, 1 << nq, size=1 << 14).astype(np.uint64)
+        err = float(np.abs(ssv.amplitudes(idx) - O.qft_amplitudes(nq, xq, idx)).max())
+        ms = min(times[1:])
+        shard = 16 * 2 ** n
+        swap_ms = d1["swap_ms"] - d0["swap_ms"]
+        sent = d1["swap_bytes_sent"] - d0["swap_bytes_sent"]
+        sharded = {"workload": f"QFT-{nq} fp64, one state sharded over {world} GPUs ({shard / 2 ** 30:.0f} GiB per GPU)",
+                   "gates": C.n_gates(qins), "ms": ms, "gates_per_s": C.n_gates(qins) / (ms / 1e3),
+                   "tile_passes_per_gpu": a1["passes"] - a0["passes"], "qubit_swaps": d1["swaps"] - d0["swaps"],
+                   "swap_GB_sent_per_gpu": sent / 1e9, "swap_ms": swap_ms,
+                   "nvlink_GBps_per_direction_per_gpu": (sent / 1e9) / (swap_ms / 1e3) if swap_ms > 0 else None,
+                   "nvlink_frac_of_770": ((sent / 1e9) / (swap_ms / 1e3)) / 770.0 if swap_ms > 0 else None,
+                   "local_GBps_per_gpu": 2 * shard * (a1["passes"] - a0["passes"]) / max(1e-9, (ms - swap_ms) / 1e3) / 1e9,
+                   "max_abs_err_vs_closed_form": err}
+        ssv.close()
+
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = gates * world / (ms_per_step / 1e3)
@@ -282,6 +326,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if sharded is not None:
+            line["sharded"] = sharded
         if world == 1 and not args.no_cpu_baseline:
             info, _ = cpu_sample()
             line["cpu_baseline"] = info

@@ -310,9 +310,10 @@ class ShardedStateVector(StateVector):
         _check(lib.cb200_dist_import_handles(self._h, flat))
 
     def dist_stats(self):
-        out = np.zeros(4, dtype=np.uint64)
+        out = np.zeros(5, dtype=np.uint64)
         _check(lib.cb200_dist_stats(self._h, out.ctypes.data_as(_c_u64_p)))
-        return {"rank": int(out[0]), "world": int(out[1]), "swaps": int(out[2]), "swap_bytes_sent": int(out[3])}
+        return {"rank": int(out[0]), "world": int(out[1]), "swaps": int(out[2]), "swap_bytes_sent": int(out[3]),
+                "swap_ms": int(out[4]) / 1000.0}
 
 
 class Backend:

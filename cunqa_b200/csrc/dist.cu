@@ -68,6 +68,8 @@ struct DistContext {
     std::vector<void *> peers;  // shard base pointer of every rank (own entry = local pointer)
     int *d_fence = nullptr;
     uint64_t swaps = 0, swap_bytes = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> swap_events;  // fence-to-fence span of every swap
+    double swap_ms = 0.0;
 };
 
 // A = the rank whose global bit is 0.  Pair element g (bit lbit removed): A's amplitude insert0(g)|1<<lbit
@@ -102,7 +104,11 @@ void State::dist_swap(int gbit, int lbit)
     const int mybit = (dist->rank >> gbit) & 1;
     const uint64_t pairs = 1ull << (n_local_ - 1);
     const uint64_t lo = mybit ? pairs / 2 : 0, hi = mybit ? pairs : pairs / 2;
+    cudaEvent_t e0, e1;
+    CB200_CUDA(cudaEventCreate(&e0));
+    CB200_CUDA(cudaEventCreate(&e1));
     dist_fence();  // both shards quiescent
+    CB200_CUDA(cudaEventRecord(e0, stream_));
     const int blocks = (int)std::min<uint64_t>((hi - lo + 255) / 256, (uint64_t)num_sms_ * 16);
     if (precision == 64)
         qubit_swap_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_, (double2 *)dist->peers[partner], lbit, lo, hi, mybit);
@@ -110,6 +116,8 @@ void State::dist_swap(int gbit, int lbit)
         qubit_swap_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, (float2 *)dist->peers[partner], lbit, lo, hi, mybit);
     CB200_CUDA(cudaGetLastError());
     dist_fence();  // the partner's writes into this shard have landed
+    CB200_CUDA(cudaEventRecord(e1, stream_));
+    dist->swap_events.emplace_back(e0, e1);
     stats.launches++;
     dist->swaps++;
     dist->swap_bytes += state_bytes_ / 2;  // sent (= received) per rank
@@ -194,6 +202,20 @@ int State::dist_rank() const { return dist ? dist->rank : 0; }
 int State::dist_world() const { return dist ? dist->world : 1; }
 uint64_t State::dist_swaps() const { return dist ? dist->swaps : 0; }
 uint64_t State::dist_swap_bytes() const { return dist ? dist->swap_bytes : 0; }
+// total device time spent in swaps so far (drains the stream)
+double State::dist_swap_ms()
+{
+    if (!dist) return 0.0;
+    cudaStreamSynchronize(stream_);
+    for (auto &ev : dist->swap_events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) dist->swap_ms += ms;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    dist->swap_events.clear();
+    return dist->swap_ms;
+}
 
 }  // namespace cb200
 
@@ -241,13 +263,14 @@ int cb200_dist_import_handles(cb200_state *s, const uint8_t *handles_all_ranks)
     catch (const std::exception &e) { g_cb200_err = e.what(); return CB200_ERR_CUDA; }
 }
 
-int cb200_dist_stats(const cb200_state *s, uint64_t out[4])
+int cb200_dist_stats(cb200_state *s, uint64_t out[5])
 {
     if (!s || !s->impl) { g_cb200_err = "null handle"; return CB200_ERR_INVALID; }
     out[0] = (uint64_t)s->impl->dist_rank();
     out[1] = (uint64_t)s->impl->dist_world();
     out[2] = s->impl->dist_swaps();
     out[3] = s->impl->dist_swap_bytes();
+    out[4] = (uint64_t)(s->impl->dist_swap_ms() * 1000.0);
     return CB200_OK;
 }
 

@@ -78,6 +78,7 @@ public:
     int dist_world() const;
     uint64_t dist_swaps() const;
     uint64_t dist_swap_bytes() const;
+    double dist_swap_ms();
 
 private:
     void construct(int rank, int world, const uint8_t *nccl_id);

@@ -151,8 +151,9 @@ int cb200_state_create_dist(cb200_state **out, int n_qubits_total, int precision
 #define CB200_IPC_HANDLE_BYTES 64
 int cb200_dist_export_handle(cb200_state *s, uint8_t handle_out[CB200_IPC_HANDLE_BYTES]);
 int cb200_dist_import_handles(cb200_state *s, const uint8_t *handles_all_ranks);
-/* out[0]=rank, [1]=world, [2]=global<->local qubit swaps performed, [3]=bytes this rank sent over NVLink */
-int cb200_dist_stats(const cb200_state *s, uint64_t out[4]);
+/* out[0]=rank, [1]=world, [2]=global<->local qubit swaps performed, [3]=bytes this rank sent over NVLink,
+ * [4]=device time spent in swaps, microseconds (drains the stream) */
+int cb200_dist_stats(cb200_state *s, uint64_t out[5]);
 
 #ifdef __cplusplus
 }
