@@ -89,13 +89,25 @@ State::~State()
 
 void State::reset()
 {
-    CB200_CUDA(cudaSetDevice(device));
     queue.reset();
+    pending_init_ = true;  // the write happens at the next flush, once the initial basis state is known
+}
+
+void State::ensure_init()
+{
+    if (!pending_init_) return;
+    pending_init_ = false;
+    queue.fresh = false;
+    CB200_CUDA(cudaSetDevice(device));
+    const uint64_t amps = 1ull << n_local_;
     const uint64_t total = (uint64_t)batch << n_local_;
     const int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)num_sms_ * 16);
-    const int origin = dist_rank() == 0;  // |0...0> lives on rank 0
-    if (precision == 64) init_zero_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_, 1ull << n_local_, total, origin);
-    else init_zero_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, 1ull << n_local_, total, origin);
+    // the basis state |queue.basis> (X gates folded into the initialisation); sharded: it lives on one rank
+    const int owner = (int)(queue.basis >> n_local_);
+    const uint64_t local = queue.basis & (amps - 1ull);
+    const int origin = dist_rank() == owner;
+    if (precision == 64) init_zero_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_, amps, total, origin, local);
+    else init_zero_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, amps, total, origin, local);
     CB200_CUDA(cudaGetLastError());
     stats.launches++;
 }
@@ -288,6 +300,7 @@ template void State::launch_ops_t<float>(std::vector<HostOp> &);
 
 void State::flush()
 {
+    ensure_init();
     if (dist) {
         if (precision == 64) flush_dist_t<double>();
         else flush_dist_t<float>();

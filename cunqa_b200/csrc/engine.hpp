@@ -93,6 +93,8 @@ private:
     template <typename T> void flush_t();
     template <typename T> void reduce2_t(uint64_t sel_mask, double *d_all, double *d_sel);
     void ensure_scratch(size_t partial_doubles);
+    void ensure_init();        // lazily writes the initial basis state (reset() only marks it)
+    bool pending_init_ = true;
     void maybe_flush() { if (queue.pending() >= 4096) flush(); }
 
     int n_local_;

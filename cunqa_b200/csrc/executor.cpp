@@ -791,6 +791,7 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
     out.set("num_qubits", Json::integer(c.num_qubits));
     out.set("gates", Json::integer((long long)q.gates));
     out.set("relabelled_swaps", Json::integer((long long)q.relabelled_swaps));
+    out.set("basis", Json::integer((long long)q.basis));  // physical index of the initial basis state (folded X-prep)
     if (world > 1) {
         // sharded state: this rank's segments (local pass groups and global<->local qubit swaps)
         const DistPlan dp = plan_distributed(q.ops(), c.num_qubits, n_local, rank);

@@ -52,11 +52,11 @@ __device__ __forceinline__ double splitmix_uniform(uint64_t seed, uint64_t count
 
 // |0...0> for every state of the batch
 template <typename V>
-__global__ void init_zero_kernel(V *state, uint64_t amps_per_state, uint64_t total, int has_origin)
+__global__ void init_zero_kernel(V *state, uint64_t amps_per_state, uint64_t total, int has_origin, uint64_t origin)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        V v; v.x = (has_origin && (i & (amps_per_state - 1)) == 0) ? 1 : 0; v.y = 0;
+        V v; v.x = (has_origin && (i & (amps_per_state - 1)) == origin) ? 1 : 0; v.y = 0;
         state[i] = v;
     }
 }

@@ -16,6 +16,9 @@ void OpQueue::reset()
 {
     clear_pending();
     for (int i = 0; i < n; i++) l2p[i] = i;
+    fresh = true;
+    basis = 0;
+    touched = 0;
 }
 
 void OpQueue::clear_pending()
@@ -49,6 +52,7 @@ void OpQueue::push_op(HostOp op, const uint8_t *flags)
         mask_rows.emplace_back(flags, flags + batch);
     }
     gates += 1;
+    touched |= op.qmask();
     fuser_.push(std::move(op));
 }
 
@@ -91,6 +95,11 @@ void OpQueue::apply_matrix(const int *qubits, int k, const int *ctrls, int nc, c
         return;
     }
     if (k == 1 && m[0] == cplx(0, 0) && m[3] == cplx(0, 0) && m[1] == cplx(1, 0) && m[2] == cplx(1, 0)) {
+        if (fresh && nc == 0 && flags == nullptr && !((touched >> op.q[0]) & 1ull)) {
+            basis ^= 1ull << op.q[0];  // X on an untouched qubit of |0...0>: a different initial basis state
+            gates += 1;
+            return;
+        }
         op.kind = HostOp::PERMX;
         push_op(std::move(op), flags);
         return;

@@ -36,6 +36,11 @@ public:
     std::vector<int> l2p;  // logical -> physical qubit; uncontrolled SWAPs only edit this table
     std::vector<std::vector<uint8_t>> mask_rows;
     uint64_t gates = 0, relabelled_swaps = 0;
+    // state-preparation peephole: while the register is still |0...0> (nothing flushed since reset), X gates on
+    // qubits nothing else has touched only change WHICH basis state is initialised -- no pass at all
+    bool fresh = true;
+    uint64_t basis = 0;     // physical index of the initial basis state
+    uint64_t touched = 0;   // physical qubits some queued op already acts on
 
 private:
     void push_op(HostOp op, const uint8_t *flags);

@@ -32,6 +32,8 @@ template <> __device__ __forceinline__ uint32_t swz<float>(uint32_t i)    // 8-b
     return i ^ (((i >> 4) & 7u) << 1);
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 __device__ __forceinline__ uint32_t insert0(uint32_t g, uint32_t pos)
 {
     const uint32_t lo = g & ((1u << pos) - 1u);
@@ -63,9 +65,30 @@ __device__ __forceinline__ void cfma(V &acc, const T mr, const T mi, const V a)
 // ---- dense k-qubit block on the tile -----------------------------------------------------------
 // K <= 2: the matrix is hoisted into registers (constant-bank loads, no shared-memory traffic);
 // K >= 3: matrix elements stream from the constant bank inside the row loop.
-template <typename T, int K, int NT>
+// phase product of the diagonal ops in slots [s0, s1] for tile index i (tables indexed through the per-op
+// bit-extract LUTs and the per-tile base `dhi`)
+template <typename T>
+__device__ __forceinline__ typename Vec2<T>::type diag_phase(const typename Vec2<T>::type *__restrict__ diag_tabs,
+                                                             const uint16_t *lut, const uint32_t *dhi, int s0, int s1, uint32_t i)
+{
+    using V = typename Vec2<T>::type;
+    const uint16_t *l0 = lut + s0 * kDiagLut + (i & 63u);
+    const uint16_t *l1 = lut + s0 * kDiagLut + 64 + (i >> 6);
+    V ph = diag_tabs[dhi[s0] + (uint32_t)(*l0 | *l1)];
+    for (int sl = s0 + 1; sl <= s1; sl++) {
+        l0 += kDiagLut; l1 += kDiagLut;
+        const V q = diag_tabs[dhi[sl] + (uint32_t)(*l0 | *l1)];
+        ph = cmul<V, T>(q.x, q.y, ph);
+    }
+    return ph;
+}
+
+// PRE: a run of diagonal ops (slots ps0..ps1) that immediately precedes this gate is folded into its load
+template <typename T, int K, int NT, bool PRE = false>
 __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
-                                         const int t, const int tid)
+                                         const int t, const int tid,
+                                         const typename Vec2<T>::type *__restrict__ diag_tabs = nullptr,
+                                         const uint16_t *lut = nullptr, const uint32_t *dhi = nullptr, int ps0 = 0, int ps1 = -1)
 {
     using V = typename Vec2<T>::type;
     constexpr int D = 1 << K;
@@ -90,7 +113,13 @@ __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const Dev
             idx |= op.ctrl_in;
             V in[D];
 #pragma unroll
-            for (int j = 0; j < D; j++) in[j] = tile[swz<T>(idx | off[j])];
+            for (int j = 0; j < D; j++) {
+                in[j] = tile[swz<T>(idx | off[j])];
+                if constexpr (PRE) {
+                    const V ph = diag_phase<T>(diag_tabs, lut, dhi, ps0, ps1, idx | off[j]);
+                    in[j] = cmul<V, T>(ph.x, ph.y, in[j]);
+                }
+            }
 #pragma unroll
             for (int r = 0; r < D; r++) {
                 V acc = cmul<V, T>(mr[r * D], mi[r * D], in[0]);
@@ -121,6 +150,28 @@ __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const Dev
             }
         }
     }
+}
+
+// explicit shared-space accesses with 32-bit addresses (no generic-pointer arithmetic in the hot loops)
+__device__ __forceinline__ double2 lds_amp(uint32_t addr, double2)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_amp(uint32_t addr, float2)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_amp(uint32_t addr, double2 v)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts_amp(uint32_t addr, float2 v)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
 
 // ---- register block: two dense gates per shared-memory round trip ---------------------------------
@@ -160,37 +211,38 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
     constexpr int D = 1 << R;
     // the swizzle is XOR-linear and the block bits are disjoint from the group bits, so
     // swz(idx | off_j) = swz(idx) ^ swz(off_j): one XOR per amplitude instead of re-swizzling
+    constexpr int kShift = sizeof(V) == 16 ? 4 : 3;
+    const uint32_t tile_s = smem_u32(tile);
     uint32_t sb[R], seg[R + 1];
 #pragma unroll
-    for (int m = 0; m < R; m++) sb[m] = swz<T>(1u << op.tbit[m]);
+    for (int m = 0; m < R; m++) sb[m] = swz<T>(1u << op.tbit[m]) << kShift;
 #pragma unroll
     for (int m = 0; m <= R; m++) seg[m] = op.seg[m];
-    uint32_t soff[D];
+    uint32_t boff[D];  // byte offset of block element j relative to the group's element 0 (XOR-combined)
 #pragma unroll
     for (int j = 0; j < D; j++) {
         uint32_t o = 0;
 #pragma unroll
         for (int m = 0; m < R; m++) if ((j >> m) & 1) o ^= sb[m];
-        soff[j] = o;
+        boff[j] = o;
     }
     const uint32_t ngroups = 1u << (t - R);
     for (uint32_t g = tid; g < ngroups; g += NT) {
         uint32_t idx = 0;
 #pragma unroll
         for (int m = 0; m <= R; m++) idx |= (g & seg[m]) << m;
-        const uint32_t sidx = swz<T>(idx);
+        const uint32_t bidx = swz<T>(idx) << kShift;
+        uint32_t addr[D];
         V a[D];
 #pragma unroll
-        for (int j = 0; j < D; j++) a[j] = tile[sidx ^ soff[j]];
+        for (int j = 0; j < D; j++) { addr[j] = tile_s + (bidx ^ boff[j]); a[j] = lds_amp(addr[j], V()); }
         block_gate<T, R, K1, 0>(a, mat);
         block_gate<T, R, K2, S>(a, mat + 2 * (1 << (2 * K1)));
 #pragma unroll
-        for (int j = 0; j < D; j++) tile[sidx ^ soff[j]] = a[j];
+        for (int j = 0; j < D; j++) sts_amp(addr[j], a[j]);
     }
 }
 
-// FULL = false keeps only the register blocks the headline circuits produce (keeps the hot kernel small
-// enough for the instruction cache); the planner sets PassParams::needs_full for anything else.
 template <typename T, int NT, bool FULL>
 __device__ __forceinline__ void op_pair_dispatch(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
                                                  const int t, const int tid)
@@ -229,6 +281,83 @@ __device__ __forceinline__ void op_perm(typename Vec2<T>::type *tile, const DevO
         const V a = tile[sa], b = tile[sb];
         tile[sa] = b;
         tile[sb] = a;
+    }
+}
+
+// ---- diagonal runs with the thread's amplitudes resident in registers -----------------------------
+// Each thread owns A = 2^t / NT amplitudes.  The tables are walked in the OUTER loop so that the A table
+// loads of one table are independent and in flight together (the lookups are L2-latency bound otherwise).
+template <typename T, int A>
+__device__ __forceinline__ void diag_run_regs(typename Vec2<T>::type (&v)[A], const uint32_t (&ti)[A],
+                                              const typename Vec2<T>::type *__restrict__ diag_tabs,
+                                              const uint16_t *lut, const uint32_t *dhi, int s0, int s1)
+{
+    using V = typename Vec2<T>::type;
+    for (int sl = s0; sl <= s1; sl++) {
+        const uint16_t *L = lut + sl * kDiagLut;
+        const uint32_t base = dhi[sl];
+        V q[A];
+#pragma unroll
+        for (int k = 0; k < A; k++) q[k] = diag_tabs[base + (uint32_t)(L[ti[k] & 63u] | L[64 + (ti[k] >> 6)])];
+#pragma unroll
+        for (int k = 0; k < A; k++) v[k] = cmul<V, T>(q[k].x, q[k].y, v[k]);
+    }
+}
+
+// standalone diagonal run: one sweep, amplitudes i = tid + k*NT
+template <typename T, int NT, int A>
+__device__ __forceinline__ void op_diag_run(typename Vec2<T>::type *tile, const typename Vec2<T>::type *__restrict__ diag_tabs,
+                                            const uint16_t *lut, const uint32_t *dhi, int s0, int s1, const int tid)
+{
+    using V = typename Vec2<T>::type;
+    V v[A];
+    uint32_t ti[A];
+#pragma unroll
+    for (int k = 0; k < A; k++) { ti[k] = tid + k * NT; v[k] = tile[swz<T>(ti[k])]; }
+    diag_run_regs<T, A>(v, ti, diag_tabs, lut, dhi, s0, s1);
+#pragma unroll
+    for (int k = 0; k < A; k++) tile[swz<T>(ti[k])] = v[k];
+}
+
+// diagonal run folded into the uncontrolled dense K-qubit gate that follows it (K <= 2): A amplitudes =
+// A >> K complete groups per thread, phases applied in registers before the butterfly
+template <typename T, int K, int NT, int A>
+__device__ __forceinline__ void op_diag_dense(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
+                                              const typename Vec2<T>::type *__restrict__ diag_tabs,
+                                              const uint16_t *lut, const uint32_t *dhi, int s0, int s1, const int tid)
+{
+    using V = typename Vec2<T>::type;
+    constexpr int D = 1 << K, G = A >> K;
+    uint32_t off[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int m = 0; m < K; m++) if ((j >> m) & 1) o |= 1u << op.tbit[m];
+        off[j] = o;
+    }
+    V v[A];
+    uint32_t ti[A];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        uint32_t idx = tid + g * NT;
+        for (int f = 0; f < K; f++) idx = insert0(idx, op.fixpos[f]);
+#pragma unroll
+        for (int j = 0; j < D; j++) { ti[g * D + j] = idx | off[j]; v[g * D + j] = tile[swz<T>(idx | off[j])]; }
+    }
+    diag_run_regs<T, A>(v, ti, diag_tabs, lut, dhi, s0, s1);
+    T mr[D * D], mi[D * D];
+#pragma unroll
+    for (int e = 0; e < D * D; e++) { mr[e] = mat[2 * e]; mi[e] = mat[2 * e + 1]; }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+#pragma unroll
+        for (int r = 0; r < D; r++) {
+            V acc = cmul<V, T>(mr[r * D], mi[r * D], v[g * D]);
+#pragma unroll
+            for (int cc = 1; cc < D; cc++) cfma<V, T>(acc, mr[r * D + cc], mi[r * D + cc], v[g * D + cc]);
+            tile[swz<T>(ti[g * D + r])] = acc;
+        }
     }
 }
 
@@ -284,27 +413,21 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                 int oe = o;
                 while (oe + 1 < p.n_ops && p.ops[oe + 1].kind == OP_DIAG) oe++;
                 if (lut != nullptr) {
-                    // table index = (bits taken from the tile base, once per tile) | pext(tile index, in-tile mask)
+                    // table index = dhi (bits taken from the tile base, filled once per tile by the caller)
+                    //             | pext(tile index, in-tile mask) through the per-op LUTs
                     const int s0 = op.k2, s1 = p.ops[oe].k2;
-                    for (int sl = s0 + tid; sl <= s1; sl += NT) {
-                        const DevOp &d = p.ops[p.diag_op[sl]];
-                        uint32_t hi = 0;
-                        for (int m = d.nfix; m < d.k; m++) hi |= (uint32_t)((base >> (d.dsrc[m] - 64)) & 1ull) << m;
-                        dhi[sl] = hi + d.mat_off;
+                    if (!COND && oe + 1 < p.n_ops && p.ops[oe + 1].kind == OP_DENSE && p.ops[oe + 1].k <= 2 &&
+                        p.ops[oe + 1].nfix == p.ops[oe + 1].k) {  // uncontrolled: the gate touches every amplitude
+                        // fold the whole run into the load of the dense gate that follows: one sweep, one barrier
+                        const DevOp &dn = p.ops[oe + 1];
+                        const T *mat = mats + dn.mat_off;
+                        if (dn.k == 1) op_diag_dense<T, 1, NT, 16>(tile, dn, mat, diag_tabs, lut, dhi, s0, s1, tid);
+                        else op_diag_dense<T, 2, NT, 16>(tile, dn, mat, diag_tabs, lut, dhi, s0, s1, tid);
+                        o = oe + 1;
+                        __syncthreads();
+                        continue;
                     }
-                    __syncthreads();
-                    for (uint32_t i = tid; i < tile_amps; i += NT) {
-                        const uint32_t s = swz<T>(i);
-                        V v = tile[s];
-                        const uint16_t *l0 = lut + s0 * kDiagLut + (i & 63u);
-                        const uint16_t *l1 = lut + s0 * kDiagLut + 64 + (i >> 6);
-                        for (int sl = s0; sl <= s1; sl++, l0 += kDiagLut, l1 += kDiagLut) {
-                            if (COND && !((active >> p.diag_op[sl]) & 1ull)) continue;
-                            const V ph = diag_tabs[dhi[sl] + (uint32_t)(*l0 | *l1)];
-                            v = cmul<V, T>(ph.x, ph.y, v);
-                        }
-                        tile[s] = v;
-                    }
+                    op_diag_run<T, NT, 16>(tile, diag_tabs, lut, dhi, s0, s1, tid);
                 } else
                 for (uint32_t i = tid; i < tile_amps; i += NT) {
                     const uint32_t s = swz<T>(i);
@@ -403,7 +526,6 @@ tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type
 // =================================================================================================
 constexpr int kAmpsPerThreadShift = 4;  // a thread owns 2^4 amplitudes of the tile (one 4-bit register block)
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -531,8 +653,10 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         }
     };
 
-    // tq[0] = tile computed in this iteration, tq[1..kStages-2] = tiles already loading,
-    // tq[kStages-1] = tile to be loaded next (all register-resident, statically indexed)
+    // tq[i] = the tile this CTA processes i iterations from now (register-resident, statically indexed).
+    // Tile j lives in slot j % kStages.  At the START of iteration k the slot of tile k-1 is recycled for tile
+    // k+kStages-1: the issuing lane only waits until its own TMA stores of tile k-1 have finished READING shared
+    // memory, so every load gets kStages-1 full compute phases of lead time.
     uint64_t tq[kStages];
     tq[0] = next_active(blockIdx.x);
 #pragma unroll
@@ -544,28 +668,36 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     int s = 0;            // slot of tq[0]
     uint32_t parity = 0;  // flips every time s wraps
     while (tq[0] != ~0ull) {
+        const int s2 = s == 0 ? kStages - 1 : s - 1;  // slot of the previous tile
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (tq[kStages - 1] != ~0ull) issue_load(s2, tq[kStages - 1]);
+
         uint64_t b;
         const uint64_t base = tile_base(tq[0], b);
         V *tile = reinterpret_cast<V *>(smem_raw + (size_t)s * buf_stride);
+        // per-tile base of every diagonal table (the index bits that come from qubits outside the tile)
+        for (int sl = tid; sl < p.n_diag; sl += NT) {
+            const DevOp &d = p.ops[p.diag_op[sl]];
+            uint32_t hi = 0;
+            for (int m = d.nfix; m < d.k; m++) hi |= (uint32_t)((base >> (d.dsrc[m] - 64)) & 1ull) << m;
+            dhi[sl] = hi + d.mat_off;
+        }
         mbar_wait(&full[s], parity);
+        if (p.n_diag) __syncthreads();
 
-        apply_ops<T, NT, COND, FULL>(p, mats_s, tile, diag_tabs, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid, lut, dhi);
+        apply_ops<T, NT, COND, FULL>(p, mats_s, tile, diag_tabs, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
+                                     (COND || (16 * NT) != (1 << t)) ? nullptr : lut, dhi);
 
         // every thread's generic-proxy writes -> visible to the async proxy; then drain the tile with TMA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        const int s2 = s == 0 ? kStages - 1 : s - 1;  // slot that held the previous tile; receives tq[kStages-1]
         if (lane == 0) {
             for (uint32_t r = warp; r < nbox; r += NT / 32) {
                 const uint64_t row = ((b << n) + base + box_off[r]) >> kAmpsPerRowShift;
                 tma_store_row(&tmap, smem_raw + (size_t)s * buf_stride + ((size_t)r << box_bits) * sizeof(V), (int)row);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            // The issuing lane refills exactly the boxes it drained one iteration ago, so it only has to wait
-            // for ITS OWN previous store to have finished reading shared memory -- no block barrier here.
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
-        if (tq[kStages - 1] != ~0ull) issue_load(s2, tq[kStages - 1]);
 #pragma unroll
         for (int i = 0; i < kStages - 1; i++) tq[i] = tq[i + 1];
         tq[kStages - 1] = tq[kStages - 1] == ~0ull ? ~0ull : next_active(tq[kStages - 1] + gridDim.x);

@@ -46,8 +46,10 @@ def _worker(rank, world, port, task, opts, out_path):
     plan = cb.plan(task, {**opts, "world": world, "rank": rank})
     nl = plan["n_local"]
     st = O.NumpyState(nl)
-    if rank != 0:
-        st.v[0] = 0.0
+    st.v[0] = 0.0
+    basis = plan.get("basis", 0)
+    if (basis >> nl) == rank:
+        st.v[basis & ((1 << nl) - 1)] = 1.0
     n_swaps = 0
     for seg in plan["segments"]:
         if "swap" in seg:

@@ -16,6 +16,9 @@ X = np.array([[0, 1], [1, 0]], dtype=complex)
 
 def replay_plan(plan, n):
     st = O.make_state(n, "numpy" if n <= 12 else "c")
+    if plan.get("basis", 0):  # leading X gates on |0...0> are folded into the initial basis state
+        st.amplitudes()[0] = 0.0
+        st.amplitudes()[plan["basis"]] = 1.0
     executed = []
     for ps in plan["passes"]:
         tile = set(ps["tile_q"])
@@ -64,6 +67,8 @@ def test_qft_plan_is_few_passes(lib_built):
     n = 30
     plan = cb.plan(C.task(C.qft(n, 0), n))
     assert plan["relabelled_swaps"] == n // 2       # uncontrolled swaps cost no pass
+    px = cb.plan(C.task(C.qft(n, 0b1011 << 20), n))
+    assert px["basis"] == 0b1011 << 20 and len(px["ops"]) == len(plan["ops"])  # X-prep costs no op at all
     assert len(plan["passes"]) <= 6                  # vs 480 per-gate sweeps
     # all cp gates were folded into diagonal tables of <= 10 qubits
     assert all(len(o["q"]) <= 10 for o in plan["ops"] if o["kind"] == "diag")

@@ -13,7 +13,11 @@ def probe(name, ins, n, precision="double", reps=2):
         sv.reset(); sv.sync()
         s0 = sv.stats()
         t0 = time.perf_counter()
-        sv.run(ins); sv.sync()
+        sv.run(ins)
+        t_queue = time.perf_counter() - t0
+        sv.flush()
+        t_flush = time.perf_counter() - t0 - t_queue
+        sv.sync()
         dt = time.perf_counter() - t0
         s1 = sv.stats()
         passes = s1["passes"] - s0["passes"]
@@ -23,7 +27,7 @@ def probe(name, ins, n, precision="double", reps=2):
     dt, passes, gbs = out[-1]
     print(json.dumps({"probe": name, "n": n, "precision": precision, "gates": C.n_gates(ins), "passes": passes,
                       "ms": round(dt * 1e3, 2), "ms_per_pass": round(dt * 1e3 / max(passes, 1), 3),
-                      "GBps": round(gbs, 1), "gates_per_s": round(C.n_gates(ins) / dt, 1),
+                      "GBps": round(gbs, 1), "gates_per_s": round(C.n_gates(ins) / dt, 1), "host_queue_ms": round(t_queue * 1e3, 1), "host_flush_ms": round(t_flush * 1e3, 1),
                       "env": {k: v for k, v in os.environ.items() if k.startswith("CB200_")}}), flush=True)
 
 if __name__ == "__main__":
@@ -37,5 +41,12 @@ if __name__ == "__main__":
         probe("qft", C.qft(n, C.qft_x(n)), n)
     if which in ("h", "all"):
         probe("h_layer", [{"name": "h", "qubits": [q]} for q in range(n)], n)
+    if which == "x1":   # streaming ceiling of the tile pipeline: one flop-free op per pass
+        probe("x1", [{"name": "x", "qubits": [n - 1]}], n, reps=3)
+    if which == "rz1":
+        probe("rz1", [{"name": "rz", "qubits": [n - 1], "params": [0.3]}], n, reps=3)
+    if which == "u2q":  # a single 2-qubit dense gate per pass
+        import numpy as np
+        probe("u2q", [C.unitary_inst(C.haar_unitary(np.random.default_rng(0), 4), [n - 1, n - 2])], n, reps=3)
     if which in ("qv32", "all"):
         probe("qv_fp32", C.quantum_volume(n, depth=min(n, 10)), n, "single")
