@@ -387,7 +387,20 @@ void State::measure(int qubit, uint64_t seed, const uint64_t *counters, const in
     flush();
     const int pq = queue.l2p[qubit];
     const uint64_t sel = 1ull << pq;
-    if (precision == 64) reduce2_t<double>(sel, d_small_, d_small_ + batch); else reduce2_t<float>(sel, d_small_, d_small_ + batch);
+    {   // norm and P(q=1) of every state in one read of the batch
+        const uint64_t amps = 1ull << n_local_;
+        int nblk = (int)std::min<uint64_t>((amps + kRedThreads * 8 - 1) / (kRedThreads * 8), std::max<uint64_t>(1, (uint64_t)num_sms_ * 8 / batch));
+        if (nblk < 1) nblk = 1;
+        ensure_scratch((size_t)2 * nblk * batch);
+        dim3 grid(nblk, batch);
+        double *pa = d_partial_, *ps = d_partial_ + (size_t)nblk * batch;
+        if (precision == 64) prob2_partial_kernel<double2><<<grid, kRedThreads, 0, stream_>>>((const double2 *)d_state_, amps, sel, pa, ps);
+        else prob2_partial_kernel<float2><<<grid, kRedThreads, 0, stream_>>>((const float2 *)d_state_, amps, sel, pa, ps);
+        sum_partials_kernel<<<batch, kRedThreads, 0, stream_>>>(pa, nblk, d_small_);
+        sum_partials_kernel<<<batch, kRedThreads, 0, stream_>>>(ps, nblk, d_small_ + batch);
+        CB200_CUDA(cudaGetLastError());
+        stats.launches += 3;
+    }
     std::vector<uint64_t> zero_ctr;
     if (!counters) { zero_ctr.assign(batch, 0); counters = zero_ctr.data(); }
     CB200_CUDA(cudaMemcpyAsync(d_counters_, counters, sizeof(uint64_t) * batch, cudaMemcpyHostToDevice, stream_));
@@ -402,7 +415,7 @@ void State::measure(int qubit, uint64_t seed, const uint64_t *counters, const in
         collapse_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, n_local_, pq, batch, d_outcome_, d_small_ + 2 * batch, reset_after ? 1 : 0);
     CB200_CUDA(cudaGetLastError());
     stats.launches += 2;
-    stats.bytes += 2ull * state_bytes_ + 2ull * state_bytes_;  // two reductions (1*S each) + collapse (2*S)
+    stats.bytes += state_bytes_ + 2ull * state_bytes_;  // one fused reduction (1*S) + collapse (2*S)
     std::vector<int> tmp;
     int *dst = bits_out;
     if (!dst) { tmp.resize(batch); dst = tmp.data(); }
@@ -472,6 +485,45 @@ void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out)
     stats.d2h_bytes += sizeof(uint64_t) * shots;
     if (!queue.identity_perm())
         for (uint64_t s = 0; s < shots; s++) out[s] = queue.logical_index(out[s]);
+}
+
+void State::sample_each(uint64_t seed, const uint64_t *counters, uint64_t *out)
+{
+    if (dist) throw Unsupported("sample_each on a sharded state is not implemented");
+    flush();
+    const int nl = n_local_;
+    const int bits0 = std::min(nl, kChunkBits);
+    const int bits1 = std::min(nl - bits0, kChunkBits);
+    const uint64_t n1 = ((uint64_t)batch << nl) >> bits0;   // level-1 entries over the whole batch
+    const uint64_t n2 = n1 >> bits1;
+    if (n1 > lvl1_cap_) { CB200_CUDA(cudaStreamSynchronize(stream_)); cudaFree(d_lvl1_); lvl1_cap_ = n1; CB200_CUDA(cudaMalloc(&d_lvl1_, n1 * sizeof(double))); }
+    if (n2 > lvl2_cap_) { CB200_CUDA(cudaStreamSynchronize(stream_)); cudaFree(d_lvl2_); lvl2_cap_ = n2; CB200_CUDA(cudaMalloc(&d_lvl2_, n2 * sizeof(double))); }
+    const int g1 = (int)std::min<uint64_t>(n1, (uint64_t)num_sms_ * 16);
+    const int g2 = (int)std::min<uint64_t>(n2, (uint64_t)num_sms_ * 16);
+    uint64_t *d_out = nullptr;
+    CB200_CUDA(cudaMalloc(&d_out, sizeof(uint64_t) * batch));
+    cudaError_t e = cudaMemcpyAsync(d_counters_, counters, sizeof(uint64_t) * batch, cudaMemcpyHostToDevice, stream_);
+    const int sblocks = std::max(1, std::min((batch * 32 + kRedThreads - 1) / kRedThreads, num_sms_ * 8));
+    if (precision == 64) {
+        chunk_sums_amp_kernel<double2><<<g1, kRedThreads, 0, stream_>>>((const double2 *)d_state_, bits0, n1, d_lvl1_);
+        chunk_sums_f64_kernel<<<g2, kRedThreads, 0, stream_>>>(d_lvl1_, bits1, n2, d_lvl2_);
+        sample_each_kernel<double2><<<sblocks, kRedThreads, 0, stream_>>>((const double2 *)d_state_, nl, bits0, bits1, d_lvl1_, d_lvl2_, batch, seed, d_counters_, d_out);
+    } else {
+        chunk_sums_amp_kernel<float2><<<g1, kRedThreads, 0, stream_>>>((const float2 *)d_state_, bits0, n1, d_lvl1_);
+        chunk_sums_f64_kernel<<<g2, kRedThreads, 0, stream_>>>(d_lvl1_, bits1, n2, d_lvl2_);
+        sample_each_kernel<float2><<<sblocks, kRedThreads, 0, stream_>>>((const float2 *)d_state_, nl, bits0, bits1, d_lvl1_, d_lvl2_, batch, seed, d_counters_, d_out);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    stats.launches += 3;
+    stats.bytes += state_bytes_;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(uint64_t) * batch, cudaMemcpyDeviceToHost, stream_);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    cudaFree(d_out);
+    if (e != cudaSuccess) throw CudaError(std::string("sample_each failed: ") + cudaGetErrorString(e));
+    stats.h2d_bytes += sizeof(uint64_t) * batch;
+    stats.d2h_bytes += sizeof(uint64_t) * batch;
+    if (!queue.identity_perm())
+        for (int b = 0; b < batch; b++) out[b] = queue.logical_index(out[b]);
 }
 
 void State::get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out)

@@ -58,6 +58,8 @@ public:
     void probabilities(int b, const int *qubits, int k, double *out);
     void measure(int qubit, uint64_t seed, const uint64_t *counters, const int8_t *forced, int *bits_out, bool reset_after);
     void sample(int b, uint64_t shots, uint64_t seed, uint64_t *out);
+    // one sample per state of the batch, draw U(seed, counters[b]) (terminal measurement of dynamic shots)
+    void sample_each(uint64_t seed, const uint64_t *counters, uint64_t *out);
     void get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out);
     void set_amplitudes(int b, const double *in);
 

@@ -130,6 +130,7 @@ struct TaskCfg {
     int n_comm = -1;
     bool bugcompat_unitary_order = false;
     bool bugcompat_teledata = false;
+    bool terminal_sampling = true;
     int max_batch = 0;
 };
 
@@ -157,6 +158,7 @@ TaskCfg parse_task(const Json &t)
     if (cfg.contains("n_communication_qubits")) c.n_comm = (int)cfg.at("n_communication_qubits").as_int();
     if (cfg.contains("b200_bugcompat_unitary_order")) c.bugcompat_unitary_order = cfg.at("b200_bugcompat_unitary_order").as_bool();
     if (cfg.contains("b200_bugcompat_teledata")) c.bugcompat_teledata = cfg.at("b200_bugcompat_teledata").as_bool();
+    if (cfg.contains("b200_terminal_sampling")) c.terminal_sampling = cfg.at("b200_terminal_sampling").as_bool();
     if (cfg.contains("b200_max_batch")) c.max_batch = (int)cfg.at("b200_max_batch").as_int();
     c.is_dynamic = t.contains("is_dynamic") ? t.at("is_dynamic").as_bool() : false;
     if (const Json *s = t.find("sending_to"))
@@ -650,10 +652,44 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                 }
             };
 
+        // terminal sampling: once every unfinished task has nothing but `measure` left (and no condition is
+        // pending), the m remaining measure+collapse rounds (3*S each) are replaced by ONE draw per state from
+        // |a|^2 (1*S): same joint distribution, one RNG draw instead of m.  The oracle restates the same rule.
+        auto try_terminal = [&]() -> bool {
+            if (!c0.terminal_sampling) return false;
+            std::vector<std::pair<int, int>> pend;  // (register qubit, global clbit) in scheduler order
+            bool any_left = false;
+            for (TaskRt &t : T) {
+                if (t.finished) continue;
+                if (t.b_td || t.b_tg || t.b_cc) return false;
+                const std::vector<Inst> &ins = t.cfg->insts;
+                for (size_t k = t.pc; k < ins.size(); k++) {
+                    if (ins[k].name != "measure") return false;
+                    const int q = ins[k].qubits.at(0), cl = ins[k].clbits.at(0);
+                    if (q < 0 || q >= t.cfg->num_qubits || cl < 0 || cl >= t.cfg->num_clbits) return false;
+                    pend.emplace_back(q + t.zq, cl + t.zc);
+                    any_left = true;
+                }
+            }
+            if (!any_left || pend.size() < 2) return false;
+            for (int b = 0; b < nb; b++) ctr[b] = ((shot0 + b + 1) << 20) + ordinal[b];
+            std::vector<uint64_t> idx(nb);
+            st.sample_each(seed, ctr.data(), idx.data());
+            std::vector<char> seen((size_t)n_total, 0);
+            for (auto &qc : pend) {
+                for (int b = 0; b < nb; b++) creg[(size_t)qc.second][b] = (uint8_t)((idx[b] >> qc.first) & 1ull);
+                seen[qc.first] = 1;
+            }
+            for (int b = 0; b < nb; b++) ordinal[b]++;
+            for (TaskRt &t : T) { t.pc = t.cfg->insts.size(); t.finished = true; }
+            return true;
+        };
+
         // round-robin scheduler (aer_simulator_adapter.cpp:755-778)
         bool ended = false;
         uint64_t guard = 0;
         while (!ended) {
+            if (try_terminal()) break;
             ended = true;
             bool progressed = false;
             for (TaskRt &t : T) {

@@ -80,6 +80,29 @@ prob_partial_kernel(const V *__restrict__ state, uint64_t amps_per_state, uint64
     if (threadIdx.x == 0) partial[b * gridDim.x + blockIdx.x] = acc;
 }
 
+// both sums in ONE read of the state: partial_all = sum |a|^2, partial_sel = sum over (index & sel_mask) == sel_mask
+template <typename V>
+__global__ void __launch_bounds__(kRedThreads)
+prob2_partial_kernel(const V *__restrict__ state, uint64_t amps_per_state, uint64_t sel_mask,
+                     double *__restrict__ partial_all, double *__restrict__ partial_sel)
+{
+    const uint64_t b = blockIdx.y;
+    const V *s = state + b * amps_per_state;
+    const uint64_t per_block = (amps_per_state + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = per_block * blockIdx.x;
+    uint64_t hi = lo + per_block;
+    if (hi > amps_per_state) hi = amps_per_state;
+    double acc = 0.0, sel = 0.0;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += kRedThreads) {
+        const double p = abs2(s[i]);
+        acc += p;
+        if ((i & sel_mask) == sel_mask) sel += p;
+    }
+    acc = block_sum(acc);
+    sel = block_sum(sel);
+    if (threadIdx.x == 0) { partial_all[b * gridDim.x + blockIdx.x] = acc; partial_sel[b * gridDim.x + blockIdx.x] = sel; }
+}
+
 // out[b] = sum_j partial[b*nblk + j]   (one block per state, fixed order)
 __global__ void __launch_bounds__(kRedThreads) sum_partials_kernel(const double *__restrict__ partial, int nblk, double *__restrict__ out)
 {
@@ -232,6 +255,31 @@ sample_kernel(const V *__restrict__ state, int n, int bits0, int bits1, const do
         const V *a = state + ((g * len1 + c) << bits0);
         const uint64_t i = warp_search([&](uint64_t j) { return abs2(a[j]); }, len0, u);
         if (lane == 0) out[s] = index_prefix | (((g * len1 + c) << bits0) + i);
+    }
+}
+
+// one sample per state of the batch (terminal measurement of a dynamic shot): one warp per state.
+// lvl1: chunk sums of 2^bits0 amplitudes over the whole batch; lvl2: sums of 2^bits1 lvl1 entries.
+template <typename V>
+__global__ void __launch_bounds__(kRedThreads)
+sample_each_kernel(const V *__restrict__ state, int n, int bits0, int bits1, const double *__restrict__ lvl1,
+                   const double *__restrict__ lvl2, int batch, uint64_t seed, const uint64_t *__restrict__ counters,
+                   uint64_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const uint64_t n2 = 1ull << (n - bits0 - bits1), len1 = 1ull << bits1, len0 = 1ull << bits0;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < batch; b += warps) {
+        const double *l2 = lvl2 + (uint64_t)b * n2;
+        double total = 0.0;
+        for (uint64_t j = 0; j < n2; j++) total += l2[j];  // n2 <= 2^14, same order on every lane
+        double u = splitmix_uniform(seed, counters[b]) * total;
+        const uint64_t g = warp_search([&](uint64_t j) { return l2[j]; }, n2, u);
+        const double *l1 = lvl1 + ((uint64_t)b * n2 + g) * len1;
+        const uint64_t c = warp_search([&](uint64_t j) { return l1[j]; }, len1, u);
+        const V *a = state + ((uint64_t)b << n) + ((g * len1 + c) << bits0);
+        const uint64_t i = warp_search([&](uint64_t j) { return abs2(a[j]); }, len0, u);
+        if (lane == 0) out[b] = ((g * len1 + c) << bits0) + i;
     }
 }
 

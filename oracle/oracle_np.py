@@ -423,13 +423,17 @@ _CIF_OPS = {
 
 
 def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channel=None,
-                reverse_unitary_qubits=False, forced_bits=None, teledata_literal=False):
+                reverse_unitary_qubits=False, forced_bits=None, teledata_literal=False, terminal_sampling=True):
     """Per-shot interpreter of one or several co-simulated tasks (aer_simulator_adapter.cpp:120-792,845-935).
 
     tasks: list of dicts {"id", "num_qubits", "num_clbits", "instructions"}.  Tasks are stepped
     round-robin in list order.  -> {task_id: {bitstring: count}}
     forced_bits: optional list; if given, measurement outcomes are taken from it in order
     (deterministic test mode; the state is collapsed onto the forced outcome).
+    terminal_sampling: once every unfinished task has only `measure` instructions left, the remaining
+    measure+collapse rounds are replaced by ONE inverse-CDF draw from |a|^2 (same joint distribution;
+    this is the engine's documented shortcut, restated here so that seeded runs stay comparable shot by
+    shot).  False = the reference's literal sequence of apply_measure calls (:185-190).
     teledata_literal: the reference's QRECV applies X on the *sent qubit's* outcome and Z on the
     *comm qubit's* outcome (aer_simulator_adapter.cpp:644-658, same in every adapter), which is the
     reverse of its own documented protocol (docs/source/_static/teledata.png: X <- comm qubit,
@@ -624,9 +628,38 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
             else:
                 apply_gate(st, inst, qmap, reverse_unitary_qubits)
 
+        def try_terminal():
+            if not terminal_sampling or forced is not None:
+                return False
+            pend = []
+            for t in T.values():
+                if t["finished"]:
+                    continue
+                if t["b_td"] or t["b_tg"] or t["b_cc"]:
+                    return False
+                for inst in t["ins"][t["pc"]:]:
+                    if inst["name"] != "measure":
+                        return False
+                    pend.append((inst["qubits"][0] + t["zq"], inst["clbits"][0] + t["zc"]))
+            if len(pend) < 2:
+                return False
+            amps = st.amplitudes()
+            cdf = np.cumsum(np.abs(amps) ** 2)
+            u = uniform(seed, meas_counter(shot, draw[0])) * cdf[-1]
+            draw[0] += 1
+            idx = min(int(np.searchsorted(cdf, u, side="right")), len(cdf) - 1)
+            for q, c in pend:
+                creg[c] = (idx >> q) & 1
+            for t in T.values():
+                t["pc"] = len(t["ins"])
+                t["finished"] = True
+            return True
+
         ended = False
         guard = 0
         while not ended:
+            if try_terminal():
+                break
             ended = True
             for t in T.values():
                 if t["finished"]:

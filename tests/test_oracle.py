@@ -114,3 +114,17 @@ def test_cif_feed_forward(lib_built):
            {"name": "measure", "qubits": [1], "clbits": [1]}]
     res = O.run_dynamic([{"id": "t", "num_qubits": 2, "num_clbits": 2, "instructions": ins}], 200, seed=4)
     assert set(res["t"]) <= {"00", "11"} and len(res["t"]) == 2
+
+
+def test_terminal_sampling_is_distribution_equivalent(lib_built):
+    """the engine's shortcut (one |a|^2 draw when only measurements remain) vs the reference's literal
+    sequence of apply_measure calls: same distribution"""
+    ins = [{"name": "h", "qubits": [0]}, {"name": "measure", "qubits": [0], "clbits": [0]},
+           {"name": "cif", "clbits": [0], "operation": "and", "condition": 1, "instructions": [{"name": "ry", "qubits": [1], "params": [1.0]}]},
+           {"name": "rx", "qubits": [2], "params": [0.8]}, {"name": "cx", "qubits": [2, 1]},
+           {"name": "measure", "qubits": [1], "clbits": [1]}, {"name": "measure", "qubits": [2], "clbits": [2]}]
+    task = [{"id": "t", "num_qubits": 3, "num_clbits": 3, "instructions": ins}]
+    shots = 3000
+    a = O.run_dynamic(task, shots, seed=1, terminal_sampling=True)["t"]
+    b = O.run_dynamic(task, shots, seed=2, terminal_sampling=False)["t"]
+    assert O.tvd(a, b) < 0.5 * math.sqrt(8 / shots) + 0.03

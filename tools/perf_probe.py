@@ -10,7 +10,7 @@ def probe(name, ins, n, precision="double", reps=2):
     bytes_amp = 16 if precision == "double" else 8
     out = []
     for r in range(reps):
-        sv.reset(); sv.sync()
+        sv.reset()
         s0 = sv.stats()
         t0 = time.perf_counter()
         sv.run(ins)
