@@ -136,7 +136,19 @@ def test_quantum_communication_joint_register(backend, maker):
     res = backend.execute(msg)
     assert "ERROR" not in res, res
     want = O.run_dynamic(tasks, shots, seed=33)
-    assert res["id_counts"] == want
+    if maker is C.hea_teledata_pair:
+        # qrecv ends with a swap, which the engine performs by relabelling qubits: its terminal inverse-CDF then
+        # walks the amplitudes in another order than the oracle's -- same distribution, not the same shots
+        for t in tasks:
+            assert sum(res["id_counts"][t["id"]].values()) == shots
+            assert O.tvd(res["id_counts"][t["id"]], want[t["id"]]) < 0.5 * math.sqrt(16 / shots) + 0.06
+        # with the shortcut off, every shot is the literal measure sequence and must match the oracle exactly
+        for m in msg:
+            m["config"]["b200_terminal_sampling"] = False
+        res = backend.execute(msg)
+        assert res["id_counts"] == O.run_dynamic(tasks, shots, seed=33, terminal_sampling=False)
+    else:
+        assert res["id_counts"] == want
 
 
 def test_teledata_teleports(backend):
