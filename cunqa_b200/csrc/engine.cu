@@ -487,6 +487,19 @@ void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out)
         for (uint64_t s = 0; s < shots; s++) out[s] = queue.logical_index(out[s]);
 }
 
+void State::broadcast_state0()
+{
+    flush();
+    if (batch == 1) return;
+    const uint64_t amps = 1ull << n_local_, total = (uint64_t)batch << n_local_;
+    const int blocks = (int)std::min<uint64_t>((total - amps + 255) / 256, (uint64_t)num_sms_ * 16);
+    if (precision == 64) broadcast_state0_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_, amps, total);
+    else broadcast_state0_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, amps, total);
+    CB200_CUDA(cudaGetLastError());
+    stats.launches++;
+    stats.bytes += state_bytes_;
+}
+
 void State::sample_each(uint64_t seed, const uint64_t *counters, uint64_t *out)
 {
     if (dist) throw Unsupported("sample_each on a sharded state is not implemented");

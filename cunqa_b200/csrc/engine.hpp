@@ -60,6 +60,7 @@ public:
     void sample(int b, uint64_t shots, uint64_t seed, uint64_t *out);
     // one sample per state of the batch, draw U(seed, counters[b]) (terminal measurement of dynamic shots)
     void sample_each(uint64_t seed, const uint64_t *counters, uint64_t *out);
+    void broadcast_state0();  // states 1..batch-1 := state 0
     void get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out);
     void set_amplitudes(int b, const double *in);
 

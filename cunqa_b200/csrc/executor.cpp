@@ -131,6 +131,7 @@ struct TaskCfg {
     bool bugcompat_unitary_order = false;
     bool bugcompat_teledata = false;
     bool terminal_sampling = true;
+    bool share_prefix = true;
     int max_batch = 0;
 };
 
@@ -158,6 +159,7 @@ TaskCfg parse_task(const Json &t)
     if (cfg.contains("n_communication_qubits")) c.n_comm = (int)cfg.at("n_communication_qubits").as_int();
     if (cfg.contains("b200_bugcompat_unitary_order")) c.bugcompat_unitary_order = cfg.at("b200_bugcompat_unitary_order").as_bool();
     if (cfg.contains("b200_bugcompat_teledata")) c.bugcompat_teledata = cfg.at("b200_bugcompat_teledata").as_bool();
+    if (cfg.contains("b200_share_prefix")) c.share_prefix = cfg.at("b200_share_prefix").as_bool();
     if (cfg.contains("b200_terminal_sampling")) c.terminal_sampling = cfg.at("b200_terminal_sampling").as_bool();
     if (cfg.contains("b200_max_batch")) c.max_batch = (int)cfg.at("b200_max_batch").as_int();
     c.is_dynamic = t.contains("is_dynamic") ? t.at("is_dynamic").as_bool() : false;
@@ -456,6 +458,17 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
         std::map<std::string, std::deque<Bits>> q_td, q_tg;
         std::map<std::pair<std::string, std::string>, std::deque<Bits>> q_cc;
         std::vector<uint64_t> ordinal(nb, 0), ctr(nb);
+        // shared prefix: until the first measurement every shot of the batch is the same state, so gates are
+        // applied to state 0 only (per-state mask: the other states' tiles are skipped, no traffic) and state 0 is
+        // broadcast right before the first measurement
+        bool diverged = nb == 1 || !c0.share_prefix;
+        Bits only0(nb, 0);
+        only0[0] = 1;
+        auto diverge = [&]() {
+            if (diverged) return;
+            st.broadcast_state0();
+            diverged = true;
+        };
 
         auto peer = [&](const std::string &id) -> TaskRt & {
             auto it = by_id.find(id);
@@ -464,6 +477,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
         };
         // measure (optionally conditioned by `flags`) every state; returns the outcome bits
         auto measure = [&](int q, bool reset_after, const uint8_t *flags) -> Bits {
+            diverge();
             std::vector<int8_t> forced;
             for (int b = 0; b < nb; b++) ctr[b] = ((shot0 + b + 1) << 20) + ordinal[b];
             if (flags) {
@@ -480,10 +494,20 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
         };
         auto any = [&](const Bits &f) { return std::any_of(f.begin(), f.end(), [](uint8_t v) { return v != 0; }); };
         auto all = [&](const Bits &f) { return std::all_of(f.begin(), f.end(), [](uint8_t v) { return v != 0; }); };
+        // per-state condition of a gate: the caller's flags, restricted to state 0 while the batch has not diverged
+        Bits pre_flags;
+        auto gate_flags = [&](const Bits *flags) -> const uint8_t * {
+            if (!diverged) {
+                pre_flags = only0;
+                if (flags) pre_flags[0] = (*flags)[0];
+                return pre_flags.data();
+            }
+            return (flags && !all(*flags)) ? flags->data() : nullptr;
+        };
         auto named = [&](const char *name, std::vector<int> qs, const Bits *flags) {
             if (flags && !any(*flags)) return;
-            const uint8_t *fp = (flags && !all(*flags)) ? flags->data() : nullptr;
-            st.apply_named(name, qs.data(), (int)qs.size(), nullptr, 0, fp);
+            if (!diverged && flags && !(*flags)[0]) return;
+            st.apply_named(name, qs.data(), (int)qs.size(), nullptr, 0, gate_flags(flags));
         };
         auto gen_ent = [&](size_t npairs) {
             std::vector<int> idx;
@@ -647,8 +671,8 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                     t.b_tg = false;
                 } else {
                     if (cond && !any(*cond)) return;
-                    const uint8_t *fp = (cond && !all(*cond)) ? cond->data() : nullptr;
-                    queue_gate(st, in, qmap, fp, c.bugcompat_unitary_order);
+                    if (!diverged && cond && !(*cond)[0]) return;
+                    queue_gate(st, in, qmap, gate_flags(cond), c.bugcompat_unitary_order);
                 }
             };
 
@@ -672,6 +696,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                 }
             }
             if (!any_left || pend.size() < 2) return false;
+            diverge();
             for (int b = 0; b < nb; b++) ctr[b] = ((shot0 + b + 1) << 20) + ordinal[b];
             std::vector<uint64_t> idx(nb);
             st.sample_each(seed, ctr.data(), idx.data());

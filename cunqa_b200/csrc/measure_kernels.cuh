@@ -61,6 +61,15 @@ __global__ void init_zero_kernel(V *state, uint64_t amps_per_state, uint64_t tot
     }
 }
 
+// copy state 0 of a batch onto states 1..batch-1 (shared deterministic prefix of batched dynamic shots)
+template <typename V>
+__global__ void broadcast_state0_kernel(V *state, uint64_t amps_per_state, uint64_t total)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = amps_per_state + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+        state[i] = state[i & (amps_per_state - 1)];
+}
+
 // partial[b*gridDim.x + blockIdx.x] = sum over this block's slice of state b of |a|^2 restricted to
 // amplitudes with (index & sel_mask) == sel_mask (sel_mask = 0: full norm; 1<<q: P(q=1)).
 template <typename V>

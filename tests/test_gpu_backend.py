@@ -124,7 +124,8 @@ def test_batching_does_not_change_results(backend):
     a = backend.execute(dyn_task(ins, 5, 5, 257, 9))
     b = backend.execute(dyn_task(ins, 5, 5, 257, 9, b200_max_batch=1))
     c = backend.execute(dyn_task(ins, 5, 5, 257, 9, b200_max_batch=100))
-    assert a["counts"] == b["counts"] == c["counts"] and sum(a["counts"].values()) == 257
+    d = backend.execute(dyn_task(ins, 5, 5, 257, 9, b200_share_prefix=False))  # no shared-prefix shortcut
+    assert a["counts"] == b["counts"] == c["counts"] == d["counts"] and sum(a["counts"].values()) == 257
 
 
 @pytest.mark.parametrize("maker", [C.hea_teledata_pair, C.hea_telegate_pair])
