@@ -53,6 +53,8 @@ void State::construct(int rank, int world, const uint8_t *nccl_id)
     max_smem_sm_ = prop.sharedMemPerMultiprocessor;
     tma_threads_ = env_int("CB200_TMA_THREADS", 0);
     tma_fold_dims_ = env_int("CB200_TMA_FOLD", 1) != 0;
+    tma_refill_after_ = env_int("CB200_TMA_REFILL_AFTER", 0);
+    tma_max_ctas_ = env_int("CB200_TMA_MAX_CTAS", 0);
     tma_stages_ = env_int("CB200_TMA_STAGES", 2) == 3 ? 3 : 2;
     n_local_ = n - gbits;
     amp_bytes_ = precision == 64 ? 16 : 8;
@@ -248,17 +250,19 @@ void State::launch_ops_t(std::vector<HostOp> &ops)
         const int stages = tma_stages_;
         const size_t smem_tma = (size_t)stages * buf_stride + sizeof(uint64_t) * (((size_t)1 << (p.t - box_bits)) + stages + 1) +
                                 sizeof(T) * (size_t)((p.n_mat + 1) & ~1) + (size_t)p.n_diag * (4 + 2 * kDiagLut) + 16 + 1024;
-        int nt = 1 << std::max(6, std::min(8, p.t - kAmpsPerThreadShift));  // 64 / 128 / 256 threads
+        int nt = 1 << std::max(5, std::min(8, p.t - kAmpsPerThreadShift));  // 32 / 64 / 128 / 256 threads
         if (tma_threads_ > 0) nt = tma_threads_;
-        const int ctas = std::max(1, (stages == 3 ? 256 : 384) / nt);
-        const bool tma = use_tma_ && p.L >= aprs + 1 && state_bytes_ >= 128 && smem_tma * ctas <= max_smem_sm_ && smem_tma <= max_smem_;
+        int ctas = std::max(1, (stages == 3 ? 256 : 384) / nt);
+        ctas = std::max(1, std::min<int>(ctas, (int)(max_smem_sm_ / (smem_tma + 1024))));  // what shared memory allows
+        if (tma_max_ctas_ > 0) ctas = std::min(ctas, tma_max_ctas_);
+        const bool tma = use_tma_ && p.L >= aprs + 1 && state_bytes_ >= 128 && smem_tma <= max_smem_;
         if (tma) {
             CUtensorMap tmap;
             make_tensor_map(&tmap, run_bits, hi_q);
             const unsigned grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_ * ctas);
             auto launch = [&](auto kern_tma) {
                 CB200_CUDA(cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
-                kern_tma<<<grid, nt, smem_tma, stream_>>>(p, tmap, (const V *)d_diag_, d_flags_, box_bits, buf_stride);
+                kern_tma<<<grid, nt, smem_tma, stream_>>>(p, tmap, (const V *)d_diag_, d_flags_, box_bits, buf_stride, tma_refill_after_);
             };
             const bool cnd = p.cond_mask != 0, full = p.needs_full != 0;
             auto pick = [&](auto nt_tag) {
@@ -275,7 +279,8 @@ void State::launch_ops_t(std::vector<HostOp> &ops)
             };
             if (nt == 256) pick(std::integral_constant<int, 256>());
             else if (nt == 128) pick(std::integral_constant<int, 128>());
-            else pick(std::integral_constant<int, 64>());
+            else if (nt == 64) pick(std::integral_constant<int, 64>());
+            else pick(std::integral_constant<int, 32>());
         } else {
             const size_t smem = sizeof(V) * ((size_t)1 << p.t) + sizeof(uint64_t) * ((size_t)1 << (p.t - p.L));
             CB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

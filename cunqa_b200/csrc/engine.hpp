@@ -112,6 +112,8 @@ private:
     void make_tensor_map(CUtensorMap *out, int run_bits, const int hi_qubits[3]);
     bool tma_fold_dims_ = true;
     int tma_stages_ = 2;
+    int tma_max_ctas_ = 0;
+    int tma_refill_after_ = 0;  // recycle the previous tile's buffer after this op index (-1: before the first op)
     // device scratch
     void *d_diag_ = nullptr; size_t diag_cap_ = 0;       // diagonal tables (elements of V)
     uint8_t *d_flags_ = nullptr; size_t flags_cap_ = 0;  // mask rows

@@ -384,15 +384,23 @@ __device__ __forceinline__ uint64_t active_ops(const PassParams<T> &p, const uin
 // whole op loop is driven by kernel parameters only and stays on the uniform datapath.
 // lut/dhi: per-diagonal-op bit-extract tables (build_diag_luts) and per-tile high index parts; lut == nullptr
 // selects the slow per-bit gather (generic kernel).
-template <typename T, int NT, bool COND, bool FULL>
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// hook() is invoked exactly once, right after the barrier that ends the first executed op whose index is
+// >= hook_at (or at the very end): the TMA kernel uses it to recycle the previous tile's buffer while the
+// remaining ops still run.
+template <typename T, int NT, bool COND, bool FULL, typename Hook = NoHook>
 __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats, typename Vec2<T>::type *tile,
                                           const typename Vec2<T>::type *__restrict__ diag_tabs,
                                           const uint64_t active, const uint64_t base, const int t, const int tid,
-                                          const uint16_t *lut = nullptr, uint32_t *dhi = nullptr)
+                                          const uint16_t *lut = nullptr, uint32_t *dhi = nullptr,
+                                          const int hook_at = 1 << 30, Hook hook = Hook())
 {
     using V = typename Vec2<T>::type;
     const uint32_t tile_amps = 1u << t;
+    bool hooked = false;
     for (int o = 0; o < p.n_ops; o++) {
+        if (!hooked && o > hook_at) { hook(); hooked = true; }
             if (COND && !((active >> o) & 1ull)) continue;
             const DevOp &op = p.ops[o];
             if (op.kind == OP_DENSE) {
@@ -453,6 +461,7 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                 __syncthreads();
             }
         }
+    if (!hooked) hook();
 }
 
 // ---- the pass kernel ---------------------------------------------------------------------------
@@ -571,7 +580,7 @@ template <typename T, int NT, bool COND, bool FULL, int kStages>
 __global__ void __launch_bounds__(NT, (kStages == 3 ? 256 : 384) / NT)
 tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_constant__ CUtensorMap tmap,
                      const typename Vec2<T>::type *__restrict__ diag_tabs, const uint8_t *__restrict__ flags,
-                     const int box_bits, const uint32_t buf_stride)
+                     const int box_bits, const uint32_t buf_stride, const int refill_after)
 {
     using V = typename Vec2<T>::type;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -593,6 +602,7 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     // per diagonal op: bit-extract tables of the in-tile index part (tile bits 0..5 and 6..12) + per-tile high part
     uint32_t *dhi = reinterpret_cast<uint32_t *>(mats_s + ((p.n_mat + 1) & ~1));
     uint16_t *lut = reinterpret_cast<uint16_t *>(dhi + p.n_diag);
+    static_assert(NT >= 32, "one warp at least");
     for (int e = tid; e < p.n_diag * kDiagLut; e += NT) {
         const int sl = e / kDiagLut, r = e - sl * kDiagLut;
         const uint32_t mask = p.ops[p.diag_op[sl]].ctrl_in;
@@ -669,8 +679,13 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     uint32_t parity = 0;  // flips every time s wraps
     while (tq[0] != ~0ull) {
         const int s2 = s == 0 ? kStages - 1 : s - 1;  // slot of the previous tile
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        if (tq[kStages - 1] != ~0ull) issue_load(s2, tq[kStages - 1]);
+        // Recycling that slot needs the previous tile's TMA stores to have finished READING shared memory, which
+        // takes as long as HBM needs to absorb them.  Doing it after the first op(s) of this tile instead of here
+        // lets the drain overlap the math, while the new load still has the rest of the tile's math to land.
+        auto refill = [&]() {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (tq[kStages - 1] != ~0ull) issue_load(s2, tq[kStages - 1]);
+        };
 
         uint64_t b;
         const uint64_t base = tile_base(tq[0], b);
@@ -686,7 +701,7 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         if (p.n_diag) __syncthreads();
 
         apply_ops<T, NT, COND, FULL>(p, mats_s, tile, diag_tabs, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
-                                     (COND || (16 * NT) != (1 << t)) ? nullptr : lut, dhi);
+                                     (COND || (16 * NT) != (1 << t)) ? nullptr : lut, dhi, refill_after, refill);
 
         // every thread's generic-proxy writes -> visible to the async proxy; then drain the tile with TMA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

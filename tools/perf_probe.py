@@ -41,6 +41,13 @@ if __name__ == "__main__":
         probe("qft", C.qft(n, C.qft_x(n)), n)
     if which in ("h", "all"):
         probe("h_layer", [{"name": "h", "qubits": [q]} for q in range(n)], n)
+    if which == "local3":  # fixed pass: 3 register-block pairs on 4 high qubits (isolates kernel efficiency)
+        import numpy as np
+        rng = np.random.default_rng(1)
+        a, b, c4, d = n - 1, n - 2, n - 3, n - 4
+        pairs = [(a, b), (c4, d), (a, c4), (b, d), (a, d), (b, c4)]
+        reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+        probe("local3", [C.unitary_inst(C.haar_unitary(rng, 4), list(pq)) for _ in range(reps) for pq in pairs], n, reps=3)
     if which == "x1":   # streaming ceiling of the tile pipeline: one flop-free op per pass
         probe("x1", [{"name": "x", "qubits": [n - 1]}], n, reps=3)
     if which == "rz1":
