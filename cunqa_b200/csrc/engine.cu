@@ -59,7 +59,7 @@ void State::construct(int rank, int world, const uint8_t *nccl_id)
     n_local_ = n - gbits;
     amp_bytes_ = precision == 64 ? 16 : 8;
     state_bytes_ = amp_bytes_ * ((size_t)batch << n_local_);
-    opt.tile_bits = env_int("CB200_TILE_BITS", precision == 64 ? 11 : 12);
+    opt.tile_bits = env_int("CB200_TILE_BITS", precision == 64 ? 11 : 13);
     opt.min_run_bits = env_int("CB200_MIN_RUN_BITS", precision == 64 ? 4 : 5);
     opt.max_pass_cost = env_int("CB200_MAX_PASS_COST", 0);
     opt.max_diag_qubits = env_int("CB200_MAX_DIAG_QUBITS", 10);
@@ -248,7 +248,7 @@ void State::launch_ops_t(std::vector<HostOp> &ops)
             for (int d = 0; d < 3 && p.L + d < p.t; d++) { hi_q[d] = p.tile_q[p.L + d]; box_bits++; }
         const uint32_t buf_stride = (uint32_t)std::max<size_t>(1024, sizeof(V) << p.t);
         const int stages = tma_stages_;
-        const size_t smem_tma = (size_t)stages * buf_stride + sizeof(uint64_t) * (((size_t)1 << (p.t - box_bits)) + stages + 1) +
+        const size_t smem_tma = (size_t)stages * buf_stride + sizeof(uint64_t) * (stages + 1) + sizeof(uint32_t) * ((((size_t)1 << (p.t - box_bits)) + 3) & ~(size_t)3) +
                                 sizeof(T) * (size_t)((p.n_mat + 1) & ~1) + (size_t)p.n_diag * (4 + 2 * kDiagLut) + 16 + 1024;
         int nt = 1 << std::max(5, std::min(8, p.t - kAmpsPerThreadShift));  // 32 / 64 / 128 / 256 threads
         if (tma_threads_ > 0) nt = tma_threads_;

@@ -780,7 +780,7 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
     const TaskCfg c = parse_task(task);
     PlanOptions opt;
     int world = 1, rank = 0;
-    opt.tile_bits = c.precision == 64 ? 11 : 12;
+    opt.tile_bits = c.precision == 64 ? 11 : 13;
     opt.min_run_bits = c.precision == 64 ? 4 : 5;
     if (!options_json.empty()) {
         const Json o = Json::parse(options_json);

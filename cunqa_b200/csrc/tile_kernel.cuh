@@ -594,10 +594,11 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     const uint32_t nbox = 1u << (t - box_bits);    // TMA ops per tile per direction
     const uint32_t tile_bytes = (uint32_t)sizeof(V) << t;
     constexpr int kAmpsPerRowShift = sizeof(V) == 16 ? 3 : 4;  // amplitudes per 128-byte row
-    uint64_t *box_off = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * buf_stride);
-    uint64_t *full = box_off + nbox;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * buf_stride);
+    // row offset (128-byte rows) of TMA box r relative to the tile's first row
+    uint32_t *box_row = reinterpret_cast<uint32_t *>(full + kStages + 1);
     // the pass's dense matrices, staged once: broadcast shared-memory loads instead of constant-bank loads
-    T *mats_s = reinterpret_cast<T *>(full + kStages + 1);
+    T *mats_s = reinterpret_cast<T *>(box_row + ((nbox + 3) & ~3u));
     for (int e = tid; e < p.n_mat; e += NT) mats_s[e] = p.mats[e];
     // per diagonal op: bit-extract tables of the in-tile index part (tile bits 0..5 and 6..12) + per-tile high part
     uint32_t *dhi = reinterpret_cast<uint32_t *>(mats_s + ((p.n_mat + 1) & ~1));
@@ -620,7 +621,7 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         uint64_t o = 0;
         for (int j = box_bits; j < t; j++)
             if ((r >> (j - box_bits)) & 1u) o |= 1ull << p.tile_q[j];
-        box_off[r] = o;
+        box_row[r] = (uint32_t)(o >> kAmpsPerRowShift);
     }
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
@@ -650,16 +651,24 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         }
         return ~0ull;
     };
-    auto issue_load = [&](int s, uint64_t tileno) {
+    const uint32_t smem_s = smem_u32(smem_raw);
+    const uint32_t box_bytes = (uint32_t)sizeof(V) << box_bits;
+    // first 128-byte row of a tile in the whole buffer
+    auto tile_row = [&](uint64_t tileno) -> uint32_t {
         uint64_t b;
         const uint64_t base = tile_base(tileno, b);
+        return (uint32_t)(((b << n) + base) >> kAmpsPerRowShift);
+    };
+    auto issue_load = [&](int s, uint32_t row0) {
         if (tid == 0) mbar_arrive_expect_tx(&full[s], tile_bytes);
         // TMA instructions take warp-uniform operands: lane 0 of warp w issues boxes w, w+nwarps, ...
         if (lane == 0) {
-            for (uint32_t r = warp; r < nbox; r += NT / 32) {
-                const uint64_t row = ((b << n) + base + box_off[r]) >> kAmpsPerRowShift;
-                tma_load_row(smem_raw + (size_t)s * buf_stride + ((size_t)r << box_bits) * sizeof(V), &tmap, &full[s], (int)row);
-            }
+            const uint32_t dst = smem_s + (uint32_t)s * buf_stride, bar = smem_u32(&full[s]);
+            for (uint32_t r = warp; r < nbox; r += NT / 32)
+                asm volatile(
+                    "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %3, %3, %3}], [%2];"
+                    ::"r"(dst + r * box_bytes), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(bar), "r"(0), "r"((int)(row0 + box_row[r]))
+                    : "memory");
         }
     };
 
@@ -668,12 +677,15 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     // k+kStages-1: the issuing lane only waits until its own TMA stores of tile k-1 have finished READING shared
     // memory, so every load gets kStages-1 full compute phases of lead time.
     uint64_t tq[kStages];
+    uint32_t trow[kStages];  // first row of each queued tile (computed once per tile)
     tq[0] = next_active(blockIdx.x);
 #pragma unroll
     for (int i = 1; i < kStages; i++) tq[i] = tq[i - 1] == ~0ull ? ~0ull : next_active(tq[i - 1] + gridDim.x);
 #pragma unroll
+    for (int i = 0; i < kStages; i++) trow[i] = tq[i] == ~0ull ? 0u : tile_row(tq[i]);
+#pragma unroll
     for (int i = 0; i < kStages - 1; i++)
-        if (tq[i] != ~0ull) issue_load(i, tq[i]);
+        if (tq[i] != ~0ull) issue_load(i, trow[i]);
 
     int s = 0;            // slot of tq[0]
     uint32_t parity = 0;  // flips every time s wraps
@@ -684,7 +696,7 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         // lets the drain overlap the math, while the new load still has the rest of the tile's math to land.
         auto refill = [&]() {
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            if (tq[kStages - 1] != ~0ull) issue_load(s2, tq[kStages - 1]);
+            if (tq[kStages - 1] != ~0ull) issue_load(s2, trow[kStages - 1]);
         };
 
         uint64_t b;
@@ -707,15 +719,17 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (lane == 0) {
-            for (uint32_t r = warp; r < nbox; r += NT / 32) {
-                const uint64_t row = ((b << n) + base + box_off[r]) >> kAmpsPerRowShift;
-                tma_store_row(&tmap, smem_raw + (size_t)s * buf_stride + ((size_t)r << box_bits) * sizeof(V), (int)row);
-            }
+            const uint32_t src = smem_s + (uint32_t)s * buf_stride;
+            for (uint32_t r = warp; r < nbox; r += NT / 32)
+                asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %2, %2, %2}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmap)), "r"(src + r * box_bytes), "r"(0), "r"((int)(trow[0] + box_row[r]))
+                             : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
 #pragma unroll
-        for (int i = 0; i < kStages - 1; i++) tq[i] = tq[i + 1];
+        for (int i = 0; i < kStages - 1; i++) { tq[i] = tq[i + 1]; trow[i] = trow[i + 1]; }
         tq[kStages - 1] = tq[kStages - 1] == ~0ull ? ~0ull : next_active(tq[kStages - 1] + gridDim.x);
+        trow[kStages - 1] = tq[kStages - 1] == ~0ull ? 0u : tile_row(tq[kStages - 1]);
         if (++s == kStages) { s = 0; parity ^= 1u; }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
