@@ -20,13 +20,15 @@ static int env_int(const char *name, int dflt)
 State::State(int n_qubits, int prec, int dev, int nbatch)
     : n(n_qubits), precision(prec), device(dev), batch(nbatch), queue(std::max(1, n_qubits), std::max(1, nbatch), PlanOptions())
 {
-    construct(0, 1, nullptr);
+    try { construct(0, 1, nullptr); }
+    catch (...) { release(); throw; }
 }
 
 State::State(int n_qubits, int prec, int dev, int nbatch, int rank, int world, const uint8_t *nccl_id)
     : n(n_qubits), precision(prec), device(dev), batch(nbatch), queue(std::max(1, n_qubits), std::max(1, nbatch), PlanOptions())
 {
-    construct(rank, world, nccl_id);
+    try { construct(rank, world, nccl_id); }
+    catch (...) { release(); throw; }
 }
 
 void State::construct(int rank, int world, const uint8_t *nccl_id)
@@ -79,14 +81,21 @@ void State::construct(int rank, int world, const uint8_t *nccl_id)
     reset();
 }
 
-State::~State()
+State::~State() { release(); }
+
+void State::release()
 {
-    cudaSetDevice(device);
+    if (device >= 0) cudaSetDevice(device);
     if (stream_) cudaStreamSynchronize(stream_);
     dist_destroy();
     cudaFree(d_state_); cudaFree(d_diag_); cudaFree(d_flags_); cudaFree(d_partial_); cudaFree(d_small_);
     cudaFree(d_outcome_); cudaFree(d_counters_); cudaFree(d_forced_); cudaFree(d_lvl1_); cudaFree(d_lvl2_);
+    d_state_ = d_diag_ = nullptr;
+    d_flags_ = nullptr; d_partial_ = d_small_ = d_lvl1_ = d_lvl2_ = nullptr;
+    d_outcome_ = nullptr; d_counters_ = nullptr; d_forced_ = nullptr;
     if (stream_) cudaStreamDestroy(stream_);
+    stream_ = nullptr;
+    cudaGetLastError();
 }
 
 void State::reset()

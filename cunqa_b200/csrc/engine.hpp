@@ -22,8 +22,10 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 #define CB200_CUDA(call)                                                                              \
     do {                                                                                              \
         cudaError_t e_ = (call);                                                                      \
-        if (e_ != cudaSuccess)                                                                        \
+        if (e_ != cudaSuccess) {                                                                      \
+            cudaGetLastError(); /* clear the (non-sticky) error so that later launch checks are clean */ \
             throw cb200::CudaError(std::string(#call) + " failed: " + cudaGetErrorString(e_));        \
+        }                                                                                             \
     } while (0)
 
 struct Stats {
@@ -85,6 +87,7 @@ public:
 
 private:
     void construct(int rank, int world, const uint8_t *nccl_id);
+    void release();  // frees every device resource (also used when construction fails half-way)
     void dist_init(int rank, int world, const uint8_t *id);
     void dist_destroy();
     void dist_fence();
