@@ -98,7 +98,8 @@ class ClockSampler:
 
 
 def cpu_sample(target_seconds=12.0, max_qubits=28):
-    """time the CPU oracle (gate-by-gate, OpenMP) on a bounded QV sample; -> dict for `cpu_baseline`"""
+    """time the CPU oracle (OpenMP over all host cores) on a bounded QV sample, gate by gate AND with greedy
+    <=4-qubit block fusion (Aer-like), and report the faster of the two; -> dict for `cpu_baseline`"""
     import numpy as np
     from cunqa_b200 import circuits as C
     from oracle import oracle_np as O
@@ -112,19 +113,34 @@ def cpu_sample(target_seconds=12.0, max_qubits=28):
     while n > 20 and 16 * 2 ** n / 2 ** 30 > 0.4 * avail_gb:
         n -= 1
     ins = C.quantum_volume(n, depth=QV_QUBITS, seed=SEED)
-    st = O.COracleState(n)
-    done, t0 = 0, time.perf_counter()
-    for inst in ins:
-        O.apply_gate(st, inst)
-        done += 1
-        if done >= n // 2 and time.perf_counter() - t0 > target_seconds:
-            break
-    dt = time.perf_counter() - t0
-    value = done * 2.0 ** n / 2.0 ** QV_QUBITS / dt
+    best = None
+    for mode in ("unfused", "fused<=4q"):
+        st = O.COracleState(n)
+        done, t0 = 0, time.perf_counter()
+        if mode == "unfused":
+            for inst in ins:
+                O.apply_gate(st, inst)
+                done += 1
+                if done >= n // 2 and time.perf_counter() - t0 > target_seconds / 2:
+                    break
+        else:
+            blocks = O.fuse_blocks(ins[:4 * (n // 2)], kmax=4)  # fusion cost is host work outside the timed loop
+            t0 = time.perf_counter()
+            for qs, m in blocks:
+                st.apply_matrix(qs, m)
+                done += 2 if len(qs) == 4 else 1
+                if time.perf_counter() - t0 > target_seconds / 2:
+                    break
+        dt = time.perf_counter() - t0
+        value = done * 2.0 ** n / 2.0 ** QV_QUBITS / dt
+        if best is None or value > best[0]:
+            best = (value, mode, done, dt)
+        del st
+    value, mode, done, dt = best
     return {"value": value, "unit": "gates/s", "cores": cores, "kind": "port",
-            "sample": f"first {done} gates of the same seeded QV circuit at {n} qubits ({16 * 2 ** n / 2 ** 30:.0f} GiB state) in {dt:.1f} s, "
-                      f"scaled by 2^{n}/2^{QV_QUBITS} to the 33-qubit state; oracle/sv_oracle.c, unfused, OpenMP x{cores} "
-                      f"(CPU restatement of the Aer statevector algorithm, not Aer)"}, dt
+            "sample": f"{done} gates of the same seeded QV circuit at {n} qubits ({16 * 2 ** n / 2 ** 30:.0f} GiB state) in {dt:.1f} s ({mode}, the faster "
+                      f"of gate-by-gate and greedy <=4-qubit block fusion), scaled by 2^{n}/2^{QV_QUBITS} to the 33-qubit state; "
+                      f"oracle/sv_oracle.c, OpenMP x{cores} (CPU restatement of the Aer statevector algorithm, not Aer)"}, dt
 
 
 def run_reference(args):

@@ -696,6 +696,41 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
     return counters
 
 
+def fuse_blocks(instructions, kmax=4):
+    """Greedy fusion of consecutive gates into dense blocks of <= kmax qubits (the idea of Aer's CPU fusion
+    pass: fewer sweeps over the state at the price of larger matrices).  Used only by the CPU-baseline legs of
+    bench.py so that the baseline is not handicapped by running gate by gate.  -> list of (qubits, matrix)"""
+    blocks, cur_q, cur_ins = [], [], []
+
+    def close():
+        if not cur_ins:
+            return
+        k = len(cur_q)
+        m = np.eye(1 << k, dtype=complex)
+        for col in range(1 << k):
+            st = NumpyState(k)
+            st.v[:] = 0
+            st.v[col] = 1
+            for inst in cur_ins:
+                apply_gate(st, inst, qmap=lambda q: cur_q.index(q))
+            m[:, col] = st.v
+        blocks.append((list(cur_q), m))
+
+    for inst in instructions:
+        if inst["name"] in ("measure", "barrier", "save_state", "id"):
+            continue
+        qs = list(inst["qubits"])
+        union = cur_q + [q for q in qs if q not in cur_q]
+        if len(union) > kmax and cur_ins:
+            close()
+            cur_q, cur_ins = [], []
+            union = qs
+        cur_q = union
+        cur_ins.append(inst)
+    close()
+    return blocks
+
+
 # ----------------------------------------------------------------------------------------------
 # analytic known answers
 # ----------------------------------------------------------------------------------------------

@@ -128,3 +128,16 @@ def test_terminal_sampling_is_distribution_equivalent(lib_built):
     a = O.run_dynamic(task, shots, seed=1, terminal_sampling=True)["t"]
     b = O.run_dynamic(task, shots, seed=2, terminal_sampling=False)["t"]
     assert O.tvd(a, b) < 0.5 * math.sqrt(8 / shots) + 0.03
+
+
+def test_block_fusion_for_the_cpu_baseline(lib_built):
+    """oracle-side greedy <=4-qubit fusion (bench.py's CPU baseline) is an exact regrouping"""
+    n = 9
+    ins = C.quantum_volume(n, depth=5, seed=3) + random_circuit(n, 40, 2)
+    ref, _ = O.run_static(ins, n, backend="numpy")
+    blocks = O.fuse_blocks(ins, kmax=4)
+    assert len(blocks) < len(ins) and all(len(q) <= 5 for q, _ in blocks)
+    st = O.COracleState(n)
+    for qs, m in blocks:
+        st.apply_matrix(qs, m)
+    assert np.abs(st.amplitudes() - ref.amplitudes()).max() < 1e-12
