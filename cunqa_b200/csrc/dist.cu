@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -67,27 +68,52 @@ struct DistContext {
     ncclComm_t comm = nullptr;
     std::vector<void *> peers;  // shard base pointer of every rank (own entry = local pointer)
     int *d_fence = nullptr;
-    uint64_t swaps = 0, swap_bytes = 0;
+    uint64_t swaps = 0, exchanges = 0, swap_bytes = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> swap_events;  // fence-to-fence span of every swap
     double swap_ms = 0.0;
 };
 
-// A = the rank whose global bit is 0.  Pair element g (bit lbit removed): A's amplitude insert0(g)|1<<lbit
-// is exchanged with B's amplitude insert0(g).  This rank handles g in [lo, hi).
+// In-place exchange of m (global bit, local bit) pairs over peer memory (NVLink P2P), all m at once.
+// Write x for this rank's values of the m global bits and y for an amplitude's values of the m local bits: the
+// amplitude (rank x, local y) trades places with (rank y, local x), everything else fixed -- a transposition, so
+// slabs with y == x stay put and each rank talks to its 2^m - 1 partners directly (one hop through the NVSwitch,
+// (2^m - 1)/2^m of the shard sent instead of m/2 for m single exchanges).  Each unordered pair {x, y} is split
+// between its two ranks: the smaller x handles the lower half of the remaining index space, the larger the upper.
+struct SwapPlan {
+    void *peer[16];   // by y (entry x unused)
+    int m, n_local;
+    int lbit[4];      // ascending
+    int perm[4];      // lbit[j] belongs to pair perm[j] (bit perm[j] of x / y)
+    uint32_t x;
+};
+
 template <typename V>
-__global__ void __launch_bounds__(256) qubit_swap_kernel(V *__restrict__ mine, V *__restrict__ peer, int lbit,
-                                                         uint64_t lo, uint64_t hi, int mybit)
+__global__ void __launch_bounds__(256) qubit_swap_kernel(V *__restrict__ mine, const __grid_constant__ SwapPlan sp)
 {
+    const int rest_bits = sp.n_local - sp.m - 1;  // index bits of one half of one slab
+    const uint64_t half = 1ull << rest_bits;
+    const uint64_t total = (uint64_t)((1u << sp.m) - 1) << rest_bits;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t bit = 1ull << lbit;
-    for (uint64_t g = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < hi; g += stride) {
-        const uint64_t i0 = insert0_64(g, (uint32_t)lbit);
-        const uint64_t mi = mybit ? i0 : (i0 | bit);
-        const uint64_t pi = mybit ? (i0 | bit) : i0;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+        uint32_t y = (uint32_t)(w >> rest_bits);
+        if (y >= sp.x) y++;
+        uint64_t r = (w & (half - 1)) | (sp.x < y ? 0 : half);
+        uint64_t mi = r, pi;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (j < sp.m) mi = insert0_64(mi, (uint32_t)sp.lbit[j]);
+        pi = mi;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (j < sp.m) {
+                mi |= (uint64_t)((y >> sp.perm[j]) & 1u) << sp.lbit[j];
+                pi |= (uint64_t)((sp.x >> sp.perm[j]) & 1u) << sp.lbit[j];
+            }
+        V *__restrict__ theirs = (V *)sp.peer[y];
         const V a = mine[mi];
-        const V b = peer[pi];
+        const V b = theirs[pi];
         mine[mi] = b;
-        peer[pi] = a;
+        theirs[pi] = a;
     }
 }
 
@@ -97,30 +123,43 @@ void State::dist_fence()
     stats.launches++;
 }
 
-void State::dist_swap(int gbit, int lbit)
+void State::dist_swap(const std::vector<std::pair<int, int>> &pairs)
 {
     if ((int)dist->peers.size() != dist->world) throw InvalidArg("sharded state: peer handles were not imported");
-    const int partner = dist->rank ^ (1 << gbit);
-    const int mybit = (dist->rank >> gbit) & 1;
-    const uint64_t pairs = 1ull << (n_local_ - 1);
-    const uint64_t lo = mybit ? pairs / 2 : 0, hi = mybit ? pairs : pairs / 2;
+    const int m = (int)pairs.size();
+    if (m < 1 || m > 4 || m >= n_local_) throw InvalidArg("sharded state: 1..4 qubit pairs per exchange");
+    SwapPlan sp{};
+    sp.m = m;
+    sp.n_local = n_local_;
+    std::vector<int> order(m);
+    for (int j = 0; j < m; j++) order[j] = j;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return pairs[a].second < pairs[b].second; });
+    for (int j = 0; j < m; j++) { sp.lbit[j] = pairs[order[j]].second; sp.perm[j] = order[j]; }
+    uint32_t x = 0;
+    for (int j = 0; j < m; j++) x |= (uint32_t)((dist->rank >> pairs[j].first) & 1) << j;
+    sp.x = x;
+    for (uint32_t y = 0; y < (1u << m); y++) {
+        int r = dist->rank;
+        for (int j = 0; j < m; j++) r = (r & ~(1 << pairs[j].first)) | (int)((y >> j) & 1u) << pairs[j].first;
+        sp.peer[y] = dist->peers[r];
+    }
+    const uint64_t total = (uint64_t)((1u << m) - 1) << (n_local_ - m - 1);
     cudaEvent_t e0, e1;
     CB200_CUDA(cudaEventCreate(&e0));
     CB200_CUDA(cudaEventCreate(&e1));
-    dist_fence();  // both shards quiescent
+    dist_fence();  // every shard quiescent
     CB200_CUDA(cudaEventRecord(e0, stream_));
-    const int blocks = (int)std::min<uint64_t>((hi - lo + 255) / 256, (uint64_t)num_sms_ * 16);
-    if (precision == 64)
-        qubit_swap_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_, (double2 *)dist->peers[partner], lbit, lo, hi, mybit);
-    else
-        qubit_swap_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, (float2 *)dist->peers[partner], lbit, lo, hi, mybit);
+    const int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)num_sms_ * 16);
+    if (precision == 64) qubit_swap_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_, sp);
+    else qubit_swap_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, sp);
     CB200_CUDA(cudaGetLastError());
-    dist_fence();  // the partner's writes into this shard have landed
+    dist_fence();  // the partners' writes into this shard have landed
     CB200_CUDA(cudaEventRecord(e1, stream_));
     dist->swap_events.emplace_back(e0, e1);
     stats.launches++;
-    dist->swaps++;
-    dist->swap_bytes += state_bytes_ / 2;  // sent (= received) per rank
+    dist->swaps += m;
+    dist->exchanges++;
+    dist->swap_bytes += (state_bytes_ >> m) * ((1u << m) - 1);  // sent (= received) per rank
 }
 
 template <typename T>
@@ -130,13 +169,23 @@ void State::flush_dist_t()
     if (ops.empty()) return;
     CB200_CUDA(cudaSetDevice(device));
     const DistPlan plan = plan_distributed(ops, n, n_local_, dist->rank);
+    static const int max_group = getenv("CB200_SWAP_GROUP") ? std::max(1, std::min(4, atoi(getenv("CB200_SWAP_GROUP")))) : 4;
+    std::vector<std::pair<int, int>> group;  // back-to-back swaps become one multi-qubit exchange
+    auto exchange = [&]() {
+        if (!group.empty()) dist_swap(group);
+        group.clear();
+    };
     for (const DistSegment &seg : plan.segments) {
-        if (seg.is_swap) dist_swap(seg.gbit, seg.lbit);
-        else {
+        if (seg.is_swap) {
+            group.emplace_back(seg.gbit, seg.lbit);
+            if ((int)group.size() == max_group) exchange();
+        } else {
+            exchange();
             std::vector<HostOp> local = seg.ops;
             launch_ops_t<T>(local);
         }
     }
+    exchange();
     for (int &p : queue.l2p) p = plan.sigma[p];
     queue.clear_pending();
 }

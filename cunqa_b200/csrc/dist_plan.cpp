@@ -36,34 +36,50 @@ DistPlan plan_distributed(const std::vector<HostOp> &ops, int n_total, int n_loc
         HostOp op = ops[i];
         for (int &x : op.q) x = sigma[x];
         for (int &x : op.ctrl) x = sigma[x];
-        // non-diagonal targets on global positions: bring them in
+        // non-diagonal targets on global positions: bring them in.  When one swap is needed, every global qubit
+        // that some op within the look-ahead window also needs non-diagonally is brought in at the same time, so
+        // that exchanges cluster (back-to-back swaps) and the local segments between them stay long.
         if (op.kind != HostOp::DIAG) {
-            for (size_t m = 0; m < op.q.size(); m++) {
-                if (op.q[m] < n_local) continue;
+            bool need_swap = false;
+            for (int x : op.q) if (x >= n_local) need_swap = true;
+            if (need_swap) {
                 flush_cur();
-                const int gpos = op.q[m];
-                // victim: a high local position (large contiguous halves), not used by this op, whose next
-                // non-diagonal use lies farthest in the future
-                int best = -1;
-                size_t best_use = 0;
-                const uint64_t mine = op.qmask();
-                for (int lp = n_local - 1; lp >= std::max(0, n_local - 6); lp--) {
-                    if ((mine >> lp) & 1ull) continue;
-                    const size_t use = next_x_use(ops, i + 1, inv[lp]);
-                    if (best < 0 || use > best_use) { best = lp; best_use = use; }
+                const size_t window = 4096;
+                std::vector<std::pair<size_t, int>> wanted;  // (first non-diagonal use, global position)
+                for (int gp = n_local; gp < n_total; gp++) {
+                    const size_t use = next_x_use(ops, i, inv[gp]);
+                    if (use < std::min(ops.size(), i + window)) wanted.emplace_back(use, gp);
                 }
-                if (best < 0) throw std::runtime_error("distributed planner: no local qubit available for a global swap");
-                DistSegment sw;
-                sw.is_swap = true;
-                sw.gbit = gpos - n_local;
-                sw.lbit = best;
-                plan.segments.push_back(sw);
-                const int og = inv[gpos], ol = inv[best];
-                sigma[og] = best; sigma[ol] = gpos;
-                inv[best] = og; inv[gpos] = ol;
-                // re-map this op through the updated placement
-                for (int &x : op.q) if (x == gpos) x = best; else if (x == best) x = gpos;
-                for (int &x : op.ctrl) if (x == gpos) x = best; else if (x == best) x = gpos;
+                std::sort(wanted.begin(), wanted.end());
+                uint64_t taken = 0;  // local positions already used as victims in this batch
+                for (auto &w : wanted) {
+                    const int gpos = w.second;
+                    // victim: a high local position (large contiguous halves) whose next non-diagonal use lies
+                    // farthest in the future, not touched by the op that triggered the exchange
+                    int best = -1;
+                    size_t best_use = 0;
+                    const uint64_t mine = op.qmask();
+                    for (int lp = n_local - 1; lp >= std::max(0, n_local - 8); lp--) {
+                        if (((mine | taken) >> lp) & 1ull) continue;
+                        const size_t use = next_x_use(ops, i, inv[lp]);
+                        if (best < 0 || use > best_use) { best = lp; best_use = use; }
+                    }
+                    if (best < 0) throw std::runtime_error("distributed planner: no local qubit available for a global swap");
+                    if (best_use <= w.first && w.first != i) continue;  // the victim is needed even sooner: not worth it
+                    taken |= 1ull << best;
+                    DistSegment sw;
+                    sw.is_swap = true;
+                    sw.gbit = gpos - n_local;
+                    sw.lbit = best;
+                    plan.segments.push_back(sw);
+                    const int og = inv[gpos], ol = inv[best];
+                    sigma[og] = best; sigma[ol] = gpos;
+                    inv[best] = og; inv[gpos] = ol;
+                    for (int &x : op.q) if (x == gpos) x = best; else if (x == best) x = gpos;
+                    for (int &x : op.ctrl) if (x == gpos) x = best; else if (x == best) x = gpos;
+                }
+                for (int x : op.q)
+                    if (x >= n_local) throw std::runtime_error("distributed planner: internal error (target still global)");
             }
         }
         // controls on global positions

@@ -428,7 +428,6 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
     const auto t0 = std::chrono::high_resolution_clock::now();
     std::map<std::string, std::map<std::string, uint64_t>> counters;
     for (const TaskCfg &c : cfgs) counters[c.id];
-    Stats acc;
     if (shots == 0) B = 1;
     State *stp = shots ? &get_state(n_total, precision, (int)B) : nullptr;
     const Stats before = stp ? stp->stats : Stats();
@@ -762,7 +761,6 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
         last_stats.d2h_bytes -= before.d2h_bytes;
         last_stats.gates = stp->queue.gates - gates_before;
     }
-    (void)acc;
     return out;
 }
 

@@ -352,7 +352,7 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
         std::sort(fix.begin(), fix.end());
         if ((int)fix.size() > kMaxFix) { err = "too many in-tile controls"; return false; }
         d.nfix = (uint8_t)fix.size();
-        for (size_t f = 0; f < fix.size(); f++) d.fixpos[f] = (uint8_t)fix[f];
+        for (int f = 0; f < d.nfix && f < kMaxFix; f++) d.fixpos[f] = (uint8_t)fix[f];
         if (op.kind == HostOp::DENSE) {
             const int sc = 2 * (1 << (2 * d.k));
             if (mat_used + sc > kMatScalars) { err = "pass matrix storage exhausted"; return false; }

@@ -632,7 +632,6 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
 
     const uint64_t total_tiles = p.tiles_per_state * (uint64_t)p.batch;
     const int tps_shift = n - t;  // tiles_per_state = 2^(n-t)
-    constexpr bool cond = COND;
     // tile number -> amplitude offset of the tile inside the whole buffer (state b, base within the state)
     auto tile_base = [&](uint64_t tileno, uint64_t &b) -> uint64_t {
         b = tileno >> tps_shift;
@@ -643,13 +642,16 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     // next tile of this CTA (stride gridDim.x) that some op acts on; ~0 = none.  Evaluated identically by
     // every thread, so the tile sequence lives in registers and needs no shared bookkeeping.
     auto next_active = [&](uint64_t from) -> uint64_t {
-        if (!cond) return from < total_tiles ? from : ~0ull;
-        for (uint64_t x = from; x < total_tiles; x += gridDim.x) {
-            uint64_t b;
-            const uint64_t base = tile_base(x, b);
-            if (active_ops(p, flags, b, base) != 0) return x;
+        if constexpr (!COND) {
+            return from < total_tiles ? from : ~0ull;
+        } else {
+            for (uint64_t x = from; x < total_tiles; x += gridDim.x) {
+                uint64_t b;
+                const uint64_t base = tile_base(x, b);
+                if (active_ops(p, flags, b, base) != 0) return x;
+            }
+            return ~0ull;
         }
-        return ~0ull;
     };
     const uint32_t smem_s = smem_u32(smem_raw);
     const uint32_t box_bytes = (uint32_t)sizeof(V) << box_bits;

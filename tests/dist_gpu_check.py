@@ -120,7 +120,8 @@ def main():
                               "gates_per_s": C.n_gates(ins) / (ms / 1e3), "tile_passes_per_rank": passes, "qubit_swaps": swaps,
                               "shard_GiB": shard / 2 ** 30, "max_abs_err_vs_closed_form": err, "norm": nrm,
                               "local_GBps_per_gpu": 2 * shard * passes / (ms / 1e3) / 1e9,
-                              "swap_GB_sent_per_gpu": (d1["swap_bytes_sent"] - d0["swap_bytes_sent"]) / 1e9}), flush=True)
+                              "swap_GB_sent_per_gpu": (d1["swap_bytes_sent"] - d0["swap_bytes_sent"]) / 1e9,
+                              "swap_ms_last_rep": d1["swap_ms"] - d0["swap_ms"]}), flush=True)
         sv.close()
     dist.barrier()
     dist.destroy_process_group()
