@@ -366,7 +366,7 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
     }
     out.n_ops = nops;
     out.n_mat = mat_used;
-    out.needs_full = 0;
+    out.needs_full = out.n_diag > 0;  // the lean kernel variant carries no diagonal-run code
     for (int o = 0; o < nops; o++) {
         const DevOp &d = out.ops[o];
         if (d.kind == OP_DENSE && d.k >= 3) out.needs_full = 1;
@@ -376,6 +376,58 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
                 out.needs_full = 1;
         }
     }
+    // Runs of consecutive diagonal ops are applied with 16 amplitudes per thread in registers: the 2^4 settings of
+    // four "register bits" of the tile index (op_diag_block).  A table none of whose qubits is a register bit costs
+    // one lookup per thread instead of one per amplitude, so pick the bits the run's tables depend on least.  When
+    // an uncontrolled dense gate of <= 2 qubits follows the run, its targets are register bits and the gate is
+    // applied in the same sweep (fixpos[0] = its width).  tbit[0..3] = register bits, tbit[4..7] = the same, ascending.
+    if (t >= 4)
+        for (int o = 0; o < nops;) {
+            if (out.ops[o].kind != OP_DIAG) { o++; continue; }
+            int oe = o;
+            while (oe + 1 < nops && out.ops[oe + 1].kind == OP_DIAG) oe++;
+            std::vector<int> rb;
+            int fuse_k = 0;
+            if (oe + 1 < nops) {
+                const DevOp &dn = out.ops[oe + 1];
+                if (dn.kind == OP_DENSE && dn.k <= 2 && dn.nfix == dn.k && dn.ctrl_out == 0 && !dn.has_mask) {
+                    fuse_k = dn.k;
+                    for (int m = 0; m < dn.k; m++) rb.push_back(dn.tbit[m]);
+                }
+            }
+            std::vector<int> users(t, 0);
+            for (int q = o; q <= oe; q++)
+                for (int pos = 0; pos < t; pos++) users[pos] += (out.ops[q].ctrl_in >> pos) & 1u;
+            std::vector<int> cand;
+            for (int pos = 0; pos < t; pos++)
+                if (std::find(rb.begin(), rb.end(), pos) == rb.end()) cand.push_back(pos);
+            // fewest dependent tables first; then bits >= 3 (a warp then reads whole 128-byte rows); then high bits
+            std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
+                if (users[a] != users[b]) return users[a] < users[b];
+                if ((a < 3) != (b < 3)) return b < 3;
+                return a > b;
+            });
+            for (size_t ci = 0; rb.size() < 4; ci++) rb.push_back(cand[ci]);
+            std::vector<int> asc = rb;
+            std::sort(asc.begin(), asc.end());
+            // diagonal ops commute: the tables that ignore the register bits go first (fixpos[1] of them)
+            uint32_t rmask = 0;
+            for (int b : rb) rmask |= 1u << b;
+            std::stable_partition(out.ops + o, out.ops + oe + 1, [&](const DevOp &x) { return (x.ctrl_in & rmask) == 0; });
+            const int slot0 = std::min_element(out.ops + o, out.ops + oe + 1,
+                                               [](const DevOp &a, const DevOp &b) { return a.k2 < b.k2; })->k2;
+            int n_indep = 0;
+            for (int q = o; q <= oe; q++) {
+                out.ops[q].k2 = (uint8_t)(slot0 + (q - o));
+                out.diag_op[slot0 + (q - o)] = (uint8_t)q;
+                n_indep += (out.ops[q].ctrl_in & rmask) == 0;
+            }
+            DevOp &run = out.ops[o];
+            for (int b = 0; b < 4; b++) { run.tbit[b] = (uint8_t)rb[b]; run.tbit[4 + b] = (uint8_t)asc[b]; }
+            run.fixpos[0] = (uint8_t)fuse_k;
+            run.fixpos[1] = (uint8_t)n_indep;
+            o = oe + 1;
+        }
     out.cond_mask = 0;
     for (int o = 0; o < nops; o++)
         if (out.ops[o].ctrl_out != 0 || out.ops[o].has_mask) out.cond_mask |= 1ull << o;

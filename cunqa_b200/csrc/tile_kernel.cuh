@@ -285,78 +285,98 @@ __device__ __forceinline__ void op_perm(typename Vec2<T>::type *tile, const DevO
 }
 
 // ---- diagonal runs with the thread's amplitudes resident in registers -----------------------------
-// Each thread owns A = 2^t / NT amplitudes.  The tables are walked in the OUTER loop so that the A table
-// loads of one table are independent and in flight together (the lookups are L2-latency bound otherwise).
-template <typename T, int A>
-__device__ __forceinline__ void diag_run_regs(typename Vec2<T>::type (&v)[A], const uint32_t (&ti)[A],
-                                              const typename Vec2<T>::type *__restrict__ diag_tabs,
-                                              const uint16_t *lut, const uint32_t *dhi, int s0, int s1)
-{
-    using V = typename Vec2<T>::type;
-    for (int sl = s0; sl <= s1; sl++) {
-        const uint16_t *L = lut + sl * kDiagLut;
-        const uint32_t base = dhi[sl];
-        V q[A];
-#pragma unroll
-        for (int k = 0; k < A; k++) q[k] = diag_tabs[base + (uint32_t)(L[ti[k] & 63u] | L[64 + (ti[k] >> 6)])];
-#pragma unroll
-        for (int k = 0; k < A; k++) v[k] = cmul<V, T>(q[k].x, q[k].y, v[k]);
-    }
-}
-
-// standalone diagonal run: one sweep, amplitudes i = tid + k*NT
-template <typename T, int NT, int A>
-__device__ __forceinline__ void op_diag_run(typename Vec2<T>::type *tile, const typename Vec2<T>::type *__restrict__ diag_tabs,
-                                            const uint16_t *lut, const uint32_t *dhi, int s0, int s1, const int tid)
-{
-    using V = typename Vec2<T>::type;
-    V v[A];
-    uint32_t ti[A];
-#pragma unroll
-    for (int k = 0; k < A; k++) { ti[k] = tid + k * NT; v[k] = tile[swz<T>(ti[k])]; }
-    diag_run_regs<T, A>(v, ti, diag_tabs, lut, dhi, s0, s1);
-#pragma unroll
-    for (int k = 0; k < A; k++) tile[swz<T>(ti[k])] = v[k];
-}
-
-// diagonal run folded into the uncontrolled dense K-qubit gate that follows it (K <= 2): A amplitudes =
-// A >> K complete groups per thread, phases applied in registers before the butterfly
-template <typename T, int K, int NT, int A>
-__device__ __forceinline__ void op_diag_dense(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
+// Each thread owns 16 amplitudes: the 2^4 settings of four "register bits" rb[0..3] of the tile index, chosen per
+// run by the host (encode_pass) among the tile bits the run's tables depend on least.  The in-tile part of a
+// table index is a bit-extract of the tile index, which is additive over disjoint bit sets: index(k) =
+// pext(thread bits) | OR_b pext(1 << rb[b]) for the bits b set in k.  A table none of whose qubits is a register
+// bit therefore costs ONE lookup and one complex multiply per thread (its factor is folded into `acc`, applied to
+// the 16 amplitudes once per run); only tables that do depend on register bits are looked up per amplitude, and
+// then the tables are walked in the outer loop so that the loads of one table are in flight together.  (Not inlined:
+// the block's register allocation must not disturb the dense-gate paths of the kernel.)
+// K > 0: the run is folded into the uncontrolled dense K-qubit gate that follows it (register bits 0..K-1 are the
+// gate's targets): phases applied in registers before the butterfly, one sweep, one barrier.
+template <typename T, int K, int NT>
+__device__ __noinline__ void op_diag_block(typename Vec2<T>::type *tile, const DevOp &run, const T *mat,
                                               const typename Vec2<T>::type *__restrict__ diag_tabs,
                                               const uint16_t *lut, const uint32_t *dhi, int s0, int s1, const int tid)
 {
     using V = typename Vec2<T>::type;
-    constexpr int D = 1 << K, G = A >> K;
-    uint32_t off[D];
+    constexpr int A = 16;
+    uint32_t bi = tid;
 #pragma unroll
-    for (int j = 0; j < D; j++) {
-        uint32_t o = 0;
+    for (int f = 0; f < 4; f++) bi = insert0(bi, run.tbit[4 + f]);  // ascending register-bit positions
+    uint32_t rbit[4];
 #pragma unroll
-        for (int m = 0; m < K; m++) if ((j >> m) & 1) o |= 1u << op.tbit[m];
-        off[j] = o;
-    }
+    for (int b = 0; b < 4; b++) rbit[b] = 1u << run.tbit[b];
     V v[A];
-    uint32_t ti[A];
+    // tile index of amplitude k (k is a compile-time constant wherever this is called: at most three ORs)
+    auto ti = [&](int k) -> uint32_t {
+        return bi | ((k & 1) ? rbit[0] : 0u) | ((k & 2) ? rbit[1] : 0u) | ((k & 4) ? rbit[2] : 0u) | ((k & 8) ? rbit[3] : 0u);
+    };
 #pragma unroll
-    for (int g = 0; g < G; g++) {
-        uint32_t idx = tid + g * NT;
-        for (int f = 0; f < K; f++) idx = insert0(idx, op.fixpos[f]);
+    for (int k = 0; k < A; k++) v[k] = tile[swz<T>(ti(k))];
+    V acc;
+    acc.x = (T)1;
+    acc.y = (T)0;
+    // tables that ignore the register bits come first in the run (host order): one lookup per thread each, four
+    // tables' loads in flight together, their product applied to the 16 amplitudes once
+    int sl = s0;
+    const int s_indep = s0 + run.fixpos[1];
+    auto index_of = [&](int s) -> uint32_t {
+        const uint16_t *L = lut + s * kDiagLut;
+        return dhi[s] + (uint32_t)(L[bi & 63u] | L[64 + (bi >> 6)]);
+    };
+    for (; sl + 4 <= s_indep; sl += 4) {
+        uint32_t ix[4];
+        V q[4];
 #pragma unroll
-        for (int j = 0; j < D; j++) { ti[g * D + j] = idx | off[j]; v[g * D + j] = tile[swz<T>(idx | off[j])]; }
+        for (int j = 0; j < 4; j++) ix[j] = index_of(sl + j);
+#pragma unroll
+        for (int j = 0; j < 4; j++) q[j] = diag_tabs[ix[j]];
+        const V q01 = cmul<V, T>(q[0].x, q[0].y, q[1]), q23 = cmul<V, T>(q[2].x, q[2].y, q[3]);
+        acc = cmul<V, T>(acc.x, acc.y, cmul<V, T>(q01.x, q01.y, q23));
     }
-    diag_run_regs<T, A>(v, ti, diag_tabs, lut, dhi, s0, s1);
-    T mr[D * D], mi[D * D];
+    for (; sl < s_indep; sl++) {
+        const V q = diag_tabs[index_of(sl)];
+        acc = cmul<V, T>(q.x, q.y, acc);
+    }
+    for (; sl <= s1; sl++) {
+        const uint16_t *L = lut + sl * kDiagLut;
+        const uint32_t i0 = index_of(sl);
+        uint32_t e[4];
 #pragma unroll
-    for (int e = 0; e < D * D; e++) { mr[e] = mat[2 * e]; mi[e] = mat[2 * e + 1]; }
+        for (int b = 0; b < 4; b++) e[b] = L[rbit[b] & 63u] | L[64 + (rbit[b] >> 6)];  // one of the two is entry 0 == 0
 #pragma unroll
-    for (int g = 0; g < G; g++) {
+        for (int h = 0; h < A; h += 8) {  // two batches of 8 independent loads (register budget)
+            V q[8];
 #pragma unroll
-        for (int r = 0; r < D; r++) {
-            V acc = cmul<V, T>(mr[r * D], mi[r * D], v[g * D]);
+            for (int j = 0; j < 8; j++) {
+                const int k = h + j;
+                q[j] = diag_tabs[i0 + (((k & 1) ? e[0] : 0u) | ((k & 2) ? e[1] : 0u) | ((k & 4) ? e[2] : 0u) | ((k & 8) ? e[3] : 0u))];
+            }
 #pragma unroll
-            for (int cc = 1; cc < D; cc++) cfma<V, T>(acc, mr[r * D + cc], mi[r * D + cc], v[g * D + cc]);
-            tile[swz<T>(ti[g * D + r])] = acc;
+            for (int j = 0; j < 8; j++) v[h + j] = cmul<V, T>(q[j].x, q[j].y, v[h + j]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < A; k++) v[k] = cmul<V, T>(acc.x, acc.y, v[k]);
+    if constexpr (K == 0) {
+#pragma unroll
+        for (int k = 0; k < A; k++) tile[swz<T>(ti(k))] = v[k];
+    } else {
+        constexpr int D = 1 << K, G = A >> K;
+        T mr[D * D], mi[D * D];
+#pragma unroll
+        for (int e2 = 0; e2 < D * D; e2++) { mr[e2] = mat[2 * e2]; mi[e2] = mat[2 * e2 + 1]; }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+#pragma unroll
+            for (int r = 0; r < D; r++) {
+                V o = cmul<V, T>(mr[r * D], mi[r * D], v[g * D]);
+#pragma unroll
+                for (int cc = 1; cc < D; cc++) cfma<V, T>(o, mr[r * D + cc], mi[r * D + cc], v[g * D + cc]);
+                tile[swz<T>(ti(g * D + r))] = o;
+            }
         }
     }
 }
@@ -417,6 +437,7 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                 op_pair_dispatch<T, NT, FULL>(tile, op, mats + op.mat_off, t, tid);
                 __syncthreads();
             } else if (op.kind == OP_DIAG) {
+                if constexpr (FULL) {  // passes with diagonal ops always take the FULL kernel (needs_full)
                 // a run of consecutive diagonal ops is applied in ONE sweep of the tile
                 int oe = o;
                 while (oe + 1 < p.n_ops && p.ops[oe + 1].kind == OP_DIAG) oe++;
@@ -424,18 +445,17 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                     // table index = dhi (bits taken from the tile base, filled once per tile by the caller)
                     //             | pext(tile index, in-tile mask) through the per-op LUTs
                     const int s0 = op.k2, s1 = p.ops[oe].k2;
-                    if (!COND && oe + 1 < p.n_ops && p.ops[oe + 1].kind == OP_DENSE && p.ops[oe + 1].k <= 2 &&
-                        p.ops[oe + 1].nfix == p.ops[oe + 1].k) {  // uncontrolled: the gate touches every amplitude
-                        // fold the whole run into the load of the dense gate that follows: one sweep, one barrier
+                    const int fuse_k = op.fixpos[0];  // host: fold the run into the uncontrolled dense gate after it
+                    if (fuse_k != 0) {
                         const DevOp &dn = p.ops[oe + 1];
                         const T *mat = mats + dn.mat_off;
-                        if (dn.k == 1) op_diag_dense<T, 1, NT, 16>(tile, dn, mat, diag_tabs, lut, dhi, s0, s1, tid);
-                        else op_diag_dense<T, 2, NT, 16>(tile, dn, mat, diag_tabs, lut, dhi, s0, s1, tid);
+                        if (fuse_k == 1) op_diag_block<T, 1, NT>(tile, op, mat, diag_tabs, lut, dhi, s0, s1, tid);
+                        else op_diag_block<T, 2, NT>(tile, op, mat, diag_tabs, lut, dhi, s0, s1, tid);
                         o = oe + 1;
                         __syncthreads();
                         continue;
                     }
-                    op_diag_run<T, NT, 16>(tile, diag_tabs, lut, dhi, s0, s1, tid);
+                    op_diag_block<T, 0, NT>(tile, op, nullptr, diag_tabs, lut, dhi, s0, s1, tid);
                 } else
                 for (uint32_t i = tid; i < tile_amps; i += NT) {
                     const uint32_t s = swz<T>(i);
@@ -456,6 +476,7 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                 }
                 o = oe;
                 __syncthreads();
+                }
             } else {
                 op_perm<T, NT>(tile, op, t, tid);
                 __syncthreads();
