@@ -336,6 +336,11 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "tile_pass_tma_kernel<double>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": 2 * S},
+            # explanatory: the co-bound.  A Haar SU(4) gate costs 16 FMA (32 flop) per amplitude; the peak is the DFMA
+            # rate measured with tools/fp64_pipes.cu on this pool's B200 (profiles/fp64_pipes_r01.txt)
+            "fp64_pipe": {"achieved": gates * float(2 ** n) * 32.0 / (ms_per_step / 1e3) / 1e12, "peak": 33.1,
+                          "unit": "TFLOP/s", "frac": gates * float(2 ** n) * 32.0 / (ms_per_step / 1e3) / 1e12 / 33.1,
+                          "peak_source": "measured DFMA rate, profiles/fp64_pipes_r01.txt"},
             "e2e": {"value": gates * world / e2e_s, "unit": "gates/s", "h2d_bytes_per_step": est["h2d_bytes"] + len(task_text),
                     "d2h_bytes_per_step": est["d2h_bytes"], "ms_per_step": e2e_s * 1e3, "shots": SHOTS,
                     "api": "cb200_backend_execute (wire-JSON task in host memory -> counts JSON)"},

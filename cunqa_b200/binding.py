@@ -77,6 +77,7 @@ SIGNATURES = {
     "cb200_backend_set_channel": (ctypes.c_int, [_vp, SEND_FN, RECV_FN, _vp]),
     "cb200_backend_execute": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "cb200_backend_stats": (ctypes.c_int, [_vp, _c_u64_p]),
+    "cb200_backend_last_mode": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int)]),
     "cb200_dist_unique_id": (ctypes.c_int, [_c_u8_p]),
     "cb200_state_create_dist": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_u8_p]),
     "cb200_dist_export_handle": (ctypes.c_int, [_vp, _c_u8_p]),
@@ -349,6 +350,12 @@ class Backend:
         out = np.zeros(8, dtype=np.uint64)
         _check(lib.cb200_backend_stats(self._h, out.ctypes.data_as(_c_u64_p)))
         return {k: int(v) for k, v in zip(STAT_KEYS, out)}
+
+    def last_mode(self):
+        """0 static, 1 dynamic with every measurement deferred, 2 dynamic on the batched per-shot interpreter"""
+        out = ctypes.c_int(0)
+        _check(lib.cb200_backend_last_mode(self._h, ctypes.byref(out)))
+        return int(out.value)
 
     def stream(self):
         return int(lib.cb200_backend_stream(self._h) or 0)

@@ -209,4 +209,12 @@ int cb200_backend_stats(const cb200_backend *b, uint64_t stats[8])
     return CB200_OK;
 }
 
+int cb200_backend_last_mode(const cb200_backend *b, int *mode_out)
+{
+    NEED(b);
+    if (!mode_out) { g_err = "null output pointer"; return CB200_ERR_INVALID; }
+    *mode_out = b->impl->last_mode;
+    return CB200_OK;
+}
+
 }  // extern "C"

@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(256) qubit_swap_kernel(V *__restrict__ mine, c
     const uint64_t total = (uint64_t)((1u << sp.m) - 1) << rest_bits;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
-        uint32_t y = (uint32_t)(w >> rest_bits);
-        if (y >= sp.x) y++;
+        // partner of step j is x ^ (j + 1): at every step the ranks pair up, so no GPU's NVLink port is oversubscribed
+        const uint32_t y = sp.x ^ ((uint32_t)(w >> rest_bits) + 1u);
         uint64_t r = (w & (half - 1)) | (sp.x < y ? 0 : half);
         uint64_t mi = r, pi;
 #pragma unroll

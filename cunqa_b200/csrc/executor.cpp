@@ -132,6 +132,7 @@ struct TaskCfg {
     bool bugcompat_teledata = false;
     bool terminal_sampling = true;
     bool share_prefix = true;
+    bool defer_measurement = true;
     int max_batch = 0;
 };
 
@@ -161,6 +162,7 @@ TaskCfg parse_task(const Json &t)
     if (cfg.contains("b200_bugcompat_teledata")) c.bugcompat_teledata = cfg.at("b200_bugcompat_teledata").as_bool();
     if (cfg.contains("b200_share_prefix")) c.share_prefix = cfg.at("b200_share_prefix").as_bool();
     if (cfg.contains("b200_terminal_sampling")) c.terminal_sampling = cfg.at("b200_terminal_sampling").as_bool();
+    if (cfg.contains("b200_defer_measurement")) c.defer_measurement = cfg.at("b200_defer_measurement").as_bool();
     if (cfg.contains("b200_max_batch")) c.max_batch = (int)cfg.at("b200_max_batch").as_int();
     c.is_dynamic = t.contains("is_dynamic") ? t.at("is_dynamic").as_bool() : false;
     if (const Json *s = t.find("sending_to"))
@@ -355,6 +357,7 @@ Json Backend::run_static(const Json &task)
     }
     const auto t1 = std::chrono::high_resolution_clock::now();
     out.set("time_taken", Json::number(std::chrono::duration<double>(t1 - t0).count()));
+    last_mode = 0;
     last_stats = st.stats;
     last_stats.passes -= before.passes;
     last_stats.launches -= before.launches;
@@ -385,6 +388,77 @@ struct TaskRt {
 };
 
 using Bits = std::vector<uint8_t>;
+
+// Deferred measurement (one state, all shots sampled at the end): a classical bit is then SYMBOLIC -- 0 / 1 are
+// constants, kSym + q means "the outcome recorded in register qubit q", which is read from the final sample.
+constexpr uint8_t kSym = 2;
+struct DeferAbort {};  // the circuit needs a real mid-circuit collapse: fall back to the batched interpreter
+enum QState : uint8_t { Q_LIVE = 0, Q_FROZEN, Q_FROZEN_RESET };
+
+// how an instruction acts on each of its qubits: 'k' = control, 'd' = target of a diagonal matrix (both commute
+// with a Z-basis measurement of that qubit), 'x' = anything else
+std::vector<char> action_kinds(const Inst &in)
+{
+    const int nq = (int)in.qubits.size();
+    std::vector<char> kinds((size_t)nq, 'x');
+    int nt = nq;
+    bool diag = false;
+    if (in.name == "diagonal") {
+        diag = true;
+    } else if (in.name == "unitary" || in.name == "cunitary") {
+        nt = log2_exact(in.matrix_dim);
+        diag = is_diagonal(in.matrix, 1 << nt);
+    } else {
+        GateSpec g;
+        std::string err;
+        if (!lookup_gate(in.name, nq, in.params.data(), (int)in.params.size(), g, err)) throw std::runtime_error(err);
+        if (g.is_global_phase) return std::vector<char>((size_t)nq, 'd');
+        nt = g.n_targets;
+        diag = is_diagonal(g.mat, 1 << nt);
+    }
+    for (int i = 0; i < nq; i++) kinds[i] = i < nq - nt ? 'k' : (diag ? 'd' : 'x');
+    return kinds;
+}
+
+// the instruction with one more control qubit (register index), for a condition that is a deferred outcome
+void queue_gate_controlled(State &st, const Inst &in, const std::vector<int> &qs, int ctrl, bool reverse_unitary_qubits)
+{
+    std::vector<int> ctrls, targets;
+    std::vector<cplx> mat;
+    if (in.name == "unitary" || in.name == "cunitary") {
+        const int k = log2_exact(in.matrix_dim);
+        const int nc = (int)qs.size() - k;
+        if (nc < 0 || (in.name == "unitary" && nc != 0)) throw std::runtime_error("unitary: matrix size does not match the qubit list");
+        ctrls.assign(qs.begin(), qs.begin() + nc);
+        targets.assign(qs.begin() + nc, qs.end());
+        if (in.name == "unitary" && reverse_unitary_qubits) std::reverse(targets.begin(), targets.end());
+        mat = in.matrix;
+    } else if (in.name == "diagonal") {
+        const int k = log2_exact(in.matrix_dim);
+        if ((int)qs.size() != k) throw std::runtime_error("diagonal: size does not match the qubit list");
+        std::vector<int> all = qs;
+        all.push_back(ctrl);
+        std::vector<cplx> d((size_t)2 << k, cplx(1, 0));
+        for (int i = 0; i < (1 << k); i++) d[(size_t)i | ((size_t)1 << k)] = in.matrix[i];
+        st.apply_diagonal(all.data(), k + 1, d.data(), nullptr);
+        return;
+    } else {
+        GateSpec g;
+        std::string err;
+        if (!lookup_gate(in.name, (int)qs.size(), in.params.data(), (int)in.params.size(), g, err)) throw std::runtime_error(err);
+        if (g.is_global_phase) {  // a conditioned global phase is a phase gate on the condition qubit
+            const cplx d[2] = {cplx(1, 0), std::exp(cplx(0, g.phase))};
+            st.apply_diagonal(&ctrl, 1, d, nullptr);
+            return;
+        }
+        const int nc = (int)qs.size() - g.n_targets;
+        ctrls.assign(qs.begin(), qs.begin() + nc);
+        targets.assign(qs.begin() + nc, qs.end());
+        mat = g.mat;
+    }
+    ctrls.push_back(ctrl);
+    st.apply_matrix(targets.data(), (int)targets.size(), ctrls.data(), (int)ctrls.size(), mat.data(), nullptr);
+}
 
 }  // namespace
 
@@ -429,15 +503,19 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
     std::map<std::string, std::map<std::string, uint64_t>> counters;
     for (const TaskCfg &c : cfgs) counters[c.id];
     if (shots == 0) B = 1;
-    State *stp = shots ? &get_state(n_total, precision, (int)B) : nullptr;
-    const Stats before = stp ? stp->stats : Stats();
-    const uint64_t gates_before = stp ? stp->queue.gates : 0;
+    State *stp = nullptr;
+    Stats before;
+    uint64_t gates_before = 0;
+    bool deferred_used = false;
 
-    for (uint64_t shot0 = 0; shot0 < shots; shot0 += B) {
-        State &st = *stp;
-        if (shot0 > 0) st.reset();
-        const int nb = (int)B;  // the last batch may carry surplus states; their results are dropped
-        const uint64_t live = std::min<uint64_t>(B, shots - shot0);
+    // one batch of nb shots starting at shot0 (the last batch may carry surplus states; their results are dropped).
+    // deferred = one state for ALL shots: measurements only freeze their qubit, classical bits are symbolic, feed-
+    // forward becomes quantum control, and every shot is drawn from the final state (principle of deferred
+    // measurement; same joint distribution of all classical outcomes).  Throws DeferAbort when the circuit needs a
+    // real collapse (a measured qubit is driven again, a live qubit is reset, a condition is not a single outcome).
+    auto run_batch = [&](State &st, const int nb, const uint64_t shot0, const uint64_t live, const bool deferred) {
+        std::vector<uint8_t> qstate((size_t)n_total, Q_LIVE);
+        std::vector<char> touched((size_t)n_total, 0);
         std::vector<TaskRt> T(cfgs.size());
         std::map<std::string, size_t> by_id;
         {
@@ -476,6 +554,16 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
         };
         // measure (optionally conditioned by `flags`) every state; returns the outcome bits
         auto measure = [&](int q, bool reset_after, const uint8_t *flags) -> Bits {
+            if (deferred) {
+                if (flags) {
+                    if (flags[0] == 0) return Bits(1, 0);
+                    if (flags[0] != 1) throw DeferAbort();  // measurement under an undecided condition
+                }
+                if (qstate[q] == Q_FROZEN_RESET) return Bits(1, 0);           // |0> again: outcome 0, nothing to do
+                if (!touched[q] && qstate[q] == Q_LIVE) return Bits(1, 0);    // still the initial |0>
+                qstate[q] = reset_after ? Q_FROZEN_RESET : Q_FROZEN;          // (a frozen qubit keeps its record)
+                return Bits(1, (uint8_t)(kSym + q));
+            }
             diverge();
             std::vector<int8_t> forced;
             for (int b = 0; b < nb; b++) ctr[b] = ((shot0 + b + 1) << 20) + ordinal[b];
@@ -503,7 +591,37 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
             }
             return (flags && !all(*flags)) ? flags->data() : nullptr;
         };
+        // deferred mode: may this instruction (register qubits qs) still run?  false = skip it (a control sits on a
+        // qubit that was measured and reset: logically |0>), DeferAbort = it would disturb a recorded outcome
+        auto admit = [&](const Inst &in, const std::vector<int> &qs) -> bool {
+            bool frozen = false;
+            for (int q : qs) frozen = frozen || qstate[q] != Q_LIVE;
+            if (frozen) {
+                const std::vector<char> kinds = action_kinds(in);
+                bool skip = false;
+                for (size_t i = 0; i < qs.size(); i++) {
+                    if (qstate[qs[i]] == Q_FROZEN && kinds[i] == 'x') throw DeferAbort();
+                    if (qstate[qs[i]] == Q_FROZEN_RESET) {
+                        if (kinds[i] != 'k') throw DeferAbort();
+                        skip = true;  // controlled on |0>: never fires
+                    }
+                }
+                if (skip) return false;
+            }
+            for (int q : qs) touched[q] = 1;
+            return true;
+        };
         auto named = [&](const char *name, std::vector<int> qs, const Bits *flags) {
+            if (deferred) {
+                Inst in;
+                in.name = name;
+                in.qubits = qs;
+                const uint8_t f = flags ? (*flags)[0] : 1;
+                if (f == 0 || !admit(in, qs)) return;
+                if (f == 1) st.apply_named(name, qs.data(), (int)qs.size(), nullptr, 0, nullptr);
+                else queue_gate_controlled(st, in, qs, f - kSym, false);
+                return;
+            }
             if (flags && !any(*flags)) return;
             if (!diverged && flags && !(*flags)[0]) return;
             st.apply_named(name, qs.data(), (int)qs.size(), nullptr, 0, gate_flags(flags));
@@ -548,6 +666,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                     return creg[(size_t)(cl + t.zc)];
                 };
                 auto assign = [&](Bits &dst, const Bits &src) {
+                    if (deferred && cond && (*cond)[0] >= kSym) throw DeferAbort();  // classically conditioned assignment
                     for (int b = 0; b < nb; b++) if (!cond || (*cond)[b]) dst[b] = src[b];
                 };
                 const std::string &name = in.name;
@@ -558,6 +677,13 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                         throw std::runtime_error("The number of copied clbits and the number of clbits copied on does not match.");
                     for (size_t i = 0; i < in.l_clbits.size(); i++) { const Bits src = clb(in.r_clbits[i]); assign(clb(in.l_clbits[i]), src); }
                 } else if (name == "reset") {
+                    if (deferred) {
+                        // only a qubit that is still (or again) |0> can be reset without a collapse
+                        const int q = qmap(in.qubits.at(0));
+                        if (cond && (*cond)[0] == 0) return;
+                        if (qstate[q] == Q_FROZEN_RESET || (qstate[q] == Q_LIVE && !touched[q])) return;
+                        throw DeferAbort();
+                    }
                     measure(qmap(in.qubits.at(0)), true, cond ? cond->data() : nullptr);
                 } else if (name == "send") {
                     if (multi) {
@@ -585,11 +711,22 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                     // fold the clbits with cif_ops (:582-600)
                     const bool cnd = in.condition != 0;
                     Bits res(nb, 0);
-                    for (int b = 0; b < nb; b++) {
+                    bool symbolic = false;
+                    if (deferred) {
+                        for (int cl : in.clbits) symbolic = symbolic || clb(cl)[0] >= kSym;
+                        if (symbolic) {
+                            // one recorded outcome, tested for 1, not nested inside another undecided condition
+                            if (in.clbits.size() != 1 || !cnd) throw DeferAbort();
+                            if (cond && (*cond)[0] >= kSym) throw DeferAbort();
+                            res[0] = (cond && (*cond)[0] == 0) ? 0 : clb(in.clbits[0])[0];
+                        }
+                    }
+                    for (int b = 0; b < nb && !symbolic; b++) {
                         bool accb = cnd ? clb(in.clbits.at(0))[b] != 0 : clb(in.clbits.at(0))[b] == 0;
                         for (size_t k = 1; k < in.clbits.size(); k++) accb = cif_op(in.operation, accb, clb(in.clbits[k])[b] != 0);
                         const bool r = cnd ? accb : !accb;
                         res[b] = (uint8_t)((cnd == r) && (!cond || (*cond)[b]));
+                        if (deferred && res[b] && cond && (*cond)[b] >= kSym) res[b] = (*cond)[b];  // decided here, undecided outside
                     }
                     if (any(res))
                         for (const Inst &sub : in.sub) step(t, sub, {}, &res);
@@ -670,6 +807,15 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                     t.b_tg = false;
                 } else {
                     if (cond && !any(*cond)) return;
+                    if (deferred) {
+                        std::vector<int> qs;
+                        for (int x : in.qubits) qs.push_back(qmap(x));
+                        if (name == "barrier" || name == "id" || name == "save_state") return;
+                        if (!admit(in, qs)) return;
+                        if (cond && (*cond)[0] >= kSym) queue_gate_controlled(st, in, qs, (*cond)[0] - kSym, c.bugcompat_unitary_order);
+                        else queue_gate(st, in, qmap, nullptr, c.bugcompat_unitary_order);
+                        return;
+                    }
                     if (!diverged && cond && !(*cond)[0]) return;
                     queue_gate(st, in, qmap, gate_flags(cond), c.bugcompat_unitary_order);
                 }
@@ -679,7 +825,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
         // pending), the m remaining measure+collapse rounds (3*S each) are replaced by ONE draw per state from
         // |a|^2 (1*S): same joint distribution, one RNG draw instead of m.  The oracle restates the same rule.
         auto try_terminal = [&]() -> bool {
-            if (!c0.terminal_sampling) return false;
+            if (!c0.terminal_sampling || deferred) return false;
             std::vector<std::pair<int, int>> pend;  // (register qubit, global clbit) in scheduler order
             bool any_left = false;
             for (TaskRt &t : T) {
@@ -737,6 +883,20 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                 throw std::runtime_error("dynamic circuit deadlock: every task is blocked on communication");
             if (progressed) guard = 0;
         }
+        if (deferred) {
+            // every shot is one draw from the final state; a symbolic bit reads its qubit from the drawn index
+            std::vector<uint64_t> samples(live);
+            st.sample(0, live, seed, samples.data());
+            std::vector<uint8_t> bits((size_t)ncl_total);
+            for (uint64_t s = 0; s < live; s++) {
+                for (int cl = 0; cl < ncl_total; cl++) {
+                    const uint8_t v = creg[cl][0];
+                    bits[cl] = v >= kSym ? (uint8_t)((samples[s] >> (v - kSym)) & 1ull) : v;
+                }
+                for (const TaskRt &t : T) counters[t.cfg->id][bits_to_string(bits, t.zc, t.cfg->num_clbits)]++;
+            }
+            return;
+        }
         st.sync();
         for (const TaskRt &t : T)
             for (uint64_t b = 0; b < live; b++) {
@@ -744,6 +904,33 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                 for (int cl = 0; cl < ncl_total; cl++) bits[cl] = creg[cl][b];
                 counters[t.cfg->id][bits_to_string(bits, t.zc, t.cfg->num_clbits)]++;
             }
+    };
+
+    // first choice: defer every measurement (one state, all shots from one final sample)
+    bool done = false;
+    if (shots > 0 && c0.defer_measurement && !external_cc && n_total + (int)kSym <= 255) {
+        State &s1 = get_state(n_total, precision, 1);
+        const Stats b1 = s1.stats;
+        const uint64_t g1 = s1.queue.gates;
+        try {
+            run_batch(s1, 1, 0, shots, true);
+            done = true;
+            stp = &s1;
+            before = b1;
+            gates_before = g1;
+            deferred_used = true;
+        } catch (const DeferAbort &) {
+            s1.reset();
+            for (auto &kv : counters) kv.second.clear();
+        }
+    }
+    if (!done) {
+        stp = shots ? &get_state(n_total, precision, (int)B) : nullptr;
+        if (stp) { before = stp->stats; gates_before = stp->queue.gates; }
+        for (uint64_t shot0 = 0; shot0 < shots; shot0 += B) {
+            if (shot0 > 0) stp->reset();
+            run_batch(*stp, (int)B, shot0, std::min<uint64_t>(B, shots - shot0), false);
+        }
     }
     const auto t1 = std::chrono::high_resolution_clock::now();
     Json idc = Json::object();
@@ -751,6 +938,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
     Json out = Json::object();
     out.set("id_counts", std::move(idc));
     out.set("time_taken", Json::number(std::chrono::duration<double>(t1 - t0).count()));
+    last_mode = deferred_used ? 1 : 2;
     if (stp) {
         last_stats = stp->stats;
         last_stats.passes -= before.passes;

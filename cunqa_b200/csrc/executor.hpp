@@ -24,6 +24,7 @@ public:
     std::string execute(const std::string &tasks_json);
     void set_channel(send_fn s, recv_fn r, void *user) { send_ = s; recv_ = r; user_ = user; }
     Stats last_stats;
+    int last_mode = 0;  // 0 static, 1 dynamic with deferred measurements, 2 dynamic on the batched interpreter
     void *stream_ptr() { return state_ ? (void *)state_->stream() : nullptr; }
 
 private:

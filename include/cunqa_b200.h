@@ -134,6 +134,10 @@ int cb200_backend_set_channel(cb200_backend *b, cb200_send_fn send, cb200_recv_f
 int cb200_backend_execute(cb200_backend *b, const char *tasks_json, char **result_json_out);
 /* counters of the backend's last execute: same layout as cb200_stats */
 int cb200_backend_stats(const cb200_backend *b, uint64_t stats[8]);
+/* how the last execute ran its measurements: 0 = static task (one state, shots sampled), 1 = dynamic task with every
+ * measurement deferred (one state, feed-forward as quantum control, shots sampled at the end), 2 = dynamic task on
+ * the batched per-shot interpreter (execute_shot_, aer_simulator_adapter.cpp:120-792) */
+int cb200_backend_last_mode(const cb200_backend *b, int *mode_out);
 /* stream of the backend's current state (NULL before the first execute) */
 void *cb200_backend_stream(cb200_backend *b);
 

@@ -130,6 +130,8 @@ def test_dynamic_edge_cases(backend):
            {"name": "copy", "l_clbits": [2], "r_clbits": [0]},
            {"name": "cif", "clbits": [0], "operation": "and", "condition": 1, "instructions": [{"name": "x", "qubits": [1]}]},
            {"name": "measure", "qubits": [1], "clbits": [1]}]
-    res = backend.execute(C.task(ins, 2, num_clbits=3, shots=300, seed=12, is_dynamic=True))
+    res = backend.execute(C.task(ins, 2, num_clbits=3, shots=300, seed=12, is_dynamic=True, b200_defer_measurement=False))
     want = O.run_dynamic([{"id": "task", "num_qubits": 2, "num_clbits": 3, "instructions": ins}], 300, seed=12)["task"]
     assert res["counts"] == want and set(want) <= {"000", "111"}
+    dfr = backend.execute(C.task(ins, 2, num_clbits=3, shots=3000, seed=12, is_dynamic=True))  # measurements deferred
+    assert backend.last_mode() == 1 and set(dfr["counts"]) == {"000", "111"} and abs(dfr["counts"]["111"] / 3000 - 0.5) < 0.05

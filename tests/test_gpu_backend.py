@@ -86,6 +86,9 @@ def test_upgrade_parameters_path(lib_built):
 
 
 def dyn_task(ins, n, ncl, shots, seed, **cfg):
+    """dynamic task on the batched per-shot interpreter (shot-identical to the oracle); pass
+    b200_defer_measurement=True for the default deferred-measurement mode (distribution-identical)"""
+    cfg.setdefault("b200_defer_measurement", False)
     return C.task(ins, n, num_clbits=ncl, shots=shots, seed=seed, is_dynamic=True, **cfg)
 
 
@@ -133,9 +136,11 @@ def test_quantum_communication_joint_register(backend, maker):
     """executor-style call: several tasks, one joint register + comm pair (aer_simulator_adapter.cpp:131-159)"""
     tasks = maker(4)
     shots = 400
-    msg = [C.task(t["instructions"], t["num_qubits"], shots=shots, seed=33, task_id=t["id"], is_dynamic=True) for t in tasks]
+    msg = [C.task(t["instructions"], t["num_qubits"], shots=shots, seed=33, task_id=t["id"], is_dynamic=True,
+                  b200_defer_measurement=False) for t in tasks]
     res = backend.execute(msg)
     assert "ERROR" not in res, res
+    assert backend.last_mode() == 2
     want = O.run_dynamic(tasks, shots, seed=33)
     if maker is C.hea_teledata_pair:
         # qrecv ends with a swap, which the engine performs by relabelling qubits: its terminal inverse-CDF then
@@ -161,8 +166,10 @@ def test_teledata_teleports(backend):
     res = backend.execute(msg)
     p1 = res["id_counts"]["B"].get("1", 0) / shots
     assert abs(p1 - math.sin(theta / 2) ** 2) < 4 * math.sqrt(0.25 / shots)
+    assert backend.last_mode() == 1  # default: measurements deferred, corrections as quantum control
     # the literal reference code (X/Z corrections swapped, quirk Q6) only under the bugcompat switch
     msg[0]["config"]["b200_bugcompat_teledata"] = True
+    msg[0]["config"]["b200_defer_measurement"] = False  # per-shot interpreter: shot-identical to the oracle
     lit = backend.execute(msg)
     want = O.run_dynamic([{"id": "A", "num_qubits": 1, "num_clbits": 1, "instructions": a},
                           {"id": "B", "num_qubits": 1, "num_clbits": 1, "instructions": b}], shots, seed=1, teledata_literal=True)
@@ -183,3 +190,73 @@ def test_classical_send_recv_between_processes(lib_built):
     assert sent == [(1, "peer")] * 8
     assert res["counts"] == {"11": 4, "01": 4}
     be.close()
+
+
+# ---- deferred measurement (default for dynamic tasks): one state, feed-forward as quantum control -------------
+def _dist(counts):
+    tot = sum(counts.values())
+    return {k: v / tot for k, v in counts.items()}
+
+
+def test_deferred_measurement_cif(backend):
+    ins = [{"name": "h", "qubits": [0]}, {"name": "ry", "qubits": [2], "params": [0.9]},
+           {"name": "measure", "qubits": [0], "clbits": [0]},
+           {"name": "cif", "clbits": [0], "operation": "and", "condition": 1,
+            "instructions": [{"name": "x", "qubits": [1]}, {"name": "rx", "qubits": [2], "params": [1.3]},
+                             C.unitary_inst(C.haar_unitary(np.random.default_rng(4), 4), [1, 2])]},
+           {"name": "cz", "qubits": [0, 2]},                      # a measured qubit may still act as a control
+           {"name": "measure", "qubits": [1], "clbits": [1]}, {"name": "measure", "qubits": [2], "clbits": [2]},
+           {"name": "measure", "qubits": [0], "clbits": [3]}]     # measured again: same outcome
+    shots = 20000
+    res = backend.execute(dyn_task(ins, 3, 4, shots, 17, b200_defer_measurement=True))
+    assert "ERROR" not in res, res
+    assert backend.last_mode() == 1
+    assert all(k[0] == k[3] for k in res["counts"])  # clbit 3 repeats clbit 0
+    ref = backend.execute(dyn_task(ins, 3, 4, shots, 18))
+    assert backend.last_mode() == 2
+    assert O.tvd(res["counts"], ref["counts"]) < 0.03
+    want = O.run_dynamic([{"id": "task", "num_qubits": 3, "num_clbits": 4, "instructions": ins}], 4000, seed=5)["task"]
+    assert O.tvd(res["counts"], want) < 0.5 * math.sqrt(8 / 4000) + 0.03
+
+
+@pytest.mark.parametrize("maker", [C.hea_teledata_pair, C.hea_telegate_pair])
+def test_deferred_measurement_quantum_communication(backend, maker):
+    tasks = maker(4, layers=2)
+    shots = 40000
+    msg = [C.task(t["instructions"], t["num_qubits"], shots=shots, seed=7, task_id=t["id"], is_dynamic=True) for t in tasks]
+    res = backend.execute(msg)
+    assert "ERROR" not in res, res
+    assert backend.last_mode() == 1
+    st = backend.stats()
+    for m in msg:
+        m["config"]["b200_defer_measurement"] = False
+        m["config"]["seed"] = 8
+    ref = backend.execute(msg)
+    assert backend.last_mode() == 2
+    assert backend.stats()["bytes"] > 20 * st["bytes"]  # the per-shot interpreter moves far more data
+    for t in tasks:
+        assert sum(res["id_counts"][t["id"]].values()) == shots
+        assert O.tvd(res["id_counts"][t["id"]], ref["id_counts"][t["id"]]) < 0.03
+    want = O.run_dynamic(tasks, 3000, seed=3)
+    for t in tasks:
+        assert O.tvd(res["id_counts"][t["id"]], want[t["id"]]) < 0.5 * math.sqrt(16 / 3000) + 0.04
+
+
+@pytest.mark.parametrize("ins", [
+    # a measured qubit is driven again
+    [{"name": "h", "qubits": [0]}, {"name": "measure", "qubits": [0], "clbits": [0]}, {"name": "h", "qubits": [0]},
+     {"name": "measure", "qubits": [0], "clbits": [1]}],
+    # reset of a live qubit
+    [{"name": "h", "qubits": [0]}, {"name": "cx", "qubits": [0, 1]}, {"name": "reset", "qubits": [0]},
+     {"name": "measure", "qubits": [0], "clbits": [0]}, {"name": "measure", "qubits": [1], "clbits": [1]}],
+    # condition "bit is 0", and a two-bit condition
+    [{"name": "h", "qubits": [0]}, {"name": "measure", "qubits": [0], "clbits": [0]},
+     {"name": "cif", "clbits": [0], "operation": "and", "condition": 0, "instructions": [{"name": "x", "qubits": [1]}]},
+     {"name": "measure", "qubits": [1], "clbits": [1]}],
+])
+def test_deferral_falls_back_when_a_collapse_is_needed(backend, ins):
+    res = backend.execute(dyn_task(ins, 2, 2, 500, 21, b200_defer_measurement=True))
+    assert "ERROR" not in res, res
+    assert backend.last_mode() == 2
+    want = O.run_dynamic([{"id": "task", "num_qubits": 2, "num_clbits": 2, "instructions": ins}], 500, seed=21)["task"]
+    assert res["counts"] == want

@@ -42,6 +42,7 @@ def test_static_amplitudes(lib_built, name, precision, tol):
 @pytest.mark.parametrize("name", ["ghz8", "qft7", "vocab5", "hea6", "dyn3"])
 def test_counts_equal_oracle(backend, name):
     rec = load(name)
+    rec["task"]["config"]["b200_defer_measurement"] = False  # dyn3: the per-shot interpreter is shot-identical
     res = backend.execute(rec["task"])
     assert "ERROR" not in res, res
     if any(i["name"] == "swap" for i in rec["task"]["instructions"]):
@@ -68,10 +69,20 @@ def test_parameter_update_roundtrip(backend):
 @pytest.mark.parametrize("name", ["teledata", "telegate"])
 def test_quantum_communication_families(backend, name):
     rec = load(name)
+    from oracle import oracle_np as O
+    # default mode (measurements deferred): distribution-equal
+    big = [dict(t, config=dict(t["config"], shots=20000)) for t in rec["tasks"]]
+    res = backend.execute(big)
+    assert "ERROR" not in res, res
+    assert backend.last_mode() == 1
+    for tid, want in rec["oracle_id_counts"].items():
+        assert O.tvd(res["id_counts"][tid], want) < 0.5 * (4 / 400) ** 0.5 + 0.06
+    # per-shot interpreter: shot-identical
+    for t in rec["tasks"]:
+        t["config"]["b200_defer_measurement"] = False
     res = backend.execute(rec["tasks"])
     assert "ERROR" not in res, res
     if name == "teledata":  # qrecv's swap is a relabelling in the engine: distribution-equal, see test_gpu_backend
-        from oracle import oracle_np as O
         for tid, want in rec["oracle_id_counts"].items():
             assert O.tvd(res["id_counts"][tid], want) < 0.5 * (4 / 400) ** 0.5 + 0.06
     else:

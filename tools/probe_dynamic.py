@@ -16,7 +16,7 @@ def run(kind, n_each, shots, layers=2, **cfg):
     st = be.stats()
     assert "ERROR" not in res, res
     print(json.dumps({"probe": kind, "joint_qubits": 2 * n_each + 2, "shots": shots, "s": round(dt, 3), "shots_per_s": round(shots / dt, 1),
-                      "circuits_per_s": round(1 / dt, 3), "passes": st["passes"], "launches": st["launches"], "cfg": cfg}), flush=True)
+                      "circuits_per_s": round(1 / dt, 3), "mode": be.last_mode(), "passes": st["passes"], "launches": st["launches"], "cfg": cfg}), flush=True)
     be.close()
 
 if __name__ == "__main__":
@@ -24,3 +24,6 @@ if __name__ == "__main__":
     shots = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
     run("teledata", n_each, shots)
     run("telegate", n_each, shots)
+    if "--both" in sys.argv:  # the batched per-shot interpreter, for comparison
+        run("teledata", n_each, shots, b200_defer_measurement=False)
+        run("telegate", n_each, shots, b200_defer_measurement=False)
