@@ -628,7 +628,12 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
         };
         auto gen_ent = [&](size_t npairs) {
             std::vector<int> idx;
-            for (size_t i = 0; i < pairs.size() && idx.size() < npairs; i++) if (pairs[i].idle) idx.push_back((int)i);
+            // (deferred mode: pairs are interchangeable, so never-used ones go first -- a used pair needs a real reset)
+            if (deferred)
+                for (size_t i = 0; i < pairs.size() && idx.size() < npairs; i++)
+                    if (pairs[i].idle && !touched[pairs[i].q0] && !touched[pairs[i].q1]) idx.push_back((int)i);
+            for (size_t i = 0; i < pairs.size() && idx.size() < npairs; i++)
+                if (pairs[i].idle && std::find(idx.begin(), idx.end(), (int)i) == idx.end()) idx.push_back((int)i);
             if (idx.size() < npairs) return std::vector<int>();
             for (int i : idx) {
                 pairs[i].idle = false;

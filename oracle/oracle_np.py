@@ -422,8 +422,21 @@ _CIF_OPS = {
 }
 
 
+class DeferAbort(Exception):
+    """the circuit needs a real mid-circuit collapse: measurements cannot all be deferred"""
+
+
+class _NeedMoreBits(Exception):
+    pass
+
+
+class _DeadBranch(Exception):
+    pass
+
+
 def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channel=None,
-                reverse_unitary_qubits=False, forced_bits=None, teledata_literal=False, terminal_sampling=True):
+                reverse_unitary_qubits=False, forced_bits=None, teledata_literal=False, terminal_sampling=True,
+                defer=False, _weight=None, _final=None):
     """Per-shot interpreter of one or several co-simulated tasks (aer_simulator_adapter.cpp:120-792,845-935).
 
     tasks: list of dicts {"id", "num_qubits", "num_clbits", "instructions"}.  Tasks are stepped
@@ -439,6 +452,11 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
     reverse of its own documented protocol (docs/source/_static/teledata.png: X <- comm qubit,
     Z <- sent qubit) and does not teleport.  Default follows the documented protocol; True mirrors
     the literal code (quirk Q6).
+    defer: the engine's deferred-measurement mode, restated: ONE state for all shots; `measure q -> c` freezes q
+    and makes c the symbol ("sym", q); a cif on such a bit and the teledata / telegate corrections become the
+    same gate with q as an extra control; all shots are drawn from the final state (u_s = U(seed, s), as on
+    the static path).  Raises DeferAbort when a frozen qubit would be driven again, a live qubit reset, or a
+    condition is not a single undecided bit tested for 1 (the engine then falls back to the per-shot mode).
     """
     multi = len(tasks) > 1
     if n_comm_qubits is None:
@@ -448,25 +466,117 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
     n_total = sum(t["num_qubits"] for t in tasks) + n_comm_qubits
     counters = {t["id"]: {} for t in tasks}
 
-    for shot in range(shots):
+    def is_sym(v):
+        return isinstance(v, tuple)
+
+    for shot in range(1 if defer else shots):
         st = make_state(n_total, backend)
         draw = [0]
         forced = deque(forced_bits) if forced_bits is not None else None
+        qstate = ["live"] * n_total   # defer: live / frozen / frozen_reset
+        touched = [False] * n_total
 
-        def measure(q):
+        def measure(q, and_reset=False):
+            if defer:
+                if qstate[q] == "frozen_reset" or (qstate[q] == "live" and not touched[q]):
+                    return 0
+                qstate[q] = "frozen_reset" if and_reset else "frozen"
+                return ("sym", q)
             if forced is not None:
+                if not forced:
+                    raise _NeedMoreBits()
                 out = forced.popleft()
                 total = st.norm()
                 p1 = st.prob1(q)
-                st.collapse(q, out, (p1 if out else total - p1) / total)
-                return out
-            out = st.measure(q, seed, meas_counter(shot, draw[0]))
-            draw[0] += 1
+                p = (p1 if out else total - p1) / total
+                if _weight is not None:
+                    _weight[0] *= p
+                if p < 1e-14:
+                    raise _DeadBranch()
+                st.collapse(q, out, p)
+            else:
+                out = st.measure(q, seed, meas_counter(shot, draw[0]))
+                draw[0] += 1
+            if and_reset and out:
+                st.apply_matrix([q], _FIXED_1Q["x"])
             return out
 
         def reset(q):
-            if measure(q):
-                st.apply_matrix([q], _FIXED_1Q["x"])
+            if defer:
+                if qstate[q] == "frozen_reset" or (qstate[q] == "live" and not touched[q]):
+                    return
+                raise DeferAbort()
+            measure(q, True)
+
+        def admit(inst, qubits):
+            """defer mode: may this instruction still run?  False = drop it (controlled on a qubit that was measured
+            and reset, logically |0>); DeferAbort = it would disturb a recorded outcome"""
+            if any(qstate[q] != "live" for q in qubits):
+                name = inst["name"]
+                if name == "diagonal":
+                    kinds = ["d"] * len(qubits)
+                elif name in ("unitary", "cunitary"):
+                    m = parse_matrix(inst["matrix"])
+                    k = int(round(math.log2(m.shape[0])))
+                    diag = np.count_nonzero(m - np.diag(np.diagonal(m))) == 0
+                    kinds = ["k"] * (len(qubits) - k) + [("d" if diag else "x")] * k
+                elif name == "gp":
+                    kinds = ["d"] * len(qubits)
+                elif name == "swap":
+                    kinds = ["x", "x"]
+                else:
+                    m, tg, ct = gate_spec(name, qubits, inst.get("params", []))
+                    diag = np.count_nonzero(m - np.diag(np.diagonal(m))) == 0
+                    kinds = ["k"] * len(ct) + [("d" if diag else "x")] * len(tg)
+                skip = False
+                for q, kind in zip(qubits, kinds):
+                    if qstate[q] == "frozen" and kind == "x":
+                        raise DeferAbort()
+                    if qstate[q] == "frozen_reset":
+                        if kind != "k":
+                            raise DeferAbort()
+                        skip = True
+                if skip:
+                    return False
+            for q in qubits:
+                touched[q] = True
+            return True
+
+        def gate(inst, qmap=lambda q: q, cond=1):
+            """one unitary instruction under a condition that is 0, 1 or a symbol (defer mode)"""
+            if inst["name"] in _NOOPS or inst["name"] == "id" or cond == 0:
+                return
+            if not defer:
+                apply_gate(st, inst, qmap, reverse_unitary_qubits)
+                return
+            qubits = [qmap(q) for q in inst.get("qubits", [])]
+            if not admit(inst, qubits):
+                return
+            if not is_sym(cond):
+                apply_gate(st, inst, qmap, reverse_unitary_qubits)
+                return
+            ctrl = cond[1]
+            name = inst["name"]
+            if name == "gp":
+                st.apply_diagonal([ctrl], np.array([1.0, np.exp(1j * inst["params"][0])]))
+            elif name == "unitary":
+                qs = qubits[::-1] if reverse_unitary_qubits else qubits
+                st.apply_matrix(qs, parse_matrix(inst["matrix"]), [ctrl])
+            elif name == "cunitary":
+                m = parse_matrix(inst["matrix"])
+                k = int(round(math.log2(m.shape[0])))
+                st.apply_matrix(qubits[-k:], m, qubits[:-k] + [ctrl])
+            elif name == "diagonal":
+                d = np.asarray(inst["matrix"][0], dtype=float)
+                st.apply_diagonal(qubits + [ctrl], np.concatenate([np.ones(len(d)), d[:, 0] + 1j * d[:, 1]]))
+            elif name == "swap":
+                st.apply_swap(qubits[0], qubits[1], [ctrl])
+            else:
+                m, tg, ct = gate_spec(name, qubits, inst.get("params", []))
+                st.apply_matrix(tg, m, list(ct) + [ctrl])
+
+        def fixed(name, qubits, cond=1):
+            gate({"name": name, "qubits": list(qubits)}, cond=cond)
 
         T = {}
         nq = ncl = 0
@@ -481,15 +591,18 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
         q_td, q_tg, q_cc = {}, {}, {}
 
         def gen_ent(npairs):
-            idx = [i for i, p in enumerate(pairs) if p["idle"]][:npairs]
+            idle = [i for i, p in enumerate(pairs) if p["idle"]]
+            if defer:  # pairs are interchangeable: take never-used ones first (a used pair would need a real reset)
+                idle.sort(key=lambda i: touched[pairs[i]["q0"]] or touched[pairs[i]["q1"]])
+            idx = idle[:npairs]
             if len(idx) < npairs:
                 return []
             for i in idx:
                 pairs[i]["idle"] = False
                 reset(pairs[i]["q1"])
                 reset(pairs[i]["q0"])
-                st.apply_matrix([pairs[i]["q0"]], _FIXED_1Q["h"])
-                st.apply_matrix([pairs[i]["q1"]], _FIXED_1Q["x"], [pairs[i]["q0"]])
+                fixed("h", [pairs[i]["q0"]])
+                fixed("cx", [pairs[i]["q0"], pairs[i]["q1"]])
             return idx
 
         def my_pairs(sendr, recvr, proto, npairs=0):
@@ -501,7 +614,7 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                     out.append(i)
             return out
 
-        def step(t, inst, comm_idx=()):
+        def step(t, inst, comm_idx=(), cond=1):
             name = inst["name"]
 
             def qmap(q):
@@ -512,6 +625,8 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                     raise RuntimeError("unresolved remote qubit")
                 return q + t["zq"]
 
+            if is_sym(cond) and name in ("measure", "copy", "recv"):
+                raise DeferAbort()  # classical state written under an undecided condition
             if name == "measure":
                 creg[inst["clbits"][0] + t["zc"]] = measure(inst["qubits"][0] + t["zq"])
             elif name == "copy":
@@ -540,15 +655,22 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                     for c in inst["clbits"]:
                         creg[c + t["zc"]] = 1 if channel.recv_measure(inst["qpus"][0]) == 1 else 0
             elif name == "cif":
-                cond = 1 if inst.get("condition", 1) else 0
+                want = 1 if inst.get("condition", 1) else 0
                 bits = [creg.get(c + t["zc"], 0) for c in inst["clbits"]]
-                acc = bits[0] if cond else 1 - bits[0]
+                if any(is_sym(b) for b in bits):
+                    # one recorded outcome, tested for 1, not nested inside another undecided condition
+                    if len(bits) != 1 or not want or is_sym(cond):
+                        raise DeferAbort()
+                    for sub in inst["instructions"]:
+                        step(t, sub, (), bits[0])
+                    return
+                acc = bits[0] if want else 1 - bits[0]
                 for b in bits[1:]:
                     acc = _CIF_OPS[inst["operation"]](acc, b)
-                res = acc if cond else 1 - acc
-                if cond == res:
+                res = acc if want else 1 - acc
+                if want == res:
                     for sub in inst["instructions"]:
-                        step(t, sub, ())
+                        step(t, sub, (), cond)
             elif name == "qsend":
                 idx = gen_ent(1)
                 if not idx:
@@ -558,13 +680,12 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                 p = pairs[idx[0]]
                 p["proto"] = "teledata"
                 q = inst["qubits"][0] + t["zq"]
-                st.apply_matrix([p["q0"]], _FIXED_1Q["x"], [q])
-                st.apply_matrix([q], _FIXED_1Q["h"])
-                r = measure(q)
-                q_td.setdefault(t["id"], deque()).append(r)
+                fixed("cx", [q, p["q0"]])
+                fixed("h", [q])
+                # measure + "reset if 1" (:622-624): the qubit is known to be |1>, so the reset is an X.  (The X comes
+                # before the comm qubit's measurement here and after it in the reference: they act on different qubits.)
+                q_td.setdefault(t["id"], deque()).append(measure(q, True))
                 q_td[t["id"]].append(measure(p["q0"]))
-                if r:  # "reset if 1" (:622-624): the qubit is known to be |1>, so the reset is an X
-                    st.apply_matrix([q], _FIXED_1Q["x"])
                 T[inst["qpus"][0]]["b_td"] = False
                 p["sendr"], p["recvr"] = t["id"], inst["qpus"][0]
             elif name == "qrecv":
@@ -578,11 +699,9 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                 m2 = q_td[src].popleft()  # outcome of the sender's comm qubit
                 p = pairs[my_pairs(src, t["id"], "teledata", 1)[0]]
                 mx, mz = (m1, m2) if teledata_literal else (m2, m1)
-                if mx:
-                    st.apply_matrix([p["q1"]], _FIXED_1Q["x"])
-                if mz:
-                    st.apply_matrix([p["q1"]], _FIXED_1Q["z"])
-                st.apply_swap(p["q1"], inst["qubits"][0] + t["zq"])
+                fixed("x", [p["q1"]], mx)
+                fixed("z", [p["q1"]], mz)
+                fixed("swap", [p["q1"], inst["qubits"][0] + t["zq"]])
                 p["idle"] = True
             elif name == "expose":
                 if not t["cat"]:
@@ -594,7 +713,7 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                         p = pairs[i]
                         p["proto"] = "telegate"
                         p["label"] = -(qid + 1)
-                        st.apply_matrix([p["q0"]], _FIXED_1Q["x"], [inst["qubits"][qid] + t["zq"]])
+                        fixed("cx", [inst["qubits"][qid] + t["zq"], p["q0"]])
                         q_tg.setdefault(t["id"], deque()).append(measure(p["q0"]))
                         t["cat"] = True
                         t["b_tg"] = True
@@ -602,8 +721,7 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                         p["sendr"], p["recvr"] = t["id"], inst["qpus"][0]
                     return
                 for i in range(len(inst["qubits"])):
-                    if q_tg[inst["qpus"][0]].popleft():
-                        st.apply_matrix([inst["qubits"][i] + t["zq"]], _FIXED_1Q["z"])
+                    fixed("z", [inst["qubits"][i] + t["zq"]], q_tg[inst["qpus"][0]].popleft())
                 t["cat"] = False
                 for i in my_pairs(t["id"], inst["qpus"][0], "telegate", len(inst["qubits"])):
                     pairs[i]["idle"] = True
@@ -616,20 +734,19 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                     return
                 idx = my_pairs(src, t["id"], "telegate")
                 for i in idx:
-                    if q_tg[src].popleft():
-                        st.apply_matrix([pairs[i]["q1"]], _FIXED_1Q["x"])
+                    fixed("x", [pairs[i]["q1"]], q_tg[src].popleft())
                 for sub in inst["instructions"]:
-                    step(t, sub, idx)
+                    step(t, sub, idx, cond)
                 for i in idx:
-                    st.apply_matrix([pairs[i]["q1"]], _FIXED_1Q["h"])
+                    fixed("h", [pairs[i]["q1"]])
                     q_tg.setdefault(t["id"], deque()).append(measure(pairs[i]["q1"]))
                 T[src]["b_tg"] = False
                 t["b_tg"] = False
             else:
-                apply_gate(st, inst, qmap, reverse_unitary_qubits)
+                gate(inst, qmap, cond)
 
         def try_terminal():
-            if not terminal_sampling or forced is not None:
+            if not terminal_sampling or forced is not None or defer:
                 return False
             pend = []
             for t in T.values():
@@ -689,11 +806,69 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
             if guard > 1_000_000:
                 raise RuntimeError("dynamic interpreter deadlock")
 
+        if defer:
+            # every shot is one draw from the final state; a symbolic bit reads its qubit from the drawn index
+            def keys_of(index):
+                out = {}
+                for t in T.values():
+                    local = {}
+                    for c, v in creg.items():
+                        if t["zc"] <= c < t["zc"] + t["ncl"]:
+                            local[c - t["zc"]] = ((index >> v[1]) & 1) if is_sym(v) else v
+                    out[t["id"]] = bits_to_string(local, t["ncl"])
+                return out
+
+            if _final is not None:  # exact joint distribution instead of samples
+                probs = np.abs(st.amplitudes()) ** 2
+                for index in np.nonzero(probs > 0)[0]:
+                    key = tuple(sorted(keys_of(int(index)).items()))
+                    _final[key] = _final.get(key, 0.0) + float(probs[index])
+                return counters
+            for s in st.sample(shots, seed):
+                for tid, key in keys_of(int(s)).items():
+                    counters[tid][key] = counters[tid].get(key, 0) + 1
+            return counters
         for t in T.values():
             local = {c - t["zc"]: v for c, v in creg.items() if t["zc"] <= c < t["zc"] + t["ncl"]}
             key = bits_to_string(local, t["ncl"])
             counters[t["id"]][key] = counters[t["id"]].get(key, 0) + 1
     return counters
+
+
+def run_dynamic_auto(tasks, shots, seed=0, **kw):
+    """the engine's default policy: defer every measurement when the circuit allows it, else shot by shot"""
+    try:
+        return run_dynamic(tasks, shots, seed, defer=True, **kw), "deferred"
+    except DeferAbort:
+        return run_dynamic(tasks, shots, seed, **kw), "per-shot"
+
+
+def deferred_distribution(tasks, **kw):
+    """exact joint distribution {((task id, bitstring), ...): p} of the deferred-measurement run"""
+    final = {}
+    run_dynamic(tasks, 1, 0, defer=True, _final=final, **kw)
+    return final
+
+
+def literal_distribution(tasks, **kw):
+    """exact joint distribution of the reference's literal per-shot semantics, by enumerating every measurement
+    branch (depth-first over forced outcomes; branches of probability 0 are cut).  Small circuits only."""
+    dist = {}
+    stack = [[]]
+    while stack:
+        prefix = stack.pop()
+        weight = [1.0]
+        try:
+            res = run_dynamic(tasks, 1, 0, forced_bits=prefix, _weight=weight, terminal_sampling=False, **kw)
+        except _NeedMoreBits:
+            stack.append(prefix + [0])
+            stack.append(prefix + [1])
+            continue
+        except _DeadBranch:
+            continue
+        key = tuple(sorted((tid, next(iter(cnt))) for tid, cnt in res.items()))
+        dist[key] = dist.get(key, 0.0) + weight[0]
+    return dist
 
 
 def fuse_blocks(instructions, kmax=4):

@@ -212,6 +212,9 @@ def test_deferred_measurement_cif(backend):
     assert "ERROR" not in res, res
     assert backend.last_mode() == 1
     assert all(k[0] == k[3] for k in res["counts"])  # clbit 3 repeats clbit 0
+    # the oracle restates the deferral rule: same final state, same u_s = U(seed, s) -> the same shots
+    assert res["counts"] == O.run_dynamic([{"id": "task", "num_qubits": 3, "num_clbits": 4, "instructions": ins}],
+                                          shots, seed=17, defer=True)["task"]
     ref = backend.execute(dyn_task(ins, 3, 4, shots, 18))
     assert backend.last_mode() == 2
     assert O.tvd(res["counts"], ref["counts"]) < 0.03
@@ -227,6 +230,8 @@ def test_deferred_measurement_quantum_communication(backend, maker):
     res = backend.execute(msg)
     assert "ERROR" not in res, res
     assert backend.last_mode() == 1
+    if maker is C.hea_telegate_pair:  # (teledata ends with a relabelled swap: distribution-equal only)
+        assert res["id_counts"] == O.run_dynamic(tasks, shots, seed=7, defer=True)
     st = backend.stats()
     for m in msg:
         m["config"]["b200_defer_measurement"] = False
@@ -260,3 +265,22 @@ def test_deferral_falls_back_when_a_collapse_is_needed(backend, ins):
     assert backend.last_mode() == 2
     want = O.run_dynamic([{"id": "task", "num_qubits": 2, "num_clbits": 2, "instructions": ins}], 500, seed=21)["task"]
     assert res["counts"] == want
+
+
+def test_deferred_measurement_takes_fresh_communication_pairs(backend):
+    """two teleports: with one pair the second needs a real reset (per-shot mode); with two pairs both are deferred"""
+    a = [{"name": "ry", "qubits": [0], "params": [0.7]}, {"name": "qsend", "qubits": [0], "qpus": ["B"]},
+         {"name": "ry", "qubits": [1], "params": [0.3]}, {"name": "qsend", "qubits": [1], "qpus": ["B"]}]
+    b = [{"name": "qrecv", "qubits": [0], "qpus": ["A"]}, {"name": "qrecv", "qubits": [1], "qpus": ["A"]}] + C.measure_all(2)
+    shots = 20000
+    p_want = {"00": math.cos(0.35) ** 2 * math.cos(0.15) ** 2, "01": math.sin(0.35) ** 2 * math.cos(0.15) ** 2,
+              "10": math.cos(0.35) ** 2 * math.sin(0.15) ** 2, "11": math.sin(0.35) ** 2 * math.sin(0.15) ** 2}
+    for n_comm, mode in ((2, 2), (4, 1)):
+        msg = [C.task(a, 2, shots=shots, seed=3, task_id="A", is_dynamic=True, n_communication_qubits=n_comm),
+               C.task(b, 2, shots=shots, seed=3, task_id="B", is_dynamic=True, n_communication_qubits=n_comm)]
+        res = backend.execute(msg)
+        assert "ERROR" not in res, res
+        assert backend.last_mode() == mode
+        got = res["id_counts"]["B"]
+        for k, p in p_want.items():
+            assert abs(got.get(k, 0) / shots - p) < 5 * math.sqrt(p * (1 - p) / shots) + 1e-3, (n_comm, k)

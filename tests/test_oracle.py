@@ -141,3 +141,80 @@ def test_block_fusion_for_the_cpu_baseline(lib_built):
     for qs, m in blocks:
         st.apply_matrix(qs, m)
     assert np.abs(st.amplitudes() - ref.amplitudes()).max() < 1e-12
+
+
+# ---- deferred measurement: the rule the engine applies by default to dynamic tasks, proven on small circuits -----
+def _cif_circuit():
+    return [{"id": "task", "num_qubits": 3, "num_clbits": 4, "instructions": [
+        {"name": "h", "qubits": [0]}, {"name": "ry", "qubits": [2], "params": [0.9]},
+        {"name": "measure", "qubits": [0], "clbits": [0]},
+        {"name": "cif", "clbits": [0], "operation": "and", "condition": 1,
+         "instructions": [{"name": "x", "qubits": [1]}, {"name": "rx", "qubits": [2], "params": [1.3]},
+                          C.unitary_inst(C.haar_unitary(np.random.default_rng(4), 4), [1, 2]),
+                          {"name": "gp", "qubits": [], "params": [0.4]}]},
+        {"name": "cz", "qubits": [0, 2]},
+        {"name": "measure", "qubits": [1], "clbits": [1]}, {"name": "measure", "qubits": [2], "clbits": [2]},
+        {"name": "measure", "qubits": [0], "clbits": [3]}]}]
+
+
+def _two_way_traffic():
+    """teledata A->B, then a classically communicated outcome B->A conditions a gate on A"""
+    a = C.hea_ansatz(2, 1, 5, measure=False) + [{"name": "qsend", "qubits": [1], "qpus": ["B"]},
+                                                 {"name": "recv", "clbits": [1], "qpus": ["B"]},
+                                                 {"name": "cif", "clbits": [1], "operation": "and", "condition": 1,
+                                                  "instructions": [{"name": "ry", "qubits": [0], "params": [0.8]}]},
+                                                 {"name": "measure", "qubits": [0], "clbits": [0]}]
+    b = C.hea_ansatz(2, 1, 6, measure=False) + [{"name": "qrecv", "qubits": [0], "qpus": ["A"]},
+                                                 {"name": "cx", "qubits": [0, 1]},
+                                                 {"name": "measure", "qubits": [1], "clbits": [1]},
+                                                 {"name": "send", "clbits": [1], "qpus": ["A"]},
+                                                 {"name": "measure", "qubits": [0], "clbits": [0]}]
+    return [{"id": "A", "num_qubits": 2, "num_clbits": 2, "instructions": a},
+            {"id": "B", "num_qubits": 2, "num_clbits": 2, "instructions": b}]
+
+
+@pytest.mark.parametrize("maker", [_cif_circuit, lambda: C.hea_teledata_pair(2, 1), lambda: C.hea_telegate_pair(2, 1),
+                                   lambda: C.hea_telegate_pair(3, 2), _two_way_traffic])
+def test_deferred_measurement_has_the_literal_distribution(maker):
+    """exact: joint distribution of all classical outcomes, deferred run vs every branch of the per-shot semantics"""
+    tasks = maker()
+    lit = O.literal_distribution(tasks)
+    dfr = O.deferred_distribution(tasks)
+    assert abs(sum(lit.values()) - 1) < 1e-12 and abs(sum(dfr.values()) - 1) < 1e-12
+    for key in set(lit) | set(dfr):
+        assert abs(lit.get(key, 0.0) - dfr.get(key, 0.0)) < 1e-12, key
+    assert len(lit) > 2
+
+
+@pytest.mark.parametrize("ins", [
+    [{"name": "h", "qubits": [0]}, {"name": "measure", "qubits": [0], "clbits": [0]}, {"name": "h", "qubits": [0]},
+     {"name": "measure", "qubits": [0], "clbits": [1]}],
+    [{"name": "h", "qubits": [0]}, {"name": "cx", "qubits": [0, 1]}, {"name": "reset", "qubits": [0]},
+     {"name": "measure", "qubits": [1], "clbits": [1]}],
+    [{"name": "h", "qubits": [0]}, {"name": "measure", "qubits": [0], "clbits": [0]},
+     {"name": "cif", "clbits": [0], "operation": "and", "condition": 0, "instructions": [{"name": "x", "qubits": [1]}]},
+     {"name": "measure", "qubits": [1], "clbits": [1]}],
+    [{"name": "h", "qubits": [0]}, {"name": "h", "qubits": [1]}, {"name": "measure", "qubits": [0], "clbits": [0]},
+     {"name": "measure", "qubits": [1], "clbits": [1]},
+     {"name": "cif", "clbits": [0, 1], "operation": "xor", "condition": 1, "instructions": [{"name": "x", "qubits": [1]}]}],
+])
+def test_deferral_is_refused_when_a_collapse_is_needed(ins):
+    tasks = [{"id": "task", "num_qubits": 2, "num_clbits": 2, "instructions": ins}]
+    with pytest.raises(O.DeferAbort):
+        O.run_dynamic(tasks, 10, seed=1, defer=True)
+    counts, mode = O.run_dynamic_auto(tasks, 50, seed=1)
+    assert mode == "per-shot" and counts == O.run_dynamic(tasks, 50, seed=1)
+
+
+def test_deferral_is_refused_when_a_communication_pair_is_reused():
+    a = [{"name": "ry", "qubits": [0], "params": [0.7]}, {"name": "qsend", "qubits": [0], "qpus": ["B"]},
+         {"name": "ry", "qubits": [1], "params": [0.3]}, {"name": "qsend", "qubits": [1], "qpus": ["B"]}]
+    b = [{"name": "qrecv", "qubits": [0], "qpus": ["A"]}, {"name": "qrecv", "qubits": [1], "qpus": ["A"]}] + C.measure_all(2)
+    tasks = [{"id": "A", "num_qubits": 2, "num_clbits": 2, "instructions": a}, {"id": "B", "num_qubits": 2, "num_clbits": 2, "instructions": b}]
+    with pytest.raises(O.DeferAbort):
+        O.run_dynamic(tasks, 10, seed=1, defer=True)
+    # with a second pair the two teleports use fresh qubits and can both be deferred
+    dfr = O.deferred_distribution(tasks, n_comm_qubits=4)
+    lit = O.literal_distribution(tasks, n_comm_qubits=4)
+    for key in set(lit) | set(dfr):
+        assert abs(lit.get(key, 0.0) - dfr.get(key, 0.0)) < 1e-12
