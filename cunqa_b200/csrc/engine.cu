@@ -394,6 +394,28 @@ void State::prob1(int qubit, double *out)
     CB200_CUDA(cudaStreamSynchronize(stream_));
 }
 
+void State::reduced_qubit(int qubit, double out[4])
+{
+    if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
+    if (dist) throw Unsupported("reduced density matrix of a sharded state is not implemented");
+    flush();
+    const int pq = queue.l2p[qubit];
+    const uint64_t amps = 1ull << n_local_;
+    int nblk = (int)std::min<uint64_t>((amps / 2 + kRedThreads * 8 - 1) / (kRedThreads * 8), (uint64_t)num_sms_ * 8);
+    if (nblk < 1) nblk = 1;
+    ensure_scratch((size_t)4 * nblk);
+    dim3 grid(nblk, 1);  // state 0 only
+    if (precision == 64) rho_partial_kernel<double2><<<grid, kRedThreads, 0, stream_>>>((const double2 *)d_state_, amps, pq, d_partial_, (size_t)nblk);
+    else rho_partial_kernel<float2><<<grid, kRedThreads, 0, stream_>>>((const float2 *)d_state_, amps, pq, d_partial_, (size_t)nblk);
+    for (int k = 0; k < 4; k++) sum_partials_kernel<<<1, kRedThreads, 0, stream_>>>(d_partial_ + (size_t)k * nblk, nblk, d_small_ + k);
+    CB200_CUDA(cudaGetLastError());
+    stats.launches += 5;
+    stats.bytes += state_bytes_ / (uint64_t)batch;
+    CB200_CUDA(cudaMemcpyAsync(out, d_small_, sizeof(double) * 4, cudaMemcpyDeviceToHost, stream_));
+    CB200_CUDA(cudaStreamSynchronize(stream_));
+    stats.d2h_bytes += sizeof(double) * 4;
+}
+
 void State::measure(int qubit, uint64_t seed, const uint64_t *counters, const int8_t *forced, int *bits_out, bool reset_after)
 {
     if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");

@@ -57,6 +57,8 @@ public:
     // ---- measurement
     void norm(double *out);
     void prob1(int qubit, double *out);
+    // reduced density matrix of one qubit of state 0: out = {rho00, rho11, Re rho01, Im rho01}
+    void reduced_qubit(int qubit, double out[4]);
     void probabilities(int b, const int *qubits, int k, double *out);
     void measure(int qubit, uint64_t seed, const uint64_t *counters, const int8_t *forced, int *bits_out, bool reset_after);
     void sample(int b, uint64_t shots, uint64_t seed, uint64_t *out);

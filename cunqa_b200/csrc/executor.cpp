@@ -591,6 +591,50 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
             }
             return (flags && !all(*flags)) ? flags->data() : nullptr;
         };
+        // deferred mode: bring a qubit that holds a recorded outcome (or any other state) back to |0> WITHOUT a collapse.
+        // Possible when no classical bit or pending message still refers to its record and the qubit has become
+        // disentangled from the rest of the register -- as the measured qubits of a completed teleportation or remote
+        // gate have (the corrections leave them in |+>): then one single-qubit unitary maps its pure state to |0>.
+        auto sym_referenced = [&](int q) -> bool {
+            const uint8_t v = (uint8_t)(kSym + q);
+            for (const Bits &b : creg) if (b[0] == v) return true;
+            for (auto &kv : q_td) for (const Bits &b : kv.second) if (b[0] == v) return true;
+            for (auto &kv : q_tg) for (const Bits &b : kv.second) if (b[0] == v) return true;
+            for (auto &kv : q_cc) for (const Bits &b : kv.second) if (b[0] == v) return true;
+            return false;
+        };
+        auto recycle = [&](int q) {
+            if (sym_referenced(q)) throw DeferAbort();
+            double r[4];
+            st.reduced_qubit(q, r);
+            const double tr = r[0] + r[1];
+            const double purity = (r[0] * r[0] + r[1] * r[1] + 2.0 * (r[2] * r[2] + r[3] * r[3])) / (tr * tr);
+            if (!(purity > 1.0 - 1e-9)) throw DeferAbort();  // still entangled: only a real measurement resets it
+            // pure state (phi0, phi1) with rho01 = phi0 conj(phi1); fix the phase on the larger component
+            cplx phi0, phi1;
+            if (r[0] >= r[1]) {
+                phi0 = std::sqrt(r[0] / tr);
+                phi1 = std::conj(cplx(r[2], r[3])) / (tr * phi0);
+            } else {
+                phi1 = std::sqrt(r[1] / tr);
+                phi0 = cplx(r[2], r[3]) / (tr * phi1);
+            }
+            const cplx u[4] = {std::conj(phi0), std::conj(phi1), -phi1, phi0};  // u (phi0, phi1)^T = (1, 0)^T
+            st.apply_matrix(&q, 1, nullptr, 0, u, nullptr);
+            qstate[q] = Q_LIVE;
+            touched[q] = 0;
+        };
+        // reset whose outcome nobody reads (the `reset` instruction, the protocol's preparation of a communication pair)
+        auto reset_q = [&](int q, const uint8_t *flags) {
+            if (!deferred) { measure(q, true, flags); return; }
+            if (flags) {
+                if (flags[0] == 0) return;
+                if (flags[0] != 1) throw DeferAbort();
+            }
+            if (qstate[q] == Q_FROZEN) { qstate[q] = Q_FROZEN_RESET; return; }  // record kept, logically |0> from here on
+            if (qstate[q] == Q_FROZEN_RESET || !touched[q]) return;
+            recycle(q);
+        };
         // deferred mode: may this instruction (register qubits qs) still run?  false = skip it (a control sits on a
         // qubit that was measured and reset: logically |0>), DeferAbort = it would disturb a recorded outcome
         auto admit = [&](const Inst &in, const std::vector<int> &qs) -> bool {
@@ -602,8 +646,8 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                 for (size_t i = 0; i < qs.size(); i++) {
                     if (qstate[qs[i]] == Q_FROZEN && kinds[i] == 'x') throw DeferAbort();
                     if (qstate[qs[i]] == Q_FROZEN_RESET) {
-                        if (kinds[i] != 'k') throw DeferAbort();
-                        skip = true;  // controlled on |0>: never fires
+                        if (kinds[i] == 'k') skip = true;  // controlled on |0>: never fires
+                        else recycle(qs[i]);               // driven again: needs the physical |0> (or DeferAbort)
                     }
                 }
                 if (skip) return false;
@@ -637,8 +681,8 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
             if (idx.size() < npairs) return std::vector<int>();
             for (int i : idx) {
                 pairs[i].idle = false;
-                measure(pairs[i].q1, true, nullptr);
-                measure(pairs[i].q0, true, nullptr);
+                reset_q(pairs[i].q1, nullptr);
+                reset_q(pairs[i].q0, nullptr);
                 named("h", {pairs[i].q0}, nullptr);
                 named("cx", {pairs[i].q0, pairs[i].q1}, nullptr);
             }
@@ -682,14 +726,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                         throw std::runtime_error("The number of copied clbits and the number of clbits copied on does not match.");
                     for (size_t i = 0; i < in.l_clbits.size(); i++) { const Bits src = clb(in.r_clbits[i]); assign(clb(in.l_clbits[i]), src); }
                 } else if (name == "reset") {
-                    if (deferred) {
-                        // only a qubit that is still (or again) |0> can be reset without a collapse
-                        const int q = qmap(in.qubits.at(0));
-                        if (cond && (*cond)[0] == 0) return;
-                        if (qstate[q] == Q_FROZEN_RESET || (qstate[q] == Q_LIVE && !touched[q])) return;
-                        throw DeferAbort();
-                    }
-                    measure(qmap(in.qubits.at(0)), true, cond ? cond->data() : nullptr);
+                    reset_q(qmap(in.qubits.at(0)), cond ? cond->data() : nullptr);
                 } else if (name == "send") {
                     if (multi) {
                         for (int cl : in.clbits) q_cc[{c.id, in.qpus.at(0)}].push_back(clb(cl));

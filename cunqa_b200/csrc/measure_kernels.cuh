@@ -112,6 +112,40 @@ prob2_partial_kernel(const V *__restrict__ state, uint64_t amps_per_state, uint6
     if (threadIdx.x == 0) { partial_all[b * gridDim.x + blockIdx.x] = acc; partial_sel[b * gridDim.x + blockIdx.x] = sel; }
 }
 
+// reduced density matrix of one qubit (physical bit `pq`), per state: partial[0] = rho00, [1] = rho11,
+// [2] + i [3] = rho01 = sum_rest a(rest,0) conj(a(rest,1)).  Each of the four arrays has batch * gridDim.x entries.
+template <typename V>
+__global__ void __launch_bounds__(kRedThreads)
+rho_partial_kernel(const V *__restrict__ state, uint64_t amps_per_state, int pq, double *__restrict__ partial, size_t arr)
+{
+    const uint64_t b = blockIdx.y;
+    const V *s = state + b * amps_per_state;
+    const uint64_t pairs = amps_per_state >> 1;
+    const uint64_t per_block = (pairs + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = per_block * blockIdx.x;
+    uint64_t hi = lo + per_block;
+    if (hi > pairs) hi = pairs;
+    const uint64_t bit = 1ull << pq;
+    double r00 = 0.0, r11 = 0.0, re = 0.0, im = 0.0;
+    for (uint64_t g = lo + threadIdx.x; g < hi; g += kRedThreads) {
+        const uint64_t i0 = ((g >> pq) << (pq + 1)) | (g & (bit - 1ull));
+        const V a0 = s[i0], a1 = s[i0 | bit];
+        const double x0 = (double)a0.x, y0 = (double)a0.y, x1 = (double)a1.x, y1 = (double)a1.y;
+        r00 += x0 * x0 + y0 * y0;
+        r11 += x1 * x1 + y1 * y1;
+        re += x0 * x1 + y0 * y1;
+        im += y0 * x1 - x0 * y1;
+    }
+    r00 = block_sum(r00);
+    r11 = block_sum(r11);
+    re = block_sum(re);
+    im = block_sum(im);
+    if (threadIdx.x == 0) {
+        const size_t o = b * gridDim.x + blockIdx.x;
+        partial[o] = r00; partial[arr + o] = r11; partial[2 * arr + o] = re; partial[3 * arr + o] = im;
+    }
+}
+
 // out[b] = sum_j partial[b*nblk + j]   (one block per state, fixed order)
 __global__ void __launch_bounds__(kRedThreads) sum_partials_kernel(const double *__restrict__ partial, int nblk, double *__restrict__ out)
 {

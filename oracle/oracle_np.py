@@ -501,11 +501,40 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                 st.apply_matrix([q], _FIXED_1Q["x"])
             return out
 
+        def sym_referenced(q):
+            v = ("sym", q)
+            queues = list(q_td.values()) + list(q_tg.values()) + list(q_cc.values())
+            return any(x == v for x in creg.values()) or any(x == v for dq in queues for x in dq)
+
+        def recycle(q):
+            """defer mode: bring a qubit back to |0> without a collapse -- possible when nothing still refers to its
+            recorded outcome and it is disentangled from the rest (pure reduced state): one single-qubit unitary"""
+            if sym_referenced(q):
+                raise DeferAbort()
+            a = st.amplitudes().reshape(1 << (n_total - q - 1), 2, 1 << q)
+            a0, a1 = a[:, 0, :].ravel(), a[:, 1, :].ravel()
+            r00, r11, r01 = float(np.vdot(a0, a0).real), float(np.vdot(a1, a1).real), complex(np.vdot(a1, a0))
+            tr = r00 + r11
+            purity = (r00 * r00 + r11 * r11 + 2 * abs(r01) ** 2) / (tr * tr)
+            if not purity > 1 - 1e-9:
+                raise DeferAbort()
+            if r00 >= r11:
+                phi0 = math.sqrt(r00 / tr)
+                phi1 = np.conj(r01) / (tr * phi0)
+            else:
+                phi1 = math.sqrt(r11 / tr)
+                phi0 = r01 / (tr * phi1)
+            st.apply_matrix([q], np.array([[np.conj(phi0), np.conj(phi1)], [-phi1, phi0]], dtype=complex))
+            qstate[q] = "live"
+            touched[q] = False
+
         def reset(q):
             if defer:
-                if qstate[q] == "frozen_reset" or (qstate[q] == "live" and not touched[q]):
-                    return
-                raise DeferAbort()
+                if qstate[q] == "frozen":
+                    qstate[q] = "frozen_reset"  # record kept, logically |0> from here on
+                elif qstate[q] == "live" and touched[q]:
+                    recycle(q)
+                return
             measure(q, True)
 
         def admit(inst, qubits):
@@ -533,9 +562,10 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                     if qstate[q] == "frozen" and kind == "x":
                         raise DeferAbort()
                     if qstate[q] == "frozen_reset":
-                        if kind != "k":
-                            raise DeferAbort()
-                        skip = True
+                        if kind == "k":
+                            skip = True      # controlled on |0>: never fires
+                        else:
+                            recycle(q)       # driven again: needs the physical |0> (or DeferAbort)
                 if skip:
                     return False
             for q in qubits:

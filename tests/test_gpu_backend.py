@@ -267,15 +267,16 @@ def test_deferral_falls_back_when_a_collapse_is_needed(backend, ins):
     assert res["counts"] == want
 
 
-def test_deferred_measurement_takes_fresh_communication_pairs(backend):
-    """two teleports: with one pair the second needs a real reset (per-shot mode); with two pairs both are deferred"""
+def test_deferred_measurement_reuses_communication_pairs(backend):
+    """two teleports through ONE pair: the first teleport leaves its measured qubits disentangled (|+>), so they are
+    reset by a unitary and the second teleport is deferred as well; with two pairs a fresh pair is taken"""
     a = [{"name": "ry", "qubits": [0], "params": [0.7]}, {"name": "qsend", "qubits": [0], "qpus": ["B"]},
          {"name": "ry", "qubits": [1], "params": [0.3]}, {"name": "qsend", "qubits": [1], "qpus": ["B"]}]
     b = [{"name": "qrecv", "qubits": [0], "qpus": ["A"]}, {"name": "qrecv", "qubits": [1], "qpus": ["A"]}] + C.measure_all(2)
     shots = 20000
     p_want = {"00": math.cos(0.35) ** 2 * math.cos(0.15) ** 2, "01": math.sin(0.35) ** 2 * math.cos(0.15) ** 2,
               "10": math.cos(0.35) ** 2 * math.sin(0.15) ** 2, "11": math.sin(0.35) ** 2 * math.sin(0.15) ** 2}
-    for n_comm, mode in ((2, 2), (4, 1)):
+    for n_comm, mode in ((2, 1), (4, 1)):
         msg = [C.task(a, 2, shots=shots, seed=3, task_id="A", is_dynamic=True, n_communication_qubits=n_comm),
                C.task(b, 2, shots=shots, seed=3, task_id="B", is_dynamic=True, n_communication_qubits=n_comm)]
         res = backend.execute(msg)
@@ -284,3 +285,24 @@ def test_deferred_measurement_takes_fresh_communication_pairs(backend):
         got = res["id_counts"]["B"]
         for k, p in p_want.items():
             assert abs(got.get(k, 0) / shots - p) < 5 * math.sqrt(p * (1 - p) / shots) + 1e-3, (n_comm, k)
+
+
+def test_deferred_measurement_many_remote_operations(backend):
+    """teleports, a re-driven sender qubit and a remote-controlled gate through one pair: all deferred, and the
+    shots equal the oracle's deferred shots except for the relabelled swaps (distribution-equal)"""
+    from test_oracle import _many_remote_ops
+    tasks = _many_remote_ops(2)
+    shots = 40000
+    msg = [C.task(t["instructions"], t["num_qubits"], shots=shots, seed=5, task_id=t["id"], is_dynamic=True) for t in tasks]
+    res = backend.execute(msg)
+    assert "ERROR" not in res, res
+    assert backend.last_mode() == 1
+    dist = O.deferred_distribution(tasks, n_comm_qubits=2)
+    for tid in ("A", "B"):
+        want = {}
+        for key, p in dist.items():
+            k = dict(key)[tid]
+            want[k] = want.get(k, 0.0) + p
+        got = res["id_counts"][tid]
+        assert sum(got.values()) == shots
+        assert 0.5 * sum(abs(got.get(k, 0) / shots - want.get(k, 0.0)) for k in set(got) | set(want)) < 0.02

@@ -206,15 +206,33 @@ def test_deferral_is_refused_when_a_collapse_is_needed(ins):
     assert mode == "per-shot" and counts == O.run_dynamic(tasks, 50, seed=1)
 
 
-def test_deferral_is_refused_when_a_communication_pair_is_reused():
+def _many_remote_ops(n_comm):
+    """two teleports A->B and a remote-controlled gate B->A through the same communication pair(s)"""
     a = [{"name": "ry", "qubits": [0], "params": [0.7]}, {"name": "qsend", "qubits": [0], "qpus": ["B"]},
-         {"name": "ry", "qubits": [1], "params": [0.3]}, {"name": "qsend", "qubits": [1], "qpus": ["B"]}]
-    b = [{"name": "qrecv", "qubits": [0], "qpus": ["A"]}, {"name": "qrecv", "qubits": [1], "qpus": ["A"]}] + C.measure_all(2)
-    tasks = [{"id": "A", "num_qubits": 2, "num_clbits": 2, "instructions": a}, {"id": "B", "num_qubits": 2, "num_clbits": 2, "instructions": b}]
-    with pytest.raises(O.DeferAbort):
-        O.run_dynamic(tasks, 10, seed=1, defer=True)
-    # with a second pair the two teleports use fresh qubits and can both be deferred
-    dfr = O.deferred_distribution(tasks, n_comm_qubits=4)
-    lit = O.literal_distribution(tasks, n_comm_qubits=4)
+         {"name": "ry", "qubits": [1], "params": [0.3]}, {"name": "h", "qubits": [0]},   # the sent qubit is driven again
+         {"name": "qsend", "qubits": [1], "qpus": ["B"]},
+         {"name": "rcontrol", "qpus": ["B"], "instructions": [{"name": "cx", "qubits": [-1, 0]}]}] + C.measure_all(2)
+    b = [{"name": "qrecv", "qubits": [0], "qpus": ["A"]}, {"name": "qrecv", "qubits": [1], "qpus": ["A"]},
+         {"name": "cx", "qubits": [0, 1]}, {"name": "expose", "qubits": [1], "qpus": ["A"]}] + C.measure_all(2)
+    return [{"id": "A", "num_qubits": 2, "num_clbits": 2, "instructions": a}, {"id": "B", "num_qubits": 2, "num_clbits": 2, "instructions": b}]
+
+
+@pytest.mark.parametrize("n_comm", [2, 4])
+def test_deferred_measurement_recycles_disentangled_qubits(n_comm):
+    """a completed teleportation / remote gate leaves its measured qubits in |+>, disentangled: they are reset by a
+    unitary, so a communication pair (and the sender's qubit) can be used again without a collapse"""
+    tasks = _many_remote_ops(n_comm)
+    dfr = O.deferred_distribution(tasks, n_comm_qubits=n_comm)   # must not raise DeferAbort
+    lit = O.literal_distribution(tasks, n_comm_qubits=n_comm)
+    assert abs(sum(lit.values()) - 1) < 1e-12 and abs(sum(dfr.values()) - 1) < 1e-12 and len(lit) > 4
     for key in set(lit) | set(dfr):
-        assert abs(lit.get(key, 0.0) - dfr.get(key, 0.0)) < 1e-12
+        assert abs(lit.get(key, 0.0) - dfr.get(key, 0.0)) < 1e-12, key
+
+
+def test_deferred_reset_of_a_disentangled_qubit():
+    ins = [{"name": "ry", "qubits": [0], "params": [1.1]}, {"name": "h", "qubits": [1]}, {"name": "cx", "qubits": [1, 2]},
+           {"name": "reset", "qubits": [0]}, {"name": "ry", "qubits": [0], "params": [0.4]}, {"name": "cx", "qubits": [0, 1]}] + C.measure_all(3)
+    tasks = [{"id": "task", "num_qubits": 3, "num_clbits": 3, "instructions": ins}]
+    dfr, lit = O.deferred_distribution(tasks), O.literal_distribution(tasks)
+    for key in set(lit) | set(dfr):
+        assert abs(lit.get(key, 0.0) - dfr.get(key, 0.0)) < 1e-12, key
