@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -190,7 +192,8 @@ std::string bits_to_string(const std::vector<uint8_t> &creg, int zero, int ncl)
 Json counts_json(const std::map<std::string, uint64_t> &counts)
 {
     Json j = Json::object();
-    for (auto &kv : counts) j.set(kv.first, Json::integer((long long)kv.second));
+    j.obj.reserve(counts.size());  // keys of a std::map are unique: append directly (Json::set searches linearly)
+    for (auto &kv : counts) j.obj.emplace_back(kv.first, Json::integer((long long)kv.second));
     return j;
 }
 
@@ -305,6 +308,7 @@ Json Backend::run(const Json &msg)
 
 Json Backend::run_static(const Json &task)
 {
+    const auto t_in = std::chrono::high_resolution_clock::now();
     const TaskCfg c = parse_task(task);
     const auto t0 = std::chrono::high_resolution_clock::now();
     State &st = get_state(c.num_qubits, c.precision, 1);
@@ -328,14 +332,24 @@ Json Backend::run_static(const Json &task)
     }
     const uint64_t seed = c.has_seed ? c.seed : fresh_seed();
     std::vector<uint64_t> samples(c.shots);
+    const auto t_q = std::chrono::high_resolution_clock::now();
+    st.flush();
+    const auto t_f = std::chrono::high_resolution_clock::now();
+    if (getenv("CB200_TRACE")) st.sync();  // (tracing only) split the wait for the tile passes from the sampling
+    const auto t_w = std::chrono::high_resolution_clock::now();
     st.sample(0, c.shots, seed, samples.data());
+    const auto t_s = std::chrono::high_resolution_clock::now();
     std::map<std::string, uint64_t> counts;
     std::string key((size_t)c.num_clbits, '0');
-    for (uint64_t s : samples) {
+    std::sort(samples.begin(), samples.end());  // equal basis states are adjacent: one string per distinct outcome
+    for (size_t i = 0; i < samples.size();) {
+        size_t j = i;
+        while (j < samples.size() && samples[j] == samples[i]) j++;
         std::fill(key.begin(), key.end(), '0');
         for (auto &qc : meas)
-            key[c.num_clbits - 1 - qc.second] = ((s >> qc.first) & 1ull) ? '1' : '0';
-        counts[key]++;
+            key[c.num_clbits - 1 - qc.second] = ((samples[i] >> qc.first) & 1ull) ? '1' : '0';
+        counts[key] += j - i;
+        i = j;
     }
     Json out = Json::object();
     out.set("counts", counts_json(counts));
@@ -357,6 +371,11 @@ Json Backend::run_static(const Json &task)
     }
     const auto t1 = std::chrono::high_resolution_clock::now();
     out.set("time_taken", Json::number(std::chrono::duration<double>(t1 - t0).count()));
+    if (getenv("CB200_TRACE")) {
+        auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        fprintf(stderr, "[cb200] static task: parse %.0f us, queue+fuse %.0f us, plan+launch %.0f us, wait for passes %.0f us, sample %.0f us, counts %.0f us\n",
+                us(t_in, t0), us(t0, t_q), us(t_q, t_f), us(t_f, t_w), us(t_w, t_s), us(t_s, t1));
+    }
     last_mode = 0;
     last_stats = st.stats;
     last_stats.passes -= before.passes;
