@@ -156,6 +156,7 @@ void State::dist_swap(const std::vector<std::pair<int, int>> &pairs)
     dist_fence();  // the partners' writes into this shard have landed
     CB200_CUDA(cudaEventRecord(e1, stream_));
     dist->swap_events.emplace_back(e0, e1);
+    if (dist->swap_events.size() >= 64) dist_swap_ms();  // fold the spans into the running total, free the events
     stats.launches++;
     dist->swaps += m;
     dist->exchanges++;
@@ -223,6 +224,7 @@ void State::dist_destroy()
     for (int r = 0; r < (int)dist->peers.size(); r++)
         if (r != dist->rank && dist->peers[r]) cudaIpcCloseMemHandle(dist->peers[r]);
     if (dist->comm) nccl().CommDestroy(dist->comm);
+    for (auto &ev : dist->swap_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaFree(dist->d_fence);
     delete dist;
     dist = nullptr;
