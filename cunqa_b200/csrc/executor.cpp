@@ -411,6 +411,9 @@ using Bits = std::vector<uint8_t>;
 // Deferred measurement (one state, all shots sampled at the end): a classical bit is then SYMBOLIC -- 0 / 1 are
 // constants, kSym + q means "the outcome recorded in register qubit q", which is read from the final sample.
 constexpr uint8_t kSym = 2;
+constexpr uint8_t kNotSym = 128;  // kNotSym + q: "NOT the outcome recorded in qubit q" (a cif that tests for 0)
+inline bool sym_negated(uint8_t v) { return v >= kNotSym; }
+inline int sym_qubit(uint8_t v) { return v >= kNotSym ? v - kNotSym : v - kSym; }
 struct DeferAbort {};  // the circuit needs a real mid-circuit collapse: fall back to the batched interpreter
 enum QState : uint8_t { Q_LIVE = 0, Q_FROZEN, Q_FROZEN_RESET };
 
@@ -440,7 +443,18 @@ std::vector<char> action_kinds(const Inst &in)
 }
 
 // the instruction with one more control qubit (register index), for a condition that is a deferred outcome
-void queue_gate_controlled(State &st, const Inst &in, const std::vector<int> &qs, int ctrl, bool reverse_unitary_qubits)
+void queue_gate_controlled_pos(State &st, const Inst &in, const std::vector<int> &qs, int ctrl, bool reverse_unitary_qubits);
+
+// sym = kSym + q (fires on outcome 1) or kNotSym + q (fires on outcome 0: the control qubit is X-conjugated)
+void queue_gate_controlled(State &st, const Inst &in, const std::vector<int> &qs, uint8_t sym, bool reverse_unitary_qubits)
+{
+    const int ctrl = sym_qubit(sym);
+    if (sym_negated(sym)) st.apply_named("x", &ctrl, 1, nullptr, 0, nullptr);
+    queue_gate_controlled_pos(st, in, qs, ctrl, reverse_unitary_qubits);
+    if (sym_negated(sym)) st.apply_named("x", &ctrl, 1, nullptr, 0, nullptr);
+}
+
+void queue_gate_controlled_pos(State &st, const Inst &in, const std::vector<int> &qs, int ctrl, bool reverse_unitary_qubits)
 {
     std::vector<int> ctrls, targets;
     std::vector<cplx> mat;
@@ -615,7 +629,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
         // disentangled from the rest of the register -- as the measured qubits of a completed teleportation or remote
         // gate have (the corrections leave them in |+>): then one single-qubit unitary maps its pure state to |0>.
         auto sym_referenced = [&](int q) -> bool {
-            const uint8_t v = (uint8_t)(kSym + q);
+            const uint8_t v = (uint8_t)(kSym + q);  // (negated symbols only live inside a cif body, never in storage)
             for (const Bits &b : creg) if (b[0] == v) return true;
             for (auto &kv : q_td) for (const Bits &b : kv.second) if (b[0] == v) return true;
             for (auto &kv : q_tg) for (const Bits &b : kv.second) if (b[0] == v) return true;
@@ -682,7 +696,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                 const uint8_t f = flags ? (*flags)[0] : 1;
                 if (f == 0 || !admit(in, qs)) return;
                 if (f == 1) st.apply_named(name, qs.data(), (int)qs.size(), nullptr, 0, nullptr);
-                else queue_gate_controlled(st, in, qs, f - kSym, false);
+                else queue_gate_controlled(st, in, qs, f, false);
                 return;
             }
             if (flags && !any(*flags)) return;
@@ -776,10 +790,11 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                     if (deferred) {
                         for (int cl : in.clbits) symbolic = symbolic || clb(cl)[0] >= kSym;
                         if (symbolic) {
-                            // one recorded outcome, tested for 1, not nested inside another undecided condition
-                            if (in.clbits.size() != 1 || !cnd) throw DeferAbort();
+                            // one recorded outcome (tested for 1 or for 0), not nested inside another undecided condition
+                            if (in.clbits.size() != 1) throw DeferAbort();
                             if (cond && (*cond)[0] >= kSym) throw DeferAbort();
-                            res[0] = (cond && (*cond)[0] == 0) ? 0 : clb(in.clbits[0])[0];
+                            const uint8_t v = clb(in.clbits[0])[0];
+                            res[0] = (cond && (*cond)[0] == 0) ? 0 : (cnd ? v : (uint8_t)(kNotSym + sym_qubit(v)));
                         }
                     }
                     for (int b = 0; b < nb && !symbolic; b++) {
@@ -873,7 +888,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                         for (int x : in.qubits) qs.push_back(qmap(x));
                         if (name == "barrier" || name == "id" || name == "save_state") return;
                         if (!admit(in, qs)) return;
-                        if (cond && (*cond)[0] >= kSym) queue_gate_controlled(st, in, qs, (*cond)[0] - kSym, c.bugcompat_unitary_order);
+                        if (cond && (*cond)[0] >= kSym) queue_gate_controlled(st, in, qs, (*cond)[0], c.bugcompat_unitary_order);
                         else queue_gate(st, in, qmap, nullptr, c.bugcompat_unitary_order);
                         return;
                     }
@@ -952,7 +967,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
             for (uint64_t s = 0; s < live; s++) {
                 for (int cl = 0; cl < ncl_total; cl++) {
                     const uint8_t v = creg[cl][0];
-                    bits[cl] = v >= kSym ? (uint8_t)((samples[s] >> (v - kSym)) & 1ull) : v;
+                    bits[cl] = v >= kSym ? (uint8_t)((samples[s] >> sym_qubit(v)) & 1ull) : v;
                 }
                 for (const TaskRt &t : T) counters[t.cfg->id][bits_to_string(bits, t.zc, t.cfg->num_clbits)]++;
             }
@@ -969,7 +984,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
 
     // first choice: defer every measurement (one state, all shots from one final sample)
     bool done = false;
-    if (shots > 0 && c0.defer_measurement && !external_cc && n_total + (int)kSym <= 255) {
+    if (shots > 0 && c0.defer_measurement && !external_cc && n_total + (int)kSym <= (int)kNotSym) {
         State &s1 = get_state(n_total, precision, 1);
         const Stats b1 = s1.stats;
         const uint64_t g1 = s1.queue.gates;

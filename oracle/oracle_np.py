@@ -586,6 +586,14 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                 apply_gate(st, inst, qmap, reverse_unitary_qubits)
                 return
             ctrl = cond[1]
+            if cond[0] == "nsym":  # fires on outcome 0: X-conjugate the control qubit
+                st.apply_matrix([ctrl], _FIXED_1Q["x"])
+                gate_controlled(inst, qubits, ctrl)
+                st.apply_matrix([ctrl], _FIXED_1Q["x"])
+            else:
+                gate_controlled(inst, qubits, ctrl)
+
+        def gate_controlled(inst, qubits, ctrl):
             name = inst["name"]
             if name == "gp":
                 st.apply_diagonal([ctrl], np.array([1.0, np.exp(1j * inst["params"][0])]))
@@ -688,11 +696,13 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                 want = 1 if inst.get("condition", 1) else 0
                 bits = [creg.get(c + t["zc"], 0) for c in inst["clbits"]]
                 if any(is_sym(b) for b in bits):
-                    # one recorded outcome, tested for 1, not nested inside another undecided condition
-                    if len(bits) != 1 or not want or is_sym(cond):
+                    # one recorded outcome (tested for 1 or for 0), not nested inside another undecided condition
+                    if len(bits) != 1 or is_sym(cond):
                         raise DeferAbort()
+                    if cond == 0:
+                        return
                     for sub in inst["instructions"]:
-                        step(t, sub, (), bits[0])
+                        step(t, sub, (), bits[0] if want else ("nsym", bits[0][1]))
                     return
                 acc = bits[0] if want else 1 - bits[0]
                 for b in bits[1:]:

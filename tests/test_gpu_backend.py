@@ -254,10 +254,10 @@ def test_deferred_measurement_quantum_communication(backend, maker):
     # reset of a live qubit
     [{"name": "h", "qubits": [0]}, {"name": "cx", "qubits": [0, 1]}, {"name": "reset", "qubits": [0]},
      {"name": "measure", "qubits": [0], "clbits": [0]}, {"name": "measure", "qubits": [1], "clbits": [1]}],
-    # condition "bit is 0", and a two-bit condition
-    [{"name": "h", "qubits": [0]}, {"name": "measure", "qubits": [0], "clbits": [0]},
-     {"name": "cif", "clbits": [0], "operation": "and", "condition": 0, "instructions": [{"name": "x", "qubits": [1]}]},
-     {"name": "measure", "qubits": [1], "clbits": [1]}],
+    # a two-bit condition on undecided bits
+    [{"name": "h", "qubits": [0]}, {"name": "h", "qubits": [1]}, {"name": "measure", "qubits": [0], "clbits": [0]},
+     {"name": "measure", "qubits": [1], "clbits": [1]},
+     {"name": "cif", "clbits": [0, 1], "operation": "xor", "condition": 1, "instructions": [{"name": "x", "qubits": [1]}]}],
 ])
 def test_deferral_falls_back_when_a_collapse_is_needed(backend, ins):
     res = backend.execute(dyn_task(ins, 2, 2, 500, 21, b200_defer_measurement=True))
@@ -306,3 +306,13 @@ def test_deferred_measurement_many_remote_operations(backend):
         got = res["id_counts"][tid]
         assert sum(got.values()) == shots
         assert 0.5 * sum(abs(got.get(k, 0) / shots - want.get(k, 0.0)) for k in set(got) | set(want)) < 0.02
+
+
+def test_deferred_measurement_negated_condition(backend):
+    from test_oracle import _negated_condition
+    t = _negated_condition()[0]
+    shots = 20000
+    res = backend.execute(dyn_task(t["instructions"], 3, 3, shots, 4, b200_defer_measurement=True))
+    assert "ERROR" not in res, res
+    assert backend.last_mode() == 1
+    assert res["counts"] == O.run_dynamic([t], shots, seed=4, defer=True)["task"]
