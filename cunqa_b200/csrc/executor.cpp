@@ -339,20 +339,34 @@ Json Backend::run_static(const Json &task)
     const auto t_w = std::chrono::high_resolution_clock::now();
     st.sample(0, c.shots, seed, samples.data());
     const auto t_s = std::chrono::high_resolution_clock::now();
-    std::map<std::string, uint64_t> counts;
-    std::string key((size_t)c.num_clbits, '0');
-    std::sort(samples.begin(), samples.end());  // equal basis states are adjacent: one string per distinct outcome
-    for (size_t i = 0; i < samples.size();) {
-        size_t j = i;
-        while (j < samples.size() && samples[j] == samples[i]) j++;
-        std::fill(key.begin(), key.end(), '0');
-        for (auto &qc : meas)
-            key[c.num_clbits - 1 - qc.second] = ((samples[i] >> qc.first) & 1ull) ? '1' : '0';
-        counts[key] += j - i;
-        i = j;
-    }
     Json out = Json::object();
-    out.set("counts", counts_json(counts));
+    std::string key((size_t)c.num_clbits, '0');
+    if (c.num_clbits <= 64) {
+        // classical register of every shot as an integer, sorted: equal outcomes are adjacent, one string each
+        for (uint64_t &s : samples) {
+            uint64_t r = 0;
+            for (auto &qc : meas) r = (r & ~(1ull << qc.second)) | (((s >> qc.first) & 1ull) << qc.second);
+            s = r;
+        }
+        std::sort(samples.begin(), samples.end());
+        Json cj = Json::object();
+        for (size_t i = 0; i < samples.size();) {
+            size_t j = i;
+            while (j < samples.size() && samples[j] == samples[i]) j++;
+            for (int b = 0; b < c.num_clbits; b++) key[c.num_clbits - 1 - b] = ((samples[i] >> b) & 1ull) ? '1' : '0';
+            cj.obj.emplace_back(key, Json::integer((long long)(j - i)));
+            i = j;
+        }
+        out.set("counts", std::move(cj));
+    } else {
+        std::map<std::string, uint64_t> counts;
+        for (uint64_t s : samples) {
+            std::fill(key.begin(), key.end(), '0');
+            for (auto &qc : meas) key[c.num_clbits - 1 - qc.second] = ((s >> qc.first) & 1ull) ? '1' : '0';
+            counts[key]++;
+        }
+        out.set("counts", counts_json(counts));
+    }
     if (save_state) {
         if (c.num_qubits > 20) throw std::runtime_error("save_state: statevector return is limited to 20 qubits");
         const uint64_t dim = 1ull << c.num_qubits;
@@ -887,6 +901,11 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                         std::vector<int> qs;
                         for (int x : in.qubits) qs.push_back(qmap(x));
                         if (name == "barrier" || name == "id" || name == "save_state") return;
+                        // active reset, "measure q -> c; if (c) x q": the qubit is |0> afterwards, its record stays
+                        if (name == "x" && qs.size() == 1 && cond && (*cond)[0] == kSym + qs[0] && qstate[qs[0]] == Q_FROZEN) {
+                            qstate[qs[0]] = Q_FROZEN_RESET;
+                            return;
+                        }
                         if (!admit(in, qs)) return;
                         if (cond && (*cond)[0] >= kSym) queue_gate_controlled(st, in, qs, (*cond)[0], c.bugcompat_unitary_order);
                         else queue_gate(st, in, qmap, nullptr, c.bugcompat_unitary_order);

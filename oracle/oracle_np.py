@@ -580,6 +580,10 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                 apply_gate(st, inst, qmap, reverse_unitary_qubits)
                 return
             qubits = [qmap(q) for q in inst.get("qubits", [])]
+            # active reset, "measure q -> c; if (c) x q": the qubit is |0> afterwards, its record stays
+            if inst["name"] == "x" and len(qubits) == 1 and cond == ("sym", qubits[0]) and qstate[qubits[0]] == "frozen":
+                qstate[qubits[0]] = "frozen_reset"
+                return
             if not admit(inst, qubits):
                 return
             if not is_sym(cond):

@@ -308,11 +308,12 @@ def test_deferred_measurement_many_remote_operations(backend):
         assert 0.5 * sum(abs(got.get(k, 0) / shots - want.get(k, 0.0)) for k in set(got) | set(want)) < 0.02
 
 
-def test_deferred_measurement_negated_condition(backend):
-    from test_oracle import _negated_condition
-    t = _negated_condition()[0]
+@pytest.mark.parametrize("which", ["_negated_condition", "_active_reset"])
+def test_deferred_measurement_condition_forms(backend, which):
+    import test_oracle
+    t = getattr(test_oracle, which)()[0]
     shots = 20000
-    res = backend.execute(dyn_task(t["instructions"], 3, 3, shots, 4, b200_defer_measurement=True))
+    res = backend.execute(dyn_task(t["instructions"], t["num_qubits"], t["num_clbits"], shots, 4, b200_defer_measurement=True))
     assert "ERROR" not in res, res
     assert backend.last_mode() == 1
     assert res["counts"] == O.run_dynamic([t], shots, seed=4, defer=True)["task"]

@@ -166,6 +166,16 @@ def _negated_condition():
         {"name": "measure", "qubits": [1], "clbits": [1]}, {"name": "measure", "qubits": [2], "clbits": [2]}]}]
 
 
+def _active_reset():
+    """measure + conditional X (the usual active reset), the qubit re-used afterwards"""
+    return [{"id": "task", "num_qubits": 2, "num_clbits": 3, "instructions": [
+        {"name": "ry", "qubits": [0], "params": [1.2]}, {"name": "cx", "qubits": [0, 1]},
+        {"name": "measure", "qubits": [0], "clbits": [0]},
+        {"name": "cif", "clbits": [0], "operation": "and", "condition": 1, "instructions": [{"name": "x", "qubits": [0]}]},
+        {"name": "cif", "clbits": [0], "operation": "and", "condition": 1, "instructions": [{"name": "ry", "qubits": [1], "params": [0.5]}]},
+        {"name": "measure", "qubits": [0], "clbits": [2]}, {"name": "measure", "qubits": [1], "clbits": [1]}]}]
+
+
 def _two_way_traffic():
     """teledata A->B, then a classically communicated outcome B->A conditions a gate on A"""
     a = C.hea_ansatz(2, 1, 5, measure=False) + [{"name": "qsend", "qubits": [1], "qpus": ["B"]},
@@ -183,7 +193,7 @@ def _two_way_traffic():
 
 
 @pytest.mark.parametrize("maker", [_cif_circuit, lambda: C.hea_teledata_pair(2, 1), lambda: C.hea_telegate_pair(2, 1),
-                                   lambda: C.hea_telegate_pair(3, 2), _two_way_traffic, _negated_condition])
+                                   lambda: C.hea_telegate_pair(3, 2), _two_way_traffic, _negated_condition, _active_reset])
 def test_deferred_measurement_has_the_literal_distribution(maker):
     """exact: joint distribution of all classical outcomes, deferred run vs every branch of the per-shot semantics"""
     tasks = maker()
