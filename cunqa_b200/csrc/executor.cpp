@@ -135,6 +135,7 @@ struct TaskCfg {
     bool terminal_sampling = true;
     bool share_prefix = true;
     bool defer_measurement = true;
+    int fusion_enable = -1, fusion_max_qubit = -1;  // -1 = the engine's default
     int max_batch = 0;
 };
 
@@ -159,6 +160,8 @@ TaskCfg parse_task(const Json &t)
         if (m != "automatic" && m != "statevector")
             throw std::runtime_error("method '" + m + "' is not supported by the B200 backend (statevector only)");
     }
+    if (cfg.contains("fusion_enable")) c.fusion_enable = cfg.at("fusion_enable").as_bool() ? 1 : 0;
+    if (cfg.contains("fusion_max_qubit")) c.fusion_max_qubit = (int)cfg.at("fusion_max_qubit").as_int();
     if (cfg.contains("n_communication_qubits")) c.n_comm = (int)cfg.at("n_communication_qubits").as_int();
     if (cfg.contains("b200_bugcompat_unitary_order")) c.bugcompat_unitary_order = cfg.at("b200_bugcompat_unitary_order").as_bool();
     if (cfg.contains("b200_bugcompat_teledata")) c.bugcompat_teledata = cfg.at("b200_bugcompat_teledata").as_bool();
@@ -312,6 +315,8 @@ Json Backend::run_static(const Json &task)
     const TaskCfg c = parse_task(task);
     const auto t0 = std::chrono::high_resolution_clock::now();
     State &st = get_state(c.num_qubits, c.precision, 1);
+    st.queue.set_fusion(c.fusion_enable < 0 ? st.opt.fuse : c.fusion_enable != 0,
+                        c.fusion_max_qubit < 0 ? st.opt.max_dense_qubits : c.fusion_max_qubit);
     const Stats before = st.stats;
     const uint64_t gates_before = st.queue.gates;
     std::vector<std::pair<int, int>> meas;  // (qubit, clbit)

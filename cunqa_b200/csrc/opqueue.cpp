@@ -27,6 +27,12 @@ void OpQueue::clear_pending()
     mask_rows.clear();
 }
 
+void OpQueue::set_fusion(bool enable, int max_dense_qubits)
+{
+    opt.fuse = fuser_.opt.fuse = enable;
+    opt.max_dense_qubits = fuser_.opt.max_dense_qubits = std::max(1, std::min(max_dense_qubits, kMaxDenseK));
+}
+
 bool OpQueue::identity_perm() const
 {
     for (int i = 0; i < n; i++) if (l2p[i] != i) return false;

@@ -30,6 +30,8 @@ public:
     uint64_t phys_index(uint64_t logical) const;
     uint64_t logical_index(uint64_t phys) const;
     bool identity_perm() const;
+    // per-task fusion switches (Aer's `fusion_enable` / `fusion_max_qubit` config keys, aer_helpers.hpp:17-86)
+    void set_fusion(bool enable, int max_dense_qubits);
 
     int n, batch;
     PlanOptions opt;

@@ -317,3 +317,19 @@ def test_deferred_measurement_condition_forms(backend, which):
     assert "ERROR" not in res, res
     assert backend.last_mode() == 1
     assert res["counts"] == O.run_dynamic([t], shots, seed=4, defer=True)["task"]
+
+
+def test_fusion_config_keys(backend):
+    """Aer's fusion switches are honoured per task: same state, different op count"""
+    ins = C.hea_ansatz(6, 3, 7, measure=False) + [{"name": "save_state", "qubits": list(range(6))}] + C.measure_all(6)
+    a = backend.execute(C.task(ins, 6, shots=50, seed=1))
+    ops_default = backend.stats()["fused_ops"]
+    b = backend.execute(C.task(ins, 6, shots=50, seed=1, fusion_enable=False))
+    ops_unfused = backend.stats()["fused_ops"]
+    c = backend.execute(C.task(ins, 6, shots=50, seed=1, fusion_enable=True, fusion_max_qubit=1))
+    for r in (a, b, c):
+        assert "ERROR" not in r, r
+    sa, sb, sc = (np.array(r["statevector"]) for r in (a, b, c))
+    assert np.abs(sa - sb).max() < 1e-12 and np.abs(sa - sc).max() < 1e-12
+    assert ops_unfused > ops_default
+    assert backend.execute(C.task(ins, 6, shots=50, seed=1))["counts"] == a["counts"]  # the switch does not stick
