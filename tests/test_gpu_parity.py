@@ -100,6 +100,47 @@ def test_quantum_volume_inverse_roundtrip_26(lib_built):
         assert abs(sv.norm()[0] - 1) < 1e-10
 
 
+def _needs_free_gib(gib):
+    import torch
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < gib * 2 ** 30:
+        pytest.skip(f"needs {gib} GiB of free HBM")
+
+
+def test_quantum_volume_33_inverse_roundtrip_full_size(lib_built):
+    """BASELINE config 3 at its full size (QV-33, depth 33, 528 Haar SU(4) gates, 128 GiB in place): the oracle cannot
+    follow, so parity rests on size-independent properties -- U^dagger U |0> = |0> to 1e-10, norm 1, P(q=1) = 0"""
+    _needs_free_gib(140)
+    n = 33
+    ins = C.quantum_volume(n, seed=2024)
+    assert C.n_gates(ins) == 528
+    with cb.StateVector(n) as sv:
+        sv.run(ins)
+        assert abs(sv.norm()[0] - 1) < 1e-10
+        mid = sv.amplitudes(np.random.default_rng(5).integers(0, 1 << n, size=4096).astype(np.uint64))
+        # a scrambled state: amplitudes of magnitude ~2^-16.5, none of them close to a basis state
+        assert 0.1 < np.mean(np.abs(mid) ** 2) * 2 ** n < 10 and np.abs(mid).max() < 1e-3
+        sv.run(C.inverse(ins))
+        idx = np.concatenate([[0, 1, (1 << n) - 1], np.random.default_rng(6).integers(1, 1 << n, size=1021)]).astype(np.uint64)
+        a = sv.amplitudes(idx)
+        assert abs(a[0] - 1) < 1e-10 and np.abs(a[1:]).max() < 1e-10
+        assert abs(sv.norm()[0] - 1) < 1e-10
+        assert max(sv.prob1(q)[0] for q in (0, 5, 17, 32)) < 1e-15
+        assert sv.stats()["passes"] < 2 * 528 / 4  # > 4 gates per HBM round trip
+
+
+def test_qft_33_closed_form_full_size(lib_built):
+    """QFT|x> on 33 qubits (128 GiB) against the closed form on 65536 random amplitudes"""
+    _needs_free_gib(140)
+    n = 33
+    x = C.qft_x(n, seed=11)
+    with cb.StateVector(n) as sv:
+        sv.run(C.qft(n, x))
+        idx = np.random.default_rng(1).integers(0, 1 << n, size=1 << 16).astype(np.uint64)
+        assert np.abs(sv.amplitudes(idx) - O.qft_amplitudes(n, x, idx)).max() < 1e-10
+        assert abs(sv.norm()[0] - 1) < 1e-10
+
+
 def test_dense_blocks_up_to_five_qubits(lib_built):
     n = 9
     rng = np.random.default_rng(3)
