@@ -65,7 +65,7 @@ struct PassParams {
     uint8_t diag_op[kMaxOps];
     uint8_t tile_q[16]; // physical qubit of tile bit j (ascending)
     DevOp ops[kMaxOps];
-    T mats[kMatScalars];
+    alignas(16) T mats[kMatScalars];  // (re, im) pairs, read as one 16-byte element
 };
 
 // dim3 / smem sizing helpers shared with the host

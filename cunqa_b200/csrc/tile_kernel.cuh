@@ -106,7 +106,7 @@ __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const Dev
     if constexpr (K <= 2) {
         T mr[D * D], mi[D * D];
 #pragma unroll
-        for (int e = 0; e < D * D; e++) { mr[e] = mat[2 * e]; mi[e] = mat[2 * e + 1]; }
+        for (int e = 0; e < D * D; e++) { const V m = reinterpret_cast<const V *>(mat)[e]; mr[e] = m.x; mi[e] = m.y; }  // one 16-byte load per element
         for (uint32_t g = tid; g < ngroups; g += NT) {
             uint32_t idx = g;
             for (int f = 0; f < nfix; f++) idx = insert0(idx, op.fixpos[f]);
@@ -184,7 +184,7 @@ __device__ __forceinline__ void block_gate(typename Vec2<T>::type (&a)[1 << R], 
     constexpr int D = 1 << K;
     T mr[D * D], mi[D * D];
 #pragma unroll
-    for (int e = 0; e < D * D; e++) { mr[e] = mat[2 * e]; mi[e] = mat[2 * e + 1]; }
+    for (int e = 0; e < D * D; e++) { const V m = reinterpret_cast<const V *>(mat)[e]; mr[e] = m.x; mi[e] = m.y; }  // one 16-byte load per element
 #pragma unroll
     for (int rest = 0; rest < (1 << (R - K)); rest++) {
         const int lo = rest & ((1 << S) - 1), hi = rest >> S;
@@ -367,7 +367,7 @@ __device__ __noinline__ void op_diag_block(typename Vec2<T>::type *tile, const D
         constexpr int D = 1 << K, G = A >> K;
         T mr[D * D], mi[D * D];
 #pragma unroll
-        for (int e2 = 0; e2 < D * D; e2++) { mr[e2] = mat[2 * e2]; mi[e2] = mat[2 * e2 + 1]; }
+        for (int e2 = 0; e2 < D * D; e2++) { const V m = reinterpret_cast<const V *>(mat)[e2]; mr[e2] = m.x; mi[e2] = m.y; }
 #pragma unroll
         for (int g = 0; g < G; g++) {
 #pragma unroll
@@ -619,7 +619,11 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     // row offset (128-byte rows) of TMA box r relative to the tile's first row
     uint32_t *box_row = reinterpret_cast<uint32_t *>(full + kStages + 1);
     // the pass's dense matrices, staged once: broadcast shared-memory loads instead of constant-bank loads
-    T *mats_s = reinterpret_cast<T *>(box_row + ((nbox + 3) & ~3u));
+    // (16-byte aligned: complex elements are read with one 128-bit load; plain pointer arithmetic keeps the
+    // shared-memory address space visible to the compiler)
+    unsigned char *mats_raw = reinterpret_cast<unsigned char *>(box_row + ((nbox + 3) & ~3u));
+    mats_raw += (16u - (smem_u32(mats_raw) & 15u)) & 15u;
+    T *mats_s = reinterpret_cast<T *>(mats_raw);
     for (int e = tid; e < p.n_mat; e += NT) mats_s[e] = p.mats[e];
     // per diagonal op: bit-extract tables of the in-tile index part (tile bits 0..5 and 6..12) + per-tile high part
     uint32_t *dhi = reinterpret_cast<uint32_t *>(mats_s + ((p.n_mat + 1) & ~1));
