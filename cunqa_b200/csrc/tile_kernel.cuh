@@ -138,10 +138,11 @@ __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const Dev
             for (int j = 0; j < D; j++) in[j] = tile[swz<T>(idx | off[j])];
 #pragma unroll 4
             for (int r = 0; r < D; r++) {
-                const T *row = mat + 2 * r * D;
-                V acc = cmul<V, T>(row[0], row[1], in[0]);
+                const V *row = reinterpret_cast<const V *>(mat) + r * D;  // one 16-byte load per element
+                const V m0 = row[0];
+                V acc = cmul<V, T>(m0.x, m0.y, in[0]);
 #pragma unroll
-                for (int c = 1; c < D; c++) cfma<V, T>(acc, row[2 * c], row[2 * c + 1], in[c]);
+                for (int c = 1; c < D; c++) { const V mc = row[c]; cfma<V, T>(acc, mc.x, mc.y, in[c]); }
                 uint32_t o = 0;
 #pragma unroll
                 for (int m = 0; m < K; m++)
