@@ -63,32 +63,11 @@ __device__ __forceinline__ void cfma(V &acc, const T mr, const T mi, const V a)
 }
 
 // ---- dense k-qubit block on the tile -----------------------------------------------------------
-// K <= 2: the matrix is hoisted into registers (constant-bank loads, no shared-memory traffic);
-// K >= 3: matrix elements stream from the constant bank inside the row loop.
-// phase product of the diagonal ops in slots [s0, s1] for tile index i (tables indexed through the per-op
-// bit-extract LUTs and the per-tile base `dhi`)
-template <typename T>
-__device__ __forceinline__ typename Vec2<T>::type diag_phase(const typename Vec2<T>::type *__restrict__ diag_tabs,
-                                                             const uint16_t *lut, const uint32_t *dhi, int s0, int s1, uint32_t i)
-{
-    using V = typename Vec2<T>::type;
-    const uint16_t *l0 = lut + s0 * kDiagLut + (i & 63u);
-    const uint16_t *l1 = lut + s0 * kDiagLut + 64 + (i >> 6);
-    V ph = diag_tabs[dhi[s0] + (uint32_t)(*l0 | *l1)];
-    for (int sl = s0 + 1; sl <= s1; sl++) {
-        l0 += kDiagLut; l1 += kDiagLut;
-        const V q = diag_tabs[dhi[sl] + (uint32_t)(*l0 | *l1)];
-        ph = cmul<V, T>(q.x, q.y, ph);
-    }
-    return ph;
-}
-
-// PRE: a run of diagonal ops (slots ps0..ps1) that immediately precedes this gate is folded into its load
-template <typename T, int K, int NT, bool PRE = false>
+// K <= 2: the matrix is hoisted into registers (16 complex elements, one 128-bit load each);
+// K >= 3: matrix elements stream in inside the row loop.
+template <typename T, int K, int NT>
 __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
-                                         const int t, const int tid,
-                                         const typename Vec2<T>::type *__restrict__ diag_tabs = nullptr,
-                                         const uint16_t *lut = nullptr, const uint32_t *dhi = nullptr, int ps0 = 0, int ps1 = -1)
+                                         const int t, const int tid)
 {
     using V = typename Vec2<T>::type;
     constexpr int D = 1 << K;
@@ -115,10 +94,6 @@ __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const Dev
 #pragma unroll
             for (int j = 0; j < D; j++) {
                 in[j] = tile[swz<T>(idx | off[j])];
-                if constexpr (PRE) {
-                    const V ph = diag_phase<T>(diag_tabs, lut, dhi, ps0, ps1, idx | off[j]);
-                    in[j] = cmul<V, T>(ph.x, ph.y, in[j]);
-                }
             }
 #pragma unroll
             for (int r = 0; r < D; r++) {
