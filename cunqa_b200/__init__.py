@@ -9,7 +9,7 @@ import importlib
 
 from . import circuits  # noqa: F401
 
-_LAZY = ("StateVector", "ShardedStateVector", "Backend", "B200Error", "plan", "gate_matrix", "version", "device_count", "update_task")
+_LAZY = ("StateVector", "ShardedStateVector", "Backend", "B200Error", "plan", "gate_matrix", "version", "device_count", "update_task", "qasm2_to_json")
 
 
 def __getattr__(name):

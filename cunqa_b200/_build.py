@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libcunqa_b200.so")
-SOURCES = ["api.cu", "engine.cu", "dist.cu", "executor.cpp", "planner.cpp", "opqueue.cpp", "gates.cpp", "dist_plan.cpp"]
+SOURCES = ["api.cu", "engine.cu", "dist.cu", "executor.cpp", "planner.cpp", "opqueue.cpp", "gates.cpp", "dist_plan.cpp", "qasm2.cpp"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",

@@ -76,6 +76,7 @@ SIGNATURES = {
     "cb200_backend_destroy": (ctypes.c_int, [_vp]),
     "cb200_backend_set_channel": (ctypes.c_int, [_vp, SEND_FN, RECV_FN, _vp]),
     "cb200_backend_execute": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "cb200_qasm2_to_json": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "cb200_backend_stats": (ctypes.c_int, [_vp, _c_u64_p]),
     "cb200_backend_last_mode": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int)]),
     "cb200_dist_unique_id": (ctypes.c_int, [_c_u8_p]),
@@ -144,6 +145,13 @@ def update_task(task, update):
     """apply a {"params":[...],"shots":N} message to a task the way the backend does; host only."""
     out = _vp()
     _check(lib.cb200_update_task_json(json.dumps(task).encode(), json.dumps(update).encode(), ctypes.byref(out)))
+    return json.loads(_take_string(out))
+
+
+def qasm2_to_json(qasm):
+    """OpenQASM 2 text -> CUNQA circuit dict (instructions, num_qubits, num_clbits, registers); host only."""
+    out = _vp()
+    _check(lib.cb200_qasm2_to_json(qasm.encode(), ctypes.byref(out)))
     return json.loads(_take_string(out))
 
 

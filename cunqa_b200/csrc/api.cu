@@ -155,6 +155,12 @@ int cb200_update_task_json(const char *task_json, const char *update_json, char 
     *out = nullptr;
     return guard([&] { *out = dup_string(update_task_json(task_json, update_json)); });
 }
+int cb200_qasm2_to_json(const char *qasm, char **out)
+{
+    if (!qasm || !out) { g_err = "null argument"; return CB200_ERR_INVALID; }
+    *out = nullptr;
+    return guard([&] { *out = dup_string(qasm2_to_json(qasm)); });
+}
 int cb200_gate_matrix(const char *name, int nq, const double *params, int np, double *out_reim)
 {
     if (!name || !out_reim || nq < 1 || nq > 6) { g_err = "bad argument"; return CB200_ERR_INVALID; }

@@ -47,5 +47,7 @@ std::string update_task_json(const std::string &task_json, const std::string &up
 
 // plan a task without a device: fused ops + tile passes as JSON (cb200_plan_json)
 std::string plan_task_json(const std::string &task_json, const std::string &options_json);
+// OpenQASM 2 text -> CUNQA circuit JSON (qasm2.cpp; replaces src/utils/helpers/qasm2_to_json.hpp:520-549)
+std::string qasm2_to_json(const std::string &qasm);
 
 }  // namespace cb200

@@ -109,6 +109,10 @@ int cb200_plan_json(const char *task_json, const char *options_json, char **plan
  * between two executes (replaces QuantumTask::update_params_, /root/reference/src/quantum_task.cpp:39-108);
  * returns the updated task as JSON text.  Host only. */
 int cb200_update_task_json(const char *task_json, const char *update_json, char **task_json_out);
+/* OpenQASM 2 text -> CUNQA circuit JSON {"instructions","num_qubits","num_clbits","quantum_registers",
+ * "classical_registers"} (replaces qasm2_to_json, /root/reference/src/utils/helpers/qasm2_to_json.hpp:520-549).
+ * Host only. */
+int cb200_qasm2_to_json(const char *qasm, char **circuit_json_out);
 /* matrix of a named gate exactly as the engine builds it: out = 2^nq x 2^nq row-major (re,im),
  * controls expanded.  nq <= 6. */
 int cb200_gate_matrix(const char *name, int nq, const double *params, int np, double *out_reim);

@@ -333,3 +333,13 @@ def test_fusion_config_keys(backend):
     assert np.abs(sa - sb).max() < 1e-12 and np.abs(sa - sc).max() < 1e-12
     assert ops_unfused > ops_default
     assert backend.execute(C.task(ins, 6, shots=50, seed=1))["counts"] == a["counts"]  # the switch does not stick
+
+
+def test_qasm2_text_runs_on_the_engine(backend):
+    """OpenQASM 2 -> circuit JSON (cb200_qasm2_to_json) -> wire task -> counts"""
+    from test_qasm2 import GHZ
+    circ = cb.qasm2_to_json(GHZ)
+    res = backend.execute(C.task(circ["instructions"], circ["num_qubits"], num_clbits=circ["num_clbits"], shots=500, seed=3))
+    assert "ERROR" not in res, res
+    assert set(res["counts"]) == {"0000", "1111"} and sum(res["counts"].values()) == 500
+    assert res["counts"] == O.run_static(circ["instructions"], 4, 4, shots=500, seed=3)[1]
