@@ -430,8 +430,9 @@ using Bits = std::vector<uint8_t>;
 // Deferred measurement (one state, all shots sampled at the end): a classical bit is then SYMBOLIC -- 0 / 1 are
 // constants, kSym + q means "the outcome recorded in register qubit q", which is read from the final sample.
 constexpr uint8_t kSym = 2;
-constexpr uint8_t kNotSym = 128;  // kNotSym + q: "NOT the outcome recorded in qubit q" (a cif that tests for 0)
-inline bool sym_negated(uint8_t v) { return v >= kNotSym; }
+constexpr uint8_t kNotSym = 64;   // kNotSym + q: "NOT the outcome recorded in qubit q" (a cif that tests for 0)
+constexpr uint8_t kConj = 128;    // kConj + i: the conjunction of literals stored in entry i of the batch's table
+inline bool sym_negated(uint8_t v) { return v >= kNotSym && v < kConj; }
 inline int sym_qubit(uint8_t v) { return v >= kNotSym ? v - kNotSym : v - kSym; }
 struct DeferAbort {};  // the circuit needs a real mid-circuit collapse: fall back to the batched interpreter
 enum QState : uint8_t { Q_LIVE = 0, Q_FROZEN, Q_FROZEN_RESET };
@@ -462,18 +463,20 @@ std::vector<char> action_kinds(const Inst &in)
 }
 
 // the instruction with one more control qubit (register index), for a condition that is a deferred outcome
-void queue_gate_controlled_pos(State &st, const Inst &in, const std::vector<int> &qs, int ctrl, bool reverse_unitary_qubits);
+void queue_gate_controlled_pos(State &st, const Inst &in, const std::vector<int> &qs, const std::vector<int> &extra, bool reverse_unitary_qubits);
 
-// sym = kSym + q (fires on outcome 1) or kNotSym + q (fires on outcome 0: the control qubit is X-conjugated)
-void queue_gate_controlled(State &st, const Inst &in, const std::vector<int> &qs, uint8_t sym, bool reverse_unitary_qubits)
+// lits: kSym + q (fires on outcome 1) or kNotSym + q (fires on outcome 0: that control qubit is X-conjugated);
+// the instruction fires when ALL literals hold
+void queue_gate_controlled(State &st, const Inst &in, const std::vector<int> &qs, const std::vector<uint8_t> &lits, bool reverse_unitary_qubits)
 {
-    const int ctrl = sym_qubit(sym);
-    if (sym_negated(sym)) st.apply_named("x", &ctrl, 1, nullptr, 0, nullptr);
-    queue_gate_controlled_pos(st, in, qs, ctrl, reverse_unitary_qubits);
-    if (sym_negated(sym)) st.apply_named("x", &ctrl, 1, nullptr, 0, nullptr);
+    std::vector<int> extra;
+    for (uint8_t l : lits) extra.push_back(sym_qubit(l));
+    for (uint8_t l : lits) if (sym_negated(l)) { const int q = sym_qubit(l); st.apply_named("x", &q, 1, nullptr, 0, nullptr); }
+    queue_gate_controlled_pos(st, in, qs, extra, reverse_unitary_qubits);
+    for (uint8_t l : lits) if (sym_negated(l)) { const int q = sym_qubit(l); st.apply_named("x", &q, 1, nullptr, 0, nullptr); }
 }
 
-void queue_gate_controlled_pos(State &st, const Inst &in, const std::vector<int> &qs, int ctrl, bool reverse_unitary_qubits)
+void queue_gate_controlled_pos(State &st, const Inst &in, const std::vector<int> &qs, const std::vector<int> &extra, bool reverse_unitary_qubits)
 {
     std::vector<int> ctrls, targets;
     std::vector<cplx> mat;
@@ -489,18 +492,22 @@ void queue_gate_controlled_pos(State &st, const Inst &in, const std::vector<int>
         const int k = log2_exact(in.matrix_dim);
         if ((int)qs.size() != k) throw std::runtime_error("diagonal: size does not match the qubit list");
         std::vector<int> all = qs;
-        all.push_back(ctrl);
-        std::vector<cplx> d((size_t)2 << k, cplx(1, 0));
-        for (int i = 0; i < (1 << k); i++) d[(size_t)i | ((size_t)1 << k)] = in.matrix[i];
-        st.apply_diagonal(all.data(), k + 1, d.data(), nullptr);
+        all.insert(all.end(), extra.begin(), extra.end());
+        const int ne = (int)extra.size();
+        std::vector<cplx> d((size_t)1 << (k + ne), cplx(1, 0));
+        const size_t on = (((size_t)1 << ne) - 1) << k;  // every extra control set
+        for (int i = 0; i < (1 << k); i++) d[(size_t)i | on] = in.matrix[i];
+        st.apply_diagonal(all.data(), k + ne, d.data(), nullptr);
         return;
     } else {
         GateSpec g;
         std::string err;
         if (!lookup_gate(in.name, (int)qs.size(), in.params.data(), (int)in.params.size(), g, err)) throw std::runtime_error(err);
-        if (g.is_global_phase) {  // a conditioned global phase is a phase gate on the condition qubit
-            const cplx d[2] = {cplx(1, 0), std::exp(cplx(0, g.phase))};
-            st.apply_diagonal(&ctrl, 1, d, nullptr);
+        if (g.is_global_phase) {  // a conditioned global phase is a (multi-controlled) phase gate on the condition qubits
+            const int ne = (int)extra.size();
+            std::vector<cplx> d((size_t)1 << ne, cplx(1, 0));
+            d.back() = std::exp(cplx(0, g.phase));
+            st.apply_diagonal(extra.data(), ne, d.data(), nullptr);
             return;
         }
         const int nc = (int)qs.size() - g.n_targets;
@@ -508,7 +515,7 @@ void queue_gate_controlled_pos(State &st, const Inst &in, const std::vector<int>
         targets.assign(qs.begin() + nc, qs.end());
         mat = g.mat;
     }
-    ctrls.push_back(ctrl);
+    ctrls.insert(ctrls.end(), extra.begin(), extra.end());
     st.apply_matrix(targets.data(), (int)targets.size(), ctrls.data(), (int)ctrls.size(), mat.data(), nullptr);
 }
 
@@ -568,6 +575,19 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
     auto run_batch = [&](State &st, const int nb, const uint64_t shot0, const uint64_t live, const bool deferred) {
         std::vector<uint8_t> qstate((size_t)n_total, Q_LIVE);
         std::vector<char> touched((size_t)n_total, 0);
+        std::vector<std::vector<uint8_t>> conj;  // deferred mode: conjunctions of literals (nested / multi-bit conditions)
+        auto literals = [&](uint8_t v) { return v >= kConj ? conj[v - kConj] : std::vector<uint8_t>{v}; };
+        auto make_cond = [&](std::vector<uint8_t> lits) -> uint8_t {
+            std::sort(lits.begin(), lits.end());
+            lits.erase(std::unique(lits.begin(), lits.end()), lits.end());
+            for (uint8_t a : lits)
+                for (uint8_t b : lits)
+                    if (sym_qubit(a) == sym_qubit(b) && sym_negated(a) != sym_negated(b)) return 0;  // q and not q
+            if (lits.size() == 1) return lits[0];
+            if (conj.size() >= 127) throw DeferAbort();
+            conj.push_back(lits);
+            return (uint8_t)(kConj + conj.size() - 1);
+        };
         std::vector<TaskRt> T(cfgs.size());
         std::map<std::string, size_t> by_id;
         {
@@ -715,7 +735,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                 const uint8_t f = flags ? (*flags)[0] : 1;
                 if (f == 0 || !admit(in, qs)) return;
                 if (f == 1) st.apply_named(name, qs.data(), (int)qs.size(), nullptr, 0, nullptr);
-                else queue_gate_controlled(st, in, qs, f, false);
+                else queue_gate_controlled(st, in, qs, literals(f), false);
                 return;
             }
             if (flags && !any(*flags)) return;
@@ -809,11 +829,24 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                     if (deferred) {
                         for (int cl : in.clbits) symbolic = symbolic || clb(cl)[0] >= kSym;
                         if (symbolic) {
-                            // one recorded outcome (tested for 1 or for 0), not nested inside another undecided condition
-                            if (in.clbits.size() != 1) throw DeferAbort();
-                            if (cond && (*cond)[0] >= kSym) throw DeferAbort();
-                            const uint8_t v = clb(in.clbits[0])[0];
-                            res[0] = (cond && (*cond)[0] == 0) ? 0 : (cnd ? v : (uint8_t)(kNotSym + sym_qubit(v)));
+                            // one recorded outcome tested for 1 or for 0, or the AND of several bits; an enclosing
+                            // undecided condition joins the conjunction.  Anything else (or / xor folds) needs real bits.
+                            std::vector<uint8_t> lits;
+                            bool never = cond && (*cond)[0] == 0;
+                            if (in.clbits.size() == 1) {
+                                const uint8_t v = clb(in.clbits[0])[0];
+                                lits.push_back(cnd ? v : (uint8_t)(kNotSym + sym_qubit(v)));
+                            } else {
+                                if (!(in.operation == "and" && cnd)) throw DeferAbort();
+                                for (int cl : in.clbits) {
+                                    const uint8_t v = clb(cl)[0];
+                                    if (v == 0) never = true;
+                                    else if (v >= kSym) lits.push_back(v);
+                                }
+                            }
+                            if (cond && (*cond)[0] >= kSym)
+                                for (uint8_t l : literals((*cond)[0])) lits.push_back(l);
+                            res[0] = never ? 0 : make_cond(lits);
                         }
                     }
                     for (int b = 0; b < nb && !symbolic; b++) {
@@ -912,7 +945,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                             return;
                         }
                         if (!admit(in, qs)) return;
-                        if (cond && (*cond)[0] >= kSym) queue_gate_controlled(st, in, qs, (*cond)[0], c.bugcompat_unitary_order);
+                        if (cond && (*cond)[0] >= kSym) queue_gate_controlled(st, in, qs, literals((*cond)[0]), c.bugcompat_unitary_order);
                         else queue_gate(st, in, qmap, nullptr, c.bugcompat_unitary_order);
                         return;
                     }
@@ -1008,7 +1041,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
 
     // first choice: defer every measurement (one state, all shots from one final sample)
     bool done = false;
-    if (shots > 0 && c0.defer_measurement && !external_cc && n_total + (int)kSym <= (int)kNotSym) {
+    if (shots > 0 && c0.defer_measurement && !external_cc && n_total + (int)kSym <= (int)kNotSym) {  // (symbol encoding: <= 62 qubits)
         State &s1 = get_state(n_total, precision, 1);
         const Stats b1 = s1.stats;
         const uint64_t g1 = s1.queue.gates;

@@ -589,33 +589,49 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
             if not is_sym(cond):
                 apply_gate(st, inst, qmap, reverse_unitary_qubits)
                 return
-            ctrl = cond[1]
-            if cond[0] == "nsym":  # fires on outcome 0: X-conjugate the control qubit
-                st.apply_matrix([ctrl], _FIXED_1Q["x"])
-                gate_controlled(inst, qubits, ctrl)
-                st.apply_matrix([ctrl], _FIXED_1Q["x"])
-            else:
-                gate_controlled(inst, qubits, ctrl)
+            lits = list(cond[1]) if cond[0] == "and" else [cond]
+            ctrls = [l[1] for l in lits]
+            for l in lits:  # a literal that fires on outcome 0: X-conjugate that control qubit
+                if l[0] == "nsym":
+                    st.apply_matrix([l[1]], _FIXED_1Q["x"])
+            gate_controlled(inst, qubits, ctrls)
+            for l in lits:
+                if l[0] == "nsym":
+                    st.apply_matrix([l[1]], _FIXED_1Q["x"])
 
-        def gate_controlled(inst, qubits, ctrl):
+        def gate_controlled(inst, qubits, ctrls):
             name = inst["name"]
+            ne = len(ctrls)
             if name == "gp":
-                st.apply_diagonal([ctrl], np.array([1.0, np.exp(1j * inst["params"][0])]))
+                d = np.ones(1 << ne, dtype=complex)
+                d[-1] = np.exp(1j * inst["params"][0])
+                st.apply_diagonal(ctrls, d)
             elif name == "unitary":
                 qs = qubits[::-1] if reverse_unitary_qubits else qubits
-                st.apply_matrix(qs, parse_matrix(inst["matrix"]), [ctrl])
+                st.apply_matrix(qs, parse_matrix(inst["matrix"]), ctrls)
             elif name == "cunitary":
                 m = parse_matrix(inst["matrix"])
                 k = int(round(math.log2(m.shape[0])))
-                st.apply_matrix(qubits[-k:], m, qubits[:-k] + [ctrl])
+                st.apply_matrix(qubits[-k:], m, qubits[:-k] + ctrls)
             elif name == "diagonal":
                 d = np.asarray(inst["matrix"][0], dtype=float)
-                st.apply_diagonal(qubits + [ctrl], np.concatenate([np.ones(len(d)), d[:, 0] + 1j * d[:, 1]]))
+                full = np.ones(len(d) << ne, dtype=complex)
+                full[-len(d):] = d[:, 0] + 1j * d[:, 1]
+                st.apply_diagonal(qubits + ctrls, full)
             elif name == "swap":
-                st.apply_swap(qubits[0], qubits[1], [ctrl])
+                st.apply_swap(qubits[0], qubits[1], ctrls)
             else:
                 m, tg, ct = gate_spec(name, qubits, inst.get("params", []))
-                st.apply_matrix(tg, m, list(ct) + [ctrl])
+                st.apply_matrix(tg, m, list(ct) + ctrls)
+
+        def make_cond(lits):
+            """conjunction of literals -> 0 (contradiction), one literal, or ("and", (lits...))"""
+            lits = sorted(set(lits))
+            for a in lits:
+                for b in lits:
+                    if a[1] == b[1] and a[0] != b[0]:
+                        return 0
+            return lits[0] if len(lits) == 1 else ("and", tuple(lits))
 
         def fixed(name, qubits, cond=1):
             gate({"name": name, "qubits": list(qubits)}, cond=cond)
@@ -700,13 +716,22 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
                 want = 1 if inst.get("condition", 1) else 0
                 bits = [creg.get(c + t["zc"], 0) for c in inst["clbits"]]
                 if any(is_sym(b) for b in bits):
-                    # one recorded outcome (tested for 1 or for 0), not nested inside another undecided condition
-                    if len(bits) != 1 or is_sym(cond):
-                        raise DeferAbort()
-                    if cond == 0:
-                        return
-                    for sub in inst["instructions"]:
-                        step(t, sub, (), bits[0] if want else ("nsym", bits[0][1]))
+                    # one recorded outcome tested for 1 or for 0, or the AND of several bits; an enclosing undecided
+                    # condition joins the conjunction.  Anything else (or / xor folds) needs real bits.
+                    never = cond == 0
+                    if len(bits) == 1:
+                        lits = [bits[0] if want else ("nsym", bits[0][1])]
+                    else:
+                        if not (inst["operation"] == "and" and want):
+                            raise DeferAbort()
+                        never = never or any(b == 0 for b in bits)
+                        lits = [b for b in bits if is_sym(b)]
+                    if is_sym(cond):
+                        lits += list(cond[1]) if cond[0] == "and" else [cond]
+                    res = 0 if never else make_cond(lits)
+                    if res != 0:
+                        for sub in inst["instructions"]:
+                            step(t, sub, (), res)
                     return
                 acc = bits[0] if want else 1 - bits[0]
                 for b in bits[1:]:

@@ -308,7 +308,7 @@ def test_deferred_measurement_many_remote_operations(backend):
         assert 0.5 * sum(abs(got.get(k, 0) / shots - want.get(k, 0.0)) for k in set(got) | set(want)) < 0.02
 
 
-@pytest.mark.parametrize("which", ["_negated_condition", "_active_reset"])
+@pytest.mark.parametrize("which", ["_negated_condition", "_active_reset", "_nested_and_multibit_conditions"])
 def test_deferred_measurement_condition_forms(backend, which):
     import test_oracle
     t = getattr(test_oracle, which)()[0]

@@ -176,6 +176,20 @@ def _active_reset():
         {"name": "measure", "qubits": [0], "clbits": [2]}, {"name": "measure", "qubits": [1], "clbits": [1]}]}]
 
 
+def _nested_and_multibit_conditions():
+    return [{"id": "task", "num_qubits": 4, "num_clbits": 4, "instructions": [
+        {"name": "ry", "qubits": [0], "params": [1.0]}, {"name": "ry", "qubits": [1], "params": [2.0]}, {"name": "h", "qubits": [2]},
+        {"name": "measure", "qubits": [0], "clbits": [0]}, {"name": "measure", "qubits": [1], "clbits": [1]},
+        {"name": "cif", "clbits": [0, 1], "operation": "and", "condition": 1,
+         "instructions": [{"name": "ry", "qubits": [3], "params": [0.9]}, {"name": "gp", "qubits": [], "params": [0.3]}]},
+        {"name": "cif", "clbits": [0], "operation": "and", "condition": 0, "instructions": [
+            {"name": "cif", "clbits": [1], "operation": "and", "condition": 1,
+             "instructions": [{"name": "cx", "qubits": [2, 3]}, {"name": "diagonal", "qubits": [2], "matrix": [[[1, 0], [0, 1]]]}]},
+            {"name": "cif", "clbits": [0], "operation": "and", "condition": 1, "instructions": [{"name": "x", "qubits": [3]}]}]},  # contradiction: never
+        {"name": "h", "qubits": [2]},
+        {"name": "measure", "qubits": [2], "clbits": [2]}, {"name": "measure", "qubits": [3], "clbits": [3]}]}]
+
+
 def _two_way_traffic():
     """teledata A->B, then a classically communicated outcome B->A conditions a gate on A"""
     a = C.hea_ansatz(2, 1, 5, measure=False) + [{"name": "qsend", "qubits": [1], "qpus": ["B"]},
@@ -193,7 +207,8 @@ def _two_way_traffic():
 
 
 @pytest.mark.parametrize("maker", [_cif_circuit, lambda: C.hea_teledata_pair(2, 1), lambda: C.hea_telegate_pair(2, 1),
-                                   lambda: C.hea_telegate_pair(3, 2), _two_way_traffic, _negated_condition, _active_reset])
+                                   lambda: C.hea_telegate_pair(3, 2), _two_way_traffic, _negated_condition, _active_reset,
+                                   _nested_and_multibit_conditions])
 def test_deferred_measurement_has_the_literal_distribution(maker):
     """exact: joint distribution of all classical outcomes, deferred run vs every branch of the per-shot semantics"""
     tasks = maker()
