@@ -174,6 +174,49 @@ static int dense_cost(const HostOp &op)
     }
 }
 
+namespace {
+
+// One pass's admission loop: walk the pending ops in program order starting at `first`; an op joins the pass when
+// none of its qubits is blocked by an earlier op that stayed behind (diagonal uses only block later non-diagonal
+// uses) and its non-diagonal targets fit into the tile.  grow = true: targets may claim free tile slots (Q grows);
+// grow = false: only ops whose targets already lie in Q.  `window` bounds how many pending ops are examined.
+// Returns the admitted op indices (and the number of them through the return value's size).
+std::vector<int> admit(const std::vector<HostOp> &ops, const std::vector<char> &done, size_t first, uint64_t &Q, bool grow,
+                       int t, const PlanOptions &opt, uint64_t all, int window)
+{
+    std::vector<int> sel;
+    uint64_t blockedX = 0, blockedZ = 0;
+    int cost = 0, mat_scalars = 0, seen = 0;
+    for (size_t i = first; i < ops.size(); i++) {
+        if (done[i]) continue;
+        if (window > 0 && seen++ >= window) break;
+        const HostOp &op = ops[i];
+        const uint64_t qx = op.xmask();
+        const uint64_t qz = op.qmask() & ~qx;
+        const bool can = !(qx & (blockedX | blockedZ)) && !(qz & blockedX);
+        if (can) {
+            const uint64_t newQ = Q | qx;
+            const int c = dense_cost(op);
+            const int ms = op.kind == HostOp::DENSE ? 2 * (1 << (2 * op.q.size())) : 0;
+            bool fits = (grow ? popcount64(newQ) <= t : newQ == Q) && (int)sel.size() < kMaxOps && mat_scalars + ms <= kMatScalars;
+            if (fits && opt.max_pass_cost > 0 && !sel.empty() && cost + c > opt.max_pass_cost) fits = false;
+            if (fits) {
+                Q = newQ;
+                cost += c;
+                mat_scalars += ms;
+                sel.push_back((int)i);
+                continue;
+            }
+        }
+        blockedX |= qx;
+        blockedZ |= qz;
+        if ((blockedX & all) == all) break;
+    }
+    return sel;
+}
+
+}  // namespace
+
 std::vector<Pass> schedule_passes(const std::vector<HostOp> &ops, int n, const PlanOptions &opt)
 {
     std::vector<Pass> passes;
@@ -182,45 +225,46 @@ std::vector<Pass> schedule_passes(const std::vector<HostOp> &ops, int n, const P
     std::vector<char> done(ops.size(), 0);
     size_t first = 0, remaining = ops.size();
     const uint64_t all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+    // tile choice by look-ahead pays when a pass is expensive (a big state) and there is a choice to make
+    const bool look = opt.lookahead > 0 && n >= 20 && n > t;
     while (remaining > 0) {
         while (first < ops.size() && done[first]) first++;
-        uint64_t Q = (lmin >= 64) ? ~0ull : ((1ull << lmin) - 1ull);
         // the first pending op always goes in; if it does not fit beside the forced low qubits,
         // shrink the forced set (its targets still span >= 1 run of the lowest qubits)
-        {
-            const uint64_t need = ops[first].xmask();
-            int forced = lmin;
-            while (forced > 0 && popcount64((((1ull << forced) - 1ull)) | need) > t) forced--;
-            Q = (forced > 0 ? ((1ull << forced) - 1ull) : 0ull);
-        }
-        uint64_t blockedX = 0, blockedZ = 0;
-        Pass pass;
-        int cost = 0, mat_scalars = 0;
-        for (size_t i = first; i < ops.size(); i++) {
-            if (done[i]) continue;
-            const HostOp &op = ops[i];
-            const uint64_t qx = op.xmask();
-            const uint64_t qz = op.qmask() & ~qx;
-            bool can = !(qx & (blockedX | blockedZ)) && !(qz & blockedX);
-            if (can) {
-                const uint64_t newQ = Q | qx;
-                const int c = dense_cost(op);
-                const int ms = op.kind == HostOp::DENSE ? 2 * (1 << (2 * op.q.size())) : 0;
-                bool fits = popcount64(newQ) <= t && (int)pass.op_idx.size() < kMaxOps &&
-                            mat_scalars + ms <= kMatScalars;
-                if (fits && opt.max_pass_cost > 0 && !pass.op_idx.empty() && cost + c > opt.max_pass_cost) fits = false;
-                if (fits) {
-                    Q = newQ;
-                    cost += c;
-                    mat_scalars += ms;
-                    pass.op_idx.push_back((int)i);
-                    continue;
+        const uint64_t need = ops[first].xmask();
+        int forced = lmin;
+        while (forced > 0 && popcount64((((1ull << forced) - 1ull)) | need) > t) forced--;
+        uint64_t Q = (forced > 0 ? ((1ull << forced) - 1ull) : 0ull) | need;
+        if (look) {
+            // Grow the tile one op's worth of qubits at a time, each time by the candidate that lets the most
+            // additional pending ops run in this pass per tile slot it costs (first-come greedy fills the tile with
+            // whatever comes next in program order; on QV-33 this look-ahead needs 66 passes instead of 92).
+            while (popcount64(Q) < t) {
+                uint64_t q0 = Q;
+                const int base = (int)admit(ops, done, first, q0, false, t, opt, all, opt.lookahead).size();
+                std::vector<uint64_t> cands;
+                int seen = 0;
+                for (size_t i = first; i < ops.size() && seen < opt.lookahead; i++) {
+                    if (done[i]) continue;
+                    seen++;
+                    const uint64_t add = ops[i].xmask() & ~Q;
+                    if (add == 0 || popcount64(Q | add) > t) continue;
+                    if (std::find(cands.begin(), cands.end(), add) == cands.end()) cands.push_back(add);
                 }
+                uint64_t best = 0;
+                double best_gain = 0.0;
+                for (uint64_t add : cands) {
+                    uint64_t q1 = Q | add;
+                    const int cnt = (int)admit(ops, done, first, q1, false, t, opt, all, opt.lookahead).size();
+                    const double gain = (double)(cnt - base) / popcount64(add);
+                    if (gain > best_gain) { best_gain = gain; best = add; }
+                }
+                if (best == 0) break;
+                Q |= best;
             }
-            blockedX |= qx;
-            blockedZ |= qz;
-            if ((blockedX & all) == all) break;
         }
+        Pass pass;
+        pass.op_idx = admit(ops, done, first, Q, true, t, opt, all, 0);
         // pad the tile with the lowest unused physical qubits (longer contiguous runs)
         for (int qb = 0; qb < n && popcount64(Q) < t; qb++) Q |= 1ull << qb;
         pass.tile_q = mask_to_list(Q);
