@@ -110,3 +110,28 @@ def test_bad_instruction_reports_error(lib_built):
         cb.plan(C.task([{"name": "h", "qubits": [5]}], 2))
     with pytest.raises(B200Error, match="duplicate"):
         cb.plan(C.task([{"name": "cx", "qubits": [1, 1]}], 2))
+
+
+@pytest.mark.parametrize("kind", ["qv", "random", "hea"])
+def test_lookahead_tile_choice_is_equivalent_and_needs_fewer_passes(lib_built, kind):
+    """the tile qubits of a pass are chosen by look-ahead for states of >= 2^20 amplitudes: same state, fewer passes"""
+    n = 20
+    ins = {"qv": lambda: C.quantum_volume(n, depth=6, seed=5), "random": lambda: random_circuit(n, 120, 17),
+           "hea": lambda: C.hea_ansatz(n, layers=3, measure=False)}[kind]()
+    opts = {"tile_bits": 9, "min_run_bits": 3}
+    look = cb.plan(C.task(ins, n), opts)
+    first_come = cb.plan(C.task(ins, n), dict(opts, lookahead=0))
+    assert len(look["ops"]) == len(first_come["ops"])
+    assert len(look["passes"]) <= len(first_come["passes"])
+    if kind != "random":
+        assert len(look["passes"]) < len(first_come["passes"])
+    ref, _ = O.run_static(ins, n, backend="c")
+    assert np.abs(replay_plan(look, n) - ref.amplitudes()).max() < 1e-12
+    assert np.abs(replay_plan(first_come, n) - ref.amplitudes()).max() < 1e-12
+
+
+def test_lookahead_pass_counts_at_the_headline_sizes(lib_built):
+    qv = C.task(C.quantum_volume(33, seed=2024), 33)
+    assert len(cb.plan(qv)["passes"]) <= 66 < 92 <= len(cb.plan(qv, {"lookahead": 0})["passes"])
+    hea = C.task(C.hea_ansatz(30, 4, 1, measure=False), 30)
+    assert len(cb.plan(hea)["passes"]) <= 6
