@@ -265,7 +265,8 @@ void State::launch_ops_t(std::vector<HostOp> &ops)
         int ctas = std::max(1, (stages == 3 ? 256 : 384) / nt);
         ctas = std::max(1, std::min<int>(ctas, (int)(max_smem_sm_ / (smem_tma + 1024))));  // what shared memory allows
         if (tma_max_ctas_ > 0) ctas = std::min(ctas, tma_max_ctas_);
-        const bool tma = use_tma_ && p.L >= aprs + 1 && state_bytes_ >= 128 && smem_tma <= max_smem_;
+        // (a run of one 128-byte row is enough once the three folded qubits make the box 1 KiB = one swizzle atom)
+        const bool tma = use_tma_ && p.L >= aprs + (box_bits >= aprs + 3 ? 0 : 1) && state_bytes_ >= 128 && smem_tma <= max_smem_;
         if (tma) {
             CUtensorMap tmap;
             make_tensor_map(&tmap, run_bits, hi_q);
