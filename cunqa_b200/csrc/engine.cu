@@ -65,6 +65,7 @@ void State::construct(int rank, int world, const uint8_t *nccl_id)
     opt.min_run_bits = env_int("CB200_MIN_RUN_BITS", precision == 64 ? 4 : 5);
     opt.max_pass_cost = env_int("CB200_MAX_PASS_COST", 0);
     opt.lookahead = env_int("CB200_LOOKAHEAD", 256);
+    opt.lookahead_min_qubits = env_int("CB200_LOOKAHEAD_MIN_QUBITS", 24);
     opt.max_diag_qubits = env_int("CB200_MAX_DIAG_QUBITS", 10);
     opt.fuse = env_int("CB200_FUSE", 1) != 0;
     opt.pair_ops = env_int("CB200_PAIR_OPS", 1) != 0;

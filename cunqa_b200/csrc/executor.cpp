@@ -1108,6 +1108,7 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
         if (o.contains("max_diag_qubits")) opt.max_diag_qubits = (int)o.at("max_diag_qubits").as_int();
         if (o.contains("max_pass_cost")) opt.max_pass_cost = (int)o.at("max_pass_cost").as_int();
         if (o.contains("lookahead")) opt.lookahead = (int)o.at("lookahead").as_int();
+        if (o.contains("lookahead_min_qubits")) opt.lookahead_min_qubits = (int)o.at("lookahead_min_qubits").as_int();
         if (o.contains("fuse")) opt.fuse = o.at("fuse").as_bool();
         if (o.contains("world")) world = (int)o.at("world").as_int();
         if (o.contains("rank")) rank = (int)o.at("rank").as_int();

@@ -225,8 +225,10 @@ std::vector<Pass> schedule_passes(const std::vector<HostOp> &ops, int n, const P
     std::vector<char> done(ops.size(), 0);
     size_t first = 0, remaining = ops.size();
     const uint64_t all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
-    // tile choice by look-ahead pays when a pass is expensive (a big state) and there is a choice to make
-    const bool look = opt.lookahead > 0 && n >= 20 && n > t;
+    // tile choice by look-ahead pays when a pass is expensive (a big state) and there is a choice to make: its host cost
+    // is ~7 * window^2 op checks per pass (0.03 ms at 64, 0.5 ms at 256) against 0.1 ms (n = 24) ... 100 ms (n = 33) per pass
+    const bool look = opt.lookahead > 0 && n >= opt.lookahead_min_qubits && n > t;
+    const int window = n >= 28 ? opt.lookahead : std::min(opt.lookahead, 64);
     while (remaining > 0) {
         while (first < ops.size() && done[first]) first++;
         // the first pending op always goes in; if it does not fit beside the forced low qubits,
@@ -241,10 +243,10 @@ std::vector<Pass> schedule_passes(const std::vector<HostOp> &ops, int n, const P
             // whatever comes next in program order; on QV-33 this look-ahead needs 66 passes instead of 92).
             while (popcount64(Q) < t) {
                 uint64_t q0 = Q;
-                const int base = (int)admit(ops, done, first, q0, false, t, opt, all, opt.lookahead).size();
+                const int base = (int)admit(ops, done, first, q0, false, t, opt, all, window).size();
                 std::vector<uint64_t> cands;
                 int seen = 0;
-                for (size_t i = first; i < ops.size() && seen < opt.lookahead; i++) {
+                for (size_t i = first; i < ops.size() && seen < window; i++) {
                     if (done[i]) continue;
                     seen++;
                     const uint64_t add = ops[i].xmask() & ~Q;
@@ -255,7 +257,7 @@ std::vector<Pass> schedule_passes(const std::vector<HostOp> &ops, int n, const P
                 double best_gain = 0.0;
                 for (uint64_t add : cands) {
                     uint64_t q1 = Q | add;
-                    const int cnt = (int)admit(ops, done, first, q1, false, t, opt, all, opt.lookahead).size();
+                    const int cnt = (int)admit(ops, done, first, q1, false, t, opt, all, window).size();
                     const double gain = (double)(cnt - base) / popcount64(add);
                     if (gain > best_gain) { best_gain = gain; best = add; }
                 }

@@ -33,7 +33,9 @@ struct PlanOptions {
     int max_diag_qubits = 10;  // width of a merged diagonal table
     int max_dense_qubits = 5;  // widest dense block the kernel accepts
     int max_pass_cost = 0;     // cap on sum over dense ops of 2^k per pass (0 = unlimited)
-    int lookahead = 256;       // pending ops examined when choosing a pass's tile qubits (0 = first-come greedy)
+    int lookahead = 256;       // pending ops examined when choosing a pass's tile qubits (0 = first-come greedy);
+                               // states below 2^28 amplitudes use at most 64 (a pass is too short to pay for more)
+    int lookahead_min_qubits = 24;  // smaller states: a pass costs less than the look-ahead that would save it
     bool fuse = true;
     bool pair_ops = true;      // register-block adjacent dense gates (two gates per shared-memory round trip)
     uint64_t global_mask = 0;  // sharded state: physical qubits that select the rank (never fused into dense blocks)

@@ -114,11 +114,11 @@ def test_bad_instruction_reports_error(lib_built):
 
 @pytest.mark.parametrize("kind", ["qv", "random", "hea"])
 def test_lookahead_tile_choice_is_equivalent_and_needs_fewer_passes(lib_built, kind):
-    """the tile qubits of a pass are chosen by look-ahead for states of >= 2^20 amplitudes: same state, fewer passes"""
+    """the tile qubits of a pass are chosen by look-ahead (by default for states of >= 2^24 amplitudes): same state, fewer passes"""
     n = 20
     ins = {"qv": lambda: C.quantum_volume(n, depth=6, seed=5), "random": lambda: random_circuit(n, 120, 17),
            "hea": lambda: C.hea_ansatz(n, layers=3, measure=False)}[kind]()
-    opts = {"tile_bits": 9, "min_run_bits": 3}
+    opts = {"tile_bits": 9, "min_run_bits": 3, "lookahead_min_qubits": 20}
     look = cb.plan(C.task(ins, n), opts)
     first_come = cb.plan(C.task(ins, n), dict(opts, lookahead=0))
     assert len(look["ops"]) == len(first_come["ops"])
