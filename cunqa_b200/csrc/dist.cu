@@ -117,6 +117,34 @@ __global__ void __launch_bounds__(256) qubit_swap_kernel(V *__restrict__ mine, c
     }
 }
 
+// measurement outcome of a GLOBAL qubit (device-side outcome[0], scale[0]): the ranks whose bit equals the outcome keep
+// their shard, rescaled; the others hold amplitude 0 from here on
+template <typename V>
+__global__ void __launch_bounds__(256) collapse_global_kernel(V *__restrict__ shard, uint64_t amps, int my_bit,
+                                                               const int *__restrict__ outcome, const double *__restrict__ scale)
+{
+    const int out = outcome[0];
+    if (out < 0) return;
+    const bool keep = out == my_bit;
+    const double sc = scale[0];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < amps; i += stride) {
+        V v = shard[i];
+        v.x = keep ? (decltype(v.x))(v.x * sc) : 0;
+        v.y = keep ? (decltype(v.y))(v.y * sc) : 0;
+        shard[i] = v;
+    }
+}
+
+void State::dist_collapse_global(int my_bit)
+{
+    const uint64_t amps = 1ull << n_local_;
+    const int blocks = (int)std::min<uint64_t>((amps + 255) / 256, (uint64_t)num_sms_ * 16);
+    if (precision == 64) collapse_global_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_, amps, my_bit, d_outcome_, d_small_ + 2);
+    else collapse_global_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, amps, my_bit, d_outcome_, d_small_ + 2);
+    CB200_CUDA(cudaGetLastError());
+}
+
 void State::dist_fence()
 {
     CB200_NCCL(nccl().AllReduce(dist->d_fence, dist->d_fence, 1, ncclInt, ncclSum, dist->comm, stream_));

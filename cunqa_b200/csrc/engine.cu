@@ -422,7 +422,44 @@ void State::reduced_qubit(int qubit, double out[4])
 void State::measure(int qubit, uint64_t seed, const uint64_t *counters, const int8_t *forced, int *bits_out, bool reset_after)
 {
     if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
-    if (dist) throw Unsupported("mid-circuit measurement of a sharded state is not implemented");
+    if (dist) {
+        // Sharded state: norm and P(q=1) are local reductions + one all-reduce each (every rank then holds the same
+        // two doubles and draws the same outcome from the shared counter stream); a local qubit collapses inside the
+        // shard, a global one keeps or clears the whole shard -- no amplitude crosses NVLink.
+        flush();
+        const int pq = queue.l2p[qubit];
+        const bool global = pq >= n_local_;
+        if (precision == 64) reduce2_t<double>(0, d_small_, nullptr); else reduce2_t<float>(0, d_small_, nullptr);
+        if (global) {
+            if ((dist_rank() >> (pq - n_local_)) & 1) CB200_CUDA(cudaMemcpyAsync(d_small_ + 1, d_small_, sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+            else CB200_CUDA(cudaMemsetAsync(d_small_ + 1, 0, sizeof(double), stream_));
+        } else {
+            if (precision == 64) reduce2_t<double>(1ull << pq, nullptr, d_small_ + 1); else reduce2_t<float>(1ull << pq, nullptr, d_small_ + 1);
+        }
+        dist_allreduce_f64(d_small_, 2);
+        const uint64_t ctr = counters ? counters[0] : 0;
+        CB200_CUDA(cudaMemcpyAsync(d_counters_, &ctr, sizeof(uint64_t), cudaMemcpyHostToDevice, stream_));
+        if (forced) CB200_CUDA(cudaMemcpyAsync(d_forced_, forced, sizeof(int8_t), cudaMemcpyHostToDevice, stream_));
+        measure_decide_kernel<<<1, 128, 0, stream_>>>(d_small_, d_small_ + 1, 1, seed, d_counters_, forced ? d_forced_ : nullptr,
+                                                      d_outcome_, d_small_ + 2);
+        const uint64_t work = (1ull << n_local_) >> 1;
+        const int blocks = (int)std::min<uint64_t>((work + 255) / 256, (uint64_t)num_sms_ * 16);
+        if (global) dist_collapse_global((dist_rank() >> (pq - n_local_)) & 1);
+        else if (precision == 64) collapse_kernel<double2><<<blocks, 256, 0, stream_>>>((double2 *)d_state_, n_local_, pq, 1, d_outcome_, d_small_ + 2, reset_after ? 1 : 0);
+        else collapse_kernel<float2><<<blocks, 256, 0, stream_>>>((float2 *)d_state_, n_local_, pq, 1, d_outcome_, d_small_ + 2, reset_after ? 1 : 0);
+        CB200_CUDA(cudaGetLastError());
+        stats.launches += 4;
+        stats.bytes += 2ull * state_bytes_ + 2ull * state_bytes_;
+        int out = 0;
+        CB200_CUDA(cudaMemcpyAsync(&out, d_outcome_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        CB200_CUDA(cudaStreamSynchronize(stream_));
+        stats.d2h_bytes += sizeof(int);
+        if (bits_out) bits_out[0] = out;
+        // reset of a global qubit that read 1: the kept shards sit on the ranks with that bit set; an X moves them
+        // (queued like any other gate -- it brings the qubit in with one exchange when it is next flushed)
+        if (global && reset_after && out == 1) apply_named("x", &qubit, 1, nullptr, 0, nullptr);
+        return;
+    }
     flush();
     const int pq = queue.l2p[qubit];
     const uint64_t sel = 1ull << pq;

@@ -93,7 +93,8 @@ private:
     void dist_init(int rank, int world, const uint8_t *id);
     void dist_destroy();
     void dist_fence();
-    void dist_swap(const std::vector<std::pair<int, int>> &pairs);  // (global bit, local bit) pairs, one exchange
+    void dist_swap(const std::vector<std::pair<int, int>> &pairs);
+    void dist_collapse_global(int my_bit);  // measurement of a global qubit: keep-and-rescale or clear this shard  // (global bit, local bit) pairs, one exchange
     void dist_allreduce_f64(double *d_buf, size_t count);
     void dist_allreduce_u64(uint64_t *d_buf, size_t count);
     template <typename T> void flush_dist_t();

@@ -76,6 +76,29 @@ def main():
         check(f"prob1({q})", abs(sv.prob1(q)[0] - ref.prob1(q)) < 1e-10)
     sv.close()
 
+    # 2b. mid-circuit measurement of the sharded state: local and global qubits, plain and with reset -- the same
+    #     outcomes (shared counter stream) and the same post-measurement state as the oracle, gates in between
+    sv = cb.ShardedStateVector(n, "double", device=local)
+    sv.run(ins)
+    ref2, _ = O.run_static(ins, n, backend="c")
+    more = random_circuit(n, 40, 33, max_unitary=3)
+    xmat = np.array([[0, 1], [1, 0]], dtype=complex)
+    for k, (q, rst) in enumerate(((0, False), (n - 1, False), (n // 2, True), (n - 2, True), (n - 1, True))):
+        ctr = O.meas_counter(0, k)
+        want = ref2.measure(q, 5, ctr)
+        if rst and want:
+            ref2.apply_matrix([q], xmat)
+        got = sv.measure(q, seed=5, counters=[ctr], reset=rst)
+        if not rst:
+            check(f"measure({q}) outcome", int(got[0]) == int(want), f"{got} vs {want}")
+        for inst in more[8 * k: 8 * k + 8]:
+            O.apply_gate(ref2, inst)
+        sv.run(more[8 * k: 8 * k + 8])
+        err = np.abs(sv.amplitudes() - ref2.amplitudes()).max()
+        check(f"state after measure({q}, reset={rst})", err < 1e-10, f"err={err}")
+        check(f"norm after measure({q})", abs(sv.norm()[0] - 1) < 1e-10)
+    sv.close()
+
     # 3. fp32 shard
     sv = cb.ShardedStateVector(n, "single", device=local)
     sv.run(ins)
