@@ -148,7 +148,10 @@ void *cb200_backend_stream(cb200_backend *b);
 /* ---- sharded state across the GPUs of one box (no reference analogue) -------------
  * One process per GPU.  The top log2(world) qubits are global (index bits select the rank).
  * Rendezvous is done by the caller (torch.distributed / MPI): rank 0 obtains an id blob with
- * cb200_dist_unique_id, broadcasts it, every rank calls cb200_state_create_dist. */
+ * cb200_dist_unique_id, broadcasts it, every rank calls cb200_state_create_dist.
+ * Every rank then issues the SAME sequence of calls on its handle (gates, flush, norm, prob1, measure,
+ * reset_qubit, sample, get_amplitudes): reductions are all-reduced, so each call returns the same values on every
+ * rank; cb200_sample returns on each rank the shots that fall into its interval of the global distribution. */
 #define CB200_DIST_ID_BYTES 128
 int cb200_dist_unique_id(uint8_t id_out[CB200_DIST_ID_BYTES]);
 int cb200_state_create_dist(cb200_state **out, int n_qubits_total, int precision, int device,
