@@ -151,7 +151,8 @@ void *cb200_backend_stream(cb200_backend *b);
  * cb200_dist_unique_id, broadcasts it, every rank calls cb200_state_create_dist.
  * Every rank then issues the SAME sequence of calls on its handle (gates, flush, norm, prob1, measure,
  * reset_qubit, sample, get_amplitudes): reductions are all-reduced, so each call returns the same values on every
- * rank; cb200_sample returns on each rank the shots that fall into its interval of the global distribution. */
+ * rank (cb200_sample: every rank resolves the shots that fall into its interval of the global cumulative
+ * distribution, the shot indices are then all-reduced). */
 #define CB200_DIST_ID_BYTES 128
 int cb200_dist_unique_id(uint8_t id_out[CB200_DIST_ID_BYTES]);
 int cb200_state_create_dist(cb200_state **out, int n_qubits_total, int precision, int device,
