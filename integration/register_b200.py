@@ -84,9 +84,8 @@ def basis_gates(text):
 
 
 def setup_qpus(text):
-    inc = ('#include "backends/simulators/B200/b200_simple_simulator.hpp"\n#include "backends/simulators/B200/b200_cc_simulator.hpp"\n'
-           '#include "backends/simulators/B200/b200_qc_simulator.hpp"\n')
-    text = insert_before(text, r'^#include "utils/constants.hpp"', inc, "b200_simple_simulator.hpp")
+    inc = '#include "backends/simulators/B200/b200_plugin.hpp"\n'
+    text = insert_before(text, r'^#include "utils/constants.hpp"', inc, "b200_plugin.hpp")
     fams = (("do not support simple simulation", "B200SimpleSimulator, SimpleConfig, SimpleBackend", "no_comm"),
             ("classical communication simulation", "B200CCSimulator, CCConfig, CCBackend", "classical_comm"),
             ("quantum communication simulation", "B200QCSimulator, QCConfig, QCBackend", "quantum_comm"))
@@ -105,7 +104,7 @@ def setup_qpus(text):
 
 
 def setup_executor(text):
-    text = insert_before(text, r'^#include "utils/constants.hpp"|^#include "logger.hpp"', '#include "backends/simulators/B200/b200_executor.hpp"\n', "b200_executor.hpp")
+    text = insert_before(text, r'^#include "utils/constants.hpp"|^#include "logger.hpp"', '#include "backends/simulators/B200/b200_plugin.hpp"\n', "b200_plugin.hpp")
     if "B200Executor" in text:
         return text
     m = re.search(r"^(\s*)default:\s*\n\s*LOGGER_ERROR\(\"Not a supported simulator", text, flags=re.M)

@@ -37,7 +37,7 @@ def test_registration_edits_apply_once_and_compile(tmp_path):
     for cls in ("B200SimpleSimulator, SimpleConfig, SimpleBackend", "B200CCSimulator, CCConfig, CCBackend", "B200QCSimulator, QCConfig, QCBackend"):
         assert qp.count(f"turn_ON_QPU<{cls}>") == 1
     assert snapshot["src/cli/setup_executor.cpp"].count("B200Executor executor(n_qpus);") == 1
-    assert os.path.exists(os.path.join(dst, "src/backends/simulators/B200/b200_simple_simulator.cpp"))
+    assert os.path.exists(os.path.join(dst, "src/backends/simulators/B200/b200_plugin.cpp"))
     # the patched constants + basis-gate lookup compile and answer for "B200"
     site = sysconfig.get_paths()["purelib"]
     nl = os.path.join(site, "include", "cudnn_frontend", "thirdparty")
