@@ -273,9 +273,24 @@ Json Backend::run(const Json &msg)
     if (msg.contains("instructions") && msg.contains("config")) {
         cached_ = msg;
         has_cached_ = true;
+        parsed_.reset();
     } else if (msg.contains("params")) {
         if (!has_cached_) throw std::runtime_error("Circuit not sent before updating parameters.");
         update_params(cached_, msg);
+        if (parsed_) {
+            // the structure is unchanged: copy the rewritten angles (and shots) into the parsed task instead of re-parsing
+            TaskCfg &pc = *std::static_pointer_cast<TaskCfg>(parsed_);
+            const Json &insts = cached_.at("instructions");
+            bool same = insts.arr.size() == pc.insts.size();
+            for (size_t i = 0; same && i < pc.insts.size(); i++) {
+                const Json *pj = insts.arr[i].find("params");
+                if (!pj) continue;
+                pc.insts[i].params.resize(pj->arr.size());
+                for (size_t k = 0; k < pj->arr.size(); k++) pc.insts[i].params[k] = pj->arr[k].as_double();
+            }
+            if (!same) parsed_.reset();
+            else if (msg.contains("shots")) pc.shots = (uint64_t)msg.at("shots").as_int();
+        }
     } else {
         throw std::runtime_error("message has neither instructions+config nor params");
     }
@@ -306,13 +321,20 @@ Json Backend::run(const Json &msg)
         out.set("time_taken", r.at("time_taken"));
         return out;
     }
-    return run_static(task);
+    if (!parsed_) parsed_ = std::make_shared<TaskCfg>(parse_task(task));
+    return run_static_parsed(parsed_.get());
 }
 
 Json Backend::run_static(const Json &task)
 {
-    const auto t_in = std::chrono::high_resolution_clock::now();
     const TaskCfg c = parse_task(task);
+    return run_static_parsed(&c);
+}
+
+Json Backend::run_static_parsed(const void *parsed_task)
+{
+    const auto t_in = std::chrono::high_resolution_clock::now();
+    const TaskCfg &c = *static_cast<const TaskCfg *>(parsed_task);
     const auto t0 = std::chrono::high_resolution_clock::now();
     State &st = get_state(c.num_qubits, c.precision, 1);
     st.queue.set_fusion(c.fusion_enable < 0 ? st.opt.fuse : c.fusion_enable != 0,

@@ -37,6 +37,8 @@ private:
     std::unique_ptr<State> state_;
     Json cached_;          // last full task message (for {"params":...} updates)
     bool has_cached_ = false;
+    std::shared_ptr<void> parsed_;   // the cached task, parsed (static tasks only): {"params"} updates rewrite its angles in place
+    Json run_static_parsed(const void *parsed_task);
     send_fn send_ = nullptr;
     recv_fn recv_ = nullptr;
     void *user_ = nullptr;
