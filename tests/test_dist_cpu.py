@@ -130,3 +130,58 @@ def test_diagonal_and_controls_on_global_qubits_need_no_exchange(lib_built):
         # the cx controlled by global qubit 5 exists only on the ranks whose bit is 1
         kinds = [op["kind"] for s in plan["segments"] for op in s["ops"]]
         assert ("permx" in kinds) == bool(rank & 2)
+
+
+# ---- index arithmetic of the multi-qubit exchange kernel (dist.cu: qubit_swap_kernel), restated in numpy ----------
+def _insert0(g, pos):
+    return ((g >> pos) << (pos + 1)) | (g & ((1 << pos) - 1))
+
+
+def _exchange_like_the_kernel(shards, n_local, pairs):
+    """every rank runs the kernel's loop over w; returns the shards after the in-place exchange"""
+    world = len(shards)
+    m = len(pairs)
+    order = sorted(range(m), key=lambda j: pairs[j][1])
+    lbit = [pairs[j][1] for j in order]
+    perm = order
+    out = [s.copy() for s in shards]
+    rest_bits = n_local - m - 1
+    half = 1 << rest_bits
+    for rank in range(world):
+        x = 0
+        for j in range(m):
+            x |= ((rank >> pairs[j][0]) & 1) << j
+        for w in range(((1 << m) - 1) << rest_bits):
+            y = x ^ ((w >> rest_bits) + 1)
+            r = (w & (half - 1)) | (0 if x < y else half)
+            mi = r
+            for j in range(m):
+                mi = _insert0(mi, lbit[j])
+            pi = mi
+            for j in range(m):
+                mi |= ((y >> perm[j]) & 1) << lbit[j]
+                pi |= ((x >> perm[j]) & 1) << lbit[j]
+            peer = rank
+            for j in range(m):
+                peer = (peer & ~(1 << pairs[j][0])) | (((y >> j) & 1) << pairs[j][0])
+            out[rank][mi], out[peer][pi] = out[peer][pi], out[rank][mi]
+    return out
+
+
+@pytest.mark.parametrize("world,pairs", [(2, [(0, 3)]), (4, [(1, 0)]), (4, [(0, 4), (1, 2)]), (8, [(2, 1), (0, 5), (1, 3)]), (8, [(1, 4), (2, 0)])])
+def test_multi_qubit_exchange_indexing(world, pairs):
+    """the kernel's one-step transposition equals the sequence of single (global bit, local bit) swaps, and every
+    amplitude is touched at most once (each unordered rank pair splits the index space in halves)"""
+    n_local = 6
+    g = world.bit_length() - 1
+    n = n_local + g
+    full = np.arange(1 << n, dtype=np.int64)            # amplitude = its own global index
+    want = full.copy()
+    for gb, lb in pairs:                                 # sequential reference: swap index bits (n_local + gb) <-> lb
+        idx = np.arange(1 << n)
+        hi, lo = (idx >> (n_local + gb)) & 1, (idx >> lb) & 1
+        swapped = idx ^ (((hi ^ lo) << (n_local + gb)) | ((hi ^ lo) << lb))
+        want = want[swapped]
+    shards = [full[r << n_local:(r + 1) << n_local] for r in range(world)]
+    got = np.concatenate(_exchange_like_the_kernel(shards, n_local, pairs))
+    assert np.array_equal(got, want)
