@@ -335,7 +335,9 @@ def main():
                        "parallelism": "1 state per GPU, no collective" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "tile_pass_tma_kernel<double>", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": 2 * S},
+                         "algorithmic_bytes_per_launch": 2 * S,
+                         "note": "the step is fp64-pipe bound (see fp64_pipe): fuller passes raise gates/s and lower this fraction; "
+                                 "with one op per pass the same kernel streams at 0.93-1.0 of the peak (DESIGN.md section 6)"},
             # explanatory: the co-bound.  A Haar SU(4) gate costs 16 FMA (32 flop) per amplitude; the peak is the DFMA
             # rate measured with tools/fp64_pipes.cu on this pool's B200 (profiles/fp64_pipes_r01.txt)
             "fp64_pipe": {"achieved": gates * float(2 ** n) * 32.0 / (ms_per_step / 1e3) / 1e12, "peak": 33.1,
