@@ -28,6 +28,8 @@ def test_own_arm_line_has_the_contract_keys():
     c = d["cpu_baseline"]
     assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    h = d["hbm_bound_regime"]  # explanatory: where memory is the bound the kernel sits at the HBM roofline
+    assert h["unit"] == "GB/s" and h["frac"] >= 0.70 and abs(h["frac"] - h["achieved"] / h["peak"]) < 1e-9
     # value is the whole-job aggregate: gates of one circuit / time of one step
     assert abs(d["value"] - 528 / (d["ms_per_step"] / 1e3)) / d["value"] < 1e-6
 
