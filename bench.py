@@ -14,12 +14,16 @@ GPU): 33-qubit random quantum-volume circuit, depth 33 (528 Haar SU(4) `unitary`
   1024 shots sampled -> D2H -> counts JSON.
 * `roofline`: the tile-pass kernel; algorithmic bytes per launch = 2*S (every amplitude read once and
   written once), duration = average launch time over the timed region.
+* `fp64_pipe` (explanatory): the co-bound.  528 gates x 2^33 amplitudes x 32 flop against the DFMA rate measured with
+  tools/fp64_pipes.cu.  `hbm_bound_regime` (explanatory, N = 1): two layers of the same circuit with the planner capped
+  at two gates per pass -- the same kernel where memory IS the bound.
 * `cpu_baseline` / `--impl reference`: the reference's CPU path for this workload is Aer's statevector
   simulator, which cannot be installed here (no network, un-vendored); the arm times oracle/sv_oracle.c
   (gate-by-gate restatement, OpenMP over all host cores) on a bounded sample and scales it to the
   33-qubit state (amplitude updates per second / 2^33).
 * N > 1 (torchrun): every rank simulates its own 33-qubit state on its own GPU (the "many independent
-  vQPUs" regime of SURVEY 8e: no data-path collective), weak scaling.
+  vQPUs" regime of SURVEY 8e: no data-path collective), weak scaling; a `sharded` object adds ONE QFT-(33+log2 N)
+  state sharded over the N GPUs (qubit exchanges over NVLink peer memory).
 """
 from __future__ import annotations
 
