@@ -108,7 +108,12 @@ def cpu_sample(target_seconds=12.0, max_qubits=28):
     from cunqa_b200 import circuits as C
     from oracle import oracle_np as O
     lib = O.c_oracle(native=True)
-    cores = lib.orc_num_threads()
+    # all host cores, whatever the launcher exported (torch.distributed.run sets OMP_NUM_THREADS=1)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        avail = os.cpu_count() or 1
+    cores = lib.orc_set_num_threads(avail)
     try:
         avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
     except (ValueError, OSError):

@@ -9,7 +9,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libcunqa_b200.so")
-SOURCES = ["api.cu", "engine.cu", "dist.cu", "executor.cpp", "planner.cpp", "opqueue.cpp", "gates.cpp", "dist_plan.cpp", "qasm2.cpp"]
+SOURCES = (["api.cu", "engine.cu", "dist.cu", "executor.cpp", "planner.cpp", "opqueue.cpp", "gates.cpp", "dist_plan.cpp", "qasm2.cpp",
+            "tile_launch_generic.cu"]
+           # the hot kernel, one translation unit per (amplitude type, threads per CTA) so that they compile side by side
+           + [f"tile_launch_{t}_{nt}.cu" for t in ("f64", "f32") for nt in (32, 64, 128, 256)])
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",
@@ -35,7 +38,7 @@ def _newest_header():
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     hdr = _newest_header()
-    objs, rebuilt = [], False
+    objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.rsplit(".", 1)[0] + ".o")
@@ -45,8 +48,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), file=sys.stderr)
-            subprocess.check_call(cmd)
-            rebuilt = True
+            jobs.append(cmd)
+    rebuilt = bool(jobs)
+    if jobs:  # translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            list(pool.map(subprocess.check_call, jobs))
     if rebuilt or not os.path.exists(LIB):
         cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         subprocess.check_call(cmd)

@@ -156,6 +156,10 @@ void State::dist_swap(const std::vector<std::pair<int, int>> &pairs)
     if ((int)dist->peers.size() != dist->world) throw InvalidArg("sharded state: peer handles were not imported");
     const int m = (int)pairs.size();
     if (m < 1 || m > 4 || m >= n_local_) throw InvalidArg("sharded state: 1..4 qubit pairs per exchange");
+    for (int a = 0; a < m; a++)
+        for (int b = a + 1; b < m; b++)
+            if (pairs[a].first == pairs[b].first || pairs[a].second == pairs[b].second)
+                throw InvalidArg("sharded state: repeated global or local bit in one exchange");
     SwapPlan sp{};
     sp.m = m;
     sp.n_local = n_local_;
@@ -199,13 +203,19 @@ void State::flush_dist_t()
     CB200_CUDA(cudaSetDevice(device));
     const DistPlan plan = plan_distributed(ops, n, n_local_, dist->rank);
     static const int max_group = getenv("CB200_SWAP_GROUP") ? std::max(1, std::min(4, atoi(getenv("CB200_SWAP_GROUP")))) : 4;
-    std::vector<std::pair<int, int>> group;  // back-to-back swaps become one multi-qubit exchange
+    // swaps planned together (same batch id) become one multi-qubit exchange.  Grouping by batch id -- not by adjacency
+    // in this rank's segment list -- keeps the number and shape of exchanges identical on every rank: a LOCAL segment
+    // that separates two batches on one rank can be empty (all its ops dropped by a global control) on another.
+    std::vector<std::pair<int, int>> group;
+    int group_batch = -1;
     auto exchange = [&]() {
         if (!group.empty()) dist_swap(group);
         group.clear();
     };
     for (const DistSegment &seg : plan.segments) {
         if (seg.is_swap) {
+            if (seg.batch != group_batch) exchange();
+            group_batch = seg.batch;
             group.emplace_back(seg.gbit, seg.lbit);
             if ((int)group.size() == max_group) exchange();
         } else {

@@ -31,6 +31,7 @@ DistPlan plan_distributed(const std::vector<HostOp> &ops, int n_total, int n_loc
         cur = DistSegment();
     };
     auto rank_bit = [&](int pos) { return (rank >> (pos - n_local)) & 1; };
+    int swap_batch = 0;
 
     for (size_t i = 0; i < ops.size(); i++) {
         HostOp op = ops[i];
@@ -71,6 +72,7 @@ DistPlan plan_distributed(const std::vector<HostOp> &ops, int n_total, int n_loc
                     sw.is_swap = true;
                     sw.gbit = gpos - n_local;
                     sw.lbit = best;
+                    sw.batch = swap_batch;
                     plan.segments.push_back(sw);
                     const int og = inv[gpos], ol = inv[best];
                     sigma[og] = best; sigma[ol] = gpos;
@@ -78,6 +80,7 @@ DistPlan plan_distributed(const std::vector<HostOp> &ops, int n_total, int n_loc
                     for (int &x : op.q) if (x == gpos) x = best; else if (x == best) x = gpos;
                     for (int &x : op.ctrl) if (x == gpos) x = best; else if (x == best) x = gpos;
                 }
+                swap_batch++;
                 for (int x : op.q)
                     if (x >= n_local) throw std::runtime_error("distributed planner: internal error (target still global)");
             }

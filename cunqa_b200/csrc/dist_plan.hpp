@@ -6,7 +6,8 @@
 //     controls on global qubits are resolved (rank bit 0: op dropped, 1: control removed);
 //   * SWAP(gbit, lbit): exchange global qubit n_local+gbit with local qubit lbit -- every rank swaps half of
 //     its shard with rank ^ (1 << gbit).  Emitted only when a non-diagonal target is global.
-// All ranks derive the same swap sequence (it depends on the op list only), so the exchange steps line up.
+// All ranks derive the same swap sequence AND the same batch ids (both depend on the op list only, never on which
+// ops a rank dropped), so the exchange steps line up even when the LOCAL segments between them differ per rank.
 #pragma once
 #include <vector>
 
@@ -17,6 +18,8 @@ namespace cb200 {
 struct DistSegment {
     bool is_swap = false;
     int gbit = 0, lbit = 0;       // SWAP
+    int batch = -1;               // SWAP: exchanges planned together carry the same id (identical on every rank); only
+                                  // swaps of one batch may be executed as ONE multi-qubit exchange
     std::vector<HostOp> ops;      // LOCAL (qubits < n_local)
 };
 

@@ -8,6 +8,7 @@
 
 #include "measure_kernels.cuh"
 #include "tile_kernel.cuh"
+#include "tile_launch.hpp"
 
 namespace cb200 {
 
@@ -246,7 +247,6 @@ void State::launch_ops_t(std::vector<HostOp> &ops)
         stats.h2d_bytes += need;
         CB200_CUDA(cudaStreamSynchronize(stream_));
     }
-    auto kern = tile_pass_kernel<T>;
     const int aprs = sizeof(V) == 16 ? 3 : 4;
     for (size_t i = 0; i < passes.size(); i++) {
         const PassParams<T> &p = params[i];
@@ -271,38 +271,25 @@ void State::launch_ops_t(std::vector<HostOp> &ops)
         if (tma) {
             CUtensorMap tmap;
             make_tensor_map(&tmap, run_bits, hi_q);
-            const unsigned grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_ * ctas);
-            auto launch = [&](auto kern_tma) {
-                CB200_CUDA(cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
-                kern_tma<<<grid, nt, smem_tma, stream_>>>(p, tmap, (const V *)d_diag_, d_flags_, box_bits, buf_stride, tma_refill_after_);
-            };
-            const bool cnd = p.cond_mask != 0, full = p.needs_full != 0;
-            auto pick = [&](auto nt_tag) {
-                constexpr int N = decltype(nt_tag)::value;
-                if (stages == 3) {
-                    if (!cnd && !full) launch(tile_pass_tma_kernel<T, N, false, false, 3>);
-                    else if (!cnd) launch(tile_pass_tma_kernel<T, N, false, true, 3>);
-                    else launch(tile_pass_tma_kernel<T, N, true, true, 3>);
-                } else {
-                    if (!cnd && !full) launch(tile_pass_tma_kernel<T, N, false, false, 2>);
-                    else if (!cnd) launch(tile_pass_tma_kernel<T, N, false, true, 2>);
-                    else launch(tile_pass_tma_kernel<T, N, true, true, 2>);
-                }
-            };
-            if (nt == 256) pick(std::integral_constant<int, 256>());
-            else if (nt == 128) pick(std::integral_constant<int, 128>());
-            else if (nt == 64) pick(std::integral_constant<int, 64>());
-            else pick(std::integral_constant<int, 32>());
+            TmaLaunch l;
+            l.grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_ * ctas);
+            l.smem = smem_tma;
+            l.stream = stream_;
+            l.diag_tabs = d_diag_;
+            l.flags = d_flags_;
+            l.box_bits = box_bits;
+            l.buf_stride = buf_stride;
+            l.refill_after = tma_refill_after_;
+            l.stages = stages;
+            l.device = device;
+            cudaError_t e;
+            if (nt == 256) e = launch_tile_pass_tma<T, 256>(p, tmap, l);
+            else if (nt == 128) e = launch_tile_pass_tma<T, 128>(p, tmap, l);
+            else if (nt == 64) e = launch_tile_pass_tma<T, 64>(p, tmap, l);
+            else e = launch_tile_pass_tma<T, 32>(p, tmap, l);
+            CB200_CUDA(e);
         } else {
-            const size_t smem = sizeof(V) * ((size_t)1 << p.t) + sizeof(uint64_t) * ((size_t)1 << (p.t - p.L));
-            CB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int occ = ctas_per_sm_;
-            if (occ <= 0) {
-                CB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTileThreads, smem));
-                if (occ < 1) occ = 1;
-            }
-            const unsigned grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_ * occ);
-            kern<<<grid, kTileThreads, smem, stream_>>>(p, (V *)d_state_, (const V *)d_diag_, d_flags_);
+            CB200_CUDA(launch_tile_pass_generic<T>(p, d_state_, d_diag_, d_flags_, num_sms_, ctas_per_sm_, device, stream_));
         }
         CB200_CUDA(cudaGetLastError());
         stats.passes++;

@@ -131,7 +131,7 @@ struct TaskCfg {
     std::vector<Inst> insts;
     int n_comm = -1;
     bool bugcompat_unitary_order = false;
-    bool bugcompat_teledata = false;
+    bool bugcompat_teledata = true;   // X <- sent qubit's outcome, Z <- comm qubit's: the reference's literal code (:653-658), quirk Q6
     bool terminal_sampling = true;
     bool share_prefix = true;
     bool defer_measurement = true;
@@ -165,6 +165,12 @@ TaskCfg parse_task(const Json &t)
     if (cfg.contains("n_communication_qubits")) c.n_comm = (int)cfg.at("n_communication_qubits").as_int();
     if (cfg.contains("b200_bugcompat_unitary_order")) c.bugcompat_unitary_order = cfg.at("b200_bugcompat_unitary_order").as_bool();
     if (cfg.contains("b200_bugcompat_teledata")) c.bugcompat_teledata = cfg.at("b200_bugcompat_teledata").as_bool();
+    if (cfg.contains("b200_teledata_corrections")) {
+        const std::string v = cfg.at("b200_teledata_corrections").as_string();
+        if (v == "reference") c.bugcompat_teledata = true;
+        else if (v == "protocol") c.bugcompat_teledata = false;
+        else throw std::runtime_error("b200_teledata_corrections must be 'reference' or 'protocol'");
+    }
     if (cfg.contains("b200_share_prefix")) c.share_prefix = cfg.at("b200_share_prefix").as_bool();
     if (cfg.contains("b200_terminal_sampling")) c.terminal_sampling = cfg.at("b200_terminal_sampling").as_bool();
     if (cfg.contains("b200_defer_measurement")) c.defer_measurement = cfg.at("b200_defer_measurement").as_bool();
@@ -198,6 +204,14 @@ Json counts_json(const std::map<std::string, uint64_t> &counts)
     j.obj.reserve(counts.size());  // keys of a std::map are unique: append directly (Json::set searches linearly)
     for (auto &kv : counts) j.obj.emplace_back(kv.first, Json::integer((long long)kv.second));
     return j;
+}
+
+// Aer's `fusion_enable` / `fusion_max_qubit` (aer_helpers.hpp:17-86); absent keys restore the engine's defaults so that a
+// cached State never inherits the previous job's setting
+void apply_fusion_cfg(State &st, const TaskCfg &c)
+{
+    st.queue.set_fusion(c.fusion_enable < 0 ? st.opt.fuse : c.fusion_enable != 0,
+                        c.fusion_max_qubit < 0 ? st.opt.max_dense_qubits : c.fusion_max_qubit);
 }
 
 bool cif_op(const std::string &op, bool a, bool b)
@@ -304,12 +318,13 @@ Json Backend::run(const Json &msg)
         for (const Json &j : insts.arr) {
             const std::string name = j.at("name").as_string();
             if (name == "measure") {
-                for (const Json &q : j.at("qubits").arr) measured |= 1ull << q.as_int();
+                for (const Json &q : j.at("qubits").arr)
+                    if (q.as_int() >= 0 && q.as_int() < 64) measured |= 1ull << q.as_int();
             } else if (is_classical_or_remote(name)) {
                 dynamic = true;
             } else if (const Json *qs = j.find("qubits")) {
                 for (const Json &q : qs->arr)
-                    if (q.as_int() >= 0 && ((measured >> q.as_int()) & 1ull)) dynamic = true;
+                    if (q.as_int() >= 0 && q.as_int() < 64 && ((measured >> q.as_int()) & 1ull)) dynamic = true;
             }
         }
     }
@@ -319,6 +334,7 @@ Json Backend::run(const Json &msg)
         const std::string id = task.contains("id") ? task.at("id").as_string() : std::string("task");
         out.set("counts", r.at("id_counts").at(id));
         out.set("time_taken", r.at("time_taken"));
+        if (r.contains("b200")) out.set("b200", r.at("b200"));
         return out;
     }
     if (!parsed_) parsed_ = std::make_shared<TaskCfg>(parse_task(task));
@@ -337,8 +353,7 @@ Json Backend::run_static_parsed(const void *parsed_task)
     const TaskCfg &c = *static_cast<const TaskCfg *>(parsed_task);
     const auto t0 = std::chrono::high_resolution_clock::now();
     State &st = get_state(c.num_qubits, c.precision, 1);
-    st.queue.set_fusion(c.fusion_enable < 0 ? st.opt.fuse : c.fusion_enable != 0,
-                        c.fusion_max_qubit < 0 ? st.opt.max_dense_qubits : c.fusion_max_qubit);
+    apply_fusion_cfg(st, c);
     const Stats before = st.stats;
     const uint64_t gates_before = st.queue.gates;
     std::vector<std::pair<int, int>> meas;  // (qubit, clbit)
@@ -588,6 +603,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
     Stats before;
     uint64_t gates_before = 0;
     bool deferred_used = false;
+    bool used_teledata = false;
 
     // one batch of nb shots starting at shot0 (the last batch may carry surplus states; their results are dropped).
     // deferred = one state for ALL shots: measurements only freeze their qubit, classical bits are symbolic, feed-
@@ -903,10 +919,12 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                     const std::vector<int> mine = my_pairs(in.qpus.at(0), c.id, "teledata", 1);
                     if (mine.empty()) throw std::runtime_error("qrecv without an entangled pair");
                     CommPair &p = pairs[mine[0]];
-                    // m1 = outcome of the sent qubit, m2 = outcome of the sender's comm qubit.  The documented
-                    // protocol (docs/source/_static/teledata.png) is X <- m2, Z <- m1; the reference code
-                    // (:653-658) has them swapped, which does not teleport -- mirrored only under bugcompat.
+                    // m1 = outcome of the sent qubit, m2 = outcome of the sender's comm qubit.  The reference code
+                    // (:653-658) applies X <- m1, Z <- m2 and that is the default here (drop-in: same histograms);
+                    // the documented protocol (docs/source/_static/teledata.png) is X <- m2, Z <- m1, selected with
+                    // b200_teledata_corrections = "protocol".  The result JSON says which one ran.
                     const bool lit = cfgs[0].bugcompat_teledata;
+                    used_teledata = true;
                     named("x", {p.q1}, lit ? &m1 : &m2);
                     named("z", {p.q1}, lit ? &m2 : &m1);
                     named("swap", {p.q1, qmap(in.qubits.at(0))}, nullptr);
@@ -1065,8 +1083,13 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
     bool done = false;
     if (shots > 0 && c0.defer_measurement && !external_cc && n_total + (int)kSym <= (int)kNotSym) {  // (symbol encoding: <= 62 qubits)
         State &s1 = get_state(n_total, precision, 1);
+        apply_fusion_cfg(s1, c0);
         const Stats b1 = s1.stats;
         const uint64_t g1 = s1.queue.gates;
+        auto undo = [&]() {
+            s1.reset();
+            for (auto &kv : counters) kv.second.clear();
+        };
         try {
             run_batch(s1, 1, 0, shots, true);
             done = true;
@@ -1075,13 +1098,18 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
             gates_before = g1;
             deferred_used = true;
         } catch (const DeferAbort &) {
-            s1.reset();
-            for (auto &kv : counters) kv.second.clear();
+            undo();
+        } catch (const Unsupported &) {
+            // turning a classical condition into extra quantum controls can exceed what the queue accepts (a diagonal
+            // wider than kMaxDiagK, ...): the per-shot interpreter runs the same task without those controls
+            undo();
+        } catch (const InvalidArg &) {
+            undo();  // e.g. a condition literal that is also an operand of the conditioned gate
         }
     }
     if (!done) {
         stp = shots ? &get_state(n_total, precision, (int)B) : nullptr;
-        if (stp) { before = stp->stats; gates_before = stp->queue.gates; }
+        if (stp) { apply_fusion_cfg(*stp, c0); before = stp->stats; gates_before = stp->queue.gates; }
         for (uint64_t shot0 = 0; shot0 < shots; shot0 += B) {
             if (shot0 > 0) stp->reset();
             run_batch(*stp, (int)B, shot0, std::min<uint64_t>(B, shots - shot0), false);
@@ -1093,6 +1121,12 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
     Json out = Json::object();
     out.set("id_counts", std::move(idc));
     out.set("time_taken", Json::number(std::chrono::duration<double>(t1 - t0).count()));
+    {
+        Json info = Json::object();
+        info.set("mode", Json::string(deferred_used ? "deferred_measurement" : "per_shot_batched"));
+        if (used_teledata) info.set("teledata_corrections", Json::string(c0.bugcompat_teledata ? "reference" : "protocol"));
+        out.set("b200", std::move(info));
+    }
     last_mode = deferred_used ? 1 : 2;
     if (stp) {
         last_stats = stp->stats;
@@ -1211,6 +1245,7 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
                 sw.arr.push_back(Json::integer(s.gbit));
                 sw.arr.push_back(Json::integer(s.lbit));
                 o.set("swap", std::move(sw));
+                o.set("batch", Json::integer(s.batch));
             } else {
                 o.set("ops", ops_json(s.ops));
                 o.set("passes", passes_json(s.ops, n_local));

@@ -1,0 +1,4 @@
+// one (amplitude type, threads per CTA) instantiation of the TMA tile-pass kernel; see tile_launch.hpp
+#define CB200_T double
+#define CB200_NT 256
+#include "tile_launch_inst.cuh"

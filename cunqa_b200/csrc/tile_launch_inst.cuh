@@ -1,0 +1,45 @@
+// tile_launch_inst.cuh -- body of one tile_launch_*.cu translation unit: define CB200_T and CB200_NT before including.
+#include "tile_kernel.cuh"
+#include "tile_launch.hpp"
+
+namespace cb200 {
+
+namespace {
+constexpr int kMaxDevices = 16;
+template <typename K>
+cudaError_t set_smem_once(K kern, size_t smem, size_t &seen)
+{
+    // (the attribute is sticky per function: raise it only when a launch needs more than any launch before it)
+    if (smem <= seen) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) seen = smem;
+    return e;
+}
+}  // namespace
+
+template <>
+cudaError_t launch_tile_pass_tma<CB200_T, CB200_NT>(const PassParams<CB200_T> &p, const CUtensorMap &tmap, const TmaLaunch &l)
+{
+    using T = CB200_T;
+    using V = typename Vec2<T>::type;
+    constexpr int N = CB200_NT;
+    static size_t seen_all[kMaxDevices][6] = {};
+    size_t *seen = seen_all[l.device & (kMaxDevices - 1)];
+    const bool cnd = p.cond_mask != 0, full = p.needs_full != 0;
+    auto go = [&](auto kern, size_t &s) -> cudaError_t {
+        cudaError_t e = set_smem_once(kern, l.smem, s);
+        if (e != cudaSuccess) return e;
+        kern<<<l.grid, N, l.smem, l.stream>>>(p, tmap, (const V *)l.diag_tabs, l.flags, l.box_bits, l.buf_stride, l.refill_after);
+        return cudaGetLastError();
+    };
+    if (l.stages == 3) {
+        if (!cnd && !full) return go(tile_pass_tma_kernel<T, N, false, false, 3>, seen[0]);
+        if (!cnd) return go(tile_pass_tma_kernel<T, N, false, true, 3>, seen[1]);
+        return go(tile_pass_tma_kernel<T, N, true, true, 3>, seen[2]);
+    }
+    if (!cnd && !full) return go(tile_pass_tma_kernel<T, N, false, false, 2>, seen[3]);
+    if (!cnd) return go(tile_pass_tma_kernel<T, N, false, true, 2>, seen[4]);
+    return go(tile_pass_tma_kernel<T, N, true, true, 2>, seen[5]);
+}
+
+}  // namespace cb200

@@ -291,6 +291,8 @@ def c_oracle(native=False):
         lib.orc_sample.argtypes = [dp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64,
                                    ctypes.POINTER(ctypes.c_uint64)]
         lib.orc_num_threads.restype = ctypes.c_int
+        lib.orc_set_num_threads.argtypes = [ctypes.c_int]
+        lib.orc_set_num_threads.restype = ctypes.c_int
         _LIB = lib
     return _LIB
 
@@ -435,7 +437,7 @@ class _DeadBranch(Exception):
 
 
 def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channel=None,
-                reverse_unitary_qubits=False, forced_bits=None, teledata_literal=False, terminal_sampling=True,
+                reverse_unitary_qubits=False, forced_bits=None, teledata_literal=True, terminal_sampling=True,
                 defer=False, _weight=None, _final=None):
     """Per-shot interpreter of one or several co-simulated tasks (aer_simulator_adapter.cpp:120-792,845-935).
 
@@ -450,8 +452,9 @@ def run_dynamic(tasks, shots, seed=0, n_comm_qubits=None, backend="auto", channe
     teledata_literal: the reference's QRECV applies X on the *sent qubit's* outcome and Z on the
     *comm qubit's* outcome (aer_simulator_adapter.cpp:644-658, same in every adapter), which is the
     reverse of its own documented protocol (docs/source/_static/teledata.png: X <- comm qubit,
-    Z <- sent qubit) and does not teleport.  Default follows the documented protocol; True mirrors
-    the literal code (quirk Q6).
+    Z <- sent qubit) and does not teleport.  The oracle restates the reference, so the default (True) is
+    the literal code; False follows the documented protocol (the engine's
+    `b200_teledata_corrections: "protocol"`; quirk Q6).
     defer: the engine's deferred-measurement mode, restated: ONE state for all shots; `measure q -> c` freezes q
     and makes c the symbol ("sym", q); a cif on such a bit and the teledata / telegate corrections become the
     same gate with q as an extra control; all shots are drawn from the final state (u_s = U(seed, s), as on

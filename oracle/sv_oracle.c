@@ -16,6 +16,21 @@
 
 #define MAXK 10
 
+/* pin the OpenMP team size (launchers such as torch.distributed.run export OMP_NUM_THREADS=1: a CPU baseline timed
+ * under them must ask for the host's cores itself); n <= 0: every online core.  Returns the team size now in force. */
+int orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n <= 0) n = omp_get_num_procs();
+    omp_set_dynamic(0);
+    omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

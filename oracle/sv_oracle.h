@@ -46,6 +46,8 @@ int orc_measure(double *state, int n, int qubit, uint64_t seed, uint64_t counter
 void orc_sample(const double *state, int n, uint64_t shots, uint64_t seed, uint64_t *out);
 /* number of OpenMP threads actually used */
 int orc_num_threads(void);
+/* set the team size (n <= 0: all online cores), overriding OMP_NUM_THREADS; returns the size in force */
+int orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,7 @@ def main():
     sv.run(C.qft(n, x))
     idx = np.random.default_rng(1).integers(0, 1 << n, size=4096).astype(np.uint64)
     err = np.abs(sv.amplitudes(idx) - O.qft_amplitudes(n, x, idx)).max()
-    check("qft closed form", err < 1e-10, f"err={err}")
+    check("qft closed form", err < 1e-10 and err * 2.0 ** (n / 2) < 1e-9, f"err={err}")
     check("qft norm", abs(sv.norm()[0] - 1) < 1e-10)
     st = sv.dist_stats()
     check("qft needed swaps", st["swaps"] >= g, str(st))

@@ -51,26 +51,55 @@ def _worker(rank, world, port, task, opts, out_path):
     if (basis >> nl) == rank:
         st.v[basis & ((1 << nl) - 1)] = 1.0
     n_swaps = 0
+    exchanges = []   # the pair lists this rank executes, in order (must be identical on every rank)
+
+    def exchange(pairs):
+        # one m-qubit exchange exactly as dist.cu's flush_dist_t issues it: amplitude (rank bits x, local bits y) trades
+        # places with (rank bits y, local bits x).  Replayed with an all-gather (the states are tiny here).
+        exchanges.append(list(pairs))
+        mine = torch.from_numpy(st.v.view(np.float64).copy())
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        allv = [a.numpy().view(np.complex128) for a in allv]
+        idx = np.arange(1 << nl)
+        src_rank = np.full(1 << nl, rank)
+        src_idx = idx.copy()
+        for gb, lb in pairs:
+            y = (idx >> lb) & 1                      # my amplitude's local bit -> the source's rank bit
+            x = (rank >> gb) & 1                     # my rank bit -> the source's local bit
+            src_rank = (src_rank & ~(1 << gb)) | (y << gb)
+            src_idx = (src_idx & ~(1 << lb)) | (x << lb)
+        st.v[:] = np.stack(allv)[src_rank, src_idx]
+
+    group, group_batch = [], None
+    max_group = int(os.environ.get("CB200_SWAP_GROUP", "4"))
+
+    def flush_group():
+        nonlocal group
+        if group:
+            exchange(group)
+        group = []
+
     for seg in plan["segments"]:
         if "swap" in seg:
             gbit, lbit = seg["swap"]
             n_swaps += 1
-            mybit = (rank >> gbit) & 1
-            peer = rank ^ (1 << gbit)
-            idx = np.arange(1 << nl)
-            send_sel = ((idx >> lbit) & 1) == (1 - mybit)
-            send = torch.from_numpy(np.ascontiguousarray(st.v[send_sel]).view(np.float64).copy())
-            recv = torch.empty_like(send)
-            if rank < peer:
-                dist.send(send, peer); dist.recv(recv, peer)
-            else:
-                dist.recv(recv, peer); dist.send(send, peer)
-            st.v[send_sel] = recv.numpy().view(np.complex128)
+            if seg["batch"] != group_batch:
+                flush_group()
+            group_batch = seg["batch"]
+            group.append((gbit, lbit))
+            if len(group) == max_group:
+                flush_group()
         else:
+            flush_group()
             # execute in the order of the tile passes (the order the GPU uses)
             for ps in seg["passes"]:
                 for oi in ps["ops"]:
                     _apply_local(st, seg["ops"][oi])
+    flush_group()
+    every = [None] * world
+    dist.all_gather_object(every, exchanges)
+    assert all(e == every[0] for e in every), f"ranks disagree on the exchange sequence: {every}"
     shard = torch.from_numpy(st.v.view(np.float64).copy())
     gathered = [torch.empty_like(shard) for _ in range(world)] if rank == 0 else None
     dist.gather(shard, gathered, dst=0)
@@ -115,6 +144,69 @@ def test_sharded_random_circuit_matches_oracle(lib_built, tmp_path):
     ins = random_circuit(n, 120, 11)
     ref, _ = O.run_static(ins, n, backend="numpy")
     got, _ = run_two_ranks(C.task(ins, n), n, {"tile_bits": 4, "min_run_bits": 1}, tmp_path, 2)
+    assert np.abs(got - ref.amplitudes()).max() < 1e-12
+
+
+def _exchange_sequence(plan, max_group=4):
+    """the exchanges dist.cu's flush_dist_t derives from a per-rank plan (grouping by batch id)"""
+    out, group, batch = [], [], None
+    for seg in plan["segments"]:
+        if "swap" in seg:
+            if seg["batch"] != batch and group:
+                out.append(group); group = []
+            batch = seg["batch"]
+            group.append(tuple(seg["swap"]))
+            if len(group) == max_group:
+                out.append(group); group = []
+        elif group:
+            out.append(group); group = []
+    if group:
+        out.append(group)
+    return out
+
+
+def test_exchange_sequence_is_rank_independent_with_global_controls(lib_built):
+    """an op controlled by a global qubit is dropped on the ranks whose bit is 0, so the LOCAL segment
+    between two swap batches exists on some ranks only; the exchanges must still be the same everywhere."""
+    import cunqa_b200 as cb
+    from cunqa_b200 import circuits as C
+    n = 16
+    ins = [{"name": "cx", "qubits": [15, 14]}] + [{"name": "cx", "qubits": [15, q]} for q in range(5, 13)] + [{"name": "h", "qubits": [13]}]
+    seqs = []
+    for rank in range(8):
+        plan = cb.plan(C.task(ins, n), {"world": 8, "rank": rank, "tile_bits": 6, "min_run_bits": 2})
+        seqs.append(_exchange_sequence(plan))
+    assert all(s == seqs[0] for s in seqs), seqs
+    for ex in seqs[0]:   # no repeated global or local bit inside one exchange
+        assert len({g for g, _ in ex}) == len(ex) and len({l for _, l in ex}) == len(ex)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_sharded_random_circuit_with_global_controls(lib_built, tmp_path, seed):
+    """random circuits whose cx / ccx controls (and targets) sit on global qubits, replayed with the GPU's grouping rule"""
+    from cunqa_b200 import circuits as C
+    from oracle import oracle_np as O
+    n, world = 9, 4
+    rng = np.random.default_rng(seed)
+    ins = [{"name": "h", "qubits": [q]} for q in range(n)]
+    for _ in range(60):
+        r = rng.integers(0, 5)
+        qs = [int(q) for q in rng.permutation(n)[:3]]
+        hi = int(rng.integers(n - 2, n))  # a global qubit
+        if r == 0:
+            ins.append({"name": "cx", "qubits": [hi, qs[0] if qs[0] != hi else qs[1]]})
+        elif r == 1:
+            a, b = [q for q in qs if q != hi][:2]
+            ins.append({"name": "ccx", "qubits": [hi, a, b]})
+        elif r == 2:
+            ins.append({"name": "h", "qubits": [hi]})
+        elif r == 3:
+            ins.append({"name": "ry", "qubits": [qs[0]], "params": [float(rng.uniform(0, 6))]})
+        else:
+            a = qs[0] if qs[0] != hi else qs[1]
+            ins.append({"name": "cx", "qubits": [a, hi]})
+    ref, _ = O.run_static(ins, n, backend="numpy")
+    got, _ = run_two_ranks(C.task(ins, n), n, {"tile_bits": 4, "min_run_bits": 1}, tmp_path, world)
     assert np.abs(got - ref.amplitudes()).max() < 1e-12
 
 

@@ -162,18 +162,25 @@ def test_teledata_teleports(backend):
     a = [{"name": "ry", "qubits": [0], "params": [theta]}, {"name": "qsend", "qubits": [0], "qpus": ["B"]}]
     b = [{"name": "qrecv", "qubits": [0], "qpus": ["A"]}, {"name": "measure", "qubits": [0], "clbits": [0]}]
     shots = 4000
-    msg = [C.task(a, 1, shots=shots, seed=1, task_id="A", is_dynamic=True), C.task(b, 1, shots=shots, seed=1, task_id="B", is_dynamic=True)]
+    msg = [C.task(a, 1, shots=shots, seed=1, task_id="A", is_dynamic=True, b200_teledata_corrections="protocol"),
+           C.task(b, 1, shots=shots, seed=1, task_id="B", is_dynamic=True)]
+    # the documented protocol (X <- comm qubit, Z <- sent qubit) is opt-in and does teleport
     res = backend.execute(msg)
     p1 = res["id_counts"]["B"].get("1", 0) / shots
     assert abs(p1 - math.sin(theta / 2) ** 2) < 4 * math.sqrt(0.25 / shots)
-    assert backend.last_mode() == 1  # default: measurements deferred, corrections as quantum control
-    # the literal reference code (X/Z corrections swapped, quirk Q6) only under the bugcompat switch
-    msg[0]["config"]["b200_bugcompat_teledata"] = True
+    assert backend.last_mode() == 1  # measurements deferred, corrections as quantum control
+    assert res["b200"] == {"mode": "deferred_measurement", "teledata_corrections": "protocol"}
+    # DEFAULT = the reference's literal code (aer_simulator_adapter.cpp:644-658: X <- sent qubit, Z <- comm qubit, quirk
+    # Q6): same histograms as the reference on the same inputs -- the received qubit reads 1 with probability 1/2
+    del msg[0]["config"]["b200_teledata_corrections"]
+    res = backend.execute(msg)
+    assert res["b200"]["teledata_corrections"] == "reference"
+    assert abs(res["id_counts"]["B"].get("1", 0) / shots - 0.5) < 4 * math.sqrt(0.25 / shots)
     msg[0]["config"]["b200_defer_measurement"] = False  # per-shot interpreter: shot-identical to the oracle
     lit = backend.execute(msg)
     want = O.run_dynamic([{"id": "A", "num_qubits": 1, "num_clbits": 1, "instructions": a},
-                          {"id": "B", "num_qubits": 1, "num_clbits": 1, "instructions": b}], shots, seed=1, teledata_literal=True)
-    assert lit["id_counts"] == want
+                          {"id": "B", "num_qubits": 1, "num_clbits": 1, "instructions": b}], shots, seed=1)
+    assert lit["id_counts"] == want and lit["b200"] == {"mode": "per_shot_batched", "teledata_corrections": "reference"}
 
 
 def test_classical_send_recv_between_processes(lib_built):

@@ -81,16 +81,23 @@ def test_bit_order_clbit0_rightmost():
 
 
 def test_teledata_moves_the_state(lib_built):
-    """QSEND/QRECV restatement: B's qubit 0 must end up in the state A prepared (any outcome bits)."""
+    """QSEND/QRECV restatement with the DOCUMENTED corrections (X <- comm qubit, Z <- sent qubit): B's qubit 0 must end
+    up in the state A prepared.  The reference's literal code has the two swapped (quirk Q6, the oracle's default):
+    the received qubit is then maximally mixed in the Z basis whatever A prepared."""
     theta = 1.1
     a = [{"name": "ry", "qubits": [0], "params": [theta]}, {"name": "qsend", "qubits": [0], "qpus": ["B"]}]
     b = [{"name": "qrecv", "qubits": [0], "qpus": ["A"]}, {"name": "measure", "qubits": [0], "clbits": [0]}]
     tasks = [{"id": "A", "num_qubits": 1, "num_clbits": 1, "instructions": a},
              {"id": "B", "num_qubits": 1, "num_clbits": 1, "instructions": b}]
     shots = 4000
-    res = O.run_dynamic(tasks, shots, seed=9)
+    res = O.run_dynamic(tasks, shots, seed=9, teledata_literal=False)
     p1 = res["B"].get("1", 0) / shots
     assert abs(p1 - math.sin(theta / 2) ** 2) < 4 * math.sqrt(0.25 / shots)
+    # the reference's literal sequence (aer_simulator_adapter.cpp:644-658): exact distribution by branch enumeration
+    lit = O.literal_distribution(tasks, teledata_literal=True)
+    assert abs(sum(p for k, p in lit.items() if dict(k)["B"] == "1") - 0.5) < 1e-12
+    doc = O.literal_distribution(tasks, teledata_literal=False)
+    assert abs(sum(p for k, p in doc.items() if dict(k)["B"] == "1") - math.sin(theta / 2) ** 2) < 1e-12
 
 
 def test_telegate_is_a_remote_cx(lib_built):
