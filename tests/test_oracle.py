@@ -258,10 +258,15 @@ def _many_remote_ops(n_comm):
 @pytest.mark.parametrize("n_comm", [2, 4])
 def test_deferred_measurement_recycles_disentangled_qubits(n_comm):
     """a completed teleportation / remote gate leaves its measured qubits in |+>, disentangled: they are reset by a
-    unitary, so a communication pair (and the sender's qubit) can be used again without a collapse"""
+    unitary, so a communication pair (and the sender's qubit) can be used again without a collapse.  This holds for the
+    documented teledata corrections; the reference's literal ones (quirk Q6) leave the measured qubits entangled with
+    the received qubit, so a pair that is used AGAIN needs a real collapse: the deferred run gives up (per-shot mode)."""
     tasks = _many_remote_ops(n_comm)
-    dfr = O.deferred_distribution(tasks, n_comm_qubits=n_comm)   # must not raise DeferAbort
-    lit = O.literal_distribution(tasks, n_comm_qubits=n_comm)
+    if n_comm == 2:
+        with pytest.raises(O.DeferAbort):
+            O.deferred_distribution(tasks, n_comm_qubits=n_comm, teledata_literal=True)
+    dfr = O.deferred_distribution(tasks, n_comm_qubits=n_comm, teledata_literal=False)   # must not raise DeferAbort
+    lit = O.literal_distribution(tasks, n_comm_qubits=n_comm, teledata_literal=False)
     assert abs(sum(lit.values()) - 1) < 1e-12 and abs(sum(dfr.values()) - 1) < 1e-12 and len(lit) > 4
     for key in set(lit) | set(dfr):
         assert abs(lit.get(key, 0.0) - dfr.get(key, 0.0)) < 1e-12, key
