@@ -77,6 +77,8 @@ SIGNATURES = {
     "cb200_backend_set_channel": (ctypes.c_int, [_vp, SEND_FN, RECV_FN, _vp]),
     "cb200_backend_execute": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "cb200_qasm2_to_json": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "cb200_backend_execute_many": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.POINTER(_vp)]),
+    "cb200_backend_batch_info": (ctypes.c_int, [_vp, _c_u64_p]),
     "cb200_backend_stats": (ctypes.c_int, [_vp, _c_u64_p]),
     "cb200_backend_last_mode": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int)]),
     "cb200_dist_unique_id": (ctypes.c_int, [_c_u8_p]),
@@ -353,6 +355,20 @@ class Backend:
         out = _vp()
         _check(lib.cb200_backend_execute(self._h, text.encode(), ctypes.byref(out)))
         return json.loads(_take_string(out))
+
+    def execute_many(self, messages, parse=True):
+        """independent messages (dicts / lists / JSON texts) as separate registers batched on the device -> list of results"""
+        texts = [(m if isinstance(m, str) else json.dumps(m)).encode() for m in messages]
+        arr = (ctypes.c_char_p * max(1, len(texts)))(*texts)
+        outs = (_vp * max(1, len(texts)))()
+        _check(lib.cb200_backend_execute_many(self._h, arr, len(texts), outs))
+        res = [_take_string(outs[i]) for i in range(len(texts))]
+        return [json.loads(r) for r in res] if parse else res
+
+    def batch_info(self):
+        out = np.zeros(3, dtype=np.uint64)
+        _check(lib.cb200_backend_batch_info(self._h, out.ctypes.data_as(_c_u64_p)))
+        return {"uniform_flushes": int(out[0]), "split_flushes": int(out[1]), "solo": int(out[2])}
 
     def stats(self):
         out = np.zeros(8, dtype=np.uint64)

@@ -151,6 +151,21 @@ def hea_telegate_pair(n_each, layers=1, seed=99, ids=("qpuA", "qpuB")):
     ]
 
 
+def config5_groups(n_groups=64, n_each=11, layers=2, shots=1024, seed=5, kinds=("teledata", "telegate"), **cfg):
+    """BASELINE config 5: `n_groups` independent quantum-communication groups, each = two n_each-qubit vQPUs running a
+    hardware-efficient ansatz (own random angles per group) joined by teledata or telegate (2 communication qubits):
+    a (2 * n_each + 2)-qubit joint register per group (24 qubits at n_each = 11).  -> list of messages, one per group
+    (each a list of two wire-format tasks, what the QC executor hands the engine in one round)."""
+    msgs = []
+    for g in range(n_groups):
+        kind = kinds[g % len(kinds)]
+        maker = hea_teledata_pair if kind == "teledata" else hea_telegate_pair
+        tasks = maker(n_each, layers, seed=seed + 2 * g, ids=(f"g{g}A", f"g{g}B"))
+        msgs.append([task(t["instructions"], t["num_qubits"], shots=shots, seed=seed + g, task_id=t["id"], is_dynamic=True, **cfg)
+                     for t in tasks])
+    return msgs
+
+
 def n_gates(instructions):
     """number of original circuit gates (everything except measure/barrier), the gates/s numerator."""
     return sum(1 for i in instructions if i["name"] not in ("measure", "barrier", "save_state"))

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "engine.hpp"
 #include "executor.hpp"
@@ -207,6 +208,26 @@ int cb200_backend_execute(cb200_backend *b, const char *tasks_json, char **resul
     if (!tasks_json || !result_json_out) { g_err = "null argument"; return CB200_ERR_INVALID; }
     *result_json_out = nullptr;
     return guard([&] { *result_json_out = dup_string(b->impl->execute(tasks_json)); });
+}
+int cb200_backend_execute_many(cb200_backend *b, const char *const *messages, int n, char **results_json_out)
+{
+    NEED(b);
+    if (!messages || !results_json_out || n < 0) { g_err = "bad argument"; return CB200_ERR_INVALID; }
+    for (int i = 0; i < n; i++) results_json_out[i] = nullptr;
+    return guard([&] {
+        std::vector<std::string> in;
+        for (int i = 0; i < n; i++) in.emplace_back(messages[i] ? messages[i] : "");
+        const std::vector<std::string> out = b->impl->execute_many(in);
+        for (int i = 0; i < n; i++) results_json_out[i] = dup_string(out[i]);
+    });
+}
+int cb200_backend_batch_info(const cb200_backend *b, uint64_t info[3])
+{
+    NEED(b);
+    info[0] = b->impl->last_uniform_flushes;
+    info[1] = b->impl->last_split_flushes;
+    info[2] = b->impl->last_solo;
+    return CB200_OK;
 }
 int cb200_backend_stats(const cb200_backend *b, uint64_t stats[8])
 {

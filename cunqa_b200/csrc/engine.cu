@@ -93,6 +93,14 @@ void State::release()
     dist_destroy();
     cudaFree(d_state_); cudaFree(d_diag_); cudaFree(d_flags_); cudaFree(d_partial_); cudaFree(d_small_);
     cudaFree(d_outcome_); cudaFree(d_counters_); cudaFree(d_forced_); cudaFree(d_lvl1_); cudaFree(d_lvl2_);
+    cudaFree(d_regmats_); cudaFree(d_seeds_); cudaFree(d_samples_);
+    d_regmats_ = nullptr; d_seeds_ = nullptr; d_samples_ = nullptr;
+    regmats_cap_ = samples_cap_ = 0;
+    for (StageSlot &sl : stage_) {
+        if (sl.ptr) cudaFreeHost(sl.ptr);
+        if (sl.ev) cudaEventDestroy(sl.ev);
+        sl = StageSlot();
+    }
     d_state_ = d_diag_ = nullptr;
     d_flags_ = nullptr; d_partial_ = d_small_ = d_lvl1_ = d_lvl2_ = nullptr;
     d_outcome_ = nullptr; d_counters_ = nullptr; d_forced_ = nullptr;
@@ -104,7 +112,50 @@ void State::release()
 void State::reset()
 {
     queue.reset();
+    for (OpQueue &q : regq_) { q.reset(); q.fresh = false; }
     pending_init_ = true;  // the write happens at the next flush, once the initial basis state is known
+}
+
+// ---- pinned staging ---------------------------------------------------------------------------------
+// Uploads of diagonal tables, condition flags and per-register matrices go through page-locked memory so that the
+// copy is a real asynchronous DMA and the flush never drains the stream.  Two slots alternate; a slot is reused only
+// after the copy that read it has completed (the event is normally long done by then).
+void *State::stage(size_t bytes)
+{
+    stage_cur_ ^= 1;
+    StageSlot &sl = stage_[stage_cur_];
+    if (sl.busy) { CB200_CUDA(cudaEventSynchronize(sl.ev)); sl.busy = false; }
+    if (bytes > sl.cap) {
+        if (sl.ptr) cudaFreeHost(sl.ptr);
+        sl.ptr = nullptr;
+        sl.cap = std::max<size_t>(bytes * 2, 1 << 16);
+        CB200_CUDA(cudaMallocHost(&sl.ptr, sl.cap));
+    }
+    if (!sl.ev) CB200_CUDA(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    return sl.ptr;
+}
+void State::stage_commit()
+{
+    StageSlot &sl = stage_[stage_cur_];
+    CB200_CUDA(cudaEventRecord(sl.ev, stream_));
+    sl.busy = true;
+}
+
+void State::use_registers(bool on)
+{
+    if (dist && on) throw Unsupported("independent registers on a sharded state");
+    if (on == registers()) return;
+    regq_.clear();
+    if (on) {
+        for (int b = 0; b < batch; b++) { regq_.emplace_back(n, 1, opt); regq_.back().fresh = false; }
+        cur_reg_ = 0;
+    }
+}
+void State::select_register(int r)
+{
+    if (regq_.empty()) throw InvalidArg("state is not in register mode");
+    if (r < 0 || r >= batch) throw InvalidArg("register index out of range");
+    cur_reg_ = r;
 }
 
 void State::ensure_init()
@@ -129,23 +180,23 @@ void State::ensure_init()
 // ---- queueing (forwarded to the host-only OpQueue) ------------------------------------------------
 void State::apply_matrix(const int *qubits, int k, const int *ctrls, int nc, const cplx *mat, const uint8_t *flags)
 {
-    queue.apply_matrix(qubits, k, ctrls, nc, mat, flags);
+    rq().apply_matrix(qubits, k, ctrls, nc, mat, flags);
     maybe_flush();
 }
 void State::apply_diagonal(const int *qubits, int k, const cplx *diag, const uint8_t *flags)
 {
-    queue.apply_diagonal(qubits, k, diag, flags);
+    rq().apply_diagonal(qubits, k, diag, flags);
     maybe_flush();
 }
 void State::global_phase(double theta, const uint8_t *flags)
 {
-    queue.global_phase(theta, flags);
+    rq().global_phase(theta, flags);
     maybe_flush();
 }
 void State::apply_named(const std::string &name, const int *qubits, int nq, const double *params, int np,
                         const uint8_t *flags)
 {
-    queue.apply_named(name, qubits, nq, params, np, flags);
+    rq().apply_named(name, qubits, nq, params, np, flags);
     maybe_flush();
 }
 
@@ -173,10 +224,13 @@ static EncodeTiledFn encode_tiled_fn()
 // {128-byte row, row index in the whole buffer, qa, qb, qc}: box = one run of 2^run_bits amplitudes (<= 256
 // rows) times the three high tile qubits qa/qb/qc (size-2 dimensions with stride 2^q amplitudes; unused
 // ones are passed as -1).  Hardware 128-byte swizzle on the shared-memory side (= swz<T>() in the kernel).
-void State::make_tensor_map(CUtensorMap *out, int run_bits, const int hi_qubits[3])
+void State::make_tensor_map(CUtensorMap *out, int run_bits, const int hi_qubits[3], int b0, int nb)
 {
     const int aprs = precision == 64 ? 3 : 4;  // log2(amplitudes per 128-byte row)
-    const uint64_t nrows = state_bytes_ >> 7;
+    const size_t one = amp_bytes_ << n_local_;  // bytes of one state of the batch
+    const size_t view_bytes = nb < 0 ? state_bytes_ : one * (size_t)nb;
+    void *view_ptr = (char *)d_state_ + (nb < 0 ? 0 : one * (size_t)b0);
+    const uint64_t nrows = view_bytes >> 7;
     if (nrows >= (1ull << 31)) throw Unsupported("state too large for one tensor map");
     const cuuint32_t inner = precision == 64 ? 16 : 32;
     cuuint64_t gdim[5] = {inner, nrows, 1, 1, 1};
@@ -190,7 +244,7 @@ void State::make_tensor_map(CUtensorMap *out, int run_bits, const int hi_qubits[
         gstride[1 + d] = (cuuint64_t)amp_bytes_ << hi_qubits[d];
     }
     const CUresult r = encode_tiled_fn()(out, precision == 64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                                         5, d_state_, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         5, view_ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
@@ -209,48 +263,51 @@ void State::flush_t()
 
 // plan `ops` (physical qubits < n_local) into tile passes and launch them on this shard
 template <typename T>
-void State::launch_ops_t(std::vector<HostOp> &ops)
+void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb)
 {
     using V = typename Vec2<T>::type;
     if (ops.empty()) return;
+    const int vbatch = nb < 0 ? batch : nb;
+    const size_t view_bytes = nb < 0 ? state_bytes_ : (amp_bytes_ << n_local_) * (size_t)nb;
+    void *view_ptr = (char *)d_state_ + (nb < 0 ? 0 : (amp_bytes_ << n_local_) * (size_t)b0);
     const std::vector<Pass> passes = schedule_passes(ops, n_local_, opt);
     std::vector<cplx> diag_host;
     std::vector<PassParams<T>> params(passes.size());
     std::string err;
     for (size_t i = 0; i < passes.size(); i++)
-        if (!encode_pass<T>(passes[i], ops, n_local_, batch, params[i], diag_host, err, opt.pair_ops)) throw Unsupported(err);
-    // diagonal tables
-    if (!diag_host.empty()) {
+        if (!encode_pass<T>(passes[i], ops, n_local_, vbatch, params[i], diag_host, err, opt.pair_ops)) throw Unsupported(err);
+    // diagonal tables and condition flags: staged in pinned memory, copied asynchronously (no stream drain)
+    const std::vector<std::vector<uint8_t>> &mask_rows = rq().mask_rows;
+    const size_t diag_bytes = diag_host.size() * sizeof(V);
+    const size_t flag_bytes = nb < 0 ? mask_rows.size() * (size_t)batch : 0;
+    if (diag_bytes + flag_bytes > 0) {
         if (diag_host.size() > diag_cap_) {
             CB200_CUDA(cudaStreamSynchronize(stream_));
             cudaFree(d_diag_);
+            d_diag_ = nullptr;
             diag_cap_ = std::max<size_t>(diag_host.size() * 2, 4096);
             CB200_CUDA(cudaMalloc(&d_diag_, diag_cap_ * sizeof(V)));
         }
-        std::vector<V> tmp(diag_host.size());
-        for (size_t i = 0; i < diag_host.size(); i++) { tmp[i].x = (T)diag_host[i].real(); tmp[i].y = (T)diag_host[i].imag(); }
-        CB200_CUDA(cudaMemcpyAsync(d_diag_, tmp.data(), tmp.size() * sizeof(V), cudaMemcpyHostToDevice, stream_));
-        stats.h2d_bytes += tmp.size() * sizeof(V);
-        CB200_CUDA(cudaStreamSynchronize(stream_));  // tmp is pageable and dies here
-    }
-    if (!queue.mask_rows.empty()) {
-        const size_t need = queue.mask_rows.size() * (size_t)batch;
-        if (need > flags_cap_) {
+        if (flag_bytes > flags_cap_) {
             CB200_CUDA(cudaStreamSynchronize(stream_));
             cudaFree(d_flags_);
-            flags_cap_ = need * 2;
+            d_flags_ = nullptr;
+            flags_cap_ = flag_bytes * 2;
             CB200_CUDA(cudaMalloc(&d_flags_, flags_cap_));
         }
-        std::vector<uint8_t> tmp(need);
-        for (size_t r = 0; r < queue.mask_rows.size(); r++) std::memcpy(tmp.data() + r * batch, queue.mask_rows[r].data(), batch);
-        CB200_CUDA(cudaMemcpyAsync(d_flags_, tmp.data(), need, cudaMemcpyHostToDevice, stream_));
-        stats.h2d_bytes += need;
-        CB200_CUDA(cudaStreamSynchronize(stream_));
+        char *host = (char *)stage(diag_bytes + flag_bytes);
+        V *tmp = reinterpret_cast<V *>(host);
+        for (size_t i = 0; i < diag_host.size(); i++) { tmp[i].x = (T)diag_host[i].real(); tmp[i].y = (T)diag_host[i].imag(); }
+        for (size_t r = 0; r < mask_rows.size() && flag_bytes; r++) std::memcpy(host + diag_bytes + r * batch, mask_rows[r].data(), batch);
+        if (diag_bytes) CB200_CUDA(cudaMemcpyAsync(d_diag_, host, diag_bytes, cudaMemcpyHostToDevice, stream_));
+        if (flag_bytes) CB200_CUDA(cudaMemcpyAsync(d_flags_, host + diag_bytes, flag_bytes, cudaMemcpyHostToDevice, stream_));
+        stage_commit();
+        stats.h2d_bytes += diag_bytes + flag_bytes;
     }
     const int aprs = sizeof(V) == 16 ? 3 : 4;
     for (size_t i = 0; i < passes.size(); i++) {
         const PassParams<T> &p = params[i];
-        const uint64_t total_tiles = p.tiles_per_state * (uint64_t)batch;
+        const uint64_t total_tiles = p.tiles_per_state * (uint64_t)vbatch;
         // TMA box: the contiguous run (at most 256 rows of it) plus up to three high tile qubits
         const int run_bits = std::min(p.L, aprs + 8);
         int hi_q[3] = {-1, -1, -1};
@@ -267,10 +324,10 @@ void State::launch_ops_t(std::vector<HostOp> &ops)
         ctas = std::max(1, std::min<int>(ctas, (int)(max_smem_sm_ / (smem_tma + 1024))));  // what shared memory allows
         if (tma_max_ctas_ > 0) ctas = std::min(ctas, tma_max_ctas_);
         // (a run of one 128-byte row is enough once the three folded qubits make the box 1 KiB = one swizzle atom)
-        const bool tma = use_tma_ && p.L >= aprs + (box_bits >= aprs + 3 ? 0 : 1) && state_bytes_ >= 128 && smem_tma <= max_smem_;
+        const bool tma = use_tma_ && p.L >= aprs + (box_bits >= aprs + 3 ? 0 : 1) && view_bytes >= 128 && smem_tma <= max_smem_;
         if (tma) {
             CUtensorMap tmap;
-            make_tensor_map(&tmap, run_bits, hi_q);
+            make_tensor_map(&tmap, run_bits, hi_q, b0, nb);
             TmaLaunch l;
             l.grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_ * ctas);
             l.smem = smem_tma;
@@ -289,18 +346,179 @@ void State::launch_ops_t(std::vector<HostOp> &ops)
             else e = launch_tile_pass_tma<T, 32>(p, tmap, l);
             CB200_CUDA(e);
         } else {
-            CB200_CUDA(launch_tile_pass_generic<T>(p, d_state_, d_diag_, d_flags_, num_sms_, ctas_per_sm_, device, stream_));
+            CB200_CUDA(launch_tile_pass_generic<T>(p, view_ptr, d_diag_, d_flags_, num_sms_, ctas_per_sm_, device, stream_));
         }
         CB200_CUDA(cudaGetLastError());
         stats.passes++;
         stats.launches++;
         stats.h2d_bytes += sizeof(PassParams<T>) + (tma ? sizeof(CUtensorMap) : 0);
-        stats.bytes += 2ull * state_bytes_;
+        stats.bytes += 2ull * view_bytes;
         stats.fused_ops += (uint64_t)p.n_ops;
     }
 }
-template void State::launch_ops_t<double>(std::vector<HostOp> &);
-template void State::launch_ops_t<float>(std::vector<HostOp> &);
+template void State::launch_ops_t<double>(std::vector<HostOp> &, int, int);
+template void State::launch_ops_t<float>(std::vector<HostOp> &, int, int);
+
+// ---- independent registers ------------------------------------------------------------------------
+static bool same_structure(const std::vector<HostOp> &a, const std::vector<HostOp> &b)
+{
+    if (a.size() != b.size()) return false;
+    for (size_t i = 0; i < a.size(); i++) {
+        const HostOp &x = a[i], &y = b[i];
+        if (x.kind != y.kind || x.q != y.q || x.ctrl != y.ctrl || x.m.size() != y.m.size() || x.mask_row >= 0 || y.mask_row >= 0)
+            return false;
+    }
+    return true;
+}
+
+template <typename T>
+void State::flush_registers_t()
+{
+    bool any = false;
+    for (OpQueue &q : regq_) any = any || q.pending() > 0;
+    if (!any) return;
+    CB200_CUDA(cudaSetDevice(device));
+    // maximal runs of consecutive registers whose fused op lists have the same structure share their launches
+    // (Backend::execute_many orders the registers so that equal circuits are neighbours)
+    const int G = (int)regq_.size();
+    for (int b0 = 0; b0 < G;) {
+        int b1 = b0 + 1;
+        if (regq_[b0].pending() == 0) { b0 = b1; continue; }
+        const bool plain = regq_[b0].mask_rows.empty();
+        while (plain && b1 < G && regq_[b1].mask_rows.empty() && same_structure(regq_[b0].ops(), regq_[b1].ops()) &&
+               regq_[b1].l2p == regq_[b0].l2p)
+            b1++;
+        cur_reg_ = b0;
+        if (b1 - b0 >= 2) {
+            launch_uniform_t<T>(b0, b1 - b0);
+            uniform_flushes++;
+        } else {
+            launch_ops_t<T>(regq_[b0].ops(), b0, 1);
+            split_flushes++;
+        }
+        b0 = b1;
+    }
+    for (OpQueue &q : regq_) q.clear_pending();
+}
+
+// every register has the same fused op list up to the numbers in its matrices: ONE schedule, ONE launch per pass over
+// the whole batch; register b reads row b of the per-register matrix / diagonal-table buffers
+template <typename T>
+void State::launch_uniform_t(int b0, int nb)
+{
+    using V = typename Vec2<T>::type;
+    const int G = nb;
+    const size_t view_bytes = (amp_bytes_ << n_local_) * (size_t)nb;
+    void *view_ptr = (char *)d_state_ + (amp_bytes_ << n_local_) * (size_t)b0;
+    std::vector<HostOp> &ops0 = regq_[b0].ops();
+    const std::vector<Pass> passes = schedule_passes(ops0, n_local_, opt);
+    std::vector<PassParams<T>> params(passes.size());
+    std::vector<cplx> diag0;
+    std::string err;
+    for (size_t i = 0; i < passes.size(); i++)
+        if (!encode_pass<T>(passes[i], ops0, n_local_, G, params[i], diag0, err, opt.pair_ops)) throw Unsupported(err);
+    const size_t D = diag0.size();
+    std::vector<size_t> mat_off(passes.size() + 1, 0);   // scalar offset of pass i's [G][stride_i] block
+    std::vector<uint32_t> mat_stride(passes.size());
+    for (size_t i = 0; i < passes.size(); i++) {
+        mat_stride[i] = (uint32_t)((params[i].n_mat + 1) & ~1);
+        mat_off[i + 1] = mat_off[i] + (size_t)mat_stride[i] * G;
+    }
+    const size_t mats_bytes = mat_off.back() * sizeof(T), diag_bytes = (size_t)G * D * sizeof(V);
+    if (mats_bytes > regmats_cap_) {
+        CB200_CUDA(cudaStreamSynchronize(stream_));
+        cudaFree(d_regmats_);
+        d_regmats_ = nullptr;
+        regmats_cap_ = mats_bytes * 2;
+        CB200_CUDA(cudaMalloc(&d_regmats_, regmats_cap_));
+    }
+    if ((size_t)G * D > diag_cap_) {
+        CB200_CUDA(cudaStreamSynchronize(stream_));
+        cudaFree(d_diag_);
+        d_diag_ = nullptr;
+        diag_cap_ = std::max<size_t>((size_t)G * D * 2, 4096);
+        CB200_CUDA(cudaMalloc(&d_diag_, diag_cap_ * sizeof(V)));
+    }
+    char *host = (char *)stage(mats_bytes + diag_bytes + 16);
+    T *hm = reinterpret_cast<T *>(host);
+    V *hd = reinterpret_cast<V *>(host + ((mats_bytes + 15) & ~(size_t)15));
+    std::vector<cplx> dg;
+    PassParams<T> tmp;
+    for (int g = 0; g < G; g++) {
+        dg.clear();
+        std::vector<HostOp> &ops = regq_[b0 + g].ops();
+        for (size_t i = 0; i < passes.size(); i++) {
+            const PassParams<T> *src = &params[i];
+            if (g > 0) {
+                if (!encode_pass<T>(passes[i], ops, n_local_, G, tmp, dg, err, opt.pair_ops)) throw Unsupported(err);
+                if (tmp.n_mat != params[i].n_mat || tmp.n_ops != params[i].n_ops) throw Unsupported("internal: register passes differ in layout");
+                src = &tmp;
+            }
+            std::memcpy(hm + mat_off[i] + (size_t)g * mat_stride[i], src->mats, sizeof(T) * (size_t)src->n_mat);
+        }
+        const std::vector<cplx> &d = g == 0 ? diag0 : dg;
+        if (d.size() != D) throw Unsupported("internal: register diagonal tables differ in layout");
+        for (size_t e = 0; e < D; e++) { hd[(size_t)g * D + e].x = (T)d[e].real(); hd[(size_t)g * D + e].y = (T)d[e].imag(); }
+    }
+    if (mats_bytes) CB200_CUDA(cudaMemcpyAsync(d_regmats_, hm, mats_bytes, cudaMemcpyHostToDevice, stream_));
+    if (diag_bytes) CB200_CUDA(cudaMemcpyAsync(d_diag_, hd, diag_bytes, cudaMemcpyHostToDevice, stream_));
+    stage_commit();
+    stats.h2d_bytes += mats_bytes + diag_bytes;
+    const int aprs = sizeof(V) == 16 ? 3 : 4;
+    for (size_t i = 0; i < passes.size(); i++) {
+        const PassParams<T> &p = params[i];
+        const uint64_t total_tiles = p.tiles_per_state * (uint64_t)G;
+        const int run_bits = std::min(p.L, aprs + 8);
+        int hi_q[3] = {-1, -1, -1};
+        int box_bits = run_bits;
+        if (run_bits == p.L && tma_fold_dims_)
+            for (int d = 0; d < 3 && p.L + d < p.t; d++) { hi_q[d] = p.tile_q[p.L + d]; box_bits++; }
+        const uint32_t buf_stride = (uint32_t)std::max<size_t>(1024, sizeof(V) << p.t);
+        const int stages = tma_stages_;
+        const size_t smem_tma = (size_t)stages * buf_stride + sizeof(uint64_t) * (stages + 1) + sizeof(uint32_t) * ((((size_t)1 << (p.t - box_bits)) + 3) & ~(size_t)3) +
+                                sizeof(T) * (size_t)((p.n_mat + 1) & ~1) + (size_t)p.n_diag * (4 + 2 * kDiagLut) + 16 + 1024;
+        int nt = 1 << std::max(5, std::min(8, p.t - kAmpsPerThreadShift));
+        if (tma_threads_ > 0) nt = tma_threads_;
+        int ctas = std::max(1, (stages == 3 ? 256 : 384) / nt);
+        ctas = std::max(1, std::min<int>(ctas, (int)(max_smem_sm_ / (smem_tma + 1024))));
+        if (tma_max_ctas_ > 0) ctas = std::min(ctas, tma_max_ctas_);
+        const bool tma = use_tma_ && p.L >= aprs + (box_bits >= aprs + 3 ? 0 : 1) && view_bytes >= 128 && smem_tma <= max_smem_;
+        const T *rm = reinterpret_cast<const T *>(d_regmats_) + mat_off[i];
+        if (tma) {
+            CUtensorMap tmap;
+            make_tensor_map(&tmap, run_bits, hi_q, b0, nb);
+            TmaLaunch l;
+            l.grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_ * ctas);
+            l.smem = smem_tma;
+            l.stream = stream_;
+            l.diag_tabs = d_diag_;
+            l.flags = d_flags_;
+            l.box_bits = box_bits;
+            l.buf_stride = buf_stride;
+            l.refill_after = tma_refill_after_;
+            l.stages = stages;
+            l.device = device;
+            l.reg_mats = rm;
+            l.reg_mat_stride = mat_stride[i];
+            l.reg_diag_stride = (uint32_t)D;
+            cudaError_t e;
+            if (nt == 256) e = launch_tile_pass_tma<T, 256>(p, tmap, l);
+            else if (nt == 128) e = launch_tile_pass_tma<T, 128>(p, tmap, l);
+            else if (nt == 64) e = launch_tile_pass_tma<T, 64>(p, tmap, l);
+            else e = launch_tile_pass_tma<T, 32>(p, tmap, l);
+            CB200_CUDA(e);
+        } else {
+            CB200_CUDA(launch_tile_pass_generic<T>(p, view_ptr, d_diag_, d_flags_, num_sms_, ctas_per_sm_, device, stream_, rm, mat_stride[i], (uint32_t)D));
+        }
+        stats.passes++;
+        stats.launches++;
+        stats.h2d_bytes += sizeof(PassParams<T>) + (tma ? sizeof(CUtensorMap) : 0);
+        stats.bytes += 2ull * view_bytes;
+        stats.fused_ops += (uint64_t)p.n_ops * (uint64_t)G;
+    }
+}
+template void State::launch_uniform_t<double>(int, int);
+template void State::launch_uniform_t<float>(int, int);
 
 void State::flush()
 {
@@ -308,6 +526,11 @@ void State::flush()
     if (dist) {
         if (precision == 64) flush_dist_t<double>();
         else flush_dist_t<float>();
+        return;
+    }
+    if (!regq_.empty()) {
+        if (precision == 64) flush_registers_t<double>();
+        else flush_registers_t<float>();
         return;
     }
     if (precision == 64) flush_t<double>();
@@ -369,6 +592,7 @@ void State::norm(double *out)
 void State::prob1(int qubit, double *out)
 {
     if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
+    if (registers()) throw Unsupported("prob1 over the whole batch is not defined for independent registers");
     flush();
     const int pq1 = queue.l2p[qubit];
     uint64_t sel = 1ull << pq1;
@@ -384,19 +608,20 @@ void State::prob1(int qubit, double *out)
     CB200_CUDA(cudaStreamSynchronize(stream_));
 }
 
-void State::reduced_qubit(int qubit, double out[4])
+void State::reduced_qubit(int qubit, double out[4], int b)
 {
     if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
+    if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
     if (dist) throw Unsupported("reduced density matrix of a sharded state is not implemented");
     flush();
-    const int pq = queue.l2p[qubit];
+    const int pq = (regq_.empty() ? queue : regq_[b]).l2p[qubit];
     const uint64_t amps = 1ull << n_local_;
     int nblk = (int)std::min<uint64_t>((amps / 2 + kRedThreads * 8 - 1) / (kRedThreads * 8), (uint64_t)num_sms_ * 8);
     if (nblk < 1) nblk = 1;
     ensure_scratch((size_t)4 * nblk);
-    dim3 grid(nblk, 1);  // state 0 only
-    if (precision == 64) rho_partial_kernel<double2><<<grid, kRedThreads, 0, stream_>>>((const double2 *)d_state_, amps, pq, d_partial_, (size_t)nblk);
-    else rho_partial_kernel<float2><<<grid, kRedThreads, 0, stream_>>>((const float2 *)d_state_, amps, pq, d_partial_, (size_t)nblk);
+    dim3 grid(nblk, 1);  // one state only
+    if (precision == 64) rho_partial_kernel<double2><<<grid, kRedThreads, 0, stream_>>>((const double2 *)d_state_ + ((size_t)b << n_local_), amps, pq, d_partial_, (size_t)nblk);
+    else rho_partial_kernel<float2><<<grid, kRedThreads, 0, stream_>>>((const float2 *)d_state_ + ((size_t)b << n_local_), amps, pq, d_partial_, (size_t)nblk);
     for (int k = 0; k < 4; k++) sum_partials_kernel<<<1, kRedThreads, 0, stream_>>>(d_partial_ + (size_t)k * nblk, nblk, d_small_ + k);
     CB200_CUDA(cudaGetLastError());
     stats.launches += 5;
@@ -409,6 +634,7 @@ void State::reduced_qubit(int qubit, double out[4])
 void State::measure(int qubit, uint64_t seed, const uint64_t *counters, const int8_t *forced, int *bits_out, bool reset_after)
 {
     if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
+    if (registers()) throw Unsupported("batch-wide measurement is not defined for independent registers");
     if (dist) {
         // Sharded state: norm and P(q=1) are local reductions + one all-reduce each (every rank then holds the same
         // two doubles and draws the same outcome from the shared counter stream); a local qubit collapses inside the
@@ -546,8 +772,8 @@ void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out)
     cudaFree(d_out);
     if (e != cudaSuccess) throw CudaError(std::string("sampling failed: ") + cudaGetErrorString(e));
     stats.d2h_bytes += sizeof(uint64_t) * shots;
-    if (!queue.identity_perm())
-        for (uint64_t s = 0; s < shots; s++) out[s] = queue.logical_index(out[s]);
+    if (!qof(b).identity_perm())
+        for (uint64_t s = 0; s < shots; s++) out[s] = qof(b).logical_index(out[s]);
 }
 
 void State::broadcast_state0()
@@ -566,6 +792,7 @@ void State::broadcast_state0()
 void State::sample_each(uint64_t seed, const uint64_t *counters, uint64_t *out)
 {
     if (dist) throw Unsupported("sample_each on a sharded state is not implemented");
+    if (registers()) throw Unsupported("sample_each is not defined for independent registers (use sample_registers)");
     flush();
     const int nl = n_local_;
     const int bits0 = std::min(nl, kChunkBits);
@@ -602,6 +829,57 @@ void State::sample_each(uint64_t seed, const uint64_t *counters, uint64_t *out)
         for (int b = 0; b < batch; b++) out[b] = queue.logical_index(out[b]);
 }
 
+void State::sample_registers(uint64_t shots, const uint64_t *seeds, uint64_t *out)
+{
+    if (dist) throw Unsupported("sample_registers on a sharded state");
+    flush();
+    if (shots == 0) return;
+    const int nl = n_local_;
+    const int bits0 = std::min(nl, kChunkBits);
+    const int bits1 = std::min(nl - bits0, kChunkBits);
+    const uint64_t n1 = ((uint64_t)batch << nl) >> bits0;
+    const uint64_t n2 = n1 >> bits1;
+    if (n1 > lvl1_cap_) { CB200_CUDA(cudaStreamSynchronize(stream_)); cudaFree(d_lvl1_); d_lvl1_ = nullptr; lvl1_cap_ = n1; CB200_CUDA(cudaMalloc(&d_lvl1_, n1 * sizeof(double))); }
+    if (n2 > lvl2_cap_) { CB200_CUDA(cudaStreamSynchronize(stream_)); cudaFree(d_lvl2_); d_lvl2_ = nullptr; lvl2_cap_ = n2; CB200_CUDA(cudaMalloc(&d_lvl2_, n2 * sizeof(double))); }
+    const size_t total = (size_t)batch * shots;
+    if (total > samples_cap_) {
+        CB200_CUDA(cudaStreamSynchronize(stream_));
+        cudaFree(d_samples_);
+        d_samples_ = nullptr;
+        samples_cap_ = total;
+        CB200_CUDA(cudaMalloc(&d_samples_, total * sizeof(uint64_t)));
+    }
+    if (!d_seeds_) CB200_CUDA(cudaMalloc(&d_seeds_, sizeof(uint64_t) * batch));
+    uint64_t *hs = (uint64_t *)stage(sizeof(uint64_t) * batch);
+    std::memcpy(hs, seeds, sizeof(uint64_t) * batch);
+    CB200_CUDA(cudaMemcpyAsync(d_seeds_, hs, sizeof(uint64_t) * batch, cudaMemcpyHostToDevice, stream_));
+    stage_commit();
+    const int g1 = (int)std::min<uint64_t>(n1, (uint64_t)num_sms_ * 16);
+    const int g2 = (int)std::min<uint64_t>(n2, (uint64_t)num_sms_ * 16);
+    const int sblocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((total * 32 + kRedThreads - 1) / kRedThreads, (uint64_t)num_sms_ * 8));
+    if (precision == 64) {
+        chunk_sums_amp_kernel<double2><<<g1, kRedThreads, 0, stream_>>>((const double2 *)d_state_, bits0, n1, d_lvl1_);
+        chunk_sums_f64_kernel<<<g2, kRedThreads, 0, stream_>>>(d_lvl1_, bits1, n2, d_lvl2_);
+        sample_regs_kernel<double2><<<sblocks, kRedThreads, 0, stream_>>>((const double2 *)d_state_, nl, bits0, bits1, d_lvl1_, d_lvl2_, batch, shots, d_seeds_, d_samples_);
+    } else {
+        chunk_sums_amp_kernel<float2><<<g1, kRedThreads, 0, stream_>>>((const float2 *)d_state_, bits0, n1, d_lvl1_);
+        chunk_sums_f64_kernel<<<g2, kRedThreads, 0, stream_>>>(d_lvl1_, bits1, n2, d_lvl2_);
+        sample_regs_kernel<float2><<<sblocks, kRedThreads, 0, stream_>>>((const float2 *)d_state_, nl, bits0, bits1, d_lvl1_, d_lvl2_, batch, shots, d_seeds_, d_samples_);
+    }
+    CB200_CUDA(cudaGetLastError());
+    stats.launches += 3;
+    stats.bytes += state_bytes_;
+    CB200_CUDA(cudaMemcpyAsync(out, d_samples_, total * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream_));
+    CB200_CUDA(cudaStreamSynchronize(stream_));
+    stats.h2d_bytes += sizeof(uint64_t) * batch;
+    stats.d2h_bytes += total * sizeof(uint64_t);
+    for (int b = 0; b < batch; b++) {
+        const OpQueue &q = regq_.empty() ? queue : regq_[b];
+        if (q.identity_perm()) continue;
+        for (uint64_t s = 0; s < shots; s++) out[(size_t)b * shots + s] = q.logical_index(out[(size_t)b * shots + s]);
+    }
+}
+
 void State::get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out)
 {
     if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
@@ -613,7 +891,7 @@ void State::get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out
     std::vector<uint8_t> owned(cnt, 1);
     for (uint64_t i = 0; i < cnt; i++) {
         if (idx[i] >= dim) throw InvalidArg("amplitude index out of range");
-        phys[i] = queue.phys_index(idx[i]);
+        phys[i] = qof(b).phys_index(idx[i]);
         if (dist) {
             owned[i] = (int)(phys[i] >> n_local_) == dist_rank();
             phys[i] = owned[i] ? (phys[i] & local_mask) : 0;  // not owned: read any valid slot, zeroed below
@@ -657,7 +935,7 @@ void State::set_amplitudes(int b, const double *in)
     const uint64_t dim = 1ull << n;
     // logical -> physical layout on the host, then one upload
     std::vector<double2> host(dim);
-    for (uint64_t i = 0; i < dim; i++) host[queue.phys_index(i)] = make_double2(in[2 * i], in[2 * i + 1]);
+    for (uint64_t i = 0; i < dim; i++) host[qof(b).phys_index(i)] = make_double2(in[2 * i], in[2 * i + 1]);
     double2 *d_in = nullptr;
     CB200_CUDA(cudaMalloc(&d_in, dim * sizeof(double2)));
     cudaError_t e = cudaMemcpyAsync(d_in, host.data(), dim * sizeof(double2), cudaMemcpyHostToDevice, stream_);
@@ -682,7 +960,7 @@ void State::probabilities(int b, const int *qubits, int k, double *out)
     flush();
     std::vector<int> pq(k);
     for (int i = 0; i < k; i++) if (qubits[i] < 0 || qubits[i] >= n) throw InvalidArg("qubit out of range");
-    for (int i = 0; i < k; i++) pq[i] = queue.l2p[qubits[i]];
+    for (int i = 0; i < k; i++) pq[i] = qof(b).l2p[qubits[i]];
     int *d_q = nullptr; double *d_o = nullptr;
     CB200_CUDA(cudaMalloc(&d_q, k * sizeof(int)));
     cudaError_t e = cudaMalloc(&d_o, sizeof(double) << k);

@@ -58,7 +58,7 @@ public:
     void norm(double *out);
     void prob1(int qubit, double *out);
     // reduced density matrix of one qubit of state 0: out = {rho00, rho11, Re rho01, Im rho01}
-    void reduced_qubit(int qubit, double out[4]);
+    void reduced_qubit(int qubit, double out[4], int b = 0);
     void probabilities(int b, const int *qubits, int k, double *out);
     void measure(int qubit, uint64_t seed, const uint64_t *counters, const int8_t *forced, int *bits_out, bool reset_after);
     void sample(int b, uint64_t shots, uint64_t seed, uint64_t *out);
@@ -67,6 +67,19 @@ public:
     void broadcast_state0();  // states 1..batch-1 := state 0
     void get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out);
     void set_amplitudes(int b, const double *in);
+
+    // ---- independent registers (BASELINE config 5: many small vQPU groups batched as separate state vectors per GPU).
+    // Every state of the batch becomes its own register with its own op queue and qubit map.  flush() runs all of them
+    // in the SAME tile passes when their fused op lists have the same structure (one launch per pass over the whole
+    // batch, per-register matrices and diagonal tables), and register by register otherwise.
+    void use_registers(bool on);
+    bool registers() const { return !regq_.empty(); }
+    void select_register(int r);
+    OpQueue &rq() { return regq_.empty() ? queue : regq_[cur_reg_]; }  // the queue ops currently go to
+    const OpQueue &qof(int b) const { return regq_.empty() ? queue : regq_[b]; }  // qubit map of state b
+    // `shots` samples of every register, u = U(seeds[r], s): out[r * shots + s] (logical indices)
+    void sample_registers(uint64_t shots, const uint64_t *seeds, uint64_t *out);
+    uint64_t uniform_flushes = 0, split_flushes = 0;  // register-mode flushes that ran batched / register by register
 
     int n, precision, device, batch;
     PlanOptions opt;
@@ -98,13 +111,26 @@ private:
     void dist_allreduce_f64(double *d_buf, size_t count);
     void dist_allreduce_u64(uint64_t *d_buf, size_t count);
     template <typename T> void flush_dist_t();
-    template <typename T> void launch_ops_t(std::vector<HostOp> &ops);
+    // plan `ops` into tile passes and launch them on states [b0, b0 + nb) of the batch (nb < 0: the whole batch)
+    template <typename T> void launch_ops_t(std::vector<HostOp> &ops, int b0 = 0, int nb = -1);
+    template <typename T> void flush_registers_t();
+    template <typename T> void launch_uniform_t(int b0, int nb);
+    // pinned staging for host->device uploads of tables / flags / matrices (two slots, reused once their copy is done)
+    void *stage(size_t bytes);
+    void stage_commit();
+    struct StageSlot { void *ptr = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool busy = false; };
+    StageSlot stage_[2];
+    int stage_cur_ = 0;
+    std::vector<OpQueue> regq_;
+    int cur_reg_ = 0;
+    void *d_regmats_ = nullptr; size_t regmats_cap_ = 0;
+    uint64_t *d_seeds_ = nullptr; uint64_t *d_samples_ = nullptr; size_t samples_cap_ = 0;
     template <typename T> void flush_t();
     template <typename T> void reduce2_t(uint64_t sel_mask, double *d_all, double *d_sel);
     void ensure_scratch(size_t partial_doubles);
     void ensure_init();        // lazily writes the initial basis state (reset() only marks it)
     bool pending_init_ = true;
-    void maybe_flush() { if (queue.pending() >= 4096) flush(); }
+    void maybe_flush() { if (regq_.empty() && queue.pending() >= 4096) flush(); }
 
     int n_local_;
     size_t amp_bytes_, state_bytes_;
@@ -115,7 +141,7 @@ private:
     int tma_threads_ = 0;
     int ctas_per_sm_ = 0;  // 0 = occupancy query (generic kernel only)
     bool use_tma_ = true;
-    void make_tensor_map(CUtensorMap *out, int run_bits, const int hi_qubits[3]);
+    void make_tensor_map(CUtensorMap *out, int run_bits, const int hi_qubits[3], int b0 = 0, int nb = -1);
     bool tma_fold_dims_ = true;
     int tma_stages_ = 2;
     int tma_max_ctas_ = 0;

@@ -210,8 +210,8 @@ Json counts_json(const std::map<std::string, uint64_t> &counts)
 // cached State never inherits the previous job's setting
 void apply_fusion_cfg(State &st, const TaskCfg &c)
 {
-    st.queue.set_fusion(c.fusion_enable < 0 ? st.opt.fuse : c.fusion_enable != 0,
-                        c.fusion_max_qubit < 0 ? st.opt.max_dense_qubits : c.fusion_max_qubit);
+    st.rq().set_fusion(c.fusion_enable < 0 ? st.opt.fuse : c.fusion_enable != 0,
+                       c.fusion_max_qubit < 0 ? st.opt.max_dense_qubits : c.fusion_max_qubit);
 }
 
 bool cif_op(const std::string &op, bool a, bool b)
@@ -242,6 +242,16 @@ std::string Backend::execute(const std::string &tasks_json)
 {
     try {
         const Json msg = Json::parse(tasks_json);
+        if (msg.is_object() && msg.contains("b200_batch")) {
+            // {"b200_batch": [message, ...]}: independent messages as separate registers (execute_many) in one call
+            std::vector<std::string> texts;
+            for (const Json &m : msg.at("b200_batch").arr) texts.push_back(m.dump());
+            Json res = Json::array();
+            for (const std::string &r : execute_many(texts)) res.arr.push_back(Json::parse(r));
+            Json out = Json::object();
+            out.set("b200_batch_results", std::move(res));
+            return out.dump();
+        }
         return run(msg).dump();
     } catch (const std::exception &e) {
         // same contract as the reference adapters (aer_simulator_adapter.cpp:836-840)
@@ -558,7 +568,20 @@ void queue_gate_controlled_pos(State &st, const Inst &in, const std::vector<int>
 
 }  // namespace
 
-Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
+// one register of a batched run: the deferred interpreter queues the group's gates on register `reg` of the shared
+// State and leaves its symbolic classical register here; sampling and decoding happen once for all registers
+struct Backend::RegJob {
+    State *st = nullptr;
+    int reg = 0;
+    // outputs
+    std::vector<uint8_t> symbols;                 // classical register after the run: 0 / 1 / kSym + q
+    struct Layout { std::string id; int zc, ncl; };
+    std::vector<Layout> tasks;
+    uint64_t shots = 0, seed = 0, gates = 0;
+    bool used_teledata = false, teledata_reference = true, multi = false;
+};
+
+Json Backend::run_dynamic(const std::vector<Json> &tasks_json, RegJob *job)
 {
     std::vector<TaskCfg> cfgs;
     for (const Json &t : tasks_json) cfgs.push_back(parse_task(t));
@@ -714,6 +737,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
             return false;
         };
         auto recycle = [&](int q) {
+            if (job) throw DeferAbort();  // batched registers: no mid-circuit device queries (the group runs on its own instead)
             if (sym_referenced(q)) throw DeferAbort();
             double r[4];
             st.reduced_qubit(q, r);
@@ -1056,6 +1080,13 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
                 throw std::runtime_error("dynamic circuit deadlock: every task is blocked on communication");
             if (progressed) guard = 0;
         }
+        if (deferred && job) {
+            // batched registers: the draw happens once for all registers (Backend::execute_many)
+            job->symbols.resize((size_t)ncl_total);
+            for (int cl = 0; cl < ncl_total; cl++) job->symbols[cl] = creg[cl][0];
+            for (const TaskRt &t : T) job->tasks.push_back({t.cfg->id, t.zc, t.cfg->num_clbits});
+            return;
+        }
         if (deferred) {
             // every shot is one draw from the final state; a symbolic bit reads its qubit from the drawn index
             std::vector<uint64_t> samples(live);
@@ -1079,6 +1110,23 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
             }
     };
 
+    if (job) {
+        // one register of a batched run: deferred measurement or nothing (DeferAbort & co. propagate to execute_many)
+        if (external_cc || n_total + (int)kSym > (int)kNotSym) throw DeferAbort();
+        State &sb = *job->st;
+        sb.select_register(job->reg);
+        if (sb.n != n_total || sb.precision != precision) throw std::runtime_error("internal: register width mismatch");
+        apply_fusion_cfg(sb, c0);
+        const uint64_t g0 = sb.rq().gates;
+        run_batch(sb, 1, 0, shots, true);
+        job->shots = shots;
+        job->seed = seed;
+        job->gates = sb.rq().gates - g0;
+        job->used_teledata = used_teledata;
+        job->teledata_reference = c0.bugcompat_teledata;
+        job->multi = multi;
+        return Json::object();
+    }
     // first choice: defer every measurement (one state, all shots from one final sample)
     bool done = false;
     if (shots > 0 && c0.defer_measurement && !external_cc && n_total + (int)kSym <= (int)kNotSym) {  // (symbol encoding: <= 62 qubits)
@@ -1139,6 +1187,204 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json)
         last_stats.gates = stp->queue.gates - gates_before;
     }
     return out;
+}
+
+// ---- many independent messages as separate registers of one batched State ------------------------------
+namespace {
+// joint-register width of one message without parsing its instructions (allocation needs it before the run)
+int message_width(const Json &msg)
+{
+    auto width1 = [](const Json &t) { return (int)t.at("config").at("num_qubits").as_int(); };
+    if (!msg.is_array()) return width1(msg);
+    if (msg.arr.empty()) throw std::runtime_error("empty task list");
+    int n = 0;
+    for (const Json &t : msg.arr) n += width1(t);
+    if (msg.arr.size() > 1) {
+        const Json &cfg = msg.arr[0].at("config");
+        int nc = cfg.contains("n_communication_qubits") ? (int)cfg.at("n_communication_qubits").as_int() : 2;
+        if (nc % 2) nc++;
+        n += nc;
+    }
+    return n;
+}
+}  // namespace
+
+std::vector<std::string> Backend::execute_many(const std::vector<std::string> &messages)
+{
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    const size_t M = messages.size();
+    std::vector<std::string> results(M);
+    std::vector<Json> msgs(M);
+    std::vector<int> width(M, -1);
+    auto error_json = [](const std::string &what) {
+        Json err = Json::object();
+        err.set("ERROR", Json::string(what));
+        return err.dump();
+    };
+    if (cached_many_.size() < M) cached_many_.resize(M);
+    // 1. parse; {"params"} updates rewrite the slot's cached message (src/quantum_task.cpp:33-35,39-108)
+    for (size_t i = 0; i < M; i++) {
+        try {
+            Json m = Json::parse(messages[i]);
+            if (m.is_object() && !m.contains("instructions") && m.contains("params")) {
+                if (!cached_many_[i].is_object() || !cached_many_[i].contains("instructions"))
+                    throw std::runtime_error("Circuit not sent before updating parameters.");
+                update_params(cached_many_[i], m);
+                m = cached_many_[i];
+            } else {
+                cached_many_[i] = m;
+            }
+            if (m.is_object() && !(m.contains("instructions") && m.contains("config")))
+                throw std::runtime_error("message has neither instructions+config nor params");
+            if (m.is_object() && m.at("config").contains("precision") && m.at("config").at("precision").as_string() == "single")
+                width[i] = -2;  // batched registers are complex128 (the dynamic path's precision, :946): single runs on its own
+            else
+                width[i] = message_width(m);
+            msgs[i] = std::move(m);
+        } catch (const std::exception &e) {
+            results[i] = error_json(e.what());
+            width[i] = -1;
+        }
+    }
+    // structure signature of a message: instruction names and operands, no angles
+    std::vector<std::string> signature(M);
+    for (size_t i = 0; i < M; i++) {
+        if (width[i] < 1) continue;
+        std::function<void(const Json &, std::string &)> sig = [&](const Json &insts, std::string &out) {
+            for (const Json &in : insts.arr) {
+                out += in.at("name").as_string();
+                for (const char *key : {"qubits", "clbits", "qpus"})
+                    if (const Json *v = in.find(key)) out += v->dump();
+                if (const Json *sub = in.find("instructions")) { out += '{'; sig(*sub, out); out += '}'; }
+                out += ';';
+            }
+        };
+        try {
+            if (msgs[i].is_array()) for (const Json &t : msgs[i].arr) { sig(t.at("instructions"), signature[i]); signature[i] += '|'; }
+            else sig(msgs[i].at("instructions"), signature[i]);
+        } catch (const std::exception &) { signature[i] = "?"; }
+    }
+    last_uniform_flushes = last_split_flushes = last_solo = 0;
+    Stats total;
+    // 2. registers of equal width share one State (as many per chunk as fit the memory budget)
+    std::vector<char> handled(M, 0);
+    for (size_t i = 0; i < M; i++) {
+        if (handled[i] || width[i] < 1) continue;
+        std::vector<size_t> members;
+        for (size_t j = i; j < M; j++)
+            if (!handled[j] && width[j] == width[i]) members.push_back(j);
+        // equal circuits become neighbouring registers (State::flush_registers_t batches runs of equal structure)
+        std::stable_sort(members.begin(), members.end(), [&](size_t a, size_t b) { return signature[a] < signature[b]; });
+        const int n = width[i];
+        const double budget = 96.0 * 1073741824.0;
+        const size_t per_chunk = (size_t)std::max(1.0, std::min(4096.0, std::floor(budget / (16.0 * std::ldexp(1.0, n)))));
+        for (size_t c0 = 0; c0 < members.size(); c0 += per_chunk) {
+            const size_t G = std::min(per_chunk, members.size() - c0);
+            std::vector<RegJob> jobs(G);
+            std::vector<char> ok(G, 0);
+            try {
+                if (!batch_state_ || batch_state_->n != n || batch_state_->batch != (int)G) {
+                    batch_state_.reset();
+                    batch_state_.reset(new State(n, 64, device_, (int)G));
+                }
+                State &st = *batch_state_;
+                st.use_registers(true);
+                st.reset();
+                const Stats before = st.stats;
+                const uint64_t uf0 = st.uniform_flushes, sf0 = st.split_flushes;
+                for (size_t g = 0; g < G; g++) {
+                    const Json &m = msgs[members[c0 + g]];
+                    jobs[g].st = &st;
+                    jobs[g].reg = (int)g;
+                    try {
+                        run_dynamic(m.is_array() ? std::vector<Json>(m.arr.begin(), m.arr.end()) : std::vector<Json>{m}, &jobs[g]);
+                        ok[g] = 1;
+                    } catch (const DeferAbort &) {
+                    } catch (const CudaError &) {
+                        throw;
+                    } catch (const std::exception &) {
+                        // Unsupported / InvalidArg from the extra controls of a deferred condition, or a malformed task:
+                        // the ordinary path below gives this message its own answer (or its own error)
+                    }
+                    if (!ok[g]) {   // needs a real collapse / an external channel: leave the register idle, run it alone below
+                        st.select_register((int)g);
+                        st.rq().clear_pending();
+                    }
+                }
+                uint64_t max_shots = 0;
+                std::vector<uint64_t> seeds(G, 0);
+                for (size_t g = 0; g < G; g++) if (ok[g]) { max_shots = std::max(max_shots, jobs[g].shots); seeds[g] = jobs[g].seed; }
+                std::vector<uint64_t> samples((size_t)G * max_shots);
+                st.flush();
+                st.sample_registers(max_shots, seeds.data(), samples.data());
+                const double secs = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+                last_uniform_flushes += st.uniform_flushes - uf0;
+                last_split_flushes += st.split_flushes - sf0;
+                total.passes += st.stats.passes - before.passes;
+                total.launches += st.stats.launches - before.launches;
+                total.bytes += st.stats.bytes - before.bytes;
+                total.fused_ops += st.stats.fused_ops - before.fused_ops;
+                total.h2d_bytes += st.stats.h2d_bytes - before.h2d_bytes;
+                total.d2h_bytes += st.stats.d2h_bytes - before.d2h_bytes;
+                for (size_t g = 0; g < G; g++) {
+                    if (!ok[g]) continue;
+                    const RegJob &jb = jobs[g];
+                    total.gates += jb.gates;
+                    // every shot is one draw from the register's final state; a symbolic bit reads its qubit from the index
+                    std::map<std::string, std::map<std::string, uint64_t>> counters;
+                    for (const RegJob::Layout &t : jb.tasks) counters[t.id];
+                    std::vector<uint8_t> bits(jb.symbols.size());
+                    for (uint64_t s = 0; s < jb.shots; s++) {
+                        const uint64_t idx = samples[g * max_shots + s];
+                        for (size_t cl = 0; cl < jb.symbols.size(); cl++) {
+                            const uint8_t v = jb.symbols[cl];
+                            bits[cl] = v >= kSym ? (uint8_t)((idx >> sym_qubit(v)) & 1ull) : v;
+                        }
+                        for (const RegJob::Layout &t : jb.tasks) counters[t.id][bits_to_string(bits, t.zc, t.ncl)]++;
+                    }
+                    Json out = Json::object();
+                    const Json &m = msgs[members[c0 + g]];
+                    if (m.is_array()) {
+                        Json idc = Json::object();
+                        for (auto &kv : counters) idc.set(kv.first, counts_json(kv.second));
+                        out.set("id_counts", std::move(idc));
+                    } else {
+                        out.set("counts", counts_json(counters.begin()->second));
+                    }
+                    out.set("time_taken", Json::number(secs));
+                    Json info = Json::object();
+                    info.set("mode", Json::string("deferred_measurement"));
+                    info.set("batched_registers", Json::integer((long long)G));
+                    if (jb.used_teledata) info.set("teledata_corrections", Json::string(jb.teledata_reference ? "reference" : "protocol"));
+                    out.set("b200", std::move(info));
+                    results[members[c0 + g]] = out.dump();
+                    handled[members[c0 + g]] = 1;
+                }
+            } catch (const std::exception &e) {
+                for (size_t g = 0; g < G; g++)
+                    if (!handled[members[c0 + g]]) { results[members[c0 + g]] = error_json(e.what()); handled[members[c0 + g]] = 1; }
+            }
+            for (size_t g = 0; g < G; g++)
+                if (!handled[members[c0 + g]]) width[members[c0 + g]] = -2;  // -> solo
+        }
+    }
+    // 3. whatever could not ride in a register runs through the ordinary path, one message at a time
+    for (size_t i = 0; i < M; i++) {
+        if (handled[i] || width[i] != -2) continue;
+        const Json keep_cached = cached_;
+        const bool keep_has = has_cached_;
+        results[i] = execute(msgs[i].dump());
+        cached_ = keep_cached;
+        has_cached_ = keep_has;
+        parsed_.reset();
+        last_solo++;
+        total.passes += last_stats.passes; total.launches += last_stats.launches; total.bytes += last_stats.bytes;
+        total.fused_ops += last_stats.fused_ops; total.h2d_bytes += last_stats.h2d_bytes; total.d2h_bytes += last_stats.d2h_bytes;
+        total.gates += last_stats.gates;
+    }
+    last_stats = total;
+    last_mode = 1;
+    return results;
 }
 
 std::string update_task_json(const std::string &task_json, const std::string &update_json)

@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "engine.hpp"
 #include "json_min.hpp"
@@ -22,6 +23,12 @@ public:
     explicit Backend(int device) : device_(device) {}
     // returns the result JSON text (never throws: failures become {"ERROR": "..."} )
     std::string execute(const std::string &tasks_json);
+    // n independent messages (each what execute() accepts: a task, a JSON array of tasks = one quantum-communication
+    // group, or a {"params":..} update of the task last sent in the same slot) run as SEPARATE registers batched on the
+    // device: one State with batch = n, one launch per tile pass over all registers when their circuits share their
+    // structure (BASELINE config 5: many small vQPU groups per GPU).  Result i has the shape execute() gives message i.
+    std::vector<std::string> execute_many(const std::vector<std::string> &messages);
+    uint64_t last_uniform_flushes = 0, last_split_flushes = 0, last_solo = 0;
     void set_channel(send_fn s, recv_fn r, void *user) { send_ = s; recv_ = r; user_ = user; }
     Stats last_stats;
     int last_mode = 0;  // 0 static, 1 dynamic with deferred measurements, 2 dynamic on the batched interpreter
@@ -30,8 +37,11 @@ public:
 private:
     Json run(const Json &msg);
     Json run_static(const Json &task);
-    Json run_dynamic(const std::vector<Json> &tasks);
+    struct RegJob;  // one register of a batched run (executor.cpp)
+    Json run_dynamic(const std::vector<Json> &tasks, RegJob *job = nullptr);
     State &get_state(int n, int precision, int batch);
+    std::unique_ptr<State> batch_state_;      // execute_many: the registers
+    std::vector<Json> cached_many_;           // execute_many: last full message per slot
 
     int device_;
     std::unique_ptr<State> state_;

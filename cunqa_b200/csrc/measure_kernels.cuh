@@ -326,6 +326,33 @@ sample_each_kernel(const V *__restrict__ state, int n, int bits0, int bits1, con
     }
 }
 
+// `shots` samples of EVERY state of the batch (independent registers, each with its own seed): one warp per (state, shot),
+// u = U(seeds[b], s) * norm_b -- the same draw cb200_sample makes for state b alone.
+template <typename V>
+__global__ void __launch_bounds__(kRedThreads)
+sample_regs_kernel(const V *__restrict__ state, int n, int bits0, int bits1, const double *__restrict__ lvl1,
+                   const double *__restrict__ lvl2, int batch, uint64_t shots, const uint64_t *__restrict__ seeds,
+                   uint64_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n2 = 1ull << (n - bits0 - bits1), len1 = 1ull << bits1, len0 = 1ull << bits0;
+    const uint64_t work = (uint64_t)batch * shots;
+    for (uint64_t w = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < work; w += warps) {
+        const uint64_t b = w / shots, s = w - b * shots;
+        const double *l2 = lvl2 + b * n2;
+        double total = 0.0;
+        for (uint64_t j = 0; j < n2; j++) total += l2[j];  // same order on every lane and for every shot of the state
+        double u = splitmix_uniform(seeds[b], s) * total;
+        const uint64_t g = warp_search([&](uint64_t j) { return l2[j]; }, n2, u);
+        const double *l1 = lvl1 + (b * n2 + g) * len1;
+        const uint64_t c = warp_search([&](uint64_t j) { return l1[j]; }, len1, u);
+        const V *a = state + (b << n) + ((g * len1 + c) << bits0);
+        const uint64_t i = warp_search([&](uint64_t j) { return abs2(a[j]); }, len0, u);
+        if (lane == 0) out[w] = ((g * len1 + c) << bits0) + i;
+    }
+}
+
 template <typename V>
 __global__ void gather_amps_kernel(const V *__restrict__ state, const uint64_t *__restrict__ idx, uint64_t n, double2 *__restrict__ out)
 {

@@ -467,7 +467,8 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
 template <typename T>
 __global__ void __launch_bounds__(kTileThreads, 2)
 tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type *__restrict__ state,
-                 const typename Vec2<T>::type *__restrict__ diag_tabs, const uint8_t *__restrict__ flags)
+                 const typename Vec2<T>::type *__restrict__ diag_tabs, const uint8_t *__restrict__ flags,
+                 const T *__restrict__ reg_mats, const uint32_t reg_mat_stride, const uint32_t reg_diag_stride)
 {
     using V = typename Vec2<T>::type;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -509,7 +510,10 @@ tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type
             tile[swz<T>(i)] = gbase[run_off[i >> L] + (i & run_mask)];
         __syncthreads();
 
-        apply_ops<T, kTileThreads, true, true>(p, p.mats, tile, diag_tabs, active, base, t, tid);
+        // reg_mats != nullptr: every state of the batch is its own register with its own matrices and diagonal tables
+        // (same pass structure): state b reads row b of the per-register buffers
+        apply_ops<T, kTileThreads, true, true>(p, reg_mats ? reg_mats + (size_t)b * reg_mat_stride : p.mats, tile,
+                                               diag_tabs + (size_t)b * reg_diag_stride, active, base, t, tid);
 
         // ---- stage out
 #pragma unroll 4
@@ -577,7 +581,8 @@ template <typename T, int NT, bool COND, bool FULL, int kStages>
 __global__ void __launch_bounds__(NT, (kStages == 3 ? 256 : 384) / NT)
 tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_constant__ CUtensorMap tmap,
                      const typename Vec2<T>::type *__restrict__ diag_tabs, const uint8_t *__restrict__ flags,
-                     const int box_bits, const uint32_t buf_stride, const int refill_after)
+                     const int box_bits, const uint32_t buf_stride, const int refill_after,
+                     const T *__restrict__ reg_mats, const uint32_t reg_mat_stride, const uint32_t reg_diag_stride)
 {
     using V = typename Vec2<T>::type;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -600,7 +605,12 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     unsigned char *mats_raw = reinterpret_cast<unsigned char *>(box_row + ((nbox + 3) & ~3u));
     mats_raw += (16u - (smem_u32(mats_raw) & 15u)) & 15u;
     T *mats_s = reinterpret_cast<T *>(mats_raw);
-    for (int e = tid; e < p.n_mat; e += NT) mats_s[e] = p.mats[e];
+    // reg_mats != nullptr: many independent registers batched in one launch (same pass structure, each state of the
+    // batch with its own matrices and diagonal tables): the matrices are (re)staged whenever the CTA moves on to a tile
+    // of another state -- tiles are numbered state-major, so that happens once per 2^(n-t)/gridDim tiles
+    if (reg_mats == nullptr)
+        for (int e = tid; e < p.n_mat; e += NT) mats_s[e] = p.mats[e];
+    uint64_t staged_b = ~0ull;
     // per diagonal op: bit-extract tables of the in-tile index part (tile bits 0..5 and 6..12) + per-tile high part
     uint32_t *dhi = reinterpret_cast<uint32_t *>(mats_s + ((p.n_mat + 1) & ~1));
     uint16_t *lut = reinterpret_cast<uint16_t *>(dhi + p.n_diag);
@@ -712,10 +722,19 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
             for (int m = d.nfix; m < d.k; m++) hi |= (uint32_t)((base >> (d.dsrc[m] - 64)) & 1ull) << m;
             dhi[sl] = hi + d.mat_off;
         }
+        bool restaged = false;
+        if (reg_mats != nullptr && b != staged_b) {
+            // (mats_s is only read inside apply_ops, and every thread left the previous tile's apply_ops through a barrier)
+            const T *src = reg_mats + (size_t)b * reg_mat_stride;
+            for (int e = tid; e < p.n_mat; e += NT) mats_s[e] = src[e];
+            staged_b = b;
+            restaged = true;
+        }
         mbar_wait(&full[s], parity);
-        if (p.n_diag) __syncthreads();
+        if (p.n_diag || restaged) __syncthreads();
 
-        apply_ops<T, NT, COND, FULL>(p, mats_s, tile, diag_tabs, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
+        apply_ops<T, NT, COND, FULL>(p, mats_s, tile, diag_tabs + (size_t)b * reg_diag_stride,
+                                     COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
                                      (COND || (16 * NT) != (1 << t)) ? nullptr : lut, dhi, refill_after, refill);
 
         // every thread's generic-proxy writes -> visible to the async proxy; then drain the tile with TMA

@@ -6,7 +6,8 @@ namespace cb200 {
 
 template <typename T>
 cudaError_t launch_tile_pass_generic(const PassParams<T> &p, void *state, const void *diag_tabs, const uint8_t *flags,
-                                     int num_sms, int ctas_per_sm, int device, cudaStream_t stream)
+                                     int num_sms, int ctas_per_sm, int device, cudaStream_t stream,
+                                     const void *reg_mats, uint32_t reg_mat_stride, uint32_t reg_diag_stride)
 {
     using V = typename Vec2<T>::type;
     auto kern = tile_pass_kernel<T>;
@@ -26,10 +27,10 @@ cudaError_t launch_tile_pass_generic(const PassParams<T> &p, void *state, const 
     }
     const uint64_t total_tiles = p.tiles_per_state * (uint64_t)p.batch;
     const unsigned grid = (unsigned)(total_tiles < (uint64_t)num_sms * occ ? total_tiles : (uint64_t)num_sms * occ);
-    kern<<<grid, kTileThreads, smem, stream>>>(p, (V *)state, (const V *)diag_tabs, flags);
+    kern<<<grid, kTileThreads, smem, stream>>>(p, (V *)state, (const V *)diag_tabs, flags, (const T *)reg_mats, reg_mat_stride, reg_diag_stride);
     return cudaGetLastError();
 }
-template cudaError_t launch_tile_pass_generic<double>(const PassParams<double> &, void *, const void *, const uint8_t *, int, int, int, cudaStream_t);
-template cudaError_t launch_tile_pass_generic<float>(const PassParams<float> &, void *, const void *, const uint8_t *, int, int, int, cudaStream_t);
+template cudaError_t launch_tile_pass_generic<double>(const PassParams<double> &, void *, const void *, const uint8_t *, int, int, int, cudaStream_t, const void *, uint32_t, uint32_t);
+template cudaError_t launch_tile_pass_generic<float>(const PassParams<float> &, void *, const void *, const uint8_t *, int, int, int, cudaStream_t, const void *, uint32_t, uint32_t);
 
 }  // namespace cb200

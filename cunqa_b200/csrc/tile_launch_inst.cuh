@@ -29,7 +29,8 @@ cudaError_t launch_tile_pass_tma<CB200_T, CB200_NT>(const PassParams<CB200_T> &p
     auto go = [&](auto kern, size_t &s) -> cudaError_t {
         cudaError_t e = set_smem_once(kern, l.smem, s);
         if (e != cudaSuccess) return e;
-        kern<<<l.grid, N, l.smem, l.stream>>>(p, tmap, (const V *)l.diag_tabs, l.flags, l.box_bits, l.buf_stride, l.refill_after);
+        kern<<<l.grid, N, l.smem, l.stream>>>(p, tmap, (const V *)l.diag_tabs, l.flags, l.box_bits, l.buf_stride, l.refill_after,
+                                                (const T *)l.reg_mats, l.reg_mat_stride, l.reg_diag_stride);
         return cudaGetLastError();
     };
     if (l.stages == 3) {

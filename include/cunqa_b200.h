@@ -136,6 +136,22 @@ int cb200_backend_set_channel(cb200_backend *b, cb200_send_fn send, cb200_recv_f
  * `{"id_counts":{id:{...}},"time_taken":s}` for several; `{"ERROR":"..."}` on failure
  * (status stays CB200_OK so that the plugin can forward the message, cf. :836-840). */
 int cb200_backend_execute(cb200_backend *b, const char *tasks_json, char **result_json_out);
+/* MANY independent messages in one call, run as SEPARATE registers batched on the device (BASELINE config 5: "many
+ * small independent virtual QPUs are batched as separate state vectors per GPU").  messages[i] is anything
+ * cb200_backend_execute accepts -- one task, a JSON array of tasks (= one quantum-communication group with its own joint
+ * register, aer_simulator_adapter.cpp:131-159), or a {"params":[...],"shots":N} update of the message last sent in slot i
+ * (src/quantum_task.cpp:33-35).  In the reference each vQPU / each executor group is its own process calling simulate()
+ * (src/cli/setup_qpus.cpp:69-82, AER/aer_executor.cpp:41-85); on one GPU they share this engine instead: registers of
+ * equal width live in ONE device buffer and advance in the same tile passes -- one launch per pass over all of them with
+ * per-register matrices when their circuits have the same structure (a VQE ansatz evaluated at many parameter sets),
+ * register by register otherwise; every measurement is deferred and all shots of all registers are drawn in one
+ * sampling pass.  A message that needs a real mid-circuit collapse or an external classical channel runs on its own
+ * through the ordinary path.  results_json_out[i] (free with cb200_free) has the shape cb200_backend_execute returns
+ * for messages[i].  The same call is reachable as the message {"b200_batch":[...]} -> {"b200_batch_results":[...]}. */
+int cb200_backend_execute_many(cb200_backend *b, const char *const *messages, int n, char **results_json_out);
+/* how the last execute_many ran: info[0] = flushes that ran all registers in the same launches, [1] = flushes that ran
+ * register by register (structures differed), [2] = messages that ran alone */
+int cb200_backend_batch_info(const cb200_backend *b, uint64_t info[3]);
 /* counters of the backend's last execute: same layout as cb200_stats */
 int cb200_backend_stats(const cb200_backend *b, uint64_t stats[8]);
 /* how the last execute ran its measurements: 0 = static task (one state, shots sampled), 1 = dynamic task with every
