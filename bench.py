@@ -255,7 +255,8 @@ def side_workloads(cb, C, torch, dist, world, rank, local_rank):
             qins = C.qft(n, x)
             best = None
             for rep in range(4):
-                sv.reset(); sv.sync()
+                sv.sync()
+                sv.reset()                         # (the initial basis state is written by the first flush: timed)
                 a0 = sv.stats()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)

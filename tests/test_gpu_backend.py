@@ -275,8 +275,10 @@ def test_deferral_falls_back_when_a_collapse_is_needed(backend, ins):
 
 
 def test_deferred_measurement_reuses_communication_pairs(backend):
-    """two teleports through ONE pair: the first teleport leaves its measured qubits disentangled (|+>), so they are
-    reset by a unitary and the second teleport is deferred as well; with two pairs a fresh pair is taken"""
+    """two teleports through ONE pair with the documented corrections: the first teleport leaves its measured qubits
+    disentangled (|+>), so they are reset by a unitary and the second teleport is deferred as well; with two pairs a fresh
+    pair is taken.  With the reference's literal corrections (the default, quirk Q6) the measured qubits stay entangled
+    with the received one: reusing the pair needs a real collapse, and the engine falls back to the per-shot interpreter."""
     a = [{"name": "ry", "qubits": [0], "params": [0.7]}, {"name": "qsend", "qubits": [0], "qpus": ["B"]},
          {"name": "ry", "qubits": [1], "params": [0.3]}, {"name": "qsend", "qubits": [1], "qpus": ["B"]}]
     b = [{"name": "qrecv", "qubits": [0], "qpus": ["A"]}, {"name": "qrecv", "qubits": [1], "qpus": ["A"]}] + C.measure_all(2)
@@ -284,7 +286,8 @@ def test_deferred_measurement_reuses_communication_pairs(backend):
     p_want = {"00": math.cos(0.35) ** 2 * math.cos(0.15) ** 2, "01": math.sin(0.35) ** 2 * math.cos(0.15) ** 2,
               "10": math.cos(0.35) ** 2 * math.sin(0.15) ** 2, "11": math.sin(0.35) ** 2 * math.sin(0.15) ** 2}
     for n_comm, mode in ((2, 1), (4, 1)):
-        msg = [C.task(a, 2, shots=shots, seed=3, task_id="A", is_dynamic=True, n_communication_qubits=n_comm),
+        msg = [C.task(a, 2, shots=shots, seed=3, task_id="A", is_dynamic=True, n_communication_qubits=n_comm,
+                      b200_teledata_corrections="protocol"),
                C.task(b, 2, shots=shots, seed=3, task_id="B", is_dynamic=True, n_communication_qubits=n_comm)]
         res = backend.execute(msg)
         assert "ERROR" not in res, res
@@ -292,6 +295,14 @@ def test_deferred_measurement_reuses_communication_pairs(backend):
         got = res["id_counts"]["B"]
         for k, p in p_want.items():
             assert abs(got.get(k, 0) / shots - p) < 5 * math.sqrt(p * (1 - p) / shots) + 1e-3, (n_comm, k)
+    # default = the reference's literal corrections: one pair cannot be recycled without a collapse -> per-shot interpreter,
+    # shot-identical to the oracle (which restates the literal code)
+    msg = [C.task(a, 2, shots=600, seed=3, task_id="A", is_dynamic=True, b200_terminal_sampling=False),
+           C.task(b, 2, shots=600, seed=3, task_id="B", is_dynamic=True)]
+    res = backend.execute(msg)
+    assert backend.last_mode() == 2 and res["b200"]["teledata_corrections"] == "reference"
+    tasks = [{"id": "A", "num_qubits": 2, "num_clbits": 2, "instructions": a}, {"id": "B", "num_qubits": 2, "num_clbits": 2, "instructions": b}]
+    assert res["id_counts"] == O.run_dynamic(tasks, 600, seed=3, terminal_sampling=False)
 
 
 def test_deferred_measurement_many_remote_operations(backend):
@@ -300,11 +311,12 @@ def test_deferred_measurement_many_remote_operations(backend):
     from test_oracle import _many_remote_ops
     tasks = _many_remote_ops(2)
     shots = 40000
-    msg = [C.task(t["instructions"], t["num_qubits"], shots=shots, seed=5, task_id=t["id"], is_dynamic=True) for t in tasks]
+    msg = [C.task(t["instructions"], t["num_qubits"], shots=shots, seed=5, task_id=t["id"], is_dynamic=True,
+                  b200_teledata_corrections="protocol") for t in tasks]
     res = backend.execute(msg)
     assert "ERROR" not in res, res
     assert backend.last_mode() == 1
-    dist = O.deferred_distribution(tasks, n_comm_qubits=2)
+    dist = O.deferred_distribution(tasks, n_comm_qubits=2, teledata_literal=False)
     for tid in ("A", "B"):
         want = {}
         for key, p in dist.items():
