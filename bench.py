@@ -284,6 +284,70 @@ def side_workloads(cb, C, torch, dist, world, rank, local_rank):
     return out
 
 
+def sharded_leg(cb, C, torch, n_per_gpu, devices):
+    """QFT-(n_per_gpu + log2 N) fp64 as ONE state over `devices`, owned by this process.  Device leg: the state-level C ABI
+    (wall clock around run + sync: every shard's stream is drained); e2e leg: cb200_backend_execute with a wire-JSON task
+    whose config.device.target_devices is the device list (1024 shots back as counts)."""
+    import numpy as np
+    from oracle import oracle_np as O   # closed form only (checker, outside the timed regions)
+    world = len(devices)
+    g = world.bit_length() - 1
+    nq = n_per_gpu + g
+    xq = C.qft_x(nq, seed=7)
+    qins = C.qft(nq, xq)
+    shard = 16 * 2 ** n_per_gpu
+    sv = cb.StateVector(nq, "double", devices=devices)
+    times = []
+    for rep in range(3):
+        sv.sync()
+        sv.reset()
+        a0 = sv.stats()
+        d0 = sv.dist_stats() if world > 1 else {"swaps": 0, "swap_bytes_sent": 0, "swap_ms": 0.0}
+        t0 = time.perf_counter()
+        sv.run(qins)
+        sv.sync()
+        times.append((time.perf_counter() - t0) * 1e3)
+    a1 = sv.stats()
+    d1 = sv.dist_stats() if world > 1 else d0
+    idx = np.random.default_rng(2).integers(0, 1 << nq, size=1 << 14).astype(np.uint64)
+    err = float(np.abs(sv.amplitudes(idx) - O.qft_amplitudes(nq, xq, idx)).max())
+    if not (err < 1e-10 and err * 2.0 ** (nq / 2) < 1e-9):
+        raise SystemExit(f"sharded QFT-{nq}: amplitude error {err} against the closed form: result invalid")
+    sv.close()
+    del sv
+    torch.cuda.empty_cache()
+    ms = min(times[1:])
+    passes = a1["passes"] - a0["passes"]
+    swap_ms = d1["swap_ms"] - d0["swap_ms"]
+    sent = d1["swap_bytes_sent"] - d0["swap_bytes_sent"]
+    out = {"workload": f"QFT-{nq} fp64, one state over {world} GPU(s) ({shard / 2 ** 30:.0f} GiB per GPU), single process, "
+                       f"config.device.target_devices = {devices}",
+           "gates": C.n_gates(qins), "ms": ms, "gates_per_s": C.n_gates(qins) / (ms / 1e3),
+           "tile_passes_per_gpu": passes, "qubit_swaps": d1["swaps"] - d0["swaps"],
+           "swap_GB_sent_per_gpu": sent / 1e9, "swap_ms": swap_ms,
+           "nvlink_GBps_per_direction_per_gpu": (sent / 1e9) / (swap_ms / 1e3) if swap_ms > 0 else None,
+           "nvlink_frac_of_770": ((sent / 1e9) / (swap_ms / 1e3)) / 770.0 if swap_ms > 0 else None,
+           "local_GBps_per_gpu": 2 * shard * passes / max(1e-9, (ms - swap_ms) / 1e3) / 1e9,
+           "max_abs_err_vs_closed_form": err, "rel_err_times_2^(n/2)": err * 2.0 ** (nq / 2)}
+    # e2e through the plugin-facing call
+    be = cb.Backend(devices=devices)
+    t = C.task(qins + C.measure_all(nq), nq, shots=SHOTS, seed=SEED)
+    t["config"]["device"]["target_devices"] = list(devices)
+    text = json.dumps(t)
+    res = be.execute(text)   # warm-up: allocates the shards
+    if "ERROR" in res:
+        raise SystemExit("sharded e2e run failed: " + res["ERROR"])
+    t0 = time.perf_counter()
+    res = be.execute(text)
+    e2e_s = time.perf_counter() - t0
+    assert sum(res["counts"].values()) == SHOTS
+    out["e2e"] = {"api": "cb200_backend_execute, config.device.target_devices = all GPUs (wire JSON -> counts JSON)",
+                  "ms": e2e_s * 1e3, "gates_per_s": C.n_gates(qins) / e2e_s, "shots": SHOTS}
+    be.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -424,48 +488,18 @@ def main():
     e2e_s = float(t.item())
     be.close()
 
-    # ---- N > 1: the other multi-GPU regime -- ONE state sharded over all ranks (BASELINE config 4):
-    # QFT on (n + log2 N) qubits, top log2 N qubits global, global<->local qubit swaps over NVLink peer memory
+    # ---- N > 1: the other multi-GPU regime -- ONE state sharded over all N GPUs (BASELINE config 4), driven the way the
+    # plugin drives it: ONE process (rank 0) owns all shards through config.device.target_devices = [0..N-1]; the other
+    # ranks have released their GPUs' memory and wait.  QFT on (n + log2 N) qubits, top log2 N qubits global,
+    # global<->local qubit swaps by a peer-memory kernel over NVLink.
     sharded = None
     if world > 1 and (world & (world - 1)) == 0 and not args.no_sharded:
-        from oracle import oracle_np as O
-        import numpy as np
-        g = world.bit_length() - 1
-        nq = n + g
-        xq = C.qft_x(nq, seed=7)
-        qins = C.qft(nq, xq)
-        ssv = cb.ShardedStateVector(nq, "double", device=local_rank)
-        sstream = torch.cuda.ExternalStream(ssv.stream(), device=torch.device("cuda", local_rank))
-        times = []
-        for rep in range(3):
-            ssv.reset(); ssv.sync()
-            barrier()
-            a0, d0 = ssv.stats(), ssv.dist_stats()
-            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            q0.record(sstream)
-            ssv.run(qins); ssv.flush()
-            q1.record(sstream)
-            ssv.sync()
-            barrier()
-            tt = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            times.append(float(tt.item()))
-        a1, d1 = ssv.stats(), ssv.dist_stats()
-        idx = np.random.default_rng(2).integers(0, 1 << nq, size=1 << 14).astype(np.uint64)
-        err = float(np.abs(ssv.amplitudes(idx) - O.qft_amplitudes(nq, xq, idx)).max())
-        ms = min(times[1:])
-        shard = 16 * 2 ** n
-        swap_ms = d1["swap_ms"] - d0["swap_ms"]
-        sent = d1["swap_bytes_sent"] - d0["swap_bytes_sent"]
-        sharded = {"workload": f"QFT-{nq} fp64, one state sharded over {world} GPUs ({shard / 2 ** 30:.0f} GiB per GPU)",
-                   "gates": C.n_gates(qins), "ms": ms, "gates_per_s": C.n_gates(qins) / (ms / 1e3),
-                   "tile_passes_per_gpu": a1["passes"] - a0["passes"], "qubit_swaps": d1["swaps"] - d0["swaps"],
-                   "swap_GB_sent_per_gpu": sent / 1e9, "swap_ms": swap_ms,
-                   "nvlink_GBps_per_direction_per_gpu": (sent / 1e9) / (swap_ms / 1e3) if swap_ms > 0 else None,
-                   "nvlink_frac_of_770": ((sent / 1e9) / (swap_ms / 1e3)) / 770.0 if swap_ms > 0 else None,
-                   "local_GBps_per_gpu": 2 * shard * (a1["passes"] - a0["passes"]) / max(1e-9, (ms - swap_ms) / 1e3) / 1e9,
-                   "max_abs_err_vs_closed_form": err}
-        ssv.close()
+        barrier()
+        if rank == 0:
+            sharded = sharded_leg(cb, C, torch, n, list(range(world)))
+        barrier()
+    elif world == 1 and not args.no_sharded and not args.no_side and n == QV_QUBITS:
+        sharded = sharded_leg(cb, C, torch, n, [local_rank])   # the N = 1 anchor of the 1 -> 8 curve: QFT-33, unsharded
 
     if rank == 0:
         ms_per_step = total_ms / args.steps

@@ -73,6 +73,8 @@ SIGNATURES = {
     "cb200_update_task_json": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "cb200_gate_matrix": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, _c_dbl_p, ctypes.c_int, _c_dbl_p]),
     "cb200_backend_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int]),
+    "cb200_backend_create_multi": (ctypes.c_int, [ctypes.POINTER(_vp), _c_int_p, ctypes.c_int]),
+    "cb200_state_create_sharded": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, _c_int_p, ctypes.c_int]),
     "cb200_backend_destroy": (ctypes.c_int, [_vp]),
     "cb200_backend_set_channel": (ctypes.c_int, [_vp, SEND_FN, RECV_FN, _vp]),
     "cb200_backend_execute": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(_vp)]),
@@ -160,10 +162,15 @@ def qasm2_to_json(qasm):
 class StateVector:
     """cb200_state: n qubits x batch independent states on one B200."""
 
-    def __init__(self, n_qubits, precision="double", device=0, batch=1):
+    def __init__(self, n_qubits, precision="double", device=0, batch=1, devices=None):
         prec = {"double": 64, "single": 32, 64: 64, 32: 32}[precision]
         self._h = _vp()
-        _check(lib.cb200_state_create(ctypes.byref(self._h), n_qubits, prec, device, batch))
+        if devices is not None and len(devices) > 1:
+            # ONE process, several GPUs: the state is sharded over `devices` inside the library
+            d, nd = _ints(devices)
+            _check(lib.cb200_state_create_sharded(ctypes.byref(self._h), n_qubits, prec, d, nd))
+        else:
+            _check(lib.cb200_state_create(ctypes.byref(self._h), n_qubits, prec, device if devices is None else devices[0], batch))
         self.n = n_qubits
         self.batch = batch
         self.precision = prec
@@ -286,6 +293,12 @@ class StateVector:
         """cudaStream_t (as int) all kernels of this state run on"""
         return int(lib.cb200_state_stream(self._h) or 0)
 
+    def dist_stats(self):
+        out = np.zeros(5, dtype=np.uint64)
+        _check(lib.cb200_dist_stats(self._h, out.ctypes.data_as(_c_u64_p)))
+        return {"rank": int(out[0]), "world": int(out[1]), "swaps": int(out[2]), "swap_bytes_sent": int(out[3]),
+                "swap_ms": int(out[4]) / 1000.0}
+
 
 class ShardedStateVector(StateVector):
     """One state sharded over the GPUs of a box: one process per GPU, top log2(world) qubits global.
@@ -330,9 +343,13 @@ class ShardedStateVector(StateVector):
 class Backend:
     """cb200_backend: what the CUNQA plugin's execute() drives (wire JSON in, result JSON out)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
         self._h = _vp()
-        _check(lib.cb200_backend_create(ctypes.byref(self._h), device))
+        if devices is not None and len(devices) > 1:
+            d, nd = _ints(devices)
+            _check(lib.cb200_backend_create_multi(ctypes.byref(self._h), d, nd))
+        else:
+            _check(lib.cb200_backend_create(ctypes.byref(self._h), device if devices is None else devices[0]))
         self._cb = None
 
     def close(self):

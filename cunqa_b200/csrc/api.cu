@@ -65,6 +65,15 @@ int cb200_state_create(cb200_state **out, int n_qubits, int precision, int devic
         *out = new cb200_state{s};
     });
 }
+int cb200_state_create_sharded(cb200_state **out, int n_qubits, int precision, const int *devices, int n_devices)
+{
+    if (!out || !devices) { g_err = "null argument"; return CB200_ERR_INVALID; }
+    *out = nullptr;
+    return guard([&] {
+        State *s = new State(n_qubits, precision, std::vector<int>(devices, devices + n_devices));
+        *out = new cb200_state{s};
+    });
+}
 int cb200_state_destroy(cb200_state *s)
 {
     if (!s) return CB200_OK;
@@ -188,6 +197,15 @@ int cb200_backend_create(cb200_backend **out, int device)
     if (!out) { g_err = "null output pointer"; return CB200_ERR_INVALID; }
     *out = nullptr;
     return guard([&] { *out = new cb200_backend{new Backend(device)}; });
+}
+int cb200_backend_create_multi(cb200_backend **out, const int *devices, int n_devices)
+{
+    if (!out || !devices || n_devices < 1) { g_err = "bad argument"; return CB200_ERR_INVALID; }
+    *out = nullptr;
+    return guard([&] {
+        if (n_devices & (n_devices - 1)) throw InvalidArg("the number of target devices must be a power of two");
+        *out = new cb200_backend{new Backend(std::vector<int>(devices, devices + n_devices))};
+    });
 }
 int cb200_backend_destroy(cb200_backend *b)
 {

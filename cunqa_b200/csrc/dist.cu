@@ -15,8 +15,13 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <array>
+#include <condition_variable>
 #include <cstring>
+#include <exception>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dist_plan.hpp"
@@ -63,8 +68,50 @@ static NcclApi &nccl()
         if (r_ != ncclSuccess) throw CudaError(std::string(#call) + " failed: " + nccl().GetErrorString(r_)); \
     } while (0)
 
+// ---- the shards of one state driven by ONE process -----------------------------------------------------
+// config.device.target_devices = [d0, d1, ...] reaches a backend as a list (/root/reference/src/utils/helpers/
+// net_functions.hpp:198-222, forwarded at AER/aer_helpers.hpp:111-116) and there is one process per vQPU
+// (src/cli/setup_qpus.cpp:69-82): a sharded state behind the plugin must therefore live in that one process.  Every shard
+// is an ordinary sharded State (same planner, same kernels as the one-process-per-GPU mode) run SPMD on its own worker
+// thread bound to its GPU; what differs is the plumbing: peers are reached through cudaDeviceEnablePeerAccess instead of
+// CUDA IPC, exchanges are fenced with cross-device stream events instead of NCCL all-reduces, and the few scalars of a
+// reduction are summed on the host.
+struct GroupAborted : std::runtime_error { GroupAborted() : std::runtime_error("shard group aborted") {} };
+
+class ShardGroup {
+public:
+    ShardGroup(int n, int precision, const std::vector<int> &devices);
+    ~ShardGroup();
+    int world() const { return (int)shards_.size(); }
+    State &shard(int r) { return *shards_[r]; }
+    void each(const std::function<void(int, State &)> &f);
+    // collectives: called by every rank, in the same order, from inside each()
+    void barrier();
+    void fence(int rank, cudaStream_t stream);
+    template <typename W> void allreduce(int rank, W *d_buf, size_t count, cudaStream_t stream);
+
+private:
+    void worker(int rank);
+    std::vector<std::unique_ptr<State>> shards_;
+    std::vector<int> devices_;
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_job_, cv_done_, cv_bar_;
+    const std::function<void(int, State &)> *job_ = nullptr;
+    uint64_t generation_ = 0;
+    int remaining_ = 0;
+    bool stop_ = false, aborted_ = false;
+    std::exception_ptr error_;
+    int bar_count_ = 0;
+    uint64_t bar_gen_ = 0;
+    std::vector<std::array<cudaEvent_t, 2>> events_;   // [rank][fence parity]
+    std::vector<uint64_t> fence_no_;
+    std::vector<std::vector<uint64_t>> host_;          // [rank]: staging of one all-reduce (8-byte words)
+};
+
 struct DistContext {
     int rank = 0, world = 1, gbits = 0;
+    ShardGroup *group = nullptr;   // single-process mode (no NCCL, no IPC)
     ncclComm_t comm = nullptr;
     std::vector<void *> peers;  // shard base pointer of every rank (own entry = local pointer)
     int *d_fence = nullptr;
@@ -147,6 +194,7 @@ void State::dist_collapse_global(int my_bit)
 
 void State::dist_fence()
 {
+    if (dist->group) { dist->group->fence(dist->rank, stream_); return; }
     CB200_NCCL(nccl().AllReduce(dist->d_fence, dist->d_fence, 1, ncclInt, ncclSum, dist->comm, stream_));
     stats.launches++;
 }
@@ -233,21 +281,24 @@ template void State::flush_dist_t<float>();
 
 void State::dist_allreduce_f64(double *d_buf, size_t count)
 {
+    if (dist->group) { dist->group->allreduce<double>(dist->rank, d_buf, count, stream_); return; }
     CB200_NCCL(nccl().AllReduce(d_buf, d_buf, count, ncclDouble, ncclSum, dist->comm, stream_));
     stats.launches++;
 }
 void State::dist_allreduce_u64(uint64_t *d_buf, size_t count)
 {
+    if (dist->group) { dist->group->allreduce<uint64_t>(dist->rank, d_buf, count, stream_); return; }
     CB200_NCCL(nccl().AllReduce(d_buf, d_buf, count, ncclUint64, ncclSum, dist->comm, stream_));
     stats.launches++;
 }
 
-void State::dist_init(int rank, int world, const uint8_t *id)
+void State::dist_init(int rank, int world, const uint8_t *id, ShardGroup *group)
 {
     dist = new DistContext();
     dist->rank = rank;
     dist->world = world;
     while ((1 << dist->gbits) < world) dist->gbits++;
+    if (group) { dist->group = group; return; }   // peers are filled in once every shard exists (ShardGroup ctor)
     ncclUniqueId uid;
     static_assert(sizeof(ncclUniqueId) == CB200_DIST_ID_BYTES, "ncclUniqueId size");
     std::memcpy(&uid, id, sizeof(uid));
@@ -258,9 +309,10 @@ void State::dist_init(int rank, int world, const uint8_t *id)
 
 void State::dist_destroy()
 {
+    if (group_) { delete group_; group_ = nullptr; }
     if (!dist) return;
     for (int r = 0; r < (int)dist->peers.size(); r++)
-        if (r != dist->rank && dist->peers[r]) cudaIpcCloseMemHandle(dist->peers[r]);
+        if (!dist->group && r != dist->rank && dist->peers[r]) cudaIpcCloseMemHandle(dist->peers[r]);
     if (dist->comm) nccl().CommDestroy(dist->comm);
     for (auto &ev : dist->swap_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaFree(dist->d_fence);
@@ -288,12 +340,17 @@ void State::dist_import(const uint8_t *all)
 }
 
 int State::dist_rank() const { return dist ? dist->rank : 0; }
-int State::dist_world() const { return dist ? dist->world : 1; }
-uint64_t State::dist_swaps() const { return dist ? dist->swaps : 0; }
-uint64_t State::dist_swap_bytes() const { return dist ? dist->swap_bytes : 0; }
+int State::dist_world() const { return group_ ? group_->world() : (dist ? dist->world : 1); }
+uint64_t State::dist_swaps() const { return group_ ? group_->shard(0).dist_swaps() : (dist ? dist->swaps : 0); }
+uint64_t State::dist_swap_bytes() const { return group_ ? group_->shard(0).dist_swap_bytes() : (dist ? dist->swap_bytes : 0); }
 // total device time spent in swaps so far (drains the stream)
 double State::dist_swap_ms()
 {
+    if (group_) {
+        double ms = 0.0;
+        group_->each([&](int r, State &sh) { const double v = sh.dist_swap_ms(); if (r == 0) ms = v; });
+        return ms;
+    }
     if (!dist) return 0.0;
     cudaStreamSynchronize(stream_);
     for (auto &ev : dist->swap_events) {
@@ -304,6 +361,224 @@ double State::dist_swap_ms()
     }
     dist->swap_events.clear();
     return dist->swap_ms;
+}
+
+
+// ---- ShardGroup ------------------------------------------------------------------------------------
+ShardGroup::ShardGroup(int n, int precision, const std::vector<int> &devices) : devices_(devices)
+{
+    const int w = (int)devices.size();
+    for (int a = 0; a < w; a++)
+        for (int b = a + 1; b < w; b++)
+            if (devices[a] == devices[b]) throw InvalidArg("target_devices lists a GPU twice");
+    // peer access between every pair of devices (NVLink / NVSwitch)
+    for (int a = 0; a < w; a++) {
+        CB200_CUDA(cudaSetDevice(devices[a]));
+        for (int b = 0; b < w; b++) {
+            if (a == b) continue;
+            int can = 0;
+            CB200_CUDA(cudaDeviceCanAccessPeer(&can, devices[a], devices[b]));
+            if (!can) throw Unsupported("GPUs " + std::to_string(devices[a]) + " and " + std::to_string(devices[b]) + " have no peer access");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CB200_CUDA(e);
+            cudaGetLastError();
+        }
+    }
+    for (int r = 0; r < w; r++) shards_.emplace_back(new State(n, precision, devices[r], r, w, this));
+    for (int r = 0; r < w; r++) {
+        State &sh = *shards_[r];
+        sh.dist->peers.assign(w, nullptr);
+        for (int p = 0; p < w; p++) sh.dist->peers[p] = shards_[p]->device_ptr();
+    }
+    events_.resize(w);
+    fence_no_.assign(w, 0);
+    host_.resize(w);
+    for (int r = 0; r < w; r++) {
+        CB200_CUDA(cudaSetDevice(devices[r]));
+        for (int k = 0; k < 2; k++) CB200_CUDA(cudaEventCreateWithFlags(&events_[r][k], cudaEventDisableTiming));
+    }
+    for (int r = 0; r < w; r++) threads_.emplace_back([this, r] { worker(r); });
+}
+
+ShardGroup::~ShardGroup()
+{
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        stop_ = true;
+    }
+    cv_job_.notify_all();
+    for (std::thread &t : threads_) t.join();
+    shards_.clear();
+    for (size_t r = 0; r < events_.size(); r++) {
+        cudaSetDevice(devices_[r]);
+        for (int k = 0; k < 2; k++) if (events_[r][k]) cudaEventDestroy(events_[r][k]);
+    }
+}
+
+void ShardGroup::worker(int rank)
+{
+    cudaSetDevice(devices_[rank]);
+    uint64_t seen = 0;
+    for (;;) {
+        const std::function<void(int, State &)> *job = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_job_.wait(lk, [&] { return stop_ || generation_ != seen; });
+            if (stop_) return;
+            seen = generation_;
+            job = job_;
+        }
+        try {
+            (*job)(rank, *shards_[rank]);
+        } catch (const GroupAborted &) {
+        } catch (...) {
+            std::lock_guard<std::mutex> lk(m_);
+            if (!error_) error_ = std::current_exception();
+            aborted_ = true;      // ranks waiting in a collective give up instead of waiting for this one
+            cv_bar_.notify_all();
+        }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            if (--remaining_ == 0) cv_done_.notify_all();
+        }
+    }
+}
+
+void ShardGroup::each(const std::function<void(int, State &)> &f)
+{
+    std::unique_lock<std::mutex> lk(m_);
+    job_ = &f;
+    remaining_ = world();
+    generation_++;
+    cv_job_.notify_all();
+    cv_done_.wait(lk, [&] { return remaining_ == 0; });
+    job_ = nullptr;
+    aborted_ = false;
+    bar_count_ = 0;
+    if (error_) {
+        std::exception_ptr e = error_;
+        error_ = nullptr;
+        std::rethrow_exception(e);
+    }
+}
+
+void ShardGroup::barrier()
+{
+    std::unique_lock<std::mutex> lk(m_);
+    if (aborted_) throw GroupAborted();
+    const uint64_t gen = bar_gen_;
+    if (++bar_count_ == world()) {
+        bar_count_ = 0;
+        bar_gen_++;
+        cv_bar_.notify_all();
+        return;
+    }
+    cv_bar_.wait(lk, [&] { return bar_gen_ != gen || aborted_; });
+    if (bar_gen_ == gen) throw GroupAborted();
+}
+
+// every shard's stream waits until every other shard's stream has reached this point.  Two event sets alternate: a rank
+// can re-record set k only after passing the barrier of fence k+1, which every rank reaches after enqueueing its waits
+// on set k.
+void ShardGroup::fence(int rank, cudaStream_t stream)
+{
+    const int k = (int)(fence_no_[rank]++ & 1);
+    CB200_CUDA(cudaEventRecord(events_[rank][k], stream));
+    barrier();
+    for (int p = 0; p < world(); p++)
+        if (p != rank) CB200_CUDA(cudaStreamWaitEvent(stream, events_[p][k], 0));
+}
+
+// sum of `count` scalars over the shards, the same bits on every rank (fixed rank order); host-mediated: these are the
+// handful of doubles of a norm / probability / marginal, or the shot indices of a sample
+template <typename W>
+void ShardGroup::allreduce(int rank, W *d_buf, size_t count, cudaStream_t stream)
+{
+    static_assert(sizeof(W) == 8, "8-byte scalars");
+    host_[rank].resize(count);
+    CB200_CUDA(cudaMemcpyAsync(host_[rank].data(), d_buf, count * sizeof(W), cudaMemcpyDeviceToHost, stream));
+    CB200_CUDA(cudaStreamSynchronize(stream));
+    barrier();
+    std::vector<W> sum(count, W(0));
+    for (int p = 0; p < world(); p++) {
+        const W *src = reinterpret_cast<const W *>(host_[p].data());
+        for (size_t i = 0; i < count; i++) sum[i] += src[i];
+    }
+    barrier();  // nobody overwrites its staging while another rank still reads it
+    CB200_CUDA(cudaMemcpyAsync(d_buf, sum.data(), count * sizeof(W), cudaMemcpyHostToDevice, stream));
+    CB200_CUDA(cudaStreamSynchronize(stream));
+}
+template void ShardGroup::allreduce<double>(int, double *, size_t, cudaStream_t);
+template void ShardGroup::allreduce<uint64_t>(int, uint64_t *, size_t, cudaStream_t);
+
+// ---- the facade State of a single-process group ------------------------------------------------------------
+State::State(int n_qubits, int prec, const std::vector<int> &devices)
+    : n(n_qubits), precision(prec), device(devices.empty() ? 0 : devices[0]), batch(1), queue(std::max(1, n_qubits), 1, PlanOptions())
+{
+    const int w = (int)devices.size();
+    if (w < 2 || (w & (w - 1))) throw InvalidArg("a sharded state needs a power of two (>= 2) of target devices");
+    if (precision != 64 && precision != 32) throw InvalidArg("precision must be 64 or 32");
+    int gbits = 0;
+    while ((1 << gbits) < w) gbits++;
+    if (n - gbits < 12 || n > 62) throw InvalidArg("sharded states need >= 12 local qubits");
+    int count = 0;
+    const cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw CudaError(std::string("no CUDA device available (") + cudaGetErrorString(e) + "); cunqa_b200 has no CPU fallback");
+    for (int d : devices) if (d < 0 || d >= count) throw InvalidArg("device index out of range");
+    init_options(gbits);
+    try { group_ = new ShardGroup(n, precision, devices); }
+    catch (...) { release(); throw; }
+    reset();
+}
+
+void State::group_each_rank(const std::function<void(int, State &)> &f) { group_->each(f); }
+void State::group_each(const std::function<void(State &)> &f) { group_->each([&](int, State &sh) { f(sh); }); }
+int State::group_world() const { return group_ ? group_->world() : 1; }
+std::vector<int> State::group_l2p() { return group_->shard(0).queue.l2p; }
+cudaStream_t State::group_stream0() const { return group_->shard(0).stream(); }
+
+void State::facade_sync_stats()
+{
+    const Stats &s0 = group_->shard(0).stats;
+    stats = s0;
+}
+
+// gates were queued and fused ONCE on the facade; every shard plans its own segments of the fused list (dist_plan.cpp)
+// and runs them, exchanges in lockstep
+void State::facade_flush()
+{
+    if (queue.pending() == 0 && !pending_init_) return;
+    const std::vector<HostOp> &ops = queue.ops();
+    group_->each([&](int, State &sh) {
+        sh.queue.l2p = queue.l2p;
+        sh.queue.basis = queue.basis;
+        sh.queue.ops() = ops;
+        sh.queue.mask_rows.clear();
+        sh.flush();
+    });
+    queue.l2p = group_->shard(0).queue.l2p;
+    queue.clear_pending();
+    queue.fresh = false;
+    pending_init_ = false;
+    facade_sync_stats();
+}
+
+// a global qubit becomes local: one pairwise exchange with the highest local position (SPMD: every rank calls it)
+void State::localize(int qubit)
+{
+    if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
+    if (group_) { flush(); group_each([&](State &sh) { sh.localize(qubit); }); queue.l2p = group_l2p(); facade_sync_stats(); return; }
+    if (!dist) return;
+    flush();
+    const int pq = queue.l2p[qubit];
+    if (pq < n_local_) return;
+    const int victim = n_local_ - 1;
+    dist_swap({{pq - n_local_, victim}});
+    for (int &p : queue.l2p) {
+        if (p == victim) p = pq;
+        else if (p == pq) p = victim;
+    }
 }
 
 }  // namespace cb200

@@ -32,7 +32,31 @@ State::State(int n_qubits, int prec, int dev, int nbatch, int rank, int world, c
     catch (...) { release(); throw; }
 }
 
-void State::construct(int rank, int world, const uint8_t *nccl_id)
+State::State(int n_qubits, int prec, int dev, int rank, int world, ShardGroup *group)
+    : n(n_qubits), precision(prec), device(dev), batch(1), queue(std::max(1, n_qubits), 1, PlanOptions())
+{
+    try { construct(rank, world, nullptr, group); }
+    catch (...) { release(); throw; }
+}
+
+void State::init_options(int gbits)
+{
+    n_local_ = n - gbits;
+    amp_bytes_ = precision == 64 ? 16 : 8;
+    state_bytes_ = amp_bytes_ * ((size_t)batch << n_local_);
+    opt.tile_bits = env_int("CB200_TILE_BITS", precision == 64 ? 11 : 13);
+    opt.min_run_bits = env_int("CB200_MIN_RUN_BITS", precision == 64 ? 4 : 5);
+    opt.max_pass_cost = env_int("CB200_MAX_PASS_COST", 0);
+    opt.lookahead = env_int("CB200_LOOKAHEAD", 256);
+    opt.lookahead_min_qubits = env_int("CB200_LOOKAHEAD_MIN_QUBITS", 24);
+    opt.max_diag_qubits = env_int("CB200_MAX_DIAG_QUBITS", 10);
+    opt.fuse = env_int("CB200_FUSE", 1) != 0;
+    opt.pair_ops = env_int("CB200_PAIR_OPS", 1) != 0;
+    if (gbits) opt.global_mask = ((1ull << gbits) - 1ull) << n_local_;
+    queue = OpQueue(n, batch, opt);
+}
+
+void State::construct(int rank, int world, const uint8_t *nccl_id, ShardGroup *group)
 {
     int gbits = 0;
     while ((1 << gbits) < world) gbits++;
@@ -59,32 +83,23 @@ void State::construct(int rank, int world, const uint8_t *nccl_id)
     tma_refill_after_ = env_int("CB200_TMA_REFILL_AFTER", 0);
     tma_max_ctas_ = env_int("CB200_TMA_MAX_CTAS", 0);
     tma_stages_ = env_int("CB200_TMA_STAGES", 2) == 3 ? 3 : 2;
-    n_local_ = n - gbits;
-    amp_bytes_ = precision == 64 ? 16 : 8;
-    state_bytes_ = amp_bytes_ * ((size_t)batch << n_local_);
-    opt.tile_bits = env_int("CB200_TILE_BITS", precision == 64 ? 11 : 13);
-    opt.min_run_bits = env_int("CB200_MIN_RUN_BITS", precision == 64 ? 4 : 5);
-    opt.max_pass_cost = env_int("CB200_MAX_PASS_COST", 0);
-    opt.lookahead = env_int("CB200_LOOKAHEAD", 256);
-    opt.lookahead_min_qubits = env_int("CB200_LOOKAHEAD_MIN_QUBITS", 24);
-    opt.max_diag_qubits = env_int("CB200_MAX_DIAG_QUBITS", 10);
-    opt.fuse = env_int("CB200_FUSE", 1) != 0;
-    opt.pair_ops = env_int("CB200_PAIR_OPS", 1) != 0;
-    if (gbits) opt.global_mask = ((1ull << gbits) - 1ull) << n_local_;
+    init_options(gbits);
     ctas_per_sm_ = env_int("CB200_CTAS_PER_SM", 0);
     use_tma_ = env_int("CB200_USE_TMA", 1) != 0;
-    queue = OpQueue(n, batch, opt);
     CB200_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CB200_CUDA(cudaMalloc(&d_state_, state_bytes_));
     CB200_CUDA(cudaMalloc(&d_small_, sizeof(double) * (4 * batch + 64)));
     CB200_CUDA(cudaMalloc(&d_outcome_, sizeof(int) * batch));
     CB200_CUDA(cudaMalloc(&d_counters_, sizeof(uint64_t) * batch));
     CB200_CUDA(cudaMalloc(&d_forced_, sizeof(int8_t) * batch));
-    if (world > 1) dist_init(rank, world, nccl_id);
+    if (world > 1) dist_init(rank, world, nccl_id, group);
+    member_of_ = group;
     reset();
 }
 
 State::~State() { release(); }
+
+cudaStream_t State::stream() const { return group_ ? group_stream0() : stream_; }
 
 void State::release()
 {
@@ -111,6 +126,7 @@ void State::release()
 
 void State::reset()
 {
+    if (group_) { queue.reset(); pending_init_ = true; group_each([](State &sh) { sh.reset(); }); return; }
     queue.reset();
     for (OpQueue &q : regq_) { q.reset(); q.fresh = false; }
     pending_init_ = true;  // the write happens at the next flush, once the initial basis state is known
@@ -143,7 +159,7 @@ void State::stage_commit()
 
 void State::use_registers(bool on)
 {
-    if (dist && on) throw Unsupported("independent registers on a sharded state");
+    if ((dist || group_) && on) throw Unsupported("independent registers on a sharded state");
     if (on == registers()) return;
     regq_.clear();
     if (on) {
@@ -522,6 +538,7 @@ template void State::launch_uniform_t<float>(int, int);
 
 void State::flush()
 {
+    if (group_) { facade_flush(); return; }
     ensure_init();
     if (dist) {
         if (precision == 64) flush_dist_t<double>();
@@ -540,6 +557,7 @@ void State::flush()
 void State::sync()
 {
     flush();
+    if (group_) { group_each([](State &sh) { sh.sync(); }); facade_sync_stats(); return; }
     CB200_CUDA(cudaSetDevice(device));
     CB200_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -581,6 +599,7 @@ void State::reduce2_t(uint64_t sel_mask, double *d_all, double *d_sel)
 
 void State::norm(double *out)
 {
+    if (group_) { group_out<double>(1, out, [&](State &sh, double *o) { sh.norm(o); }); return; }
     flush();
     if (precision == 64) reduce2_t<double>(0, d_small_, nullptr); else reduce2_t<float>(0, d_small_, nullptr);
     if (dist) dist_allreduce_f64(d_small_, 1);
@@ -593,6 +612,7 @@ void State::prob1(int qubit, double *out)
 {
     if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
     if (registers()) throw Unsupported("prob1 over the whole batch is not defined for independent registers");
+    if (group_) { group_out<double>(1, out, [&](State &sh, double *o) { sh.prob1(qubit, o); }); return; }
     flush();
     const int pq1 = queue.l2p[qubit];
     uint64_t sel = 1ull << pq1;
@@ -612,7 +632,8 @@ void State::reduced_qubit(int qubit, double out[4], int b)
 {
     if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
     if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
-    if (dist) throw Unsupported("reduced density matrix of a sharded state is not implemented");
+    if (group_) { group_out<double>(4, out, [&](State &sh, double *o) { sh.reduced_qubit(qubit, o, b); }); queue.l2p = group_l2p(); return; }
+    if (dist) localize(qubit);  // rho01 pairs amplitudes that differ in this qubit: bring it into the shard first
     flush();
     const int pq = (regq_.empty() ? queue : regq_[b]).l2p[qubit];
     const uint64_t amps = 1ull << n_local_;
@@ -624,6 +645,7 @@ void State::reduced_qubit(int qubit, double out[4], int b)
     else rho_partial_kernel<float2><<<grid, kRedThreads, 0, stream_>>>((const float2 *)d_state_ + ((size_t)b << n_local_), amps, pq, d_partial_, (size_t)nblk);
     for (int k = 0; k < 4; k++) sum_partials_kernel<<<1, kRedThreads, 0, stream_>>>(d_partial_ + (size_t)k * nblk, nblk, d_small_ + k);
     CB200_CUDA(cudaGetLastError());
+    if (dist) dist_allreduce_f64(d_small_, 4);
     stats.launches += 5;
     stats.bytes += state_bytes_ / (uint64_t)batch;
     CB200_CUDA(cudaMemcpyAsync(out, d_small_, sizeof(double) * 4, cudaMemcpyDeviceToHost, stream_));
@@ -635,6 +657,16 @@ void State::measure(int qubit, uint64_t seed, const uint64_t *counters, const in
 {
     if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
     if (registers()) throw Unsupported("batch-wide measurement is not defined for independent registers");
+    if (group_) {
+        flush();
+        const bool global = queue.l2p[qubit] >= n_local_;
+        int bit = 0;
+        group_out<int>(1, &bit, [&](State &sh, int *o) { sh.measure(qubit, seed, counters, forced, o, reset_after); });
+        if (bits_out) bits_out[0] = bit;
+        // reset of a global qubit that read 1: the kept shards sit on the ranks with that bit set; an X moves them
+        if (global && reset_after && bit == 1) apply_named("x", &qubit, 1, nullptr, 0, nullptr);
+        return;
+    }
     if (dist) {
         // Sharded state: norm and P(q=1) are local reductions + one all-reduce each (every rank then holds the same
         // two doubles and draws the same outcome from the shared counter stream); a local qubit collapses inside the
@@ -670,7 +702,7 @@ void State::measure(int qubit, uint64_t seed, const uint64_t *counters, const in
         if (bits_out) bits_out[0] = out;
         // reset of a global qubit that read 1: the kept shards sit on the ranks with that bit set; an X moves them
         // (queued like any other gate -- it brings the qubit in with one exchange when it is next flushed)
-        if (global && reset_after && out == 1) apply_named("x", &qubit, 1, nullptr, 0, nullptr);
+        if (global && reset_after && out == 1 && !member_of_) apply_named("x", &qubit, 1, nullptr, 0, nullptr);  // (a group's facade queues it)
         return;
     }
     flush();
@@ -714,9 +746,10 @@ void State::measure(int qubit, uint64_t seed, const uint64_t *counters, const in
     stats.d2h_bytes += sizeof(int) * batch;
 }
 
-void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out)
+void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out, uint64_t ctr0)
 {
     if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
+    if (group_) { group_out<uint64_t>(shots, out, [&](State &sh, uint64_t *o) { sh.sample(b, shots, seed, o, ctr0); }); return; }
     flush();
     const int nl = n_local_;
     const int bits0 = std::min(nl, kChunkBits);
@@ -755,13 +788,13 @@ void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out)
         chunk_sums_amp_kernel<double2><<<g1, kRedThreads, 0, stream_>>>(st, bits0, n1, d_lvl1_);
         chunk_sums_f64_kernel<<<g2, kRedThreads, 0, stream_>>>(d_lvl1_, bits1, n2, d_lvl2_);
         top_prefix_kernel<<<1, 32, 0, stream_>>>(d_lvl2_, n2);
-        if (shots) sample_kernel<double2><<<std::max(sblocks, 1), kRedThreads, 0, stream_>>>(st, nl, bits0, bits1, d_lvl1_, d_lvl2_, n2, shots, seed, d_out, total_all, off_lo, off_hi, prefix);
+        if (shots) sample_kernel<double2><<<std::max(sblocks, 1), kRedThreads, 0, stream_>>>(st, nl, bits0, bits1, d_lvl1_, d_lvl2_, n2, shots, seed, d_out, total_all, off_lo, off_hi, prefix, ctr0);
     } else {
         const float2 *st = (const float2 *)d_state_ + ((size_t)b << nl);
         chunk_sums_amp_kernel<float2><<<g1, kRedThreads, 0, stream_>>>(st, bits0, n1, d_lvl1_);
         chunk_sums_f64_kernel<<<g2, kRedThreads, 0, stream_>>>(d_lvl1_, bits1, n2, d_lvl2_);
         top_prefix_kernel<<<1, 32, 0, stream_>>>(d_lvl2_, n2);
-        if (shots) sample_kernel<float2><<<std::max(sblocks, 1), kRedThreads, 0, stream_>>>(st, nl, bits0, bits1, d_lvl1_, d_lvl2_, n2, shots, seed, d_out, total_all, off_lo, off_hi, prefix);
+        if (shots) sample_kernel<float2><<<std::max(sblocks, 1), kRedThreads, 0, stream_>>>(st, nl, bits0, bits1, d_lvl1_, d_lvl2_, n2, shots, seed, d_out, total_all, off_lo, off_hi, prefix, ctr0);
     }
     cudaError_t e = cudaGetLastError();
     stats.launches += 4;
@@ -778,6 +811,7 @@ void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out)
 
 void State::broadcast_state0()
 {
+    if (group_) { flush(); return; }
     flush();
     if (batch == 1) return;
     const uint64_t amps = 1ull << n_local_, total = (uint64_t)batch << n_local_;
@@ -791,7 +825,10 @@ void State::broadcast_state0()
 
 void State::sample_each(uint64_t seed, const uint64_t *counters, uint64_t *out)
 {
-    if (dist) throw Unsupported("sample_each on a sharded state is not implemented");
+    if (group_ || dist) {   // one state: a single draw with the caller's counter
+        sample(0, 1, seed, out, counters[0]);
+        return;
+    }
     if (registers()) throw Unsupported("sample_each is not defined for independent registers (use sample_registers)");
     flush();
     const int nl = n_local_;
@@ -883,6 +920,7 @@ void State::sample_registers(uint64_t shots, const uint64_t *seeds, uint64_t *ou
 void State::get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out)
 {
     if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
+    if (group_) { group_out<double>(2 * cnt, out, [&](State &sh, double *o) { sh.get_amplitudes(b, idx, cnt, o); }); return; }
     flush();
     if (cnt == 0) return;
     std::vector<uint64_t> phys(cnt);
@@ -929,13 +967,17 @@ void State::get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out
 void State::set_amplitudes(int b, const double *in)
 {
     if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
-    if (dist) throw Unsupported("set_amplitudes on a sharded state is not implemented");
+    if (group_) { flush(); group_each([&](State &sh) { sh.set_amplitudes(b, in); }); return; }
     flush();
     CB200_CUDA(cudaStreamSynchronize(stream_));
-    const uint64_t dim = 1ull << n;
-    // logical -> physical layout on the host, then one upload
+    const uint64_t dim = 1ull << n_local_;
+    // logical -> physical layout on the host (a sharded state keeps the slice whose global bits are this rank's), one upload
     std::vector<double2> host(dim);
-    for (uint64_t i = 0; i < dim; i++) host[qof(b).phys_index(i)] = make_double2(in[2 * i], in[2 * i + 1]);
+    const uint64_t full = 1ull << n, mine = (uint64_t)dist_rank();
+    for (uint64_t i = 0; i < full; i++) {
+        const uint64_t p = qof(b).phys_index(i);
+        if ((p >> n_local_) == mine) host[p & (dim - 1)] = make_double2(in[2 * i], in[2 * i + 1]);
+    }
     double2 *d_in = nullptr;
     CB200_CUDA(cudaMalloc(&d_in, dim * sizeof(double2)));
     cudaError_t e = cudaMemcpyAsync(d_in, host.data(), dim * sizeof(double2), cudaMemcpyHostToDevice, stream_);
@@ -956,24 +998,34 @@ void State::probabilities(int b, const int *qubits, int k, double *out)
 {
     if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
     if (k < 1 || k > 20) throw InvalidArg("marginal over 1..20 qubits");
-    if (dist) throw Unsupported("marginals of a sharded state are not implemented");
+    if (group_) { group_out<double>((size_t)1 << k, out, [&](State &sh, double *o) { sh.probabilities(b, qubits, k, o); }); return; }
     flush();
-    std::vector<int> pq(k);
     for (int i = 0; i < k; i++) if (qubits[i] < 0 || qubits[i] >= n) throw InvalidArg("qubit out of range");
-    for (int i = 0; i < k; i++) pq[i] = qof(b).l2p[qubits[i]];
+    // local qubits of the list are reduced over the shard; global ones are constant here (the rank's bits)
+    std::vector<int> pq, ob;
+    uint32_t fixed = 0;
+    for (int i = 0; i < k; i++) {
+        const int p = qof(b).l2p[qubits[i]];
+        if (p < n_local_) { pq.push_back(p); ob.push_back(i); }
+        else if ((dist_rank() >> (p - n_local_)) & 1) fixed |= 1u << i;
+    }
+    const int kl = (int)pq.size();
+    pq.insert(pq.end(), ob.begin(), ob.end());  // one upload: positions, then output bits
+    pq.resize(2 * (size_t)k + 2, 0);
     int *d_q = nullptr; double *d_o = nullptr;
-    CB200_CUDA(cudaMalloc(&d_q, k * sizeof(int)));
+    CB200_CUDA(cudaMalloc(&d_q, pq.size() * sizeof(int)));
     cudaError_t e = cudaMalloc(&d_o, sizeof(double) << k);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, pq.data(), k * sizeof(int), cudaMemcpyHostToDevice, stream_);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, pq.data(), pq.size() * sizeof(int), cudaMemcpyHostToDevice, stream_);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_o, 0, sizeof(double) << k, stream_);
     if (e == cudaSuccess) {
         const uint64_t amps = 1ull << n_local_;
         const int blocks = (int)std::min<uint64_t>((amps + 255) / 256, (uint64_t)num_sms_ * 16);
-        if (precision == 64) marginal_kernel<double2><<<blocks, 256, 0, stream_>>>((const double2 *)d_state_ + ((size_t)b << n_local_), amps, d_q, k, d_o);
-        else marginal_kernel<float2><<<blocks, 256, 0, stream_>>>((const float2 *)d_state_ + ((size_t)b << n_local_), amps, d_q, k, d_o);
+        if (precision == 64) marginal_kernel<double2><<<blocks, 256, 0, stream_>>>((const double2 *)d_state_ + ((size_t)b << n_local_), amps, d_q, kl, d_o, d_q + kl, fixed);
+        else marginal_kernel<float2><<<blocks, 256, 0, stream_>>>((const float2 *)d_state_ + ((size_t)b << n_local_), amps, d_q, kl, d_o, d_q + kl, fixed);
         e = cudaGetLastError();
         stats.launches++;
     }
+    if (e == cudaSuccess && dist) dist_allreduce_f64(d_o, (size_t)1 << k);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, sizeof(double) << k, cudaMemcpyDeviceToHost, stream_);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
     cudaFree(d_q); cudaFree(d_o);

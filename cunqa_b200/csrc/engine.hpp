@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <functional>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -34,12 +36,19 @@ struct Stats {
 };
 
 struct DistContext;  // dist.cu
+class ShardGroup;    // dist.cu: the shards of one state driven by ONE process (one worker thread per GPU)
 
 class State {
 public:
     State(int n_qubits, int precision, int device, int batch);
     // sharded over `world` ranks (one process per GPU): n_qubits is the TOTAL width
     State(int n_qubits, int precision, int device, int batch, int rank, int world, const uint8_t *nccl_id);
+    // ONE process, several GPUs (config.device.target_devices = [d0, d1, ...], a power of two of them): this object is a
+    // facade that owns one shard State per device; gates are queued and fused here once, every other call is forwarded to
+    // the shards (SPMD on worker threads; peer access instead of IPC, stream events instead of NCCL fences)
+    State(int n_qubits, int precision, const std::vector<int> &devices);
+    // shard of a single-process group (constructed by ShardGroup)
+    State(int n_qubits, int precision, int device, int rank, int world, ShardGroup *group);
     ~State();
     State(const State &) = delete;
     State &operator=(const State &) = delete;
@@ -61,7 +70,8 @@ public:
     void reduced_qubit(int qubit, double out[4], int b = 0);
     void probabilities(int b, const int *qubits, int k, double *out);
     void measure(int qubit, uint64_t seed, const uint64_t *counters, const int8_t *forced, int *bits_out, bool reset_after);
-    void sample(int b, uint64_t shots, uint64_t seed, uint64_t *out);
+    // u_s = U(seed, ctr0 + s) * norm
+    void sample(int b, uint64_t shots, uint64_t seed, uint64_t *out, uint64_t ctr0 = 0);
     // one sample per state of the batch, draw U(seed, counters[b]) (terminal measurement of dynamic shots)
     void sample_each(uint64_t seed, const uint64_t *counters, uint64_t *out);
     void broadcast_state0();  // states 1..batch-1 := state 0
@@ -89,7 +99,7 @@ public:
     int n_local() const { return n_local_; }
     void *device_ptr() { return d_state_; }
     size_t state_bytes() const { return state_bytes_; }
-    cudaStream_t stream() const { return stream_; }
+    cudaStream_t stream() const;
 
     // ---- sharded mode (dist.cu)
     void dist_export(uint8_t *handle_out);
@@ -99,11 +109,20 @@ public:
     uint64_t dist_swaps() const;
     uint64_t dist_swap_bytes() const;
     double dist_swap_ms();
+    bool is_facade() const { return group_ != nullptr; }
+    bool sharded() const { return dist != nullptr || group_ != nullptr; }
+    // bring a global qubit into the shard (one pairwise exchange with the highest free local position)
+    void localize(int qubit);
 
 private:
-    void construct(int rank, int world, const uint8_t *nccl_id);
+    friend class ShardGroup;
+    ShardGroup *group_ = nullptr;         // facade only (owned; destroyed in dist_destroy)
+    ShardGroup *member_of_ = nullptr;     // shard of a single-process group
+    void init_options(int gbits);
+    template <typename T, typename F> void group_out(size_t count, T *out, F f);
+    void construct(int rank, int world, const uint8_t *nccl_id, ShardGroup *group = nullptr);
     void release();  // frees every device resource (also used when construction fails half-way)
-    void dist_init(int rank, int world, const uint8_t *id);
+    void dist_init(int rank, int world, const uint8_t *id, ShardGroup *group);
     void dist_destroy();
     void dist_fence();
     void dist_swap(const std::vector<std::pair<int, int>> &pairs);
@@ -130,6 +149,13 @@ private:
     void ensure_scratch(size_t partial_doubles);
     void ensure_init();        // lazily writes the initial basis state (reset() only marks it)
     bool pending_init_ = true;
+    void facade_flush();
+    void facade_sync_stats();
+    void group_each(const std::function<void(State &)> &f);
+    void group_each_rank(const std::function<void(int, State &)> &f);
+    int group_world() const;
+    std::vector<int> group_l2p();
+    cudaStream_t group_stream0() const;
     void maybe_flush() { if (regq_.empty() && queue.pending() >= 4096) flush(); }
 
     int n_local_;
@@ -155,5 +181,16 @@ private:
     uint64_t *d_counters_ = nullptr; int8_t *d_forced_ = nullptr;
     double *d_lvl1_ = nullptr, *d_lvl2_ = nullptr; size_t lvl1_cap_ = 0, lvl2_cap_ = 0;
 };
+
+// facade: run f(shard, out_r) on every shard; rank 0 writes the caller's buffer (every rank computes the same values)
+template <typename T, typename F>
+void State::group_out(size_t count, T *out, F f)
+{
+    const int w = group_world();
+    std::vector<std::vector<T>> tmp((size_t)w);
+    for (int r = 1; r < w; r++) tmp[r].resize(count > 0 ? count : 1);
+    group_each_rank([&](int r, State &sh) { f(sh, r == 0 ? out : tmp[r].data()); });
+    facade_sync_stats();
+}
 
 }  // namespace cb200

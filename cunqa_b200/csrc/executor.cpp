@@ -137,6 +137,7 @@ struct TaskCfg {
     bool defer_measurement = true;
     int fusion_enable = -1, fusion_max_qubit = -1;  // -1 = the engine's default
     int max_batch = 0;
+    int shard_min_qubits = 30;      // with several target devices: registers at least this wide are sharded over them
 };
 
 // config keys honoured (cf. quantum_task_to_AER, aer_helpers.hpp:93-140)
@@ -175,6 +176,7 @@ TaskCfg parse_task(const Json &t)
     if (cfg.contains("b200_terminal_sampling")) c.terminal_sampling = cfg.at("b200_terminal_sampling").as_bool();
     if (cfg.contains("b200_defer_measurement")) c.defer_measurement = cfg.at("b200_defer_measurement").as_bool();
     if (cfg.contains("b200_max_batch")) c.max_batch = (int)cfg.at("b200_max_batch").as_int();
+    if (cfg.contains("b200_shard_min_qubits")) c.shard_min_qubits = (int)cfg.at("b200_shard_min_qubits").as_int();
     c.is_dynamic = t.contains("is_dynamic") ? t.at("is_dynamic").as_bool() : false;
     if (const Json *s = t.find("sending_to"))
         for (const Json &v : s->arr) c.sending_to.push_back(v.as_string());
@@ -227,14 +229,24 @@ bool cif_op(const std::string &op, bool a, bool b)
 
 }  // namespace
 
-State &Backend::get_state(int n, int precision, int batch)
+bool Backend::shards(int n, int shard_min_qubits) const
 {
-    if (state_ && state_->n == n && state_->precision == precision && state_->batch == batch) {
+    const int w = (int)devices_.size();
+    if (w < 2 || (w & (w - 1))) return false;
+    int g = 0;
+    while ((1 << g) < w) g++;
+    return n >= shard_min_qubits && n - g >= 12;
+}
+
+State &Backend::get_state(int n, int precision, int batch, bool shard)
+{
+    if (state_ && state_->n == n && state_->precision == precision && state_->batch == batch && state_->is_facade() == shard) {
         state_->reset();
         return *state_;
     }
     state_.reset();
-    state_.reset(new State(n, precision, device_, batch));
+    if (shard) state_.reset(new State(n, precision, devices_));   // one state over all target devices (dist.cu: ShardGroup)
+    else state_.reset(new State(n, precision, device_, batch));
     return *state_;
 }
 
@@ -362,7 +374,7 @@ Json Backend::run_static_parsed(const void *parsed_task)
     const auto t_in = std::chrono::high_resolution_clock::now();
     const TaskCfg &c = *static_cast<const TaskCfg *>(parsed_task);
     const auto t0 = std::chrono::high_resolution_clock::now();
-    State &st = get_state(c.num_qubits, c.precision, 1);
+    State &st = get_state(c.num_qubits, c.precision, 1, shards(c.num_qubits, c.shard_min_qubits));
     apply_fusion_cfg(st, c);
     const Stats before = st.stats;
     const uint64_t gates_before = st.queue.gates;
@@ -616,6 +628,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json, RegJob *job)
         if (c0.max_batch > 0) cap = std::min<uint64_t>(cap, (uint64_t)c0.max_batch);
         B = std::max<uint64_t>(1, std::min(B, cap));
         if (external_cc) B = 1;
+        if (!job && shards(n_total, c0.shard_min_qubits)) B = 1;   // a sharded register holds one state: shots run one by one
     }
 
     const auto t0 = std::chrono::high_resolution_clock::now();
@@ -1130,7 +1143,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json, RegJob *job)
     // first choice: defer every measurement (one state, all shots from one final sample)
     bool done = false;
     if (shots > 0 && c0.defer_measurement && !external_cc && n_total + (int)kSym <= (int)kNotSym) {  // (symbol encoding: <= 62 qubits)
-        State &s1 = get_state(n_total, precision, 1);
+        State &s1 = get_state(n_total, precision, 1, shards(n_total, c0.shard_min_qubits));
         apply_fusion_cfg(s1, c0);
         const Stats b1 = s1.stats;
         const uint64_t g1 = s1.queue.gates;
@@ -1156,7 +1169,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json, RegJob *job)
         }
     }
     if (!done) {
-        stp = shots ? &get_state(n_total, precision, (int)B) : nullptr;
+        stp = shots ? &get_state(n_total, precision, (int)B, shards(n_total, c0.shard_min_qubits)) : nullptr;
         if (stp) { apply_fusion_cfg(*stp, c0); before = stp->stats; gates_before = stp->queue.gates; }
         for (uint64_t shot0 = 0; shot0 < shots; shot0 += B) {
             if (shot0 > 0) stp->reset();

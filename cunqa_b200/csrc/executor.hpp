@@ -20,7 +20,10 @@ typedef int (*recv_fn)(void *user, const char *origin);
 
 class Backend {
 public:
-    explicit Backend(int device) : device_(device) {}
+    explicit Backend(int device) : device_(device), devices_{device} {}
+    // several GPUs of one box (config.device.target_devices, net_functions.hpp:198-222): registers of at least
+    // `b200_shard_min_qubits` qubits (default 30) are sharded over all of them, smaller ones run on the first
+    explicit Backend(const std::vector<int> &devices) : device_(devices.empty() ? 0 : devices[0]), devices_(devices) {}
     // returns the result JSON text (never throws: failures become {"ERROR": "..."} )
     std::string execute(const std::string &tasks_json);
     // n independent messages (each what execute() accepts: a task, a JSON array of tasks = one quantum-communication
@@ -39,7 +42,9 @@ private:
     Json run_static(const Json &task);
     struct RegJob;  // one register of a batched run (executor.cpp)
     Json run_dynamic(const std::vector<Json> &tasks, RegJob *job = nullptr);
-    State &get_state(int n, int precision, int batch);
+    State &get_state(int n, int precision, int batch, bool shard = false);
+    bool shards(int n, int shard_min_qubits) const;
+    std::vector<int> devices_;
     std::unique_ptr<State> batch_state_;      // execute_many: the registers
     std::vector<Json> cached_many_;           // execute_many: last full message per slot
 

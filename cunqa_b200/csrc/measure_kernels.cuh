@@ -270,7 +270,7 @@ template <typename V>
 __global__ void __launch_bounds__(kRedThreads)
 sample_kernel(const V *__restrict__ state, int n, int bits0, int bits1, const double *__restrict__ lvl1,
               const double *__restrict__ lvl2_prefix, uint64_t n2, uint64_t shots, uint64_t seed, uint64_t *__restrict__ out,
-              double total_all, double off_lo, double off_hi, uint64_t index_prefix)
+              double total_all, double off_lo, double off_hi, uint64_t index_prefix, uint64_t ctr0)
 {
     // sharded state: total_all = norm of the whole state, this shard owns the CDF interval [off_lo, off_hi) and
     // writes 0 for shots that fall elsewhere (an all-reduce sums the ranks' answers); single GPU: total_all < 0
@@ -278,7 +278,7 @@ sample_kernel(const V *__restrict__ state, int n, int bits0, int bits1, const do
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t s = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); s < shots; s += warps) {
         const double total = total_all < 0.0 ? lvl2_prefix[n2 - 1] : total_all;
-        double u = splitmix_uniform(seed, s) * total;
+        double u = splitmix_uniform(seed, ctr0 + s) * total;
         if (total_all >= 0.0) {
             if (!(u >= off_lo && u < off_hi)) { if (lane == 0) out[s] = 0; continue; }
             u -= off_lo;
@@ -372,12 +372,15 @@ __global__ void scatter_amps_kernel(V *__restrict__ state, const double2 *__rest
 
 // marginal distribution over k qubits: out[2^k] += |a|^2 (global atomics; diagnostics path)
 template <typename V>
-__global__ void marginal_kernel(const V *__restrict__ state, uint64_t amps, const int *__restrict__ qubits, int k, double *__restrict__ out)
+__global__ void marginal_kernel(const V *__restrict__ state, uint64_t amps, const int *__restrict__ qubits, int k, double *__restrict__ out,
+                                const int *__restrict__ outbit = nullptr, uint32_t fixed = 0)
 {
+    // outbit[m]: position of qubits[m] in the output index (default m); fixed: output bits that are constant for this
+    // shard (marginal qubits that are global: their value is the rank's bit)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < amps; i += stride) {
-        uint32_t j = 0;
-        for (int m = 0; m < k; m++) j |= (uint32_t)((i >> qubits[m]) & 1ull) << m;
+        uint32_t j = fixed;
+        for (int m = 0; m < k; m++) j |= (uint32_t)((i >> qubits[m]) & 1ull) << (outbit ? outbit[m] : m);
         atomicAdd(&out[j], abs2(state[i]));
     }
 }

@@ -30,13 +30,19 @@ public:
     cb200_backend* get(const JSON& task_config)
     {
         if (!handle_) {
-            int device = 0;
+            // the whole list is handed over: with 2^g GPUs, registers of >= `b200_shard_min_qubits` qubits are sharded over
+            // all of them inside the library (cb200_backend_create_multi), smaller ones run on the first
+            std::vector<int> devices;
             if (task_config.contains("device") && task_config.at("device").contains("target_devices")) {
                 const auto& devs = task_config.at("device").at("target_devices");
-                if (devs.is_array() && !devs.empty()) device = devs.at(0).get<int>();
+                if (devs.is_array())
+                    for (const auto& d : devs) devices.push_back(d.get<int>());
             }
-            if (cb200_backend_create(&handle_, device) != CB200_OK)
-                throw std::runtime_error(std::string("B200 backend: ") + cb200_last_error());
+            if (devices.empty()) devices.push_back(0);
+            const bool pow2 = (devices.size() & (devices.size() - 1)) == 0;
+            const int rc = devices.size() > 1 && pow2 ? cb200_backend_create_multi(&handle_, devices.data(), (int)devices.size())
+                                                      : cb200_backend_create(&handle_, devices.front());
+            if (rc != CB200_OK) throw std::runtime_error(std::string("B200 backend: ") + cb200_last_error());
         }
         return handle_;
     }

@@ -161,7 +161,20 @@ int cb200_backend_last_mode(const cb200_backend *b, int *mode_out);
 /* stream of the backend's current state (NULL before the first execute) */
 void *cb200_backend_stream(cb200_backend *b);
 
-/* ---- sharded state across the GPUs of one box (no reference analogue) -------------
+/* ---- sharded state across the GPUs of one box, ONE process (what the plugin uses) -------------------
+ * The reference hands a backend its devices as config.device = {"device_name":"GPU","target_devices":[...]}
+ * (/root/reference/src/utils/helpers/net_functions.hpp:198-222, forwarded at AER/aer_helpers.hpp:111-116) and runs one
+ * process per vQPU (src/cli/setup_qpus.cpp:69-82).  cb200_backend_create_multi is the backend for such a list: registers
+ * of at least `b200_shard_min_qubits` (config key, default 30) qubits are sharded over all listed GPUs -- top
+ * log2(n_devices) qubits global, exchanges over NVLink peer memory (cudaDeviceEnablePeerAccess), one worker thread per
+ * GPU inside the library, no NCCL / IPC / rendezvous -- and everything cb200_backend_execute accepts works on them
+ * (static and dynamic tasks, {"params"} updates, amplitude / marginal return); smaller registers run on devices[0].
+ * cb200_state_create_sharded gives the same sharded register to the state-level calls (every entry point of the
+ * "state lifecycle", "gate application" and "measurement" sections, plus cb200_dist_stats). */
+int cb200_backend_create_multi(cb200_backend **out, const int *devices, int n_devices);
+int cb200_state_create_sharded(cb200_state **out, int n_qubits, int precision, const int *devices, int n_devices);
+
+/* ---- sharded state, one PROCESS per GPU (no reference analogue) -------------
  * One process per GPU.  The top log2(world) qubits are global (index bits select the rank).
  * Rendezvous is done by the caller (torch.distributed / MPI): rank 0 obtains an id blob with
  * cb200_dist_unique_id, broadcasts it, every rank calls cb200_state_create_dist.
