@@ -548,7 +548,12 @@ void State::facade_sync_stats()
 // and runs them, exchanges in lockstep
 void State::facade_flush()
 {
-    if (queue.pending() == 0 && !pending_init_) return;
+    if (queue.pending() == 0 && !pending_init_) {
+        // nothing to run, but uncontrolled SWAPs may have relabelled qubits since the last flush: the shards map logical
+        // qubits themselves (measure, amplitudes, marginals), so their tables follow (the workers are idle here)
+        for (int r = 0; r < group_->world(); r++) group_->shard(r).queue.l2p = queue.l2p;
+        return;
+    }
     const std::vector<HostOp> &ops = queue.ops();
     group_->each([&](int, State &sh) {
         sh.queue.l2p = queue.l2p;

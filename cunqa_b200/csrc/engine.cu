@@ -599,7 +599,7 @@ void State::reduce2_t(uint64_t sel_mask, double *d_all, double *d_sel)
 
 void State::norm(double *out)
 {
-    if (group_) { group_out<double>(1, out, [&](State &sh, double *o) { sh.norm(o); }); return; }
+    if (group_) { flush(); group_out<double>(1, out, [&](State &sh, double *o) { sh.norm(o); }); return; }
     flush();
     if (precision == 64) reduce2_t<double>(0, d_small_, nullptr); else reduce2_t<float>(0, d_small_, nullptr);
     if (dist) dist_allreduce_f64(d_small_, 1);
@@ -612,7 +612,7 @@ void State::prob1(int qubit, double *out)
 {
     if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
     if (registers()) throw Unsupported("prob1 over the whole batch is not defined for independent registers");
-    if (group_) { group_out<double>(1, out, [&](State &sh, double *o) { sh.prob1(qubit, o); }); return; }
+    if (group_) { flush(); group_out<double>(1, out, [&](State &sh, double *o) { sh.prob1(qubit, o); }); return; }
     flush();
     const int pq1 = queue.l2p[qubit];
     uint64_t sel = 1ull << pq1;
@@ -632,7 +632,7 @@ void State::reduced_qubit(int qubit, double out[4], int b)
 {
     if (qubit < 0 || qubit >= n) throw InvalidArg("qubit out of range");
     if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
-    if (group_) { group_out<double>(4, out, [&](State &sh, double *o) { sh.reduced_qubit(qubit, o, b); }); queue.l2p = group_l2p(); return; }
+    if (group_) { flush(); group_out<double>(4, out, [&](State &sh, double *o) { sh.reduced_qubit(qubit, o, b); }); queue.l2p = group_l2p(); return; }
     if (dist) localize(qubit);  // rho01 pairs amplitudes that differ in this qubit: bring it into the shard first
     flush();
     const int pq = (regq_.empty() ? queue : regq_[b]).l2p[qubit];
@@ -749,7 +749,7 @@ void State::measure(int qubit, uint64_t seed, const uint64_t *counters, const in
 void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out, uint64_t ctr0)
 {
     if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
-    if (group_) { group_out<uint64_t>(shots, out, [&](State &sh, uint64_t *o) { sh.sample(b, shots, seed, o, ctr0); }); return; }
+    if (group_) { flush(); group_out<uint64_t>(shots, out, [&](State &sh, uint64_t *o) { sh.sample(b, shots, seed, o, ctr0); }); return; }
     flush();
     const int nl = n_local_;
     const int bits0 = std::min(nl, kChunkBits);
@@ -920,7 +920,7 @@ void State::sample_registers(uint64_t shots, const uint64_t *seeds, uint64_t *ou
 void State::get_amplitudes(int b, const uint64_t *idx, uint64_t cnt, double *out)
 {
     if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
-    if (group_) { group_out<double>(2 * cnt, out, [&](State &sh, double *o) { sh.get_amplitudes(b, idx, cnt, o); }); return; }
+    if (group_) { flush(); group_out<double>(2 * cnt, out, [&](State &sh, double *o) { sh.get_amplitudes(b, idx, cnt, o); }); return; }
     flush();
     if (cnt == 0) return;
     std::vector<uint64_t> phys(cnt);
@@ -998,7 +998,7 @@ void State::probabilities(int b, const int *qubits, int k, double *out)
 {
     if (b < 0 || b >= batch) throw InvalidArg("state index out of range");
     if (k < 1 || k > 20) throw InvalidArg("marginal over 1..20 qubits");
-    if (group_) { group_out<double>((size_t)1 << k, out, [&](State &sh, double *o) { sh.probabilities(b, qubits, k, o); }); return; }
+    if (group_) { flush(); group_out<double>((size_t)1 << k, out, [&](State &sh, double *o) { sh.probabilities(b, qubits, k, o); }); return; }
     flush();
     for (int i = 0; i < k; i++) if (qubits[i] < 0 || qubits[i] >= n) throw InvalidArg("qubit out of range");
     // local qubits of the list are reduced over the shard; global ones are constant here (the rank's bits)

@@ -138,6 +138,9 @@ struct TaskCfg {
     int fusion_enable = -1, fusion_max_qubit = -1;  // -1 = the engine's default
     int max_batch = 0;
     int shard_min_qubits = 30;      // with several target devices: registers at least this wide are sharded over them
+    // out-of-band state return: amplitudes at chosen basis states / a marginal distribution in the result JSON
+    std::vector<uint64_t> amplitude_indices;
+    std::vector<int> marginal_qubits;
 };
 
 // config keys honoured (cf. quantum_task_to_AER, aer_helpers.hpp:93-140)
@@ -177,6 +180,12 @@ TaskCfg parse_task(const Json &t)
     if (cfg.contains("b200_defer_measurement")) c.defer_measurement = cfg.at("b200_defer_measurement").as_bool();
     if (cfg.contains("b200_max_batch")) c.max_batch = (int)cfg.at("b200_max_batch").as_int();
     if (cfg.contains("b200_shard_min_qubits")) c.shard_min_qubits = (int)cfg.at("b200_shard_min_qubits").as_int();
+    if (const Json *a = cfg.find("b200_amplitude_indices"))
+        for (const Json &v : a->arr) {
+            if (v.as_int() < 0) throw std::runtime_error("b200_amplitude_indices: negative index");
+            c.amplitude_indices.push_back((uint64_t)v.as_int());
+        }
+    if (const Json *m = cfg.find("b200_marginal_qubits")) c.marginal_qubits = int_list(*m);
     c.is_dynamic = t.contains("is_dynamic") ? t.at("is_dynamic").as_bool() : false;
     if (const Json *s = t.find("sending_to"))
         for (const Json &v : s->arr) c.sending_to.push_back(v.as_string());
@@ -402,6 +411,7 @@ Json Backend::run_static_parsed(const void *parsed_task)
     if (getenv("CB200_TRACE")) st.sync();  // (tracing only) split the wait for the tile passes from the sampling
     const auto t_w = std::chrono::high_resolution_clock::now();
     st.sample(0, c.shots, seed, samples.data());
+    const std::vector<uint64_t> raw_samples = (save_state && c.num_qubits > 20) ? samples : std::vector<uint64_t>();
     const auto t_s = std::chrono::high_resolution_clock::now();
     Json out = Json::object();
     std::string key((size_t)c.num_clbits, '0');
@@ -431,21 +441,55 @@ Json Backend::run_static_parsed(const void *parsed_task)
         }
         out.set("counts", counts_json(counts));
     }
-    if (save_state) {
-        if (c.num_qubits > 20) throw std::runtime_error("save_state: statevector return is limited to 20 qubits");
-        const uint64_t dim = 1ull << c.num_qubits;
-        std::vector<uint64_t> idx(dim);
-        for (uint64_t i = 0; i < dim; i++) idx[i] = i;
-        std::vector<double> amps(2 * dim);
-        st.get_amplitudes(0, idx.data(), dim, amps.data());
+    auto amplitudes_json = [&](const std::vector<uint64_t> &idx) {
+        std::vector<double> amps(2 * idx.size());
+        st.get_amplitudes(0, idx.data(), idx.size(), amps.data());
         Json sv = Json::array();
-        for (uint64_t i = 0; i < dim; i++) {
+        sv.arr.reserve(idx.size());
+        for (size_t i = 0; i < idx.size(); i++) {
             Json z = Json::array();
             z.arr.push_back(Json::number(amps[2 * i]));
             z.arr.push_back(Json::number(amps[2 * i + 1]));
             sv.arr.push_back(std::move(z));
         }
-        out.set("statevector", std::move(sv));
+        return sv;
+    };
+    if (save_state) {
+        // the reference returns the whole vector as [[re, im], ...] (cunqa/result.py:151-187): feasible up to 20 qubits.
+        // Above that the amplitudes of the basis states the shots landed on are returned instead (at most `shots` of
+        // them, the heavy part of the distribution), with their indices; b200_amplitude_indices asks for chosen ones.
+        if (c.num_qubits <= 20) {
+            std::vector<uint64_t> idx((size_t)1 << c.num_qubits);
+            for (uint64_t i = 0; i < idx.size(); i++) idx[i] = i;
+            out.set("statevector", amplitudes_json(idx));
+        } else {
+            std::vector<uint64_t> idx(raw_samples);
+            std::sort(idx.begin(), idx.end());
+            idx.erase(std::unique(idx.begin(), idx.end()), idx.end());
+            Json sampled = Json::object();
+            Json ji = Json::array();
+            for (uint64_t i : idx) ji.arr.push_back(Json::integer((long long)i));
+            sampled.set("indices", std::move(ji));
+            sampled.set("amplitudes", amplitudes_json(idx));
+            out.set("statevector_sampled", std::move(sampled));
+        }
+    }
+    if (!c.amplitude_indices.empty()) {
+        for (uint64_t i : c.amplitude_indices)
+            if (c.num_qubits < 64 && (i >> c.num_qubits)) throw std::runtime_error("b200_amplitude_indices: index out of range");
+        out.set("b200_amplitudes", amplitudes_json(c.amplitude_indices));
+    }
+    if (!c.marginal_qubits.empty()) {
+        // P(qubits = j), index bit m <-> b200_marginal_qubits[m]: the on-device equivalent of recombine_probs
+        // (/root/reference/src/utils/probabilities/process_counts.hpp:71-131), exact instead of estimated from counts
+        const int k = (int)c.marginal_qubits.size();
+        if (k > 20) throw std::runtime_error("b200_marginal_qubits: at most 20 qubits");
+        std::vector<double> p((size_t)1 << k);
+        st.probabilities(0, c.marginal_qubits.data(), k, p.data());
+        Json jp = Json::array();
+        jp.arr.reserve(p.size());
+        for (double v : p) jp.arr.push_back(Json::number(v));
+        out.set("b200_marginal", std::move(jp));
     }
     const auto t1 = std::chrono::high_resolution_clock::now();
     out.set("time_taken", Json::number(std::chrono::duration<double>(t1 - t0).count()));

@@ -362,3 +362,33 @@ def test_qasm2_text_runs_on_the_engine(backend):
     assert "ERROR" not in res, res
     assert set(res["counts"]) == {"0000", "1111"} and sum(res["counts"].values()) == 500
     assert res["counts"] == O.run_static(circ["instructions"], 4, 4, shots=500, seed=3)[1]
+
+
+def test_out_of_band_amplitudes_and_marginals_through_the_wire_format(backend):
+    """config keys b200_amplitude_indices / b200_marginal_qubits, and save_state above 20 qubits
+    (consumers: cunqa/result.py:151-187, src/utils/probabilities/process_counts.hpp:71-131)"""
+    n = 22
+    ins = C.quantum_volume(n, depth=3, seed=12)
+    ref, _ = O.run_static(ins, n, backend="c")
+    idx = [0, 5, (1 << n) - 1, 123456]
+    qs = [3, 21, 0, 11]
+    t = C.task(ins + [{"name": "save_state", "qubits": list(range(n))}] + C.measure_all(n), n, shots=300, seed=2,
+               b200_amplitude_indices=idx, b200_marginal_qubits=qs)
+    res = backend.execute(t)
+    assert "ERROR" not in res, res
+    got = np.array([complex(*z) for z in res["b200_amplitudes"]])
+    assert np.abs(got - ref.amplitudes()[idx]).max() < 1e-12
+    p = np.abs(ref.amplitudes()) ** 2
+    i = np.arange(1 << n)
+    j = sum(((i >> q) & 1) << m for m, q in enumerate(qs))
+    assert np.abs(np.array(res["b200_marginal"]) - np.bincount(j, weights=p, minlength=16)).max() < 1e-12
+    # 22 qubits: the statevector comes back sampled -- the amplitudes of the basis states the shots landed on
+    sam = res["statevector_sampled"]
+    assert "statevector" not in res and 1 <= len(sam["indices"]) <= 300
+    a = np.array([complex(*z) for z in sam["amplitudes"]])
+    assert np.abs(a - ref.amplitudes()[sam["indices"]]).max() < 1e-12
+    assert {int(k, 2) for k in res["counts"]} == set(sam["indices"])
+    # up to 20 qubits the reference's shape: the whole vector under "statevector"
+    small = backend.execute(C.task(C.ghz(3, measure=False) + [{"name": "save_state", "qubits": [0, 1, 2]}] + C.measure_all(3), 3, shots=10, seed=1))
+    v = np.array([complex(*z) for z in small["statevector"]])
+    assert abs(v[0] - 2 ** -0.5) < 1e-15 and abs(v[7] - 2 ** -0.5) < 1e-15 and np.abs(v[1:7]).max() < 1e-15
