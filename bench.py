@@ -373,8 +373,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: cunqa_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a host-side group for the waits around rank 0's single-process sharded leg: an NCCL barrier would keep a kernel
+        # spinning on every other GPU, time-slicing with the shards that rank 0 runs there
+        cpu_group = dist.new_group(backend="gloo")
 
     side = {} if args.no_side else side_workloads(cb, C, torch, dist, world, rank, local_rank)
 
@@ -495,9 +499,10 @@ def main():
     sharded = None
     if world > 1 and (world & (world - 1)) == 0 and not args.no_sharded:
         barrier()
+        dist.barrier(group=cpu_group)
         if rank == 0:
             sharded = sharded_leg(cb, C, torch, n, list(range(world)))
-        barrier()
+        dist.barrier(group=cpu_group)
     elif world == 1 and not args.no_sharded and not args.no_side and n == QV_QUBITS:
         sharded = sharded_leg(cb, C, torch, n, [local_rank])   # the N = 1 anchor of the 1 -> 8 curve: QFT-33, unsharded
 

@@ -1323,6 +1323,11 @@ std::vector<std::string> Backend::execute_many(const std::vector<std::string> &m
     }
     last_uniform_flushes = last_split_flushes = last_solo = 0;
     Stats total;
+    const bool trace = getenv("CB200_TRACE") != nullptr;
+    auto now = [] { return std::chrono::high_resolution_clock::now(); };
+    auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    const auto t_parsed = now();
+    double us_queue = 0, us_flush = 0, us_sample = 0, us_decode = 0;
     // 2. registers of equal width share one State (as many per chunk as fit the memory budget)
     std::vector<char> handled(M, 0);
     for (size_t i = 0; i < M; i++) {
@@ -1349,6 +1354,7 @@ std::vector<std::string> Backend::execute_many(const std::vector<std::string> &m
                 st.reset();
                 const Stats before = st.stats;
                 const uint64_t uf0 = st.uniform_flushes, sf0 = st.split_flushes;
+                const auto tq0 = now();
                 for (size_t g = 0; g < G; g++) {
                     const Json &m = msgs[members[c0 + g]];
                     jobs[g].st = &st;
@@ -1372,8 +1378,12 @@ std::vector<std::string> Backend::execute_many(const std::vector<std::string> &m
                 std::vector<uint64_t> seeds(G, 0);
                 for (size_t g = 0; g < G; g++) if (ok[g]) { max_shots = std::max(max_shots, jobs[g].shots); seeds[g] = jobs[g].seed; }
                 std::vector<uint64_t> samples((size_t)G * max_shots);
+                const auto tq1 = now();
                 st.flush();
+                const auto tq2 = now();
                 st.sample_registers(max_shots, seeds.data(), samples.data());
+                const auto tq3 = now();
+                us_queue += us(tq0, tq1); us_flush += us(tq1, tq2); us_sample += us(tq2, tq3);
                 const double secs = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
                 last_uniform_flushes += st.uniform_flushes - uf0;
                 last_split_flushes += st.split_flushes - sf0;
@@ -1417,6 +1427,7 @@ std::vector<std::string> Backend::execute_many(const std::vector<std::string> &m
                     results[members[c0 + g]] = out.dump();
                     handled[members[c0 + g]] = 1;
                 }
+                us_decode += us(tq3, now());
             } catch (const std::exception &e) {
                 for (size_t g = 0; g < G; g++)
                     if (!handled[members[c0 + g]]) { results[members[c0 + g]] = error_json(e.what()); handled[members[c0 + g]] = 1; }
@@ -1441,6 +1452,9 @@ std::vector<std::string> Backend::execute_many(const std::vector<std::string> &m
     }
     last_stats = total;
     last_mode = 1;
+    if (trace)
+        fprintf(stderr, "[cb200] execute_many(%zu): parse %.0f us, interpret+queue+fuse %.0f us, plan+encode+launch %.0f us, wait+sample %.0f us, "
+                        "decode+counts %.0f us, total %.0f us\n", M, us(t0, t_parsed), us_queue, us_flush, us_sample, us_decode, us(t0, now()));
     return results;
 }
 

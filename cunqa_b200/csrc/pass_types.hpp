@@ -16,7 +16,10 @@ constexpr int kMaxDenseK = 5;     // dense block width (qubits)
 constexpr int kMaxDiagK = 12;     // diagonal table width (qubits)
 constexpr int kMaxFix = 12;       // targets + in-tile controls of one op
 constexpr int kMatScalars = 2560; // scalars (re/im) of dense-matrix storage per pass (kernel params)
-constexpr int kDiagLut = 192;     // per diagonal op: 64 entries for tile bits 0..5 + 128 for tile bits 6..12
+constexpr int kDiagLut = 192;
+constexpr int kStabEntries = 1024;      // per-tile store of small diagonal sub-tables (entries; 16 KB of complex128)
+constexpr int kStabMaxBits = 6;        // a diagonal op is staged when at most this many of its qubits are tile qubits
+constexpr uint16_t kNotStaged = 0xFFFF;     // per diagonal op: 64 entries for tile bits 0..5 + 128 for tile bits 6..12
 
 enum OpKind : uint8_t {
     OP_DENSE = 0,  // dense 2^k x 2^k on in-tile targets, optional controls
@@ -44,7 +47,7 @@ struct DevOp {
     int32_t mask_row;   // row of the per-state flag matrix (batched feed-forward) when has_mask
     uint8_t k2, s;      // PAIR: #targets of gate B and its first local bit; B's matrix follows A's in mats
                         // DIAG: k2 = slot of this op among the pass's diagonal ops (index of its pext tables)
-    uint8_t pad_[2];
+    uint16_t stage_off;  // DIAG: entry offset of this op's per-tile sub-table in the shared-memory table store; kNotStaged = read from global memory
 };
 static_assert(sizeof(DevOp) == 64, "DevOp layout");
 
@@ -59,10 +62,12 @@ struct PassParams {
     uint64_t tiles_per_state;
     uint64_t cond_mask; // ops whose activity depends on the tile (controls outside the tile / per-state mask)
     int32_t n_mat;      // scalars used in mats (staged into shared memory once per CTA)
-    int32_t needs_full; // 1: some op needs the FULL kernel variant (dense k>=3, unusual register blocks)
+    int32_t needs_full; // kernel variant: 0 = lean (1-2 qubit dense gates, common register blocks, permutations), 1 = lean +
+                        // diagonal runs, 2 = full (dense k>=3, unusual register blocks, generic diagonal path)
     int32_t n_diag;     // number of OP_DIAG ops; diag_op[slot] = op index of the slot-th one
-    int32_t pad2_;
+    int32_t n_stab;     // entries of the shared-memory sub-table store used by this pass (multiple of 8)
     uint8_t diag_op[kMaxOps];
+    uint8_t stab_slot[kStabEntries / 8];  // diagonal slot that owns each 8-entry chunk of the store
     uint8_t tile_q[16]; // physical qubit of tile bit j (ascending)
     DevOp ops[kMaxOps];
     alignas(16) T mats[kMatScalars];  // (re, im) pairs, read as one 16-byte element

@@ -412,14 +412,14 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
     }
     out.n_ops = nops;
     out.n_mat = mat_used;
-    out.needs_full = out.n_diag > 0;  // the lean kernel variant carries no diagonal-run code
+    out.needs_full = out.n_diag > 0 ? 1 : 0;  // the lean kernel variant carries no diagonal-run code
     for (int o = 0; o < nops; o++) {
         const DevOp &d = out.ops[o];
-        if (d.kind == OP_DENSE && d.k >= 3) out.needs_full = 1;
+        if (d.kind == OP_DENSE && d.k >= 3) out.needs_full = 2;
         if (d.kind == OP_PAIR) {
             const int code = (d.k << 4) | (d.k2 << 2) | d.s;
             if (code != ((2 << 4) | (2 << 2) | 2) && code != ((2 << 4) | (2 << 2) | 1) && code != ((1 << 4) | (1 << 2) | 1))
-                out.needs_full = 1;
+                out.needs_full = 2;
         }
     }
     // Runs of consecutive diagonal ops are applied with 16 amplitudes per thread in registers: the 2^4 settings of
@@ -477,6 +477,22 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
     out.cond_mask = 0;
     for (int o = 0; o < nops; o++)
         if (out.ops[o].ctrl_out != 0 || out.ops[o].has_mask) out.cond_mask |= 1ull << o;
+    // Per-tile staging of small diagonal sub-tables.  For a given tile the table-index bits that come from qubits outside
+    // the tile are constants, so the op only ever reads the 2^nfix consecutive entries that start at its per-tile base
+    // (in-tile qubits are the low index bits, see above).  Ops with few in-tile qubits -- the CP ladders of a QFT are
+    // tables over ten qubits of which one to five lie in the tile -- are copied into shared memory at the start of the
+    // tile and looked up there instead of in L2 (one global load per ENTRY per tile instead of one per amplitude per op).
+    out.n_stab = 0;
+    for (int o = 0; o < nops; o++) out.ops[o].stage_off = kNotStaged;
+    for (int sl = 0; sl < out.n_diag; sl++) {
+        DevOp &d = out.ops[out.diag_op[sl]];
+        if (d.nfix > kStabMaxBits || d.has_mask || d.ctrl_out) continue;
+        const int need = std::max(8, 1 << d.nfix);  // (chunks of 8 entries)
+        if (out.n_stab + need > kStabEntries) continue;
+        d.stage_off = (uint16_t)out.n_stab;
+        for (int c = 0; c < need / 8; c++) out.stab_slot[out.n_stab / 8 + c] = (uint8_t)sl;
+        out.n_stab += need;
+    }
     return true;
 }
 

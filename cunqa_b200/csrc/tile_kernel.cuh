@@ -219,7 +219,7 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
     }
 }
 
-template <typename T, int NT, bool FULL>
+template <typename T, int NT, int VAR>
 __device__ __forceinline__ void op_pair_dispatch(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
                                                  const int t, const int tid)
 {
@@ -227,7 +227,7 @@ __device__ __forceinline__ void op_pair_dispatch(typename Vec2<T>::type *tile, c
     if (code == ((2 << 4) | (2 << 2) | 2)) { op_pair<T, 2, 2, 2, NT>(tile, op, mat, t, tid); return; }
     if (code == ((2 << 4) | (2 << 2) | 1)) { op_pair<T, 2, 2, 1, NT>(tile, op, mat, t, tid); return; }
     if (code == ((1 << 4) | (1 << 2) | 1)) { op_pair<T, 1, 1, 1, NT>(tile, op, mat, t, tid); return; }
-    if constexpr (FULL) {
+    if constexpr (VAR == 2) {
         switch (code) {
         case (1 << 4) | (1 << 2) | 0: op_pair<T, 1, 1, 0, NT>(tile, op, mat, t, tid); break;
         case (1 << 4) | (2 << 2) | 1: op_pair<T, 1, 2, 1, NT>(tile, op, mat, t, tid); break;
@@ -273,8 +273,8 @@ __device__ __forceinline__ void op_perm(typename Vec2<T>::type *tile, const DevO
 // gate's targets): phases applied in registers before the butterfly, one sweep, one barrier.
 template <typename T, int K, int NT>
 __device__ __noinline__ void op_diag_block(typename Vec2<T>::type *tile, const DevOp &run, const T *mat,
-                                              const typename Vec2<T>::type *__restrict__ diag_tabs,
-                                              const uint16_t *lut, const uint32_t *dhi, int s0, int s1, const int tid)
+                                              const typename Vec2<T>::type *const *tptr,
+                                              const uint16_t *lut, int s0, int s1, const int tid)
 {
     using V = typename Vec2<T>::type;
     constexpr int A = 16;
@@ -298,9 +298,11 @@ __device__ __noinline__ void op_diag_block(typename Vec2<T>::type *tile, const D
     // tables' loads in flight together, their product applied to the 16 amplitudes once
     int sl = s0;
     const int s_indep = s0 + run.fixpos[1];
+    // tptr[s]: this tile's sub-table of diagonal op s -- in the shared-memory store when the op is staged, else the slice
+    // of the global table that starts at the op's per-tile base (generic loads serve both)
     auto index_of = [&](int s) -> uint32_t {
         const uint16_t *L = lut + s * kDiagLut;
-        return dhi[s] + (uint32_t)(L[bi & 63u] | L[64 + (bi >> 6)]);
+        return (uint32_t)(L[bi & 63u] | L[64 + (bi >> 6)]);
     };
     for (; sl + 4 <= s_indep; sl += 4) {
         uint32_t ix[4];
@@ -308,17 +310,17 @@ __device__ __noinline__ void op_diag_block(typename Vec2<T>::type *tile, const D
 #pragma unroll
         for (int j = 0; j < 4; j++) ix[j] = index_of(sl + j);
 #pragma unroll
-        for (int j = 0; j < 4; j++) q[j] = diag_tabs[ix[j]];
+        for (int j = 0; j < 4; j++) q[j] = tptr[sl + j][ix[j]];
         const V q01 = cmul<V, T>(q[0].x, q[0].y, q[1]), q23 = cmul<V, T>(q[2].x, q[2].y, q[3]);
         acc = cmul<V, T>(acc.x, acc.y, cmul<V, T>(q01.x, q01.y, q23));
     }
     for (; sl < s_indep; sl++) {
-        const V q = diag_tabs[index_of(sl)];
+        const V q = tptr[sl][index_of(sl)];
         acc = cmul<V, T>(q.x, q.y, acc);
     }
     for (; sl <= s1; sl++) {
         const uint16_t *L = lut + sl * kDiagLut;
-        const uint32_t i0 = index_of(sl);
+        const V *tb = tptr[sl] + index_of(sl);
         uint32_t e[4];
 #pragma unroll
         for (int b = 0; b < 4; b++) e[b] = L[rbit[b] & 63u] | L[64 + (rbit[b] >> 6)];  // one of the two is entry 0 == 0
@@ -328,7 +330,7 @@ __device__ __noinline__ void op_diag_block(typename Vec2<T>::type *tile, const D
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int k = h + j;
-                q[j] = diag_tabs[i0 + (((k & 1) ? e[0] : 0u) | ((k & 2) ? e[1] : 0u) | ((k & 4) ? e[2] : 0u) | ((k & 8) ? e[3] : 0u))];
+                q[j] = tb[((k & 1) ? e[0] : 0u) | ((k & 2) ? e[1] : 0u) | ((k & 4) ? e[2] : 0u) | ((k & 8) ? e[3] : 0u)];
             }
 #pragma unroll
             for (int j = 0; j < 8; j++) v[h + j] = cmul<V, T>(q[j].x, q[j].y, v[h + j]);
@@ -385,11 +387,13 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 // hook() is invoked exactly once, right after the barrier that ends the first executed op whose index is
 // >= hook_at (or at the very end): the TMA kernel uses it to recycle the previous tile's buffer while the
 // remaining ops still run.
-template <typename T, int NT, bool COND, bool FULL, typename Hook = NoHook>
+// VAR: 0 = lean (1-2 qubit dense gates, the common register blocks, permutations), 1 = lean + diagonal runs through the
+// LUT / register-block path, 2 = everything (dense k >= 3, all register blocks, the generic per-bit diagonal gather)
+template <typename T, int NT, bool COND, int VAR, typename Hook = NoHook>
 __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats, typename Vec2<T>::type *tile,
                                           const typename Vec2<T>::type *__restrict__ diag_tabs,
                                           const uint64_t active, const uint64_t base, const int t, const int tid,
-                                          const uint16_t *lut = nullptr, uint32_t *dhi = nullptr,
+                                          const uint16_t *lut = nullptr, const typename Vec2<T>::type *const *tptr = nullptr,
                                           const int hook_at = 1 << 30, Hook hook = Hook())
 {
     using V = typename Vec2<T>::type;
@@ -403,52 +407,57 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                 const T *mat = mats + op.mat_off;
                 if (op.k == 1) op_dense<T, 1, NT>(tile, op, mat, t, tid);
                 else if (op.k == 2) op_dense<T, 2, NT>(tile, op, mat, t, tid);
-                else if constexpr (FULL) {
+                else if constexpr (VAR == 2) {
                     if (op.k == 3) op_dense<T, 3, NT>(tile, op, mat, t, tid);
                     else if (op.k == 4) op_dense<T, 4, NT>(tile, op, mat, t, tid);
                     else op_dense<T, 5, NT>(tile, op, mat, t, tid);
                 }
                 __syncthreads();
             } else if (op.kind == OP_PAIR) {
-                op_pair_dispatch<T, NT, FULL>(tile, op, mats + op.mat_off, t, tid);
+                op_pair_dispatch<T, NT, VAR>(tile, op, mats + op.mat_off, t, tid);
                 __syncthreads();
             } else if (op.kind == OP_DIAG) {
-                if constexpr (FULL) {  // passes with diagonal ops always take the FULL kernel (needs_full)
+                if constexpr (VAR >= 1) {  // (passes with diagonal ops never take the lean kernel, see needs_full)
                 // a run of consecutive diagonal ops is applied in ONE sweep of the tile
                 int oe = o;
                 while (oe + 1 < p.n_ops && p.ops[oe + 1].kind == OP_DIAG) oe++;
-                if (lut != nullptr) {
-                    // table index = dhi (bits taken from the tile base, filled once per tile by the caller)
-                    //             | pext(tile index, in-tile mask) through the per-op LUTs
+                bool done = false;
+                if (VAR == 1 || lut != nullptr) {
+                    // table index = pext(tile index, in-tile mask) through the per-op LUTs, relative to this tile's
+                    // sub-table (tptr, filled once per tile by the caller)
                     const int s0 = op.k2, s1 = p.ops[oe].k2;
                     const int fuse_k = op.fixpos[0];  // host: fold the run into the uncontrolled dense gate after it
                     if (fuse_k != 0) {
                         const DevOp &dn = p.ops[oe + 1];
                         const T *mat = mats + dn.mat_off;
-                        if (fuse_k == 1) op_diag_block<T, 1, NT>(tile, op, mat, diag_tabs, lut, dhi, s0, s1, tid);
-                        else op_diag_block<T, 2, NT>(tile, op, mat, diag_tabs, lut, dhi, s0, s1, tid);
+                        if (fuse_k == 1) op_diag_block<T, 1, NT>(tile, op, mat, tptr, lut, s0, s1, tid);
+                        else op_diag_block<T, 2, NT>(tile, op, mat, tptr, lut, s0, s1, tid);
                         o = oe + 1;
                         __syncthreads();
                         continue;
                     }
-                    op_diag_block<T, 0, NT>(tile, op, nullptr, diag_tabs, lut, dhi, s0, s1, tid);
-                } else
-                for (uint32_t i = tid; i < tile_amps; i += NT) {
-                    const uint32_t s = swz<T>(i);
-                    V v = tile[s];
-                    for (int q = o; q <= oe; q++) {
-                        if (COND && !((active >> q) & 1ull)) continue;
-                        const DevOp &d = p.ops[q];
-                        uint32_t ti = 0;
-                        for (int m = 0; m < d.k; m++) {
-                            const uint32_t src = d.dsrc[m];
-                            const uint32_t bit = src < 64 ? ((i >> src) & 1u) : (uint32_t)((base >> (src - 64)) & 1ull);
-                            ti |= bit << m;
+                    op_diag_block<T, 0, NT>(tile, op, nullptr, tptr, lut, s0, s1, tid);
+                    done = true;
+                }
+                if constexpr (VAR == 2) {
+                    if (!done)
+                        for (uint32_t i = tid; i < tile_amps; i += NT) {
+                            const uint32_t s = swz<T>(i);
+                            V v = tile[s];
+                            for (int q = o; q <= oe; q++) {
+                                if (COND && !((active >> q) & 1ull)) continue;
+                                const DevOp &d = p.ops[q];
+                                uint32_t ti = 0;
+                                for (int m = 0; m < d.k; m++) {
+                                    const uint32_t src = d.dsrc[m];
+                                    const uint32_t bit = src < 64 ? ((i >> src) & 1u) : (uint32_t)((base >> (src - 64)) & 1ull);
+                                    ti |= bit << m;
+                                }
+                                const V ph = diag_tabs[d.mat_off + ti];
+                                v = cmul<V, T>(ph.x, ph.y, v);
+                            }
+                            tile[s] = v;
                         }
-                        const V ph = diag_tabs[d.mat_off + ti];
-                        v = cmul<V, T>(ph.x, ph.y, v);
-                    }
-                    tile[s] = v;
                 }
                 o = oe;
                 __syncthreads();
@@ -512,7 +521,7 @@ tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type
 
         // reg_mats != nullptr: every state of the batch is its own register with its own matrices and diagonal tables
         // (same pass structure): state b reads row b of the per-register buffers
-        apply_ops<T, kTileThreads, true, true>(p, reg_mats ? reg_mats + (size_t)b * reg_mat_stride : p.mats, tile,
+        apply_ops<T, kTileThreads, true, 2>(p, reg_mats ? reg_mats + (size_t)b * reg_mat_stride : p.mats, tile,
                                                diag_tabs + (size_t)b * reg_diag_stride, active, base, t, tid);
 
         // ---- stage out
@@ -577,7 +586,7 @@ __device__ __forceinline__ void tma_store_row(const CUtensorMap *map, const void
 // tiles, so the load / math / store / barrier phases of different CTAs interleave on an SM.
 // kStages tile buffers per CTA: 3 = the CTA overlaps its own load / math / store; 2 = one more CTA fits per
 // SM and the overlap comes from the other resident CTAs.
-template <typename T, int NT, bool COND, bool FULL, int kStages>
+template <typename T, int NT, bool COND, int VAR, int kStages>
 __global__ void __launch_bounds__(NT, (kStages == 3 ? 256 : 384) / NT)
 tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_constant__ CUtensorMap tmap,
                      const typename Vec2<T>::type *__restrict__ diag_tabs, const uint8_t *__restrict__ flags,
@@ -611,8 +620,11 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     if (reg_mats == nullptr)
         for (int e = tid; e < p.n_mat; e += NT) mats_s[e] = p.mats[e];
     uint64_t staged_b = ~0ull;
-    // per diagonal op: bit-extract tables of the in-tile index part (tile bits 0..5 and 6..12) + per-tile high part
-    uint32_t *dhi = reinterpret_cast<uint32_t *>(mats_s + ((p.n_mat + 1) & ~1));
+    // per diagonal op: this tile's sub-table pointer, the per-tile index part that comes from qubits outside the tile,
+    // bit-extract tables of the in-tile index part (tile bits 0..5 and 6..12), and the store of staged sub-tables
+    const V **tptr = reinterpret_cast<const V **>(mats_s + ((p.n_mat + 1) & ~1));
+    V *stab = reinterpret_cast<V *>(tptr + ((p.n_diag + 1) & ~1));
+    uint32_t *dhi = reinterpret_cast<uint32_t *>(stab + p.n_stab);
     uint16_t *lut = reinterpret_cast<uint16_t *>(dhi + p.n_diag);
     static_assert(NT >= 32, "one warp at least");
     for (int e = tid; e < p.n_diag * kDiagLut; e += NT) {
@@ -716,11 +728,23 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         const uint64_t base = tile_base(tq[0], b);
         V *tile = reinterpret_cast<V *>(smem_raw + (size_t)s * buf_stride);
         // per-tile base of every diagonal table (the index bits that come from qubits outside the tile)
+        const V *tabs_b = diag_tabs + (size_t)b * reg_diag_stride;
         for (int sl = tid; sl < p.n_diag; sl += NT) {
             const DevOp &d = p.ops[p.diag_op[sl]];
             uint32_t hi = 0;
             for (int m = d.nfix; m < d.k; m++) hi |= (uint32_t)((base >> (d.dsrc[m] - 64)) & 1ull) << m;
             dhi[sl] = hi + d.mat_off;
+            tptr[sl] = d.stage_off != kNotStaged ? stab + d.stage_off : tabs_b + hi + d.mat_off;
+        }
+        if (p.n_stab) {
+            // small sub-tables (few in-tile qubits) are copied into shared memory: 2^nfix entries per op per tile
+            __syncthreads();
+            for (int x = tid; x < p.n_stab; x += NT) {
+                const int sl = p.stab_slot[x >> 3];
+                const DevOp &d = p.ops[p.diag_op[sl]];
+                const uint32_t e = (uint32_t)x - d.stage_off;
+                if (e < (1u << d.nfix)) stab[x] = tabs_b[dhi[sl] + e];
+            }
         }
         bool restaged = false;
         if (reg_mats != nullptr && b != staged_b) {
@@ -733,9 +757,8 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         mbar_wait(&full[s], parity);
         if (p.n_diag || restaged) __syncthreads();
 
-        apply_ops<T, NT, COND, FULL>(p, mats_s, tile, diag_tabs + (size_t)b * reg_diag_stride,
-                                     COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
-                                     (COND || (16 * NT) != (1 << t)) ? nullptr : lut, dhi, refill_after, refill);
+        apply_ops<T, NT, COND, VAR>(p, mats_s, tile, tabs_b, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
+                                    (COND || (16 * NT) != (1 << t)) ? nullptr : lut, tptr, refill_after, refill);
 
         // every thread's generic-proxy writes -> visible to the async proxy; then drain the tile with TMA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

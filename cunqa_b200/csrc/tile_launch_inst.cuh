@@ -23,9 +23,13 @@ cudaError_t launch_tile_pass_tma<CB200_T, CB200_NT>(const PassParams<CB200_T> &p
     using T = CB200_T;
     using V = typename Vec2<T>::type;
     constexpr int N = CB200_NT;
-    static size_t seen_all[kMaxDevices][6] = {};
+    static size_t seen_all[kMaxDevices][8] = {};
     size_t *seen = seen_all[l.device & (kMaxDevices - 1)];
-    const bool cnd = p.cond_mask != 0, full = p.needs_full != 0;
+    const bool cnd = p.cond_mask != 0;
+    // kernel variant: 0 lean, 1 lean + diagonal runs, 2 full.  The diagonal-run path needs the LUT route (no per-tile
+    // conditions, 16 amplitudes per thread); anything else falls back to the full variant.
+    int var = p.needs_full;
+    if (cnd || (var == 1 && 16 * N != (1 << p.t))) var = 2;
     auto go = [&](auto kern, size_t &s) -> cudaError_t {
         cudaError_t e = set_smem_once(kern, l.smem, s);
         if (e != cudaSuccess) return e;
@@ -34,13 +38,13 @@ cudaError_t launch_tile_pass_tma<CB200_T, CB200_NT>(const PassParams<CB200_T> &p
         return cudaGetLastError();
     };
     if (l.stages == 3) {
-        if (!cnd && !full) return go(tile_pass_tma_kernel<T, N, false, false, 3>, seen[0]);
-        if (!cnd) return go(tile_pass_tma_kernel<T, N, false, true, 3>, seen[1]);
-        return go(tile_pass_tma_kernel<T, N, true, true, 3>, seen[2]);
+        if (cnd) return go(tile_pass_tma_kernel<T, N, true, 2, 3>, seen[0]);
+        return go(tile_pass_tma_kernel<T, N, false, 2, 3>, seen[1]);   // (three stages: experiments only, full variant)
     }
-    if (!cnd && !full) return go(tile_pass_tma_kernel<T, N, false, false, 2>, seen[3]);
-    if (!cnd) return go(tile_pass_tma_kernel<T, N, false, true, 2>, seen[4]);
-    return go(tile_pass_tma_kernel<T, N, true, true, 2>, seen[5]);
+    if (cnd) return go(tile_pass_tma_kernel<T, N, true, 2, 2>, seen[2]);
+    if (var == 0) return go(tile_pass_tma_kernel<T, N, false, 0, 2>, seen[3]);
+    if (var == 1) return go(tile_pass_tma_kernel<T, N, false, 1, 2>, seen[4]);
+    return go(tile_pass_tma_kernel<T, N, false, 2, 2>, seen[5]);
 }
 
 }  // namespace cb200
