@@ -167,6 +167,16 @@ void State::use_registers(bool on)
         cur_reg_ = 0;
     }
 }
+static thread_local int tl_bound_register = -1;
+void State::bind_register_for_this_thread(int r) { tl_bound_register = r; }
+OpQueue &State::rq()
+{
+    if (regq_.empty()) return queue;
+    const int r = tl_bound_register >= 0 ? tl_bound_register : cur_reg_;
+    if (r >= (int)regq_.size()) throw InvalidArg("register index out of range");
+    return regq_[r];
+}
+
 void State::select_register(int r)
 {
     if (regq_.empty()) throw InvalidArg("state is not in register mode");

@@ -85,7 +85,10 @@ public:
     void use_registers(bool on);
     bool registers() const { return !regq_.empty(); }
     void select_register(int r);
-    OpQueue &rq() { return regq_.empty() ? queue : regq_[cur_reg_]; }  // the queue ops currently go to
+    // the queue ops currently go to; a host thread may bind itself to one register (bind_register_for_this_thread) so that
+    // several threads queue into different registers at the same time
+    OpQueue &rq();
+    static void bind_register_for_this_thread(int r);  // -1: unbind (follow select_register)
     const OpQueue &qof(int b) const { return regq_.empty() ? queue : regq_[b]; }  // qubit map of state b
     // `shots` samples of every register, u = U(seeds[r], s): out[r * shots + s] (logical indices)
     void sample_registers(uint64_t shots, const uint64_t *seeds, uint64_t *out);

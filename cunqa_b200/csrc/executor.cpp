@@ -13,6 +13,8 @@
 #include <map>
 #include <random>
 #include <set>
+#include <thread>
+#include <atomic>
 
 namespace cb200 {
 
@@ -1171,7 +1173,7 @@ Json Backend::run_dynamic(const std::vector<Json> &tasks_json, RegJob *job)
         // one register of a batched run: deferred measurement or nothing (DeferAbort & co. propagate to execute_many)
         if (external_cc || n_total + (int)kSym > (int)kNotSym) throw DeferAbort();
         State &sb = *job->st;
-        sb.select_register(job->reg);
+        State::bind_register_for_this_thread(job->reg);   // (execute_many runs the registers' interpreters on several threads)
         if (sb.n != n_total || sb.precision != precision) throw std::runtime_error("internal: register width mismatch");
         apply_fusion_cfg(sb, c0);
         const uint64_t g0 = sb.rq().gates;
@@ -1266,12 +1268,27 @@ int message_width(const Json &msg)
 }
 }  // namespace
 
+namespace {
+// f(i) for i in [0, count) on up to `max_threads` host threads (exceptions must be handled inside f)
+template <typename F>
+void parallel_for(size_t count, F f, unsigned max_threads = 16)
+{
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nt = std::min<size_t>({count, (size_t)hw, (size_t)max_threads});
+    if (nt <= 1) { for (size_t i = 0; i < count; i++) f(i); return; }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([&] { for (size_t i = next++; i < count; i = next++) f(i); });
+    for (std::thread &t : th) t.join();
+}
+}  // namespace
+
 std::vector<std::string> Backend::execute_many(const std::vector<std::string> &messages)
 {
     const auto t0 = std::chrono::high_resolution_clock::now();
     const size_t M = messages.size();
     std::vector<std::string> results(M);
-    std::vector<Json> msgs(M);
     std::vector<int> width(M, -1);
     auto error_json = [](const std::string &what) {
         Json err = Json::object();
@@ -1279,30 +1296,31 @@ std::vector<std::string> Backend::execute_many(const std::vector<std::string> &m
         return err.dump();
     };
     if (cached_many_.size() < M) cached_many_.resize(M);
-    // 1. parse; {"params"} updates rewrite the slot's cached message (src/quantum_task.cpp:33-35,39-108)
-    for (size_t i = 0; i < M; i++) {
+    // 1. parse (in parallel); {"params"} updates rewrite the slot's cached message (src/quantum_task.cpp:33-35,39-108)
+    std::vector<const Json *> mp(M, nullptr);
+    parallel_for(M, [&](size_t i) {
         try {
             Json m = Json::parse(messages[i]);
             if (m.is_object() && !m.contains("instructions") && m.contains("params")) {
                 if (!cached_many_[i].is_object() || !cached_many_[i].contains("instructions"))
                     throw std::runtime_error("Circuit not sent before updating parameters.");
                 update_params(cached_many_[i], m);
-                m = cached_many_[i];
             } else {
-                cached_many_[i] = m;
+                cached_many_[i] = std::move(m);
             }
-            if (m.is_object() && !(m.contains("instructions") && m.contains("config")))
+            const Json &c = cached_many_[i];
+            if (c.is_object() && !(c.contains("instructions") && c.contains("config")))
                 throw std::runtime_error("message has neither instructions+config nor params");
-            if (m.is_object() && m.at("config").contains("precision") && m.at("config").at("precision").as_string() == "single")
+            if (c.is_object() && c.at("config").contains("precision") && c.at("config").at("precision").as_string() == "single")
                 width[i] = -2;  // batched registers are complex128 (the dynamic path's precision, :946): single runs on its own
             else
-                width[i] = message_width(m);
-            msgs[i] = std::move(m);
+                width[i] = message_width(c);
+            mp[i] = &c;
         } catch (const std::exception &e) {
             results[i] = error_json(e.what());
             width[i] = -1;
         }
-    }
+    });
     // structure signature of a message: instruction names and operands, no angles
     std::vector<std::string> signature(M);
     for (size_t i = 0; i < M; i++) {
@@ -1317,8 +1335,8 @@ std::vector<std::string> Backend::execute_many(const std::vector<std::string> &m
             }
         };
         try {
-            if (msgs[i].is_array()) for (const Json &t : msgs[i].arr) { sig(t.at("instructions"), signature[i]); signature[i] += '|'; }
-            else sig(msgs[i].at("instructions"), signature[i]);
+            if (mp[i]->is_array()) for (const Json &t : mp[i]->arr) { sig(t.at("instructions"), signature[i]); signature[i] += '|'; }
+            else sig(mp[i]->at("instructions"), signature[i]);
         } catch (const std::exception &) { signature[i] = "?"; }
     }
     last_uniform_flushes = last_split_flushes = last_solo = 0;
@@ -1355,8 +1373,9 @@ std::vector<std::string> Backend::execute_many(const std::vector<std::string> &m
                 const Stats before = st.stats;
                 const uint64_t uf0 = st.uniform_flushes, sf0 = st.split_flushes;
                 const auto tq0 = now();
-                for (size_t g = 0; g < G; g++) {
-                    const Json &m = msgs[members[c0 + g]];
+                std::atomic<bool> cuda_failed{false};
+                parallel_for(G, [&](size_t g) {
+                    const Json &m = *mp[members[c0 + g]];
                     jobs[g].st = &st;
                     jobs[g].reg = (int)g;
                     try {
@@ -1364,16 +1383,18 @@ std::vector<std::string> Backend::execute_many(const std::vector<std::string> &m
                         ok[g] = 1;
                     } catch (const DeferAbort &) {
                     } catch (const CudaError &) {
-                        throw;
+                        cuda_failed = true;
                     } catch (const std::exception &) {
                         // Unsupported / InvalidArg from the extra controls of a deferred condition, or a malformed task:
                         // the ordinary path below gives this message its own answer (or its own error)
                     }
                     if (!ok[g]) {   // needs a real collapse / an external channel: leave the register idle, run it alone below
-                        st.select_register((int)g);
+                        State::bind_register_for_this_thread((int)g);
                         st.rq().clear_pending();
                     }
-                }
+                    State::bind_register_for_this_thread(-1);
+                });
+                if (cuda_failed) throw CudaError("CUDA failure while queueing a register");
                 uint64_t max_shots = 0;
                 std::vector<uint64_t> seeds(G, 0);
                 for (size_t g = 0; g < G; g++) if (ok[g]) { max_shots = std::max(max_shots, jobs[g].shots); seeds[g] = jobs[g].seed; }
@@ -1393,30 +1414,66 @@ std::vector<std::string> Backend::execute_many(const std::vector<std::string> &m
                 total.fused_ops += st.stats.fused_ops - before.fused_ops;
                 total.h2d_bytes += st.stats.h2d_bytes - before.h2d_bytes;
                 total.d2h_bytes += st.stats.d2h_bytes - before.d2h_bytes;
-                for (size_t g = 0; g < G; g++) {
-                    if (!ok[g]) continue;
+                for (size_t g = 0; g < G; g++) if (ok[g]) total.gates += jobs[g].gates;
+                parallel_for(G, [&](size_t g) {
+                    if (!ok[g]) return;
                     const RegJob &jb = jobs[g];
-                    total.gates += jb.gates;
-                    // every shot is one draw from the register's final state; a symbolic bit reads its qubit from the index
-                    std::map<std::string, std::map<std::string, uint64_t>> counters;
-                    for (const RegJob::Layout &t : jb.tasks) counters[t.id];
-                    std::vector<uint8_t> bits(jb.symbols.size());
-                    for (uint64_t s = 0; s < jb.shots; s++) {
-                        const uint64_t idx = samples[g * max_shots + s];
-                        for (size_t cl = 0; cl < jb.symbols.size(); cl++) {
-                            const uint8_t v = jb.symbols[cl];
-                            bits[cl] = v >= kSym ? (uint8_t)((idx >> sym_qubit(v)) & 1ull) : v;
+                    // every shot is one draw from the register's final state; a symbolic bit reads its qubit from the index.
+                    // Per task: the classical register of every shot as an integer, sorted -> one string per distinct outcome
+                    std::vector<Json> per_task;
+                    for (const RegJob::Layout &t : jb.tasks) {
+                        Json cj = Json::object();
+                        if (t.ncl <= 64) {
+                            uint64_t konst = 0;
+                            std::vector<std::pair<int, int>> src;  // (register qubit, clbit of this task)
+                            for (int c = 0; c < t.ncl; c++) {
+                                const uint8_t v = jb.symbols[(size_t)(t.zc + c)];
+                                if (v >= kSym) src.emplace_back(sym_qubit(v), c);
+                                else if (v) konst |= 1ull << c;
+                            }
+                            std::vector<uint64_t> keys(jb.shots);
+                            for (uint64_t s = 0; s < jb.shots; s++) {
+                                const uint64_t idx = samples[g * max_shots + s];
+                                uint64_t k = konst;
+                                for (auto &qc : src) k |= ((idx >> qc.first) & 1ull) << qc.second;
+                                keys[s] = k;
+                            }
+                            std::sort(keys.begin(), keys.end());
+                            std::string key((size_t)t.ncl, '0');
+                            for (size_t a = 0; a < keys.size();) {
+                                size_t b = a;
+                                while (b < keys.size() && keys[b] == keys[a]) b++;
+                                for (int c = 0; c < t.ncl; c++) key[t.ncl - 1 - c] = ((keys[a] >> c) & 1ull) ? '1' : '0';
+                                cj.obj.emplace_back(key, Json::integer((long long)(b - a)));
+                                a = b;
+                            }
+                        } else {
+                            std::map<std::string, uint64_t> counts;
+                            std::vector<uint8_t> bits(jb.symbols.size());
+                            for (uint64_t s = 0; s < jb.shots; s++) {
+                                const uint64_t idx = samples[g * max_shots + s];
+                                for (size_t cl = 0; cl < jb.symbols.size(); cl++) {
+                                    const uint8_t v = jb.symbols[cl];
+                                    bits[cl] = v >= kSym ? (uint8_t)((idx >> sym_qubit(v)) & 1ull) : v;
+                                }
+                                counts[bits_to_string(bits, t.zc, t.ncl)]++;
+                            }
+                            cj = counts_json(counts);
                         }
-                        for (const RegJob::Layout &t : jb.tasks) counters[t.id][bits_to_string(bits, t.zc, t.ncl)]++;
+                        per_task.push_back(std::move(cj));
                     }
                     Json out = Json::object();
-                    const Json &m = msgs[members[c0 + g]];
+                    const Json &m = *mp[members[c0 + g]];
                     if (m.is_array()) {
+                        // (id_counts is keyed by task id; ids are unique within a message)
+                        std::vector<size_t> order(jb.tasks.size());
+                        for (size_t k = 0; k < order.size(); k++) order[k] = k;
+                        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return jb.tasks[a].id < jb.tasks[b].id; });
                         Json idc = Json::object();
-                        for (auto &kv : counters) idc.set(kv.first, counts_json(kv.second));
+                        for (size_t k : order) idc.set(jb.tasks[k].id, std::move(per_task[k]));
                         out.set("id_counts", std::move(idc));
                     } else {
-                        out.set("counts", counts_json(counters.begin()->second));
+                        out.set("counts", std::move(per_task[0]));
                     }
                     out.set("time_taken", Json::number(secs));
                     Json info = Json::object();
@@ -1426,7 +1483,7 @@ std::vector<std::string> Backend::execute_many(const std::vector<std::string> &m
                     out.set("b200", std::move(info));
                     results[members[c0 + g]] = out.dump();
                     handled[members[c0 + g]] = 1;
-                }
+                });
                 us_decode += us(tq3, now());
             } catch (const std::exception &e) {
                 for (size_t g = 0; g < G; g++)
@@ -1441,7 +1498,7 @@ std::vector<std::string> Backend::execute_many(const std::vector<std::string> &m
         if (handled[i] || width[i] != -2) continue;
         const Json keep_cached = cached_;
         const bool keep_has = has_cached_;
-        results[i] = execute(msgs[i].dump());
+        results[i] = execute(mp[i]->dump());
         cached_ = keep_cached;
         has_cached_ = keep_has;
         parsed_.reset();

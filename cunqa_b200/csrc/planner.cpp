@@ -432,28 +432,48 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
             if (out.ops[o].kind != OP_DIAG) { o++; continue; }
             int oe = o;
             while (oe + 1 < nops && out.ops[oe + 1].kind == OP_DIAG) oe++;
-            std::vector<int> rb;
-            int fuse_k = 0;
-            if (oe + 1 < nops) {
-                const DevOp &dn = out.ops[oe + 1];
-                if (dn.kind == OP_DENSE && dn.k <= 2 && dn.nfix == dn.k && dn.ctrl_out == 0 && !dn.has_mask) {
-                    fuse_k = dn.k;
-                    for (int m = 0; m < dn.k; m++) rb.push_back(dn.tbit[m]);
-                }
-            }
+            // register bits for the run: the candidates are ranked by how few of the run's tables depend on them (fewest
+            // dependent tables first; then bits >= 3, so that a warp reads whole 128-byte rows; then high bits).  A table that
+            // depends on a register bit costs 16 lookups + 16 complex multiplies per thread instead of one of each.
             std::vector<int> users(t, 0);
             for (int q = o; q <= oe; q++)
                 for (int pos = 0; pos < t; pos++) users[pos] += (out.ops[q].ctrl_in >> pos) & 1u;
-            std::vector<int> cand;
-            for (int pos = 0; pos < t; pos++)
-                if (std::find(rb.begin(), rb.end(), pos) == rb.end()) cand.push_back(pos);
-            // fewest dependent tables first; then bits >= 3 (a warp then reads whole 128-byte rows); then high bits
-            std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
-                if (users[a] != users[b]) return users[a] < users[b];
-                if ((a < 3) != (b < 3)) return b < 3;
-                return a > b;
-            });
-            for (size_t ci = 0; rb.size() < 4; ci++) rb.push_back(cand[ci]);
+            auto choose = [&](std::vector<int> forced) {
+                std::vector<int> cand;
+                for (int pos = 0; pos < t; pos++)
+                    if (std::find(forced.begin(), forced.end(), pos) == forced.end()) cand.push_back(pos);
+                std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
+                    if (users[a] != users[b]) return users[a] < users[b];
+                    if ((a < 3) != (b < 3)) return b < 3;
+                    return a > b;
+                });
+                for (size_t ci = 0; forced.size() < 4; ci++) forced.push_back(cand[ci]);
+                return forced;
+            };
+            auto dependent_tables = [&](const std::vector<int> &bits) {
+                uint32_t m = 0;
+                for (int b : bits) m |= 1u << b;
+                int cnt = 0;
+                for (int q = o; q <= oe; q++) cnt += (out.ops[q].ctrl_in & m) != 0;
+                return cnt;
+            };
+            std::vector<int> rb = choose({});
+            int fuse_k = 0;
+            if (oe + 1 < nops) {
+                // an uncontrolled dense gate of <= 2 qubits right after the run can be applied in the same sweep (its
+                // targets become register bits: one shared-memory round trip and one barrier saved) -- unless that makes
+                // more of the run's tables depend on register bits, which costs more than the round trip saves
+                const DevOp &dn = out.ops[oe + 1];
+                if (dn.kind == OP_DENSE && dn.k <= 2 && dn.nfix == dn.k && dn.ctrl_out == 0 && !dn.has_mask) {
+                    std::vector<int> forced;
+                    for (int m = 0; m < dn.k; m++) forced.push_back(dn.tbit[m]);
+                    const std::vector<int> with = choose(forced);
+                    if (dependent_tables(with) <= dependent_tables(rb)) {
+                        fuse_k = dn.k;
+                        rb = with;
+                    }
+                }
+            }
             std::vector<int> asc = rb;
             std::sort(asc.begin(), asc.end());
             // diagonal ops commute: the tables that ignore the register bits go first (fixpos[1] of them)
