@@ -52,6 +52,8 @@ void State::init_options(int gbits)
     opt.max_diag_qubits = env_int("CB200_MAX_DIAG_QUBITS", 10);
     opt.fuse = env_int("CB200_FUSE", 1) != 0;
     opt.pair_ops = env_int("CB200_PAIR_OPS", 1) != 0;
+    opt.diag_fuse_always = env_int("CB200_DIAG_FUSE_ALWAYS", 0) != 0;
+    opt.stage_diag = env_int("CB200_STAGE_DIAG", 1) != 0;
     if (gbits) opt.global_mask = ((1ull << gbits) - 1ull) << n_local_;
     queue = OpQueue(n, batch, opt);
 }
@@ -301,7 +303,7 @@ void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb)
     std::vector<PassParams<T>> params(passes.size());
     std::string err;
     for (size_t i = 0; i < passes.size(); i++)
-        if (!encode_pass<T>(passes[i], ops, n_local_, vbatch, params[i], diag_host, err, opt.pair_ops)) throw Unsupported(err);
+        if (!encode_pass<T>(passes[i], ops, n_local_, vbatch, params[i], diag_host, err, opt.enc_flags())) throw Unsupported(err);
     // diagonal tables and condition flags: staged in pinned memory, copied asynchronously (no stream drain)
     const std::vector<std::vector<uint8_t>> &mask_rows = rq().mask_rows;
     const size_t diag_bytes = diag_host.size() * sizeof(V);
@@ -342,12 +344,23 @@ void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb)
             for (int d = 0; d < 3 && p.L + d < p.t; d++) { hi_q[d] = p.tile_q[p.L + d]; box_bits++; }
         const uint32_t buf_stride = (uint32_t)std::max<size_t>(1024, sizeof(V) << p.t);
         const int stages = tma_stages_;
-        const size_t smem_tma = (size_t)stages * buf_stride + sizeof(uint64_t) * (stages + 1) + sizeof(uint32_t) * ((((size_t)1 << (p.t - box_bits)) + 3) & ~(size_t)3) +
-                                sizeof(T) * (size_t)((p.n_mat + 1) & ~1) + (size_t)((p.n_diag + 1) & ~1) * 8 + (size_t)p.n_stab * sizeof(V) +
-                                (size_t)p.n_diag * (4 + 2 * kDiagLut) + 16 + 1024;
+        size_t smem_tma = (size_t)stages * buf_stride + sizeof(uint64_t) * (stages + 1) + sizeof(uint32_t) * ((((size_t)1 << (p.t - box_bits)) + 3) & ~(size_t)3) +
+                          sizeof(T) * (size_t)((p.n_mat + 1) & ~1) + (size_t)((p.n_diag + 1) & ~1) * 8 + (size_t)p.n_stab * sizeof(V) +
+                          (size_t)p.n_diag * (4 + 2 * kDiagLut) + 16 + 1024;
         int nt = 1 << std::max(5, std::min(8, p.t - kAmpsPerThreadShift));  // 32 / 64 / 128 / 256 threads
         if (tma_threads_ > 0) nt = tma_threads_;
         int ctas = std::max(1, (stages == 3 ? 256 : 384) / nt);
+        {   // staged diagonal sub-tables must not cost a resident CTA: drop them when they would
+            const size_t without = smem_tma - (size_t)p.n_stab * sizeof(V);
+            const int c_with = std::min<int>(ctas, (int)(max_smem_sm_ / (smem_tma + 1024)));
+            const int c_without = std::min<int>(ctas, (int)(max_smem_sm_ / (without + 1024)));
+            if (p.n_stab && c_with < c_without) {
+                PassParams<T> &pm = params[i];
+                for (int o = 0; o < pm.n_ops; o++) pm.ops[o].stage_off = kNotStaged;
+                pm.n_stab = 0;
+                smem_tma = without;
+            }
+        }
         ctas = std::max(1, std::min<int>(ctas, (int)(max_smem_sm_ / (smem_tma + 1024))));  // what shared memory allows
         if (tma_max_ctas_ > 0) ctas = std::min(ctas, tma_max_ctas_);
         // (a run of one 128-byte row is enough once the three folded qubits make the box 1 KiB = one swizzle atom)
@@ -443,7 +456,7 @@ void State::launch_uniform_t(int b0, int nb)
     std::vector<cplx> diag0;
     std::string err;
     for (size_t i = 0; i < passes.size(); i++)
-        if (!encode_pass<T>(passes[i], ops0, n_local_, G, params[i], diag0, err, opt.pair_ops)) throw Unsupported(err);
+        if (!encode_pass<T>(passes[i], ops0, n_local_, G, params[i], diag0, err, opt.enc_flags())) throw Unsupported(err);
     const size_t D = diag0.size();
     std::vector<size_t> mat_off(passes.size() + 1, 0);   // scalar offset of pass i's [G][stride_i] block
     std::vector<uint32_t> mat_stride(passes.size());
@@ -477,7 +490,7 @@ void State::launch_uniform_t(int b0, int nb)
         for (size_t i = 0; i < passes.size(); i++) {
             const PassParams<T> *src = &params[i];
             if (g > 0) {
-                if (!encode_pass<T>(passes[i], ops, n_local_, G, tmp, dg, err, opt.pair_ops)) throw Unsupported(err);
+                if (!encode_pass<T>(passes[i], ops, n_local_, G, tmp, dg, err, opt.enc_flags())) throw Unsupported(err);
                 if (tmp.n_mat != params[i].n_mat || tmp.n_ops != params[i].n_ops) throw Unsupported("internal: register passes differ in layout");
                 src = &tmp;
             }

@@ -46,7 +46,8 @@ struct DevOp {
     uint64_t ctrl_out;  // physical-qubit mask of controls outside the tile (tested on the tile base)
     int32_t mask_row;   // row of the per-state flag matrix (batched feed-forward) when has_mask
     uint8_t k2, s;      // PAIR: #targets of gate B and its first local bit; B's matrix follows A's in mats
-                        // DIAG: k2 = slot of this op among the pass's diagonal ops (index of its pext tables)
+                        // DIAG: k2 = slot of this op among the pass's diagonal ops (index of its pext tables); s = 1 when the
+                        // table depends on a register bit of its run (looked up per amplitude)
     uint16_t stage_off;  // DIAG: entry offset of this op's per-tile sub-table in the shared-memory table store; kNotStaged = read from global memory
 };
 static_assert(sizeof(DevOp) == 64, "DevOp layout");

@@ -280,8 +280,9 @@ std::vector<Pass> schedule_passes(const std::vector<HostOp> &ops, int n, const P
 
 template <typename T>
 bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int batch, PassParams<T> &out,
-                 std::vector<cplx> &diag_host, std::string &err, bool pair_ops)
+                 std::vector<cplx> &diag_host, std::string &err, int flags)
 {
+    const bool pair_ops = (flags & kEncPairOps) != 0;
     std::memset(&out, 0, sizeof(out));
     const int t = (int)pass.tile_q.size();
     out.n = n;
@@ -468,7 +469,7 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
                     std::vector<int> forced;
                     for (int m = 0; m < dn.k; m++) forced.push_back(dn.tbit[m]);
                     const std::vector<int> with = choose(forced);
-                    if (dependent_tables(with) <= dependent_tables(rb)) {
+                    if ((flags & kEncDiagFuseAlways) || dependent_tables(with) <= dependent_tables(rb)) {
                         fuse_k = dn.k;
                         rb = with;
                     }
@@ -487,6 +488,7 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
                 out.ops[q].k2 = (uint8_t)(slot0 + (q - o));
                 out.diag_op[slot0 + (q - o)] = (uint8_t)q;
                 n_indep += (out.ops[q].ctrl_in & rmask) == 0;
+                out.ops[q].s = (out.ops[q].ctrl_in & rmask) != 0;  // DIAG: 1 = looked up per amplitude (depends on a register bit)
             }
             DevOp &run = out.ops[o];
             for (int b = 0; b < 4; b++) { run.tbit[b] = (uint8_t)rb[b]; run.tbit[4 + b] = (uint8_t)asc[b]; }
@@ -506,7 +508,8 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
     for (int o = 0; o < nops; o++) out.ops[o].stage_off = kNotStaged;
     for (int sl = 0; sl < out.n_diag; sl++) {
         DevOp &d = out.ops[out.diag_op[sl]];
-        if (d.nfix > kStabMaxBits || d.has_mask || d.ctrl_out) continue;
+        // (only tables that are looked up per amplitude are worth a slot: the others cost one lookup per thread anyway)
+        if ((flags & kEncNoStage) || !d.s || d.nfix > kStabMaxBits || d.has_mask || d.ctrl_out) continue;
         const int need = std::max(8, 1 << d.nfix);  // (chunks of 8 entries)
         if (out.n_stab + need > kStabEntries) continue;
         d.stage_off = (uint16_t)out.n_stab;
@@ -517,8 +520,8 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
 }
 
 template bool encode_pass<double>(const Pass &, const std::vector<HostOp> &, int, int, PassParams<double> &,
-                                  std::vector<cplx> &, std::string &, bool);
+                                  std::vector<cplx> &, std::string &, int);
 template bool encode_pass<float>(const Pass &, const std::vector<HostOp> &, int, int, PassParams<float> &,
-                                 std::vector<cplx> &, std::string &, bool);
+                                 std::vector<cplx> &, std::string &, int);
 
 }  // namespace cb200

@@ -27,6 +27,11 @@ struct HostOp {
     uint64_t xmask() const;   // qubits acted on non-diagonally
 };
 
+// encode_pass flags
+constexpr int kEncPairOps = 1;         // register-block adjacent dense gates
+constexpr int kEncDiagFuseAlways = 2;  // always fold a diagonal run into the dense gate that follows it (experiments)
+constexpr int kEncNoStage = 4;         // no per-tile shared-memory staging of diagonal sub-tables (experiments)
+
 struct PlanOptions {
     int tile_bits = 12;        // t: 2^t amplitudes staged per tile
     int min_run_bits = 4;      // L_min: low physical qubits forced into every tile (coalescing)
@@ -38,6 +43,8 @@ struct PlanOptions {
     int lookahead_min_qubits = 24;  // smaller states: a pass costs less than the look-ahead that would save it
     bool fuse = true;
     bool pair_ops = true;      // register-block adjacent dense gates (two gates per shared-memory round trip)
+    bool diag_fuse_always = false, stage_diag = true;  // experiments (CB200_DIAG_FUSE_ALWAYS, CB200_STAGE_DIAG)
+    int enc_flags() const { return (pair_ops ? kEncPairOps : 0) | (diag_fuse_always ? kEncDiagFuseAlways : 0) | (stage_diag ? 0 : kEncNoStage); }
     uint64_t global_mask = 0;  // sharded state: physical qubits that select the rank (never fused into dense blocks)
 };
 
@@ -72,6 +79,6 @@ std::vector<Pass> schedule_passes(const std::vector<HostOp> &ops, int n, const P
 // (element units) and referenced by offset.  Returns false + err if the pass cannot be encoded.
 template <typename T>
 bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int batch, PassParams<T> &out,
-                 std::vector<cplx> &diag_host, std::string &err, bool pair_ops = true);
+                 std::vector<cplx> &diag_host, std::string &err, int flags = kEncPairOps);
 
 }  // namespace cb200
