@@ -89,8 +89,11 @@ public:
     void barrier();
     void fence(int rank, cudaStream_t stream);
     template <typename W> void allreduce(int rank, W *d_buf, size_t count, cudaStream_t stream);
+    static constexpr int kMaxChunks = 8;
+    cudaEvent_t chunk_event(int rank, int c) { return chunk_events_[rank][c]; }
 
 private:
+    std::vector<std::array<cudaEvent_t, kMaxChunks>> chunk_events_;   // [rank][chunk of the exchange in flight]
     void worker(int rank);
     std::vector<std::unique_ptr<State>> shards_;
     std::vector<int> devices_;
@@ -132,6 +135,10 @@ struct SwapPlan {
     int lbit[4];      // ascending
     int perm[4];      // lbit[j] belongs to pair perm[j] (bit perm[j] of x / y)
     uint32_t x;
+    // chunked exchange (pipelined with the tile passes around it): this launch only moves the elements whose top
+    // `chunk_bits` rest bits (below the bit that splits a pair's work between its two ranks) equal `chunk`
+    int chunk_bits;
+    uint32_t chunk;
 };
 
 template <typename V>
@@ -139,12 +146,14 @@ __global__ void __launch_bounds__(256) qubit_swap_kernel(V *__restrict__ mine, c
 {
     const int rest_bits = sp.n_local - sp.m - 1;  // index bits of one half of one slab
     const uint64_t half = 1ull << rest_bits;
-    const uint64_t total = (uint64_t)((1u << sp.m) - 1) << rest_bits;
+    const int cr_bits = rest_bits - sp.chunk_bits;  // index bits of this launch's chunk of a half
+    const uint64_t total = (uint64_t)((1u << sp.m) - 1) << cr_bits;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+    for (uint64_t wc = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wc < total; wc += stride) {
         // partner of step j is x ^ (j + 1): at every step the ranks pair up, so no GPU's NVLink port is oversubscribed
-        const uint32_t y = sp.x ^ ((uint32_t)(w >> rest_bits) + 1u);
-        uint64_t r = (w & (half - 1)) | (sp.x < y ? 0 : half);
+        const uint32_t y = sp.x ^ ((uint32_t)(wc >> cr_bits) + 1u);
+        const uint64_t rl = (wc & ((1ull << cr_bits) - 1ull)) | ((uint64_t)sp.chunk << cr_bits);
+        uint64_t r = rl | (sp.x < y ? 0 : half);
         uint64_t mi = r, pi;
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -199,30 +208,37 @@ void State::dist_fence()
     stats.launches++;
 }
 
-void State::dist_swap(const std::vector<std::pair<int, int>> &pairs)
+static SwapPlan make_swap_plan(const DistContext &dc, int n_local, const std::vector<std::pair<int, int>> &pairs)
 {
-    if ((int)dist->peers.size() != dist->world) throw InvalidArg("sharded state: peer handles were not imported");
+    if ((int)dc.peers.size() != dc.world) throw InvalidArg("sharded state: peer handles were not imported");
     const int m = (int)pairs.size();
-    if (m < 1 || m > 4 || m >= n_local_) throw InvalidArg("sharded state: 1..4 qubit pairs per exchange");
+    if (m < 1 || m > 4 || m >= n_local) throw InvalidArg("sharded state: 1..4 qubit pairs per exchange");
     for (int a = 0; a < m; a++)
         for (int b = a + 1; b < m; b++)
             if (pairs[a].first == pairs[b].first || pairs[a].second == pairs[b].second)
                 throw InvalidArg("sharded state: repeated global or local bit in one exchange");
     SwapPlan sp{};
     sp.m = m;
-    sp.n_local = n_local_;
+    sp.n_local = n_local;
     std::vector<int> order(m);
     for (int j = 0; j < m; j++) order[j] = j;
     std::sort(order.begin(), order.end(), [&](int a, int b) { return pairs[a].second < pairs[b].second; });
     for (int j = 0; j < m; j++) { sp.lbit[j] = pairs[order[j]].second; sp.perm[j] = order[j]; }
     uint32_t x = 0;
-    for (int j = 0; j < m; j++) x |= (uint32_t)((dist->rank >> pairs[j].first) & 1) << j;
+    for (int j = 0; j < m; j++) x |= (uint32_t)((dc.rank >> pairs[j].first) & 1) << j;
     sp.x = x;
     for (uint32_t y = 0; y < (1u << m); y++) {
-        int r = dist->rank;
+        int r = dc.rank;
         for (int j = 0; j < m; j++) r = (r & ~(1 << pairs[j].first)) | (int)((y >> j) & 1u) << pairs[j].first;
-        sp.peer[y] = dist->peers[r];
+        sp.peer[y] = dc.peers[r];
     }
+    return sp;
+}
+
+void State::dist_swap(const std::vector<std::pair<int, int>> &pairs)
+{
+    const int m = (int)pairs.size();
+    SwapPlan sp = make_swap_plan(*dist, n_local_, pairs);
     const uint64_t total = (uint64_t)((1u << m) - 1) << (n_local_ - m - 1);
     cudaEvent_t e0, e1;
     CB200_CUDA(cudaEventCreate(&e0));
@@ -243,6 +259,74 @@ void State::dist_swap(const std::vector<std::pair<int, int>> &pairs)
     dist->swap_bytes += (state_bytes_ >> m) * ((1u << m) - 1);  // sent (= received) per rank
 }
 
+// The same exchange in 2^chunk_bits chunks on a second stream, so that the tile passes AFTER it can start on the chunks
+// that have arrived while the rest is still crossing NVLink (single-process groups: chunk completion is a CUDA event per
+// rank and chunk, waited on across devices).  The chunk is selected by the highest local positions that are neither
+// exchanged nor the position that splits a pair's work between its two ranks; `pipe` tells the passes which they are.
+void State::dist_swap_chunked(const std::vector<std::pair<int, int>> &pairs, int chunk_bits, ChunkPipe &pipe)
+{
+    ShardGroup *grp = dist->group;
+    const int m = (int)pairs.size();
+    SwapPlan sp = make_swap_plan(*dist, n_local_, pairs);
+    const int rest_bits = n_local_ - m - 1;
+    chunk_bits = std::max(0, std::min(chunk_bits, std::min(3, rest_bits - 8)));
+    const int K = 1 << chunk_bits;
+    // local positions that are not exchanged, ascending: the top one splits the pair's work, the next chunk_bits select the chunk
+    std::vector<int> rest;
+    for (int p = 0; p < n_local_; p++) {
+        bool ex = false;
+        for (auto &pr : pairs) ex = ex || pr.second == p;
+        if (!ex) rest.push_back(p);
+    }
+    pipe.mask = 0;
+    pipe.vals.assign(K, 0);
+    for (int b = 0; b < chunk_bits; b++) {
+        const int pos = rest[rest.size() - 1 - chunk_bits + b];   // rest index (rest_bits - chunk_bits + b)
+        pipe.mask |= 1ull << pos;
+        for (int c = 0; c < K; c++) if ((c >> b) & 1) pipe.vals[c] |= 1ull << pos;
+    }
+    if (!xstream_) CB200_CUDA(cudaStreamCreateWithFlags(&xstream_, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1;
+    CB200_CUDA(cudaEventCreate(&e0));
+    CB200_CUDA(cudaEventCreate(&e1));
+    dist_fence();  // every shard quiescent (and every rank has enqueued its waits on the previous exchange's chunk events)
+    CB200_CUDA(cudaEventRecord(e0, stream_));
+    CB200_CUDA(cudaStreamWaitEvent(xstream_, e0, 0));
+    const uint64_t total = (uint64_t)((1u << m) - 1) << (rest_bits - chunk_bits);
+    const int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)num_sms_ * 16);
+    for (int c = 0; c < K; c++) {
+        sp.chunk_bits = chunk_bits;
+        sp.chunk = (uint32_t)c;
+        if (precision == 64) qubit_swap_kernel<double2><<<blocks, 256, 0, xstream_>>>((double2 *)d_state_, sp);
+        else qubit_swap_kernel<float2><<<blocks, 256, 0, xstream_>>>((float2 *)d_state_, sp);
+        CB200_CUDA(cudaGetLastError());
+        CB200_CUDA(cudaEventRecord(grp->chunk_event(dist->rank, c), xstream_));
+        stats.launches++;
+    }
+    CB200_CUDA(cudaEventRecord(e1, xstream_));
+    dist->swap_events.emplace_back(e0, e1);
+    if (dist->swap_events.size() >= 64) dist_swap_ms();
+    grp->barrier();   // every rank has recorded its chunk events: they can be waited on now
+    // the ranks that write into this shard: the 2^m - 1 partners of the exchange (and this rank's own kernel)
+    std::vector<int> writers;
+    for (uint32_t y = 0; y < (1u << m); y++) {
+        int r = dist->rank;
+        for (int j = 0; j < m; j++) r = (r & ~(1 << pairs[j].first)) | (int)((y >> j) & 1u) << pairs[j].first;
+        writers.push_back(r);
+    }
+    cudaStream_t s = stream_;
+    pipe.wait_chunk = [grp, writers, s](int c) {
+        for (int r : writers) CB200_CUDA(cudaStreamWaitEvent(s, grp->chunk_event(r, c), 0));
+    };
+    pipe.wait_all = [grp, writers, s, K]() {
+        for (int c = 0; c < K; c++)
+            for (int r : writers) CB200_CUDA(cudaStreamWaitEvent(s, grp->chunk_event(r, c), 0));
+    };
+    dist->swaps += m;
+    dist->exchanges++;
+    dist->swap_bytes += (state_bytes_ >> m) * ((1u << m) - 1);
+}
+
 template <typename T>
 void State::flush_dist_t()
 {
@@ -254,10 +338,19 @@ void State::flush_dist_t()
     // swaps planned together (same batch id) become one multi-qubit exchange.  Grouping by batch id -- not by adjacency
     // in this rank's segment list -- keeps the number and shape of exchanges identical on every rank: a LOCAL segment
     // that separates two batches on one rank can be empty (all its ops dropped by a global control) on another.
+    // single-process groups pipeline the exchange with the pass that follows it (CB200_SWAP_CHUNK_BITS, default 2: four
+    // chunks; 0 = one kernel on the main stream as in the one-process-per-GPU mode)
+    static const int chunk_bits_cfg = getenv("CB200_SWAP_CHUNK_BITS") ? std::max(0, std::min(3, atoi(getenv("CB200_SWAP_CHUNK_BITS")))) : 2;
+    const int chunk_bits = (dist->group && n_local_ >= 24) ? chunk_bits_cfg : 0;
     std::vector<std::pair<int, int>> group;
     int group_batch = -1;
+    ChunkPipe pipe;   // the exchange in flight, if any
     auto exchange = [&]() {
-        if (!group.empty()) dist_swap(group);
+        if (!group.empty()) {
+            if (pipe.wait_all) { pipe.wait_all(); pipe = ChunkPipe(); }   // two exchanges back to back: the first one completes first
+            if (chunk_bits > 0) dist_swap_chunked(group, chunk_bits, pipe);
+            else dist_swap(group);
+        }
         group.clear();
     };
     for (const DistSegment &seg : plan.segments) {
@@ -269,10 +362,12 @@ void State::flush_dist_t()
         } else {
             exchange();
             std::vector<HostOp> local = seg.ops;
-            launch_ops_t<T>(local);
+            launch_ops_t<T>(local, 0, -1, pipe.wait_all ? &pipe : nullptr);
+            pipe = ChunkPipe();
         }
     }
     exchange();
+    if (pipe.wait_all) pipe.wait_all();   // an exchange at the very end: the stream's next user sees it complete
     for (int &p : queue.l2p) p = plan.sigma[p];
     queue.clear_pending();
 }
@@ -393,9 +488,11 @@ ShardGroup::ShardGroup(int n, int precision, const std::vector<int> &devices) : 
     events_.resize(w);
     fence_no_.assign(w, 0);
     host_.resize(w);
+    chunk_events_.resize(w);
     for (int r = 0; r < w; r++) {
         CB200_CUDA(cudaSetDevice(devices[r]));
         for (int k = 0; k < 2; k++) CB200_CUDA(cudaEventCreateWithFlags(&events_[r][k], cudaEventDisableTiming));
+        for (int c = 0; c < kMaxChunks; c++) CB200_CUDA(cudaEventCreateWithFlags(&chunk_events_[r][c], cudaEventDisableTiming));
     }
     for (int r = 0; r < w; r++) threads_.emplace_back([this, r] { worker(r); });
 }
@@ -412,6 +509,7 @@ ShardGroup::~ShardGroup()
     for (size_t r = 0; r < events_.size(); r++) {
         cudaSetDevice(devices_[r]);
         for (int k = 0; k < 2; k++) if (events_[r][k]) cudaEventDestroy(events_[r][k]);
+        for (int c = 0; c < kMaxChunks; c++) if (chunk_events_[r][c]) cudaEventDestroy(chunk_events_[r][c]);
     }
 }
 

@@ -52,8 +52,8 @@ void State::init_options(int gbits)
     opt.max_diag_qubits = env_int("CB200_MAX_DIAG_QUBITS", 10);
     opt.fuse = env_int("CB200_FUSE", 1) != 0;
     opt.pair_ops = env_int("CB200_PAIR_OPS", 1) != 0;
-    opt.diag_fuse_always = env_int("CB200_DIAG_FUSE_ALWAYS", 0) != 0;
-    opt.stage_diag = env_int("CB200_STAGE_DIAG", 1) != 0;
+    opt.diag_fuse_always = env_int("CB200_DIAG_FUSE_ALWAYS", 1) != 0;
+    opt.stage_diag = env_int("CB200_STAGE_DIAG", 0) != 0;
     if (gbits) opt.global_mask = ((1ull << gbits) - 1ull) << n_local_;
     queue = OpQueue(n, batch, opt);
 }
@@ -123,6 +123,8 @@ void State::release()
     d_outcome_ = nullptr; d_counters_ = nullptr; d_forced_ = nullptr;
     if (stream_) cudaStreamDestroy(stream_);
     stream_ = nullptr;
+    if (xstream_) cudaStreamDestroy(xstream_);
+    xstream_ = nullptr;
     cudaGetLastError();
 }
 
@@ -291,10 +293,10 @@ void State::flush_t()
 
 // plan `ops` (physical qubits < n_local) into tile passes and launch them on this shard
 template <typename T>
-void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb)
+void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb, ChunkPipe *pipe)
 {
     using V = typename Vec2<T>::type;
-    if (ops.empty()) return;
+    if (ops.empty()) { if (pipe && pipe->wait_all) pipe->wait_all(); return; }
     const int vbatch = nb < 0 ? batch : nb;
     const size_t view_bytes = nb < 0 ? state_bytes_ : (amp_bytes_ << n_local_) * (size_t)nb;
     void *view_ptr = (char *)d_state_ + (nb < 0 ? 0 : (amp_bytes_ << n_local_) * (size_t)b0);
@@ -336,6 +338,15 @@ void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb)
     for (size_t i = 0; i < passes.size(); i++) {
         const PassParams<T> &p = params[i];
         const uint64_t total_tiles = p.tiles_per_state * (uint64_t)vbatch;
+        // a chunked exchange is still in flight: the first pass runs chunk by chunk as the chunks arrive -- possible when
+        // none of its tile qubits selects the chunk (every tile then lies inside one chunk)
+        int n_chunks = 1;
+        if (i == 0 && pipe && pipe->wait_all) {
+            bool clash = pipe->mask == 0 || pipe->vals.size() < 2;
+            for (int j = 0; j < p.t; j++) clash = clash || ((pipe->mask >> p.tile_q[j]) & 1ull);
+            if (clash) pipe->wait_all();
+            else n_chunks = (int)pipe->vals.size();
+        }
         // TMA box: the contiguous run (at most 256 rows of it) plus up to three high tile qubits
         const int run_bits = std::min(p.L, aprs + 8);
         int hi_q[3] = {-1, -1, -1};
@@ -365,11 +376,17 @@ void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb)
         if (tma_max_ctas_ > 0) ctas = std::min(ctas, tma_max_ctas_);
         // (a run of one 128-byte row is enough once the three folded qubits make the box 1 KiB = one swizzle atom)
         const bool tma = use_tma_ && p.L >= aprs + (box_bits >= aprs + 3 ? 0 : 1) && view_bytes >= 128 && smem_tma <= max_smem_;
+        for (int c = 0; c < n_chunks; c++) {
+        if (n_chunks > 1) {
+            pipe->wait_chunk(c);
+            params[i].chunk_mask = pipe->mask;
+            params[i].chunk_val = pipe->vals[c];
+        }
         if (tma) {
             CUtensorMap tmap;
             make_tensor_map(&tmap, run_bits, hi_q, b0, nb);
             TmaLaunch l;
-            l.grid = (unsigned)std::min<uint64_t>(total_tiles, (uint64_t)num_sms_ * ctas);
+            l.grid = (unsigned)std::min<uint64_t>(total_tiles / n_chunks, (uint64_t)num_sms_ * ctas);
             l.smem = smem_tma;
             l.stream = stream_;
             l.diag_tabs = d_diag_;
@@ -389,15 +406,16 @@ void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb)
             CB200_CUDA(launch_tile_pass_generic<T>(p, view_ptr, d_diag_, d_flags_, num_sms_, ctas_per_sm_, device, stream_));
         }
         CB200_CUDA(cudaGetLastError());
-        stats.passes++;
         stats.launches++;
+        }
+        stats.passes++;
         stats.h2d_bytes += sizeof(PassParams<T>) + (tma ? sizeof(CUtensorMap) : 0);
         stats.bytes += 2ull * view_bytes;
         stats.fused_ops += (uint64_t)p.n_ops;
     }
 }
-template void State::launch_ops_t<double>(std::vector<HostOp> &, int, int);
-template void State::launch_ops_t<float>(std::vector<HostOp> &, int, int);
+template void State::launch_ops_t<double>(std::vector<HostOp> &, int, int, ChunkPipe *);
+template void State::launch_ops_t<float>(std::vector<HostOp> &, int, int, ChunkPipe *);
 
 // ---- independent registers ------------------------------------------------------------------------
 static bool same_structure(const std::vector<HostOp> &a, const std::vector<HostOp> &b)

@@ -10,6 +10,7 @@
 
 #include <cstdint>
 #include <functional>
+#include <utility>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -33,6 +34,15 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 struct Stats {
     uint64_t passes = 0, gates = 0, fused_ops = 0, bytes = 0, launches = 0;
     uint64_t relabelled_swaps = 0, h2d_bytes = 0, d2h_bytes = 0;
+};
+
+// one chunked qubit exchange as seen by the tile passes that follow it (dist.cu): the exchange moves the shard in 2^c
+// chunks on a second stream; the first pass after it runs chunk by chunk as the chunks arrive
+struct ChunkPipe {
+    uint64_t mask = 0;                        // physical local bits that select the chunk (0: nothing in flight)
+    std::vector<uint64_t> vals;               // vals[c]: those bits for chunk c, in the order the chunks are exchanged
+    std::function<void(int)> wait_chunk;      // this shard's stream waits until chunk c has arrived from every partner
+    std::function<void()> wait_all;
 };
 
 struct DistContext;  // dist.cu
@@ -134,7 +144,10 @@ private:
     void dist_allreduce_u64(uint64_t *d_buf, size_t count);
     template <typename T> void flush_dist_t();
     // plan `ops` into tile passes and launch them on states [b0, b0 + nb) of the batch (nb < 0: the whole batch)
-    template <typename T> void launch_ops_t(std::vector<HostOp> &ops, int b0 = 0, int nb = -1);
+    template <typename T> void launch_ops_t(std::vector<HostOp> &ops, int b0 = 0, int nb = -1, ChunkPipe *pipe = nullptr);
+    // chunked exchange on a second stream (single-process groups): fills `pipe` for the passes that follow
+    void dist_swap_chunked(const std::vector<std::pair<int, int>> &pairs, int chunk_bits, ChunkPipe &pipe);
+    cudaStream_t xstream_ = nullptr;
     template <typename T> void flush_registers_t();
     template <typename T> void launch_uniform_t(int b0, int nb);
     // pinned staging for host->device uploads of tables / flags / matrices (two slots, reused once their copy is done)

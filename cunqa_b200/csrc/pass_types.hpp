@@ -62,6 +62,8 @@ struct PassParams {
     int32_t pad_;
     uint64_t tiles_per_state;
     uint64_t cond_mask; // ops whose activity depends on the tile (controls outside the tile / per-state mask)
+    uint64_t chunk_mask, chunk_val;  // only tiles whose base satisfies (base & chunk_mask) == chunk_val are processed
+                                     // (a sharded pass pipelined behind a chunked qubit exchange); 0 / 0 = every tile
     int32_t n_mat;      // scalars used in mats (staged into shared memory once per CTA)
     int32_t needs_full; // kernel variant: 0 = lean (1-2 qubit dense gates, common register blocks, permutations), 1 = lean +
                         // diagonal runs, 2 = full (dense k>=3, unusual register blocks, generic diagonal path)

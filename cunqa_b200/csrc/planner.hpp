@@ -43,7 +43,11 @@ struct PlanOptions {
     int lookahead_min_qubits = 24;  // smaller states: a pass costs less than the look-ahead that would save it
     bool fuse = true;
     bool pair_ops = true;      // register-block adjacent dense gates (two gates per shared-memory round trip)
-    bool diag_fuse_always = false, stage_diag = true;  // experiments (CB200_DIAG_FUSE_ALWAYS, CB200_STAGE_DIAG)
+    // measured on QFT-30 (profiles/qft30_diag_ab_r02.txt): folding a diagonal run into the dense gate after it always pays
+    // (81.6 ms against 84.9 when it is skipped where it makes more tables depend on register bits), and staging the
+    // per-amplitude sub-tables in shared memory does not (82.6 against 81.6): the pass is bound by its instruction count
+    // (258 per amplitude), not by the table loads.  Both stay switchable: CB200_DIAG_FUSE_ALWAYS, CB200_STAGE_DIAG.
+    bool diag_fuse_always = true, stage_diag = false;
     int enc_flags() const { return (pair_ops ? kEncPairOps : 0) | (diag_fuse_always ? kEncDiagFuseAlways : 0) | (stage_diag ? 0 : kEncNoStage); }
     uint64_t global_mask = 0;  // sharded state: physical qubits that select the rank (never fused into dense blocks)
 };

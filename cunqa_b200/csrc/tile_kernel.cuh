@@ -508,6 +508,7 @@ tile_pass_kernel(const __grid_constant__ PassParams<T> p, typename Vec2<T>::type
         for (int j = L; j < t; j++) base = insert0_64(base, p.tile_q[j] - L);
         base <<= L;  // tile qubits 0..L-1 are the L lowest physical qubits
 
+        if ((base & p.chunk_mask) != p.chunk_val) continue;  // not this launch's chunk of the state
         // which ops act on this tile (controls outside the tile, per-state masks)
         const uint64_t active = active_ops(p, flags, b, base);
         if (active == 0) continue;  // untouched tile: no traffic at all
@@ -666,11 +667,17 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     // every thread, so the tile sequence lives in registers and needs no shared bookkeeping.
     auto next_active = [&](uint64_t from) -> uint64_t {
         if constexpr (!COND) {
-            return from < total_tiles ? from : ~0ull;
+            if (p.chunk_mask == 0) return from < total_tiles ? from : ~0ull;
+            for (uint64_t x = from; x < total_tiles; x += gridDim.x) {   // chunked pass: skip the tiles of other chunks
+                uint64_t b;
+                if ((tile_base(x, b) & p.chunk_mask) == p.chunk_val) return x;
+            }
+            return ~0ull;
         } else {
             for (uint64_t x = from; x < total_tiles; x += gridDim.x) {
                 uint64_t b;
                 const uint64_t base = tile_base(x, b);
+                if ((base & p.chunk_mask) != p.chunk_val) continue;
                 if (active_ops(p, flags, b, base) != 0) return x;
             }
             return ~0ull;
