@@ -91,6 +91,7 @@ public:
     template <typename W> void allreduce(int rank, W *d_buf, size_t count, cudaStream_t stream);
     static constexpr int kMaxChunks = 8;
     cudaEvent_t chunk_event(int rank, int c) { return chunk_events_[rank][c]; }
+    uint64_t all_or(int rank, uint64_t v);   // bitwise OR of one host word over the ranks (collective)
 
 private:
     std::vector<std::array<cudaEvent_t, kMaxChunks>> chunk_events_;   // [rank][chunk of the exchange in flight]
@@ -139,6 +140,7 @@ struct SwapPlan {
     // `chunk_bits` rest bits (below the bit that splits a pair's work between its two ranks) equal `chunk`
     int chunk_bits;
     uint32_t chunk;
+    int cpos[3];      // ascending positions of the chunk bits in the pair-half index r (below its top bit)
 };
 
 template <typename V>
@@ -152,7 +154,10 @@ __global__ void __launch_bounds__(256) qubit_swap_kernel(V *__restrict__ mine, c
     for (uint64_t wc = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wc < total; wc += stride) {
         // partner of step j is x ^ (j + 1): at every step the ranks pair up, so no GPU's NVLink port is oversubscribed
         const uint32_t y = sp.x ^ ((uint32_t)(wc >> cr_bits) + 1u);
-        const uint64_t rl = (wc & ((1ull << cr_bits) - 1ull)) | ((uint64_t)sp.chunk << cr_bits);
+        uint64_t rl = wc & ((1ull << cr_bits) - 1ull);
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            if (c < sp.chunk_bits) rl = insert0_64(rl, (uint32_t)sp.cpos[c]) | ((uint64_t)((sp.chunk >> c) & 1u) << sp.cpos[c]);
         uint64_t r = rl | (sp.x < y ? 0 : half);
         uint64_t mi = r, pi;
 #pragma unroll
@@ -263,14 +268,16 @@ void State::dist_swap(const std::vector<std::pair<int, int>> &pairs)
 // that have arrived while the rest is still crossing NVLink (single-process groups: chunk completion is a CUDA event per
 // rank and chunk, waited on across devices).  The chunk is selected by the highest local positions that are neither
 // exchanged nor the position that splits a pair's work between its two ranks; `pipe` tells the passes which they are.
-void State::dist_swap_chunked(const std::vector<std::pair<int, int>> &pairs, int chunk_bits, ChunkPipe &pipe)
+void State::dist_swap_chunked(const std::vector<std::pair<int, int>> &pairs, int chunk_bits, ChunkPipe &pipe, uint64_t avoid)
 {
     ShardGroup *grp = dist->group;
     const int m = (int)pairs.size();
     SwapPlan sp = make_swap_plan(*dist, n_local_, pairs);
     const int rest_bits = n_local_ - m - 1;
     chunk_bits = std::max(0, std::min(chunk_bits, std::min(3, rest_bits - 8)));
-    const int K = 1 << chunk_bits;
+    // every rank must cut the same chunks: the positions to keep clear are the union over the ranks (their next passes
+    // differ where ops controlled by global qubits were dropped)
+    avoid = grp->all_or(dist->rank, avoid);
     // local positions that are not exchanged, ascending: the top one splits the pair's work, the next chunk_bits select the chunk
     std::vector<int> rest;
     for (int p = 0; p < n_local_; p++) {
@@ -278,12 +285,21 @@ void State::dist_swap_chunked(const std::vector<std::pair<int, int>> &pairs, int
         for (auto &pr : pairs) ex = ex || pr.second == p;
         if (!ex) rest.push_back(p);
     }
+    // chunk bits: the highest of those positions (below the top one) that are not tile qubits of the pass that follows --
+    // a tile must lie inside one chunk for the pass to run chunk by chunk
+    std::vector<int> cidx;   // indices into `rest` (= bit positions in the pair-half index r), descending
+    for (int i = (int)rest.size() - 2; i >= 6 && (int)cidx.size() < chunk_bits; i--)
+        if (!((avoid >> rest[i]) & 1ull)) cidx.push_back(i);
+    if ((int)cidx.size() < chunk_bits) { chunk_bits = 0; cidx.clear(); }
+    std::sort(cidx.begin(), cidx.end());
+    const int K2 = 1 << chunk_bits;
     pipe.mask = 0;
-    pipe.vals.assign(K, 0);
+    pipe.vals.assign(K2, 0);
     for (int b = 0; b < chunk_bits; b++) {
-        const int pos = rest[rest.size() - 1 - chunk_bits + b];   // rest index (rest_bits - chunk_bits + b)
+        const int pos = rest[cidx[b]];
+        sp.cpos[b] = cidx[b];
         pipe.mask |= 1ull << pos;
-        for (int c = 0; c < K; c++) if ((c >> b) & 1) pipe.vals[c] |= 1ull << pos;
+        for (int c = 0; c < K2; c++) if ((c >> b) & 1) pipe.vals[c] |= 1ull << pos;
     }
     if (!xstream_) CB200_CUDA(cudaStreamCreateWithFlags(&xstream_, cudaStreamNonBlocking));
     cudaEvent_t e0, e1;
@@ -294,6 +310,7 @@ void State::dist_swap_chunked(const std::vector<std::pair<int, int>> &pairs, int
     CB200_CUDA(cudaStreamWaitEvent(xstream_, e0, 0));
     const uint64_t total = (uint64_t)((1u << m) - 1) << (rest_bits - chunk_bits);
     const int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)num_sms_ * 16);
+    const int K = 1 << chunk_bits;
     for (int c = 0; c < K; c++) {
         sp.chunk_bits = chunk_bits;
         sp.chunk = (uint32_t)c;
@@ -345,28 +362,41 @@ void State::flush_dist_t()
     std::vector<std::pair<int, int>> group;
     int group_batch = -1;
     ChunkPipe pipe;   // the exchange in flight, if any
-    auto exchange = [&]() {
+    auto exchange = [&](const DistSegment *next_local) {
         if (!group.empty()) {
             if (pipe.wait_all) { pipe.wait_all(); pipe = ChunkPipe(); }   // two exchanges back to back: the first one completes first
-            if (chunk_bits > 0) dist_swap_chunked(group, chunk_bits, pipe);
-            else dist_swap(group);
+            if (chunk_bits > 0) {
+                // (chunked or not is decided by rank-independent facts only: every rank takes the same path)
+                // the tile qubits of the pass that will follow the exchange on this rank (same schedule launch_ops_t derives)
+                uint64_t avoid = 0;
+                if (next_local && !next_local->ops.empty()) {
+                    const std::vector<Pass> nxt = schedule_passes(next_local->ops, n_local_, opt);
+                    if (!nxt.empty()) for (int q : nxt[0].tile_q) avoid |= 1ull << q;
+                }
+                dist_swap_chunked(group, chunk_bits, pipe, avoid);
+            } else {
+                dist_swap(group);
+            }
         }
         group.clear();
     };
-    for (const DistSegment &seg : plan.segments) {
+    for (size_t si = 0; si < plan.segments.size(); si++) {
+        const DistSegment &seg = plan.segments[si];
+        // the LOCAL segment that follows the exchange being assembled, if the next segment is one
+        const DistSegment *after = (si + 1 < plan.segments.size() && !plan.segments[si + 1].is_swap) ? &plan.segments[si + 1] : nullptr;
         if (seg.is_swap) {
-            if (seg.batch != group_batch) exchange();
+            if (seg.batch != group_batch) exchange(nullptr);
             group_batch = seg.batch;
             group.emplace_back(seg.gbit, seg.lbit);
-            if ((int)group.size() == max_group) exchange();
+            if ((int)group.size() == max_group) exchange(after);
         } else {
-            exchange();
+            exchange(&seg);
             std::vector<HostOp> local = seg.ops;
             launch_ops_t<T>(local, 0, -1, pipe.wait_all ? &pipe : nullptr);
             pipe = ChunkPipe();
         }
     }
-    exchange();
+    exchange(nullptr);
     if (pipe.wait_all) pipe.wait_all();   // an exchange at the very end: the stream's next user sees it complete
     for (int &p : queue.l2p) p = plan.sigma[p];
     queue.clear_pending();
@@ -589,6 +619,16 @@ void ShardGroup::fence(int rank, cudaStream_t stream)
 
 // sum of `count` scalars over the shards, the same bits on every rank (fixed rank order); host-mediated: these are the
 // handful of doubles of a norm / probability / marginal, or the shot indices of a sample
+uint64_t ShardGroup::all_or(int rank, uint64_t v)
+{
+    host_[rank].assign(1, v);
+    barrier();
+    uint64_t out = 0;
+    for (int p = 0; p < world(); p++) out |= host_[p][0];
+    barrier();
+    return out;
+}
+
 template <typename W>
 void ShardGroup::allreduce(int rank, W *d_buf, size_t count, cudaStream_t stream)
 {

@@ -146,7 +146,7 @@ private:
     // plan `ops` into tile passes and launch them on states [b0, b0 + nb) of the batch (nb < 0: the whole batch)
     template <typename T> void launch_ops_t(std::vector<HostOp> &ops, int b0 = 0, int nb = -1, ChunkPipe *pipe = nullptr);
     // chunked exchange on a second stream (single-process groups): fills `pipe` for the passes that follow
-    void dist_swap_chunked(const std::vector<std::pair<int, int>> &pairs, int chunk_bits, ChunkPipe &pipe);
+    void dist_swap_chunked(const std::vector<std::pair<int, int>> &pairs, int chunk_bits, ChunkPipe &pipe, uint64_t avoid);
     cudaStream_t xstream_ = nullptr;
     template <typename T> void flush_registers_t();
     template <typename T> void launch_uniform_t(int b0, int nb);
