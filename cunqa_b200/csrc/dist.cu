@@ -355,9 +355,13 @@ void State::flush_dist_t()
     // swaps planned together (same batch id) become one multi-qubit exchange.  Grouping by batch id -- not by adjacency
     // in this rank's segment list -- keeps the number and shape of exchanges identical on every rank: a LOCAL segment
     // that separates two batches on one rank can be empty (all its ops dropped by a global control) on another.
-    // single-process groups pipeline the exchange with the pass that follows it (CB200_SWAP_CHUNK_BITS, default 2: four
-    // chunks; 0 = one kernel on the main stream as in the one-process-per-GPU mode)
-    static const int chunk_bits_cfg = getenv("CB200_SWAP_CHUNK_BITS") ? std::max(0, std::min(3, atoi(getenv("CB200_SWAP_CHUNK_BITS")))) : 2;
+    // single-process groups CAN pipeline the exchange with the pass that follows it (CB200_SWAP_CHUNK_BITS = 1..3: the
+    // exchange runs in 2^bits chunks on a second stream and the pass starts on the chunks that have arrived).  Measured
+    // on 2 x B200 (profiles/exchange_overlap_r02.txt): QFT-32 takes 222 ms with or without it -- the tile-pass kernel
+    // holds the whole register file of every SM (3 CTAs x 128 threads x 168 registers), so the exchange kernel's CTAs and
+    // the pass's CTAs take turns instead of running side by side.  Hiding the exchange needs the copy engines (peer DMA
+    // through a staging buffer), not a second kernel; until then the default is one exchange kernel on the main stream.
+    static const int chunk_bits_cfg = getenv("CB200_SWAP_CHUNK_BITS") ? std::max(0, std::min(3, atoi(getenv("CB200_SWAP_CHUNK_BITS")))) : 0;
     const int chunk_bits = (dist->group && n_local_ >= 24) ? chunk_bits_cfg : 0;
     std::vector<std::pair<int, int>> group;
     int group_batch = -1;

@@ -291,6 +291,30 @@ void State::flush_t()
     queue.clear_pending();
 }
 
+// The pass schedule depends on the STRUCTURE of the fused op list only (kinds, targets, controls), not on the numbers in
+// the matrices: a VQE loop that re-sends angles (`upgrade_parameters`, /root/reference/src/quantum_task.cpp:39-108) gets
+// the same fused structure every time, so the schedule of the last few structures is kept.
+const std::vector<Pass> &State::cached_schedule(const std::vector<HostOp> &ops)
+{
+    std::vector<uint64_t> sig;
+    sig.reserve(ops.size() * 3 + 4);
+    sig.push_back(((uint64_t)n_local_ << 48) | ((uint64_t)opt.tile_bits << 40) | ((uint64_t)opt.min_run_bits << 32) |
+                  ((uint64_t)opt.max_pass_cost << 16) | (uint64_t)opt.lookahead);
+    for (const HostOp &op : ops) {
+        uint64_t tm = 0, cm = 0;
+        for (int q : op.q) tm |= 1ull << q;
+        for (int q : op.ctrl) cm |= 1ull << q;
+        sig.push_back(((uint64_t)op.kind << 60) | ((uint64_t)op.q.size() << 52) | (uint64_t)(op.mask_row >= 0));
+        sig.push_back(tm);
+        sig.push_back(cm);
+    }
+    for (auto &e : sched_cache_)
+        if (e.first == sig) return e.second;
+    if (sched_cache_.size() >= 8) sched_cache_.erase(sched_cache_.begin());
+    sched_cache_.emplace_back(std::move(sig), schedule_passes(ops, n_local_, opt));
+    return sched_cache_.back().second;
+}
+
 // plan `ops` (physical qubits < n_local) into tile passes and launch them on this shard
 template <typename T>
 void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb, ChunkPipe *pipe)
@@ -300,7 +324,7 @@ void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb, ChunkPipe *pi
     const int vbatch = nb < 0 ? batch : nb;
     const size_t view_bytes = nb < 0 ? state_bytes_ : (amp_bytes_ << n_local_) * (size_t)nb;
     void *view_ptr = (char *)d_state_ + (nb < 0 ? 0 : (amp_bytes_ << n_local_) * (size_t)b0);
-    const std::vector<Pass> passes = schedule_passes(ops, n_local_, opt);
+    const std::vector<Pass> &passes = cached_schedule(ops);
     std::vector<cplx> diag_host;
     std::vector<PassParams<T>> params(passes.size());
     std::string err;
@@ -803,8 +827,14 @@ void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out, uint64_t
     if (n2 > lvl2_cap_) { CB200_CUDA(cudaStreamSynchronize(stream_)); cudaFree(d_lvl2_); lvl2_cap_ = n2; CB200_CUDA(cudaMalloc(&d_lvl2_, n2 * sizeof(double))); }
     const int g1 = (int)std::min<uint64_t>(n1, (uint64_t)num_sms_ * 16);
     const int g2 = (int)std::min<uint64_t>(n2, (uint64_t)num_sms_ * 16);
-    uint64_t *d_out = nullptr;
-    CB200_CUDA(cudaMalloc(&d_out, sizeof(uint64_t) * std::max<uint64_t>(shots, 1)));
+    if (std::max<uint64_t>(shots, 1) > samples_cap_) {
+        CB200_CUDA(cudaStreamSynchronize(stream_));
+        cudaFree(d_samples_);
+        d_samples_ = nullptr;
+        samples_cap_ = std::max<uint64_t>(shots, 4096);
+        CB200_CUDA(cudaMalloc(&d_samples_, samples_cap_ * sizeof(uint64_t)));
+    }
+    uint64_t *d_out = d_samples_;
     double total_all = -1.0, off_lo = 0.0, off_hi = 0.0;
     uint64_t prefix = 0;
     if (dist) {
@@ -845,7 +875,6 @@ void State::sample(int b, uint64_t shots, uint64_t seed, uint64_t *out, uint64_t
     if (e == cudaSuccess && dist && shots) dist_allreduce_u64(d_out, shots);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(uint64_t) * shots, cudaMemcpyDeviceToHost, stream_);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
-    cudaFree(d_out);
     if (e != cudaSuccess) throw CudaError(std::string("sampling failed: ") + cudaGetErrorString(e));
     stats.d2h_bytes += sizeof(uint64_t) * shots;
     if (!qof(b).identity_perm())

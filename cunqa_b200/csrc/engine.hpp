@@ -151,6 +151,8 @@ private:
     template <typename T> void flush_registers_t();
     template <typename T> void launch_uniform_t(int b0, int nb);
     // pinned staging for host->device uploads of tables / flags / matrices (two slots, reused once their copy is done)
+    const std::vector<Pass> &cached_schedule(const std::vector<HostOp> &ops);
+    std::vector<std::pair<std::vector<uint64_t>, std::vector<Pass>>> sched_cache_;
     void *stage(size_t bytes);
     void stage_commit();
     struct StageSlot { void *ptr = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool busy = false; };

@@ -425,15 +425,26 @@ Json Backend::run_static_parsed(const void *parsed_task)
             s = r;
         }
         std::sort(samples.begin(), samples.end());
-        Json cj = Json::object();
+        // the counts object is rendered straight into JSON text: {"<bits>":n,...} (a 16-qubit ansatz at 1024 shots has
+        // about a thousand distinct outcomes; building and dumping a node per outcome was a quarter of the evaluation)
+        std::string text;
+        text.reserve(samples.size() * (size_t)(c.num_clbits + 8) + 2);
+        text += '{';
+        char num[24];
         for (size_t i = 0; i < samples.size();) {
             size_t j = i;
             while (j < samples.size() && samples[j] == samples[i]) j++;
             for (int b = 0; b < c.num_clbits; b++) key[c.num_clbits - 1 - b] = ((samples[i] >> b) & 1ull) ? '1' : '0';
-            cj.obj.emplace_back(key, Json::integer((long long)(j - i)));
+            if (i) text += ',';
+            text += '"';
+            text += key;
+            text += "\":";
+            const int len = std::snprintf(num, sizeof num, "%zu", j - i);
+            text.append(num, (size_t)len);
             i = j;
         }
-        out.set("counts", std::move(cj));
+        text += '}';
+        out.set("counts", Json::raw(std::move(text)));
     } else {
         std::map<std::string, uint64_t> counts;
         for (uint64_t s : samples) {

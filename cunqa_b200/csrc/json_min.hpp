@@ -15,7 +15,7 @@ namespace cb200 {
 
 class Json {
 public:
-    enum Type { NUL, BOOL, NUM, STR, ARR, OBJ };
+    enum Type { NUL, BOOL, NUM, STR, ARR, OBJ, RAW };  // RAW: pre-rendered JSON text (big count tables are written directly)
     Type type = NUL;
     bool b = false;
     double num = 0.0;
@@ -32,6 +32,7 @@ public:
     static Json integer(long long v) { Json j; j.type = NUM; j.num = (double)v; j.is_int = true; j.inum = v; return j; }
     static Json string(const std::string &s) { Json j; j.type = STR; j.str = s; return j; }
     static Json boolean(bool v) { Json j; j.type = BOOL; j.b = v; return j; }
+    static Json raw(std::string text) { Json j; j.type = RAW; j.str = std::move(text); return j; }
 
     bool is_object() const { return type == OBJ; }
     bool is_array() const { return type == ARR; }
@@ -239,6 +240,7 @@ private:
             break;
         }
         case STR: dump_string(str, out); break;
+        case RAW: out += str; break;
         case ARR:
             out += '[';
             for (size_t i = 0; i < arr.size(); i++) { if (i) out += ','; arr[i].dump_to(out); }
