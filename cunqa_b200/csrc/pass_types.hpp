@@ -36,10 +36,11 @@ struct DevOp {
     uint8_t nfix;    // DENSE/PERM/PAIR: number of entries in fixpos (targets + in-tile controls)
     uint8_t has_mask;
     uint8_t tbit[8];        // DENSE/PERM: tile-bit position of target m
-    uint8_t fixpos[kMaxFix]; // ascending tile-bit positions where a bit is inserted into the group index
+    uint8_t fixpos[kMaxFix]; // DENSE/PERM: ascending tile-bit positions where a bit is inserted into the group index;
+                             // PAIR: tile bit of group-index bit i (bank-friendly positions first)
     union {
         uint8_t dsrc[kMaxDiagK]; // DIAG: source of table-index bit m: <64 tile bit, >=64 physical qubit (v-64) outside the tile
-        uint16_t seg[6];         // PAIR: group index -> tile index deposit, idx = sum_k (g & seg[k]) << k  (k <= nfix)
+        uint16_t seg[6];         // (unused since round 2: PAIR ops keep the group-bit -> tile-bit map in fixpos)
     };
     uint32_t ctrl_in;   // in-tile control bits (OR-ed into the tile index; those bits are in fixpos)
     uint32_t mat_off;   // DENSE: scalar offset into PassParams::mats; DIAG: element offset into the diag-table buffer

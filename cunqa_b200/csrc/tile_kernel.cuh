@@ -189,11 +189,9 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
     // swz(idx | off_j) = swz(idx) ^ swz(off_j): one XOR per amplitude instead of re-swizzling
     constexpr int kShift = sizeof(V) == 16 ? 4 : 3;
     const uint32_t tile_s = smem_u32(tile);
-    uint32_t sb[R], seg[R + 1];
+    uint32_t sb[R];
 #pragma unroll
     for (int m = 0; m < R; m++) sb[m] = swz<T>(1u << op.tbit[m]) << kShift;
-#pragma unroll
-    for (int m = 0; m <= R; m++) seg[m] = op.seg[m];
     uint32_t boff[D];  // byte offset of block element j relative to the group's element 0 (XOR-combined)
 #pragma unroll
     for (int j = 0; j < D; j++) {
@@ -204,9 +202,10 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
     }
     const uint32_t ngroups = 1u << (t - R);
     for (uint32_t g = tid; g < ngroups; g += NT) {
+        // group index -> tile index: group bit i sits at tile bit fixpos[i] (host order: the lowest group bits, i.e. the
+        // lanes of a quarter-warp, go to tile bits that reach distinct shared-memory banks -- see encode_pass)
         uint32_t idx = 0;
-#pragma unroll
-        for (int m = 0; m <= R; m++) idx |= (g & seg[m]) << m;
+        for (int i = 0; i < t - R; i++) idx |= ((g >> i) & 1u) << op.fixpos[i];
         const uint32_t bidx = swz<T>(idx) << kShift;
         uint32_t addr[D];
         V a[D];
