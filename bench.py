@@ -440,36 +440,39 @@ def main():
 
     # ---- explanatory: the same kernel where HBM IS the bound.  Two layers of the same circuit with the planner capped at
     # two 2-qubit gates per pass (CB200_MAX_PASS_COST=8): few flops per byte, so the pass streams at the memory roofline.
-    hbm_regime = None
+    regimes = {}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        os.environ["CB200_MAX_PASS_COST"] = "8"
-        try:
-            sv2 = cb.StateVector(n, "double", device=local_rank)
-            st2 = torch.cuda.ExternalStream(sv2.stream(), device=torch.device("cuda", local_rank))
-            short = C.quantum_volume(n, depth=2, seed=SEED)
-            best = None
-            for rep in range(3):
-                sv2.reset(); sv2.run(short[:1]); sv2.flush(); sv2.sync()      # state initialised, first gate done
-                a0 = sv2.stats()
-                h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                h0.record(st2)
-                sv2.run(short[1:]); sv2.flush()
-                h1.record(st2)
-                sv2.sync()
-                a1 = sv2.stats()
-                ms = h0.elapsed_time(h1)
-                best = ms if best is None else min(best, ms)
-            np2 = a1["passes"] - a0["passes"]
-            peak2, _ = load_peaks()
-            gbs = 2.0 * S * np2 / (best / 1e3) / 1e9
-            hbm_regime = {"workload": f"QV-{n} depth 2 ({len(short) - 1} gates), at most two 2-qubit gates per pass",
-                          "tile_passes": np2, "ms": best, "achieved": gbs, "peak": peak2, "unit": "GB/s", "frac": gbs / peak2,
-                          "gates_per_s": (len(short) - 1) / (best / 1e3)}
-            sv2.close()
-            del sv2
-            torch.cuda.empty_cache()
-        finally:
-            del os.environ["CB200_MAX_PASS_COST"]
+        # cost = sum over a pass's dense ops of 2^k: 8 = two 2-qubit gates per pass (memory IS the bound), 12 = three (the
+        # balance point asked for by the north star: HBM fraction >= 0.70 with the kernel still doing useful flops)
+        for cost, key in ((8, "hbm_bound_regime"), (12, "balanced_regime")):
+            os.environ["CB200_MAX_PASS_COST"] = str(cost)
+            try:
+                sv2 = cb.StateVector(n, "double", device=local_rank)
+                st2 = torch.cuda.ExternalStream(sv2.stream(), device=torch.device("cuda", local_rank))
+                short = C.quantum_volume(n, depth=2, seed=SEED)
+                best = None
+                for rep in range(3):
+                    sv2.reset(); sv2.run(short[:1]); sv2.flush(); sv2.sync()      # state initialised, first gate done
+                    a0 = sv2.stats()
+                    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    h0.record(st2)
+                    sv2.run(short[1:]); sv2.flush()
+                    h1.record(st2)
+                    sv2.sync()
+                    a1 = sv2.stats()
+                    ms = h0.elapsed_time(h1)
+                    best = ms if best is None else min(best, ms)
+                np2 = a1["passes"] - a0["passes"]
+                peak2, _ = load_peaks()
+                gbs = 2.0 * S * np2 / (best / 1e3) / 1e9
+                regimes[key] = {"workload": f"QV-{n} depth 2 ({len(short) - 1} gates), planner capped at {cost // 4} two-qubit gates per pass",
+                                "tile_passes": np2, "gates_per_pass": (len(short) - 1) / np2, "ms": best, "achieved": gbs, "peak": peak2,
+                                "unit": "GB/s", "frac": gbs / peak2, "gates_per_s": (len(short) - 1) / (best / 1e3)}
+                sv2.close()
+                del sv2
+                torch.cuda.empty_cache()
+            finally:
+                del os.environ["CB200_MAX_PASS_COST"]
 
     # ---- end-to-end through the plugin-facing call: wire JSON (host) -> counts (host)
     task_text = json.dumps(C.task(ins + C.measure_all(n), n, shots=SHOTS, seed=SEED, device=local_rank))
@@ -542,8 +545,7 @@ def main():
             "clocks": clocks,
         }
         line.update(side)
-        if hbm_regime is not None:
-            line["hbm_bound_regime"] = hbm_regime
+        line.update(regimes)
         if sharded is not None:
             line["sharded"] = sharded
         if world == 1 and not args.no_cpu_baseline:

@@ -366,12 +366,12 @@ class Backend:
         self._cb = (s, r)
         _check(lib.cb200_backend_set_channel(self._h, s, r, None))
 
-    def execute(self, task):
-        """task: dict / list of dicts / JSON text.  -> result dict ({"ERROR":...} on failure)"""
-        text = task if isinstance(task, str) else json.dumps(task)
+    def execute(self, task, parse=True):
+        """task: dict / list of dicts / JSON text.  -> result dict ({"ERROR":...} on failure); parse=False: the JSON text"""
+        text = task if isinstance(task, (str, bytes)) else json.dumps(task)
         out = _vp()
-        _check(lib.cb200_backend_execute(self._h, text.encode(), ctypes.byref(out)))
-        return json.loads(_take_string(out))
+        _check(lib.cb200_backend_execute(self._h, text if isinstance(text, bytes) else text.encode(), ctypes.byref(out)))
+        return json.loads(_take_string(out)) if parse else _take_string(out)
 
     def execute_many(self, messages, parse=True):
         """independent messages (dicts / lists / JSON texts) as separate registers batched on the device -> list of results"""

@@ -26,8 +26,14 @@ def main():
         walls.append(time.perf_counter() - t0)
         inner.append(res["time_taken"])
         assert "ERROR" not in res, res
+    # the C ABI alone: message bytes in, result text out (no Python-side JSON work inside the timed region)
+    msgs = [json.dumps({"params": list(rng.uniform(0, 6.28, npar)), "shots": 1024}).encode() for _ in range(iters)]
+    t0 = time.perf_counter()
+    for m in msgs:
+        be.execute(m, parse=False)
+    abi = (time.perf_counter() - t0) / iters
     st = be.stats()
-    print(json.dumps({"probe": "vqe_loop", "n": n, "layers": layers, "gates": C.n_gates(ins), "params": npar, "first_ms": round(first * 1e3, 3),
+    print(json.dumps({"probe": "vqe_loop", "c_abi_ms_per_eval": round(abi * 1e3, 3), "c_abi_evals_per_s": round(1 / abi, 1), "n": n, "layers": layers, "gates": C.n_gates(ins), "params": npar, "first_ms": round(first * 1e3, 3),
                       "wall_ms_median": round(float(np.median(walls)) * 1e3, 3), "engine_ms_median": round(float(np.median(inner)) * 1e3, 3),
                       "passes": st["passes"], "launches": st["launches"], "evals_per_s": round(1 / float(np.median(walls)), 1)}), flush=True)
     be.close()
