@@ -349,6 +349,8 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
                     if (std::find(order.begin(), order.end(), pos) == order.end()) order.push_back(pos);
                 if ((int)order.size() > kMaxFix) { err = "internal: tile too wide for a register block"; return false; }
                 for (size_t f = 0; f < order.size(); f++) d.fixpos[f] = (uint8_t)order[f];
+                d.ctrl_in = (uint32_t)out.n_pair;   // PAIR: slot of its group-index table
+                out.pair_op[out.n_pair++] = (uint8_t)(nops - 1);
                 d.mat_off = (uint32_t)mat_used;
                 const std::vector<cplx> MA = embed_dense(A, la), MB = embed_dense(B, lb);
                 for (const std::vector<cplx> *M : {&MA, &MB})

@@ -178,9 +178,10 @@ __device__ __forceinline__ void block_gate(typename Vec2<T>::type (&a)[1 << R], 
     }
 }
 
+// glut: per-op table group index -> tile index built once per CTA (TMA kernel); nullptr: computed from op.fixpos here
 template <typename T, int K1, int K2, int S, int NT>
 __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
-                                        const int t, const int tid)
+                                        const int t, const int tid, const uint16_t *glut = nullptr)
 {
     using V = typename Vec2<T>::type;
     constexpr int R = (K1 > S + K2) ? K1 : (S + K2);
@@ -205,7 +206,8 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
         // group index -> tile index: group bit i sits at tile bit fixpos[i] (host order: the lowest group bits, i.e. the
         // lanes of a quarter-warp, go to tile bits that reach distinct shared-memory banks -- see encode_pass)
         uint32_t idx = 0;
-        for (int i = 0; i < t - R; i++) idx |= ((g >> i) & 1u) << op.fixpos[i];
+        if (glut != nullptr) idx = glut[g];
+        else for (int i = 0; i < t - R; i++) idx |= ((g >> i) & 1u) << op.fixpos[i];
         const uint32_t bidx = swz<T>(idx) << kShift;
         uint32_t addr[D];
         V a[D];
@@ -220,12 +222,12 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
 
 template <typename T, int NT, int VAR>
 __device__ __forceinline__ void op_pair_dispatch(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
-                                                 const int t, const int tid)
+                                                 const int t, const int tid, const uint16_t *glut)
 {
     const int code = (op.k << 4) | (op.k2 << 2) | op.s;
-    if (code == ((2 << 4) | (2 << 2) | 2)) { op_pair<T, 2, 2, 2, NT>(tile, op, mat, t, tid); return; }
-    if (code == ((2 << 4) | (2 << 2) | 1)) { op_pair<T, 2, 2, 1, NT>(tile, op, mat, t, tid); return; }
-    if (code == ((1 << 4) | (1 << 2) | 1)) { op_pair<T, 1, 1, 1, NT>(tile, op, mat, t, tid); return; }
+    if (code == ((2 << 4) | (2 << 2) | 2)) { op_pair<T, 2, 2, 2, NT>(tile, op, mat, t, tid, glut); return; }
+    if (code == ((2 << 4) | (2 << 2) | 1)) { op_pair<T, 2, 2, 1, NT>(tile, op, mat, t, tid, glut); return; }
+    if (code == ((1 << 4) | (1 << 2) | 1)) { op_pair<T, 1, 1, 1, NT>(tile, op, mat, t, tid, glut); return; }
     if constexpr (VAR == 2) {
         switch (code) {
         case (1 << 4) | (1 << 2) | 0: op_pair<T, 1, 1, 0, NT>(tile, op, mat, t, tid); break;
@@ -393,7 +395,7 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                                           const typename Vec2<T>::type *__restrict__ diag_tabs,
                                           const uint64_t active, const uint64_t base, const int t, const int tid,
                                           const uint16_t *lut = nullptr, const typename Vec2<T>::type *const *tptr = nullptr,
-                                          const int hook_at = 1 << 30, Hook hook = Hook())
+                                          const int hook_at = 1 << 30, Hook hook = Hook(), const uint16_t *glut_all = nullptr)
 {
     using V = typename Vec2<T>::type;
     const uint32_t tile_amps = 1u << t;
@@ -413,7 +415,10 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                 }
                 __syncthreads();
             } else if (op.kind == OP_PAIR) {
-                op_pair_dispatch<T, NT, VAR>(tile, op, mats + op.mat_off, t, tid);
+                // (group-index tables exist for the 4-bit register blocks: 2^(t-4) entries per pair op)
+                const bool r4 = (op.k == 2 && op.k2 == 2 && op.s == 2) && t > 4;
+                op_pair_dispatch<T, NT, VAR>(tile, op, mats + op.mat_off, t, tid,
+                                             (glut_all != nullptr && r4) ? glut_all + ((size_t)op.ctrl_in << (t - 4)) : nullptr);
                 __syncthreads();
             } else if (op.kind == OP_DIAG) {
                 if constexpr (VAR >= 1) {  // (passes with diagonal ops never take the lean kernel, see needs_full)
@@ -626,6 +631,17 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     V *stab = reinterpret_cast<V *>(tptr + ((p.n_diag + 1) & ~1));
     uint32_t *dhi = reinterpret_cast<uint32_t *>(stab + p.n_stab);
     uint16_t *lut = reinterpret_cast<uint16_t *>(dhi + p.n_diag);
+    // per register-block pair op: group index -> tile index (the host's bank-aware placement of the group bits), built
+    // once per CTA so that the per-tile cost is one 16-bit load
+    uint16_t *glut = lut + (size_t)p.n_diag * kDiagLut;
+    const int gbits = t > 4 ? t - 4 : 0;
+    for (int e = tid; e < (p.n_pair << gbits); e += NT) {
+        const DevOp &po = p.ops[p.pair_op[e >> gbits]];
+        const uint32_t g = (uint32_t)e & ((1u << gbits) - 1u);
+        uint32_t idx = 0;
+        for (int i = 0; i < gbits; i++) idx |= ((g >> i) & 1u) << po.fixpos[i];
+        glut[e] = (uint16_t)idx;
+    }
     static_assert(NT >= 32, "one warp at least");
     for (int e = tid; e < p.n_diag * kDiagLut; e += NT) {
         const int sl = e / kDiagLut, r = e - sl * kDiagLut;
@@ -764,7 +780,7 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         if (p.n_diag || restaged) __syncthreads();
 
         apply_ops<T, NT, COND, VAR>(p, mats_s, tile, tabs_b, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
-                                    (COND || (16 * NT) != (1 << t)) ? nullptr : lut, tptr, refill_after, refill);
+                                    (COND || (16 * NT) != (1 << t)) ? nullptr : lut, tptr, refill_after, refill, glut);
 
         // every thread's generic-proxy writes -> visible to the async proxy; then drain the tile with TMA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
