@@ -46,7 +46,7 @@ void fill_stats(const Stats &st, uint64_t gates, uint64_t relabelled, uint64_t o
 
 extern "C" {
 
-const char *cb200_version(void) { return "cunqa_b200 0.1.0 (sm_100a)"; }
+const char *cb200_version(void) { return "cunqa_b200 0.2.0 (sm_100a)"; }
 const char *cb200_last_error(void) { return g_err.c_str(); }
 int cb200_device_count(void)
 {

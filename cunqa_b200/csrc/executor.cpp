@@ -439,8 +439,10 @@ Json Backend::run_static_parsed(const void *parsed_task)
             text += '"';
             text += key;
             text += "\":";
-            const int len = std::snprintf(num, sizeof num, "%zu", j - i);
-            text.append(num, (size_t)len);
+            size_t v = j - i;
+            int len = 0;
+            do { num[sizeof num - 1 - len++] = (char)('0' + v % 10); v /= 10; } while (v);
+            text.append(num + sizeof num - len, (size_t)len);
             i = j;
         }
         text += '}';

@@ -72,8 +72,9 @@ struct PassParams {
     int32_t n_stab;     // entries of the shared-memory sub-table store used by this pass (multiple of 8)
     uint8_t diag_op[kMaxOps];
     uint8_t stab_slot[kStabEntries / 8];  // diagonal slot that owns each 8-entry chunk of the store
-    int32_t n_pair;     // number of OP_PAIR ops; pair_op[slot] = op index of the slot-th one (DevOp::ctrl_in = its slot):
-    int32_t pad3_;      // the TMA kernel keeps one group-index -> tile-index table per slot in shared memory
+    int32_t n_pair;     // number of OP_PAIR ops; pair_op[slot] = op index of the slot-th one.  The TMA kernel keeps one
+    int32_t n_glut;     // group-index -> tile-index table per pair op in shared memory: 2^(t - R) uint16 entries starting at
+                        // entry DevOp::ctrl_in of the table store, n_glut entries in all
     uint8_t pair_op[kMaxOps];
     uint8_t tile_q[16]; // physical qubit of tile bit j (ascending)
     DevOp ops[kMaxOps];

@@ -344,12 +344,13 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
                 std::vector<int> order;
                 bool used_res[3] = {false, false, false};
                 for (int pos : freeb)
-                    if (pos < 6 && !used_res[pos % 3] && order.size() < 3) { order.push_back(pos); used_res[pos % 3] = true; }
+                    if (!(flags & kEncNoBankAware) && pos < 6 && !used_res[pos % 3] && order.size() < 3) { order.push_back(pos); used_res[pos % 3] = true; }
                 for (int pos : freeb)
                     if (std::find(order.begin(), order.end(), pos) == order.end()) order.push_back(pos);
                 if ((int)order.size() > kMaxFix) { err = "internal: tile too wide for a register block"; return false; }
                 for (size_t f = 0; f < order.size(); f++) d.fixpos[f] = (uint8_t)order[f];
-                d.ctrl_in = (uint32_t)out.n_pair;   // PAIR: slot of its group-index table
+                d.ctrl_in = (uint32_t)out.n_glut;   // PAIR: first entry of its group-index table (2^(t - R) entries)
+                out.n_glut += 1 << (t - R);
                 out.pair_op[out.n_pair++] = (uint8_t)(nops - 1);
                 d.mat_off = (uint32_t)mat_used;
                 const std::vector<cplx> MA = embed_dense(A, la), MB = embed_dense(B, lb);

@@ -179,7 +179,8 @@ __device__ __forceinline__ void block_gate(typename Vec2<T>::type (&a)[1 << R], 
 }
 
 // glut: per-op table group index -> tile index built once per CTA (TMA kernel); nullptr: computed from op.fixpos here
-template <typename T, int K1, int K2, int S, int NT>
+// GL: the kernel keeps a group-index table per pair op in shared memory (no per-tile bit loop)
+template <typename T, int K1, int K2, int S, int NT, bool GL = false>
 __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
                                         const int t, const int tid, const uint16_t *glut = nullptr)
 {
@@ -205,10 +206,14 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
     for (uint32_t g = tid; g < ngroups; g += NT) {
         // group index -> tile index: group bit i sits at tile bit fixpos[i] (host order: the lowest group bits, i.e. the
         // lanes of a quarter-warp, go to tile bits that reach distinct shared-memory banks -- see encode_pass)
-        uint32_t idx = 0;
-        if (glut != nullptr) idx = glut[g];
-        else for (int i = 0; i < t - R; i++) idx |= ((g >> i) & 1u) << op.fixpos[i];
-        const uint32_t bidx = swz<T>(idx) << kShift;
+        uint32_t bidx;   // swizzled byte offset of the group's element 0
+        if constexpr (GL) {
+            bidx = glut[g];  // (the table holds the finished byte offset: < 64 KiB)
+        } else {
+            uint32_t idx = 0;
+            for (int i = 0; i < t - R; i++) idx |= ((g >> i) & 1u) << op.fixpos[i];
+            bidx = swz<T>(idx) << kShift;
+        }
         uint32_t addr[D];
         V a[D];
 #pragma unroll
@@ -220,22 +225,22 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
     }
 }
 
-template <typename T, int NT, int VAR>
+template <typename T, int NT, int VAR, bool GL>
 __device__ __forceinline__ void op_pair_dispatch(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
                                                  const int t, const int tid, const uint16_t *glut)
 {
     const int code = (op.k << 4) | (op.k2 << 2) | op.s;
-    if (code == ((2 << 4) | (2 << 2) | 2)) { op_pair<T, 2, 2, 2, NT>(tile, op, mat, t, tid, glut); return; }
-    if (code == ((2 << 4) | (2 << 2) | 1)) { op_pair<T, 2, 2, 1, NT>(tile, op, mat, t, tid, glut); return; }
-    if (code == ((1 << 4) | (1 << 2) | 1)) { op_pair<T, 1, 1, 1, NT>(tile, op, mat, t, tid, glut); return; }
+    if (code == ((2 << 4) | (2 << 2) | 2)) { op_pair<T, 2, 2, 2, NT, GL>(tile, op, mat, t, tid, glut); return; }
+    if (code == ((2 << 4) | (2 << 2) | 1)) { op_pair<T, 2, 2, 1, NT, GL>(tile, op, mat, t, tid, glut); return; }
+    if (code == ((1 << 4) | (1 << 2) | 1)) { op_pair<T, 1, 1, 1, NT, GL>(tile, op, mat, t, tid, glut); return; }
     if constexpr (VAR == 2) {
         switch (code) {
-        case (1 << 4) | (1 << 2) | 0: op_pair<T, 1, 1, 0, NT>(tile, op, mat, t, tid); break;
-        case (1 << 4) | (2 << 2) | 1: op_pair<T, 1, 2, 1, NT>(tile, op, mat, t, tid); break;
-        case (1 << 4) | (2 << 2) | 0: op_pair<T, 1, 2, 0, NT>(tile, op, mat, t, tid); break;
-        case (2 << 4) | (1 << 2) | 2: op_pair<T, 2, 1, 2, NT>(tile, op, mat, t, tid); break;
-        case (2 << 4) | (1 << 2) | 1: op_pair<T, 2, 1, 1, NT>(tile, op, mat, t, tid); break;
-        default: op_pair<T, 2, 2, 0, NT>(tile, op, mat, t, tid); break;
+        case (1 << 4) | (1 << 2) | 0: op_pair<T, 1, 1, 0, NT, GL>(tile, op, mat, t, tid, glut); break;
+        case (1 << 4) | (2 << 2) | 1: op_pair<T, 1, 2, 1, NT, GL>(tile, op, mat, t, tid, glut); break;
+        case (1 << 4) | (2 << 2) | 0: op_pair<T, 1, 2, 0, NT, GL>(tile, op, mat, t, tid, glut); break;
+        case (2 << 4) | (1 << 2) | 2: op_pair<T, 2, 1, 2, NT, GL>(tile, op, mat, t, tid, glut); break;
+        case (2 << 4) | (1 << 2) | 1: op_pair<T, 2, 1, 1, NT, GL>(tile, op, mat, t, tid, glut); break;
+        default: op_pair<T, 2, 2, 0, NT, GL>(tile, op, mat, t, tid, glut); break;
         }
     }
 }
@@ -390,7 +395,7 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 // remaining ops still run.
 // VAR: 0 = lean (1-2 qubit dense gates, the common register blocks, permutations), 1 = lean + diagonal runs through the
 // LUT / register-block path, 2 = everything (dense k >= 3, all register blocks, the generic per-bit diagonal gather)
-template <typename T, int NT, bool COND, int VAR, typename Hook = NoHook>
+template <typename T, int NT, bool COND, int VAR, typename Hook = NoHook, bool GL = false>
 __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats, typename Vec2<T>::type *tile,
                                           const typename Vec2<T>::type *__restrict__ diag_tabs,
                                           const uint64_t active, const uint64_t base, const int t, const int tid,
@@ -416,9 +421,8 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                 __syncthreads();
             } else if (op.kind == OP_PAIR) {
                 // (group-index tables exist for the 4-bit register blocks: 2^(t-4) entries per pair op)
-                const bool r4 = (op.k == 2 && op.k2 == 2 && op.s == 2) && t > 4;
-                op_pair_dispatch<T, NT, VAR>(tile, op, mats + op.mat_off, t, tid,
-                                             (glut_all != nullptr && r4) ? glut_all + ((size_t)op.ctrl_in << (t - 4)) : nullptr);
+                if constexpr (GL) op_pair_dispatch<T, NT, VAR, true>(tile, op, mats + op.mat_off, t, tid, glut_all + op.ctrl_in);
+                else op_pair_dispatch<T, NT, VAR, false>(tile, op, mats + op.mat_off, t, tid, nullptr);
                 __syncthreads();
             } else if (op.kind == OP_DIAG) {
                 if constexpr (VAR >= 1) {  // (passes with diagonal ops never take the lean kernel, see needs_full)
@@ -634,13 +638,14 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     // per register-block pair op: group index -> tile index (the host's bank-aware placement of the group bits), built
     // once per CTA so that the per-tile cost is one 16-bit load
     uint16_t *glut = lut + (size_t)p.n_diag * kDiagLut;
-    const int gbits = t > 4 ? t - 4 : 0;
-    for (int e = tid; e < (p.n_pair << gbits); e += NT) {
-        const DevOp &po = p.ops[p.pair_op[e >> gbits]];
-        const uint32_t g = (uint32_t)e & ((1u << gbits) - 1u);
-        uint32_t idx = 0;
-        for (int i = 0; i < gbits; i++) idx |= ((g >> i) & 1u) << po.fixpos[i];
-        glut[e] = (uint16_t)idx;
+    for (int sl = 0; sl < p.n_pair; sl++) {
+        const DevOp &po = p.ops[p.pair_op[sl]];
+        const int gb = t - po.nfix;   // nfix = R, the register-block width
+        for (uint32_t g = tid; g < (1u << gb); g += NT) {
+            uint32_t idx = 0;
+            for (int i = 0; i < gb; i++) idx |= ((g >> i) & 1u) << po.fixpos[i];
+            glut[po.ctrl_in + g] = (uint16_t)(swz<T>(idx) << (sizeof(V) == 16 ? 4 : 3));
+        }
     }
     static_assert(NT >= 32, "one warp at least");
     for (int e = tid; e < p.n_diag * kDiagLut; e += NT) {
@@ -779,7 +784,7 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         mbar_wait(&full[s], parity);
         if (p.n_diag || restaged) __syncthreads();
 
-        apply_ops<T, NT, COND, VAR>(p, mats_s, tile, tabs_b, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
+        apply_ops<T, NT, COND, VAR, decltype(refill), true>(p, mats_s, tile, tabs_b, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
                                     (COND || (16 * NT) != (1 << t)) ? nullptr : lut, tptr, refill_after, refill, glut);
 
         // every thread's generic-proxy writes -> visible to the async proxy; then drain the tile with TMA
