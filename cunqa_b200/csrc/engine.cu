@@ -54,7 +54,6 @@ void State::init_options(int gbits)
     opt.pair_ops = env_int("CB200_PAIR_OPS", 1) != 0;
     opt.diag_fuse_always = env_int("CB200_DIAG_FUSE_ALWAYS", 1) != 0;
     opt.stage_diag = env_int("CB200_STAGE_DIAG", 0) != 0;
-    opt.bank_aware = env_int("CB200_BANK_AWARE", 1) != 0;
     if (gbits) opt.global_mask = ((1ull << gbits) - 1ull) << n_local_;
     queue = OpQueue(n, batch, opt);
 }
@@ -382,7 +381,7 @@ void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb, ChunkPipe *pi
         const int stages = tma_stages_;
         size_t smem_tma = (size_t)stages * buf_stride + sizeof(uint64_t) * (stages + 1) + sizeof(uint32_t) * ((((size_t)1 << (p.t - box_bits)) + 3) & ~(size_t)3) +
                           sizeof(T) * (size_t)((p.n_mat + 1) & ~1) + (size_t)((p.n_diag + 1) & ~1) * 8 + (size_t)p.n_stab * sizeof(V) +
-                          (size_t)p.n_diag * (4 + 2 * kDiagLut) + (size_t)p.n_glut * 2 + 16 + 1024;
+                          (size_t)p.n_diag * (4 + 2 * kDiagLut) + 16 + 1024;
         int nt = 1 << std::max(5, std::min(8, p.t - kAmpsPerThreadShift));  // 32 / 64 / 128 / 256 threads
         if (tma_threads_ > 0) nt = tma_threads_;
         int ctas = std::max(1, (stages == 3 ? 256 : 384) / nt);
@@ -560,7 +559,7 @@ void State::launch_uniform_t(int b0, int nb)
         const int stages = tma_stages_;
         const size_t smem_tma = (size_t)stages * buf_stride + sizeof(uint64_t) * (stages + 1) + sizeof(uint32_t) * ((((size_t)1 << (p.t - box_bits)) + 3) & ~(size_t)3) +
                                 sizeof(T) * (size_t)((p.n_mat + 1) & ~1) + (size_t)((p.n_diag + 1) & ~1) * 8 + (size_t)p.n_stab * sizeof(V) +
-                                (size_t)p.n_diag * (4 + 2 * kDiagLut) + (size_t)p.n_glut * 2 + 16 + 1024;
+                                (size_t)p.n_diag * (4 + 2 * kDiagLut) + 16 + 1024;
         int nt = 1 << std::max(5, std::min(8, p.t - kAmpsPerThreadShift));
         if (tma_threads_ > 0) nt = tma_threads_;
         int ctas = std::max(1, (stages == 3 ? 256 : 384) / nt);

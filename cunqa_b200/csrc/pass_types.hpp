@@ -36,11 +36,10 @@ struct DevOp {
     uint8_t nfix;    // DENSE/PERM/PAIR: number of entries in fixpos (targets + in-tile controls)
     uint8_t has_mask;
     uint8_t tbit[8];        // DENSE/PERM: tile-bit position of target m
-    uint8_t fixpos[kMaxFix]; // DENSE/PERM: ascending tile-bit positions where a bit is inserted into the group index;
-                             // PAIR: tile bit of group-index bit i (bank-friendly positions first)
+    uint8_t fixpos[kMaxFix]; // ascending tile-bit positions where a bit is inserted into the group index
     union {
         uint8_t dsrc[kMaxDiagK]; // DIAG: source of table-index bit m: <64 tile bit, >=64 physical qubit (v-64) outside the tile
-        uint16_t seg[6];         // (unused since round 2: PAIR ops keep the group-bit -> tile-bit map in fixpos)
+        uint16_t seg[6];         // PAIR: group index -> tile index deposit, idx = sum_k (g & seg[k]) << k  (k <= nfix)
     };
     uint32_t ctrl_in;   // in-tile control bits (OR-ed into the tile index; those bits are in fixpos)
     uint32_t mat_off;   // DENSE: scalar offset into PassParams::mats; DIAG: element offset into the diag-table buffer
@@ -72,10 +71,6 @@ struct PassParams {
     int32_t n_stab;     // entries of the shared-memory sub-table store used by this pass (multiple of 8)
     uint8_t diag_op[kMaxOps];
     uint8_t stab_slot[kStabEntries / 8];  // diagonal slot that owns each 8-entry chunk of the store
-    int32_t n_pair;     // number of OP_PAIR ops; pair_op[slot] = op index of the slot-th one.  The TMA kernel keeps one
-    int32_t n_glut;     // group-index -> tile-index table per pair op in shared memory: 2^(t - R) uint16 entries starting at
-                        // entry DevOp::ctrl_in of the table store, n_glut entries in all
-    uint8_t pair_op[kMaxOps];
     uint8_t tile_q[16]; // physical qubit of tile bit j (ascending)
     DevOp ops[kMaxOps];
     alignas(16) T mats[kMatScalars];  // (re, im) pairs, read as one 16-byte element

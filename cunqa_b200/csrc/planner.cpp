@@ -333,25 +333,13 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
                 }
                 std::sort(fix.begin(), fix.end());
                 d.nfix = (uint8_t)R;
-                // group bit i -> tile bit fixpos[i].  A thread owns one group; the 8 lanes of a quarter-warp (group bits
-                // 0..2) issue one 128-byte shared-memory wavefront when their tile bits select distinct 16-byte chunks.
-                // With the 128-byte swizzle the chunk is (index bits 0..2) XOR (index bits 3..5): tile bits p < 6 with
-                // distinct p mod 3 do that, tile bits >= 6 never change the bank.  So the lowest group bits take such
-                // positions first (measured: 14.9 / 21.7 TFLOP/s in the register block when they collide, 25.5 when not).
-                std::vector<int> freeb;
-                for (int pos = 0; pos < t; pos++)
-                    if (std::find(fix.begin(), fix.end(), pos) == fix.end()) freeb.push_back(pos);
-                std::vector<int> order;
-                bool used_res[3] = {false, false, false};
-                for (int pos : freeb)
-                    if (!(flags & kEncNoBankAware) && pos < 6 && !used_res[pos % 3] && order.size() < 3) { order.push_back(pos); used_res[pos % 3] = true; }
-                for (int pos : freeb)
-                    if (std::find(order.begin(), order.end(), pos) == order.end()) order.push_back(pos);
-                if ((int)order.size() > kMaxFix) { err = "internal: tile too wide for a register block"; return false; }
-                for (size_t f = 0; f < order.size(); f++) d.fixpos[f] = (uint8_t)order[f];
-                d.ctrl_in = (uint32_t)out.n_glut;   // PAIR: first entry of its group-index table (2^(t - R) entries)
-                out.n_glut += 1 << (t - R);
-                out.pair_op[out.n_pair++] = (uint8_t)(nops - 1);
+                for (int f = 0; f < R; f++) d.fixpos[f] = (uint8_t)fix[f];
+                // segment masks of the group index: bits between consecutive fixed positions move up together
+                for (int k = 0; k <= R; k++) {
+                    const int lo = k == 0 ? 0 : fix[k - 1] - (k - 1);
+                    const int hi = k == R ? 16 : fix[k] - k;
+                    d.seg[k] = (uint16_t)(hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u);
+                }
                 d.mat_off = (uint32_t)mat_used;
                 const std::vector<cplx> MA = embed_dense(A, la), MB = embed_dense(B, lb);
                 for (const std::vector<cplx> *M : {&MA, &MB})

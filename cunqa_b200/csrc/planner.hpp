@@ -30,8 +30,7 @@ struct HostOp {
 // encode_pass flags
 constexpr int kEncPairOps = 1;         // register-block adjacent dense gates
 constexpr int kEncDiagFuseAlways = 2;  // always fold a diagonal run into the dense gate that follows it (experiments)
-constexpr int kEncNoStage = 4;
-constexpr int kEncNoBankAware = 8;     // register-block group bits in ascending tile-bit order (experiments)         // no per-tile shared-memory staging of diagonal sub-tables (experiments)
+constexpr int kEncNoStage = 4;         // no per-tile shared-memory staging of diagonal sub-tables (experiments)
 
 struct PlanOptions {
     int tile_bits = 12;        // t: 2^t amplitudes staged per tile
@@ -49,8 +48,7 @@ struct PlanOptions {
     // per-amplitude sub-tables in shared memory does not (82.6 against 81.6): the pass is bound by its instruction count
     // (258 per amplitude), not by the table loads.  Both stay switchable: CB200_DIAG_FUSE_ALWAYS, CB200_STAGE_DIAG.
     bool diag_fuse_always = true, stage_diag = false;
-    bool bank_aware = true;    // CB200_BANK_AWARE
-    int enc_flags() const { return (pair_ops ? kEncPairOps : 0) | (diag_fuse_always ? kEncDiagFuseAlways : 0) | (stage_diag ? 0 : kEncNoStage) | (bank_aware ? 0 : kEncNoBankAware); }
+    int enc_flags() const { return (pair_ops ? kEncPairOps : 0) | (diag_fuse_always ? kEncDiagFuseAlways : 0) | (stage_diag ? 0 : kEncNoStage); }
     uint64_t global_mask = 0;  // sharded state: physical qubits that select the rank (never fused into dense blocks)
 };
 

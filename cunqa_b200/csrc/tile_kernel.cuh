@@ -178,11 +178,9 @@ __device__ __forceinline__ void block_gate(typename Vec2<T>::type (&a)[1 << R], 
     }
 }
 
-// glut: per-op table group index -> tile index built once per CTA (TMA kernel); nullptr: computed from op.fixpos here
-// GL: the kernel keeps a group-index table per pair op in shared memory (no per-tile bit loop)
-template <typename T, int K1, int K2, int S, int NT, bool GL = false>
+template <typename T, int K1, int K2, int S, int NT>
 __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
-                                        const int t, const int tid, const uint16_t *glut = nullptr)
+                                        const int t, const int tid)
 {
     using V = typename Vec2<T>::type;
     constexpr int R = (K1 > S + K2) ? K1 : (S + K2);
@@ -191,9 +189,11 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
     // swz(idx | off_j) = swz(idx) ^ swz(off_j): one XOR per amplitude instead of re-swizzling
     constexpr int kShift = sizeof(V) == 16 ? 4 : 3;
     const uint32_t tile_s = smem_u32(tile);
-    uint32_t sb[R];
+    uint32_t sb[R], seg[R + 1];
 #pragma unroll
     for (int m = 0; m < R; m++) sb[m] = swz<T>(1u << op.tbit[m]) << kShift;
+#pragma unroll
+    for (int m = 0; m <= R; m++) seg[m] = op.seg[m];
     uint32_t boff[D];  // byte offset of block element j relative to the group's element 0 (XOR-combined)
 #pragma unroll
     for (int j = 0; j < D; j++) {
@@ -204,16 +204,10 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
     }
     const uint32_t ngroups = 1u << (t - R);
     for (uint32_t g = tid; g < ngroups; g += NT) {
-        // group index -> tile index: group bit i sits at tile bit fixpos[i] (host order: the lowest group bits, i.e. the
-        // lanes of a quarter-warp, go to tile bits that reach distinct shared-memory banks -- see encode_pass)
-        uint32_t bidx;   // swizzled byte offset of the group's element 0
-        if constexpr (GL) {
-            bidx = glut[g];  // (the table holds the finished byte offset: < 64 KiB)
-        } else {
-            uint32_t idx = 0;
-            for (int i = 0; i < t - R; i++) idx |= ((g >> i) & 1u) << op.fixpos[i];
-            bidx = swz<T>(idx) << kShift;
-        }
+        uint32_t idx = 0;
+#pragma unroll
+        for (int m = 0; m <= R; m++) idx |= (g & seg[m]) << m;
+        const uint32_t bidx = swz<T>(idx) << kShift;
         uint32_t addr[D];
         V a[D];
 #pragma unroll
@@ -225,22 +219,22 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
     }
 }
 
-template <typename T, int NT, int VAR, bool GL>
+template <typename T, int NT, int VAR>
 __device__ __forceinline__ void op_pair_dispatch(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
-                                                 const int t, const int tid, const uint16_t *glut)
+                                                 const int t, const int tid)
 {
     const int code = (op.k << 4) | (op.k2 << 2) | op.s;
-    if (code == ((2 << 4) | (2 << 2) | 2)) { op_pair<T, 2, 2, 2, NT, GL>(tile, op, mat, t, tid, glut); return; }
-    if (code == ((2 << 4) | (2 << 2) | 1)) { op_pair<T, 2, 2, 1, NT, GL>(tile, op, mat, t, tid, glut); return; }
-    if (code == ((1 << 4) | (1 << 2) | 1)) { op_pair<T, 1, 1, 1, NT, GL>(tile, op, mat, t, tid, glut); return; }
+    if (code == ((2 << 4) | (2 << 2) | 2)) { op_pair<T, 2, 2, 2, NT>(tile, op, mat, t, tid); return; }
+    if (code == ((2 << 4) | (2 << 2) | 1)) { op_pair<T, 2, 2, 1, NT>(tile, op, mat, t, tid); return; }
+    if (code == ((1 << 4) | (1 << 2) | 1)) { op_pair<T, 1, 1, 1, NT>(tile, op, mat, t, tid); return; }
     if constexpr (VAR == 2) {
         switch (code) {
-        case (1 << 4) | (1 << 2) | 0: op_pair<T, 1, 1, 0, NT, GL>(tile, op, mat, t, tid, glut); break;
-        case (1 << 4) | (2 << 2) | 1: op_pair<T, 1, 2, 1, NT, GL>(tile, op, mat, t, tid, glut); break;
-        case (1 << 4) | (2 << 2) | 0: op_pair<T, 1, 2, 0, NT, GL>(tile, op, mat, t, tid, glut); break;
-        case (2 << 4) | (1 << 2) | 2: op_pair<T, 2, 1, 2, NT, GL>(tile, op, mat, t, tid, glut); break;
-        case (2 << 4) | (1 << 2) | 1: op_pair<T, 2, 1, 1, NT, GL>(tile, op, mat, t, tid, glut); break;
-        default: op_pair<T, 2, 2, 0, NT, GL>(tile, op, mat, t, tid, glut); break;
+        case (1 << 4) | (1 << 2) | 0: op_pair<T, 1, 1, 0, NT>(tile, op, mat, t, tid); break;
+        case (1 << 4) | (2 << 2) | 1: op_pair<T, 1, 2, 1, NT>(tile, op, mat, t, tid); break;
+        case (1 << 4) | (2 << 2) | 0: op_pair<T, 1, 2, 0, NT>(tile, op, mat, t, tid); break;
+        case (2 << 4) | (1 << 2) | 2: op_pair<T, 2, 1, 2, NT>(tile, op, mat, t, tid); break;
+        case (2 << 4) | (1 << 2) | 1: op_pair<T, 2, 1, 1, NT>(tile, op, mat, t, tid); break;
+        default: op_pair<T, 2, 2, 0, NT>(tile, op, mat, t, tid); break;
         }
     }
 }
@@ -395,12 +389,12 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 // remaining ops still run.
 // VAR: 0 = lean (1-2 qubit dense gates, the common register blocks, permutations), 1 = lean + diagonal runs through the
 // LUT / register-block path, 2 = everything (dense k >= 3, all register blocks, the generic per-bit diagonal gather)
-template <typename T, int NT, bool COND, int VAR, typename Hook = NoHook, bool GL = false>
+template <typename T, int NT, bool COND, int VAR, typename Hook = NoHook>
 __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats, typename Vec2<T>::type *tile,
                                           const typename Vec2<T>::type *__restrict__ diag_tabs,
                                           const uint64_t active, const uint64_t base, const int t, const int tid,
                                           const uint16_t *lut = nullptr, const typename Vec2<T>::type *const *tptr = nullptr,
-                                          const int hook_at = 1 << 30, Hook hook = Hook(), const uint16_t *glut_all = nullptr)
+                                          const int hook_at = 1 << 30, Hook hook = Hook())
 {
     using V = typename Vec2<T>::type;
     const uint32_t tile_amps = 1u << t;
@@ -420,9 +414,7 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                 }
                 __syncthreads();
             } else if (op.kind == OP_PAIR) {
-                // (group-index tables exist for the 4-bit register blocks: 2^(t-4) entries per pair op)
-                if constexpr (GL) op_pair_dispatch<T, NT, VAR, true>(tile, op, mats + op.mat_off, t, tid, glut_all + op.ctrl_in);
-                else op_pair_dispatch<T, NT, VAR, false>(tile, op, mats + op.mat_off, t, tid, nullptr);
+                op_pair_dispatch<T, NT, VAR>(tile, op, mats + op.mat_off, t, tid);
                 __syncthreads();
             } else if (op.kind == OP_DIAG) {
                 if constexpr (VAR >= 1) {  // (passes with diagonal ops never take the lean kernel, see needs_full)
@@ -635,18 +627,6 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     V *stab = reinterpret_cast<V *>(tptr + ((p.n_diag + 1) & ~1));
     uint32_t *dhi = reinterpret_cast<uint32_t *>(stab + p.n_stab);
     uint16_t *lut = reinterpret_cast<uint16_t *>(dhi + p.n_diag);
-    // per register-block pair op: group index -> tile index (the host's bank-aware placement of the group bits), built
-    // once per CTA so that the per-tile cost is one 16-bit load
-    uint16_t *glut = lut + (size_t)p.n_diag * kDiagLut;
-    for (int sl = 0; sl < p.n_pair; sl++) {
-        const DevOp &po = p.ops[p.pair_op[sl]];
-        const int gb = t - po.nfix;   // nfix = R, the register-block width
-        for (uint32_t g = tid; g < (1u << gb); g += NT) {
-            uint32_t idx = 0;
-            for (int i = 0; i < gb; i++) idx |= ((g >> i) & 1u) << po.fixpos[i];
-            glut[po.ctrl_in + g] = (uint16_t)(swz<T>(idx) << (sizeof(V) == 16 ? 4 : 3));
-        }
-    }
     static_assert(NT >= 32, "one warp at least");
     for (int e = tid; e < p.n_diag * kDiagLut; e += NT) {
         const int sl = e / kDiagLut, r = e - sl * kDiagLut;
@@ -784,8 +764,8 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         mbar_wait(&full[s], parity);
         if (p.n_diag || restaged) __syncthreads();
 
-        apply_ops<T, NT, COND, VAR, decltype(refill), true>(p, mats_s, tile, tabs_b, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
-                                    (COND || (16 * NT) != (1 << t)) ? nullptr : lut, tptr, refill_after, refill, glut);
+        apply_ops<T, NT, COND, VAR>(p, mats_s, tile, tabs_b, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
+                                    (COND || (16 * NT) != (1 << t)) ? nullptr : lut, tptr, refill_after, refill);
 
         // every thread's generic-proxy writes -> visible to the async proxy; then drain the tile with TMA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

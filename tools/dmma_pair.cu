@@ -158,14 +158,10 @@ int main(int argc, char **argv)
         d.kind = OP_PAIR; d.k = 2; d.k2 = 2; d.s = 2; d.nfix = 4;
         std::vector<int> fix(cs.bits, cs.bits + 4);
         for (int m = 0; m < 4; m++) d.tbit[m] = (uint8_t)cs.bits[m];
-        {   // group bit i -> tile bit fixpos[i], bank-friendly positions first (encode_pass)
-            std::vector<int> order;
-            bool used_res[3] = {false, false, false};
-            for (int pos : freeb)
-                if (pos < 6 && !used_res[pos % 3] && order.size() < 3) { order.push_back(pos); used_res[pos % 3] = true; }
-            for (int pos : freeb)
-                if (std::find(order.begin(), order.end(), pos) == order.end()) order.push_back(pos);
-            for (size_t f = 0; f < order.size(); f++) d.fixpos[f] = (uint8_t)order[f];
+        std::sort(fix.begin(), fix.end());
+        for (int k = 0; k <= 4; k++) {   // segment masks of the group index, as encode_pass builds them
+            const int lo = k == 0 ? 0 : fix[k - 1] - (k - 1), hi = k == 4 ? 16 : fix[k] - k;
+            d.seg[k] = (uint16_t)(hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u);
         }
         std::vector<double> hm(64);
         // op_pair's matrices index the local bits (m = 0,1): bit m of the row/column index <-> tbit[m]; the DMMA kernel uses
