@@ -37,6 +37,7 @@ DistPlan plan_distributed(const std::vector<HostOp> &ops, int n_total, int n_loc
         HostOp op = ops[i];
         for (int &x : op.q) x = sigma[x];
         for (int &x : op.ctrl) x = sigma[x];
+        for (PhaseTerm &t : op.terms) { if (t.a >= 0) t.a = sigma[t.a]; if (t.b >= 0) t.b = sigma[t.b]; }
         // non-diagonal targets on global positions: bring them in.  When one swap is needed, every global qubit
         // that some op within the look-ahead window also needs non-diagonally is brought in at the same time, so
         // that exchanges cluster (back-to-back swaps) and the local segments between them stay long.
@@ -79,6 +80,7 @@ DistPlan plan_distributed(const std::vector<HostOp> &ops, int n_total, int n_loc
                     inv[best] = og; inv[gpos] = ol;
                     for (int &x : op.q) if (x == gpos) x = best; else if (x == best) x = gpos;
                     for (int &x : op.ctrl) if (x == gpos) x = best; else if (x == best) x = gpos;
+                    // (only non-diagonal ops trigger an exchange: no phase terms to remap here)
                 }
                 swap_batch++;
                 for (int x : op.q)
@@ -110,6 +112,20 @@ DistPlan plan_distributed(const std::vector<HostOp> &ops, int n_total, int n_loc
                 d.kind = HostOp::DIAG;
                 d.mask_row = op.mask_row;
                 d.n_orig = op.n_orig;
+                // the phase terms sliced the same way: a global qubit is this rank's bit
+                d.has_terms = op.has_terms;
+                for (PhaseTerm t : op.terms) {
+                    bool gone = false;
+                    for (int *e : {&t.a, &t.b}) {
+                        if (*e >= n_local) {
+                            if (!rank_bit(*e)) gone = true;   // factor 1 on this rank
+                            *e = -1;
+                        }
+                    }
+                    if (gone) continue;
+                    if (t.a < 0 && t.b >= 0) std::swap(t.a, t.b);
+                    d.terms.push_back(t);
+                }
                 if (lq.empty()) {  // a rank-dependent scalar phase
                     d.q = {0};
                     d.m = {op.m[fixed], op.m[fixed]};

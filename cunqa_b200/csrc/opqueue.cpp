@@ -51,8 +51,30 @@ uint64_t OpQueue::logical_index(uint64_t phys) const
     return l;
 }
 
+// a diagonal over one or two qubits as a product of phase terms (exact for any such table)
+static void terms_of_small_diag(HostOp &d)
+{
+    const size_t k = d.q.size();
+    if (k == 0 || k > 2) return;
+    for (const cplx &z : d.m) if (std::abs(z) == 0.0) return;
+    d.terms.clear();
+    PhaseTerm t;
+    t.z = d.m[0];
+    d.terms.push_back(t);                                   // scalar: the |0..0> entry
+    t.a = d.q[0]; t.z = d.m[1] / d.m[0];
+    d.terms.push_back(t);
+    if (k == 2) {
+        t.a = d.q[1]; t.b = -1; t.z = d.m[2] / d.m[0];
+        d.terms.push_back(t);
+        t.a = d.q[0]; t.b = d.q[1]; t.z = d.m[3] * d.m[0] / (d.m[1] * d.m[2]);
+        d.terms.push_back(t);
+    }
+    d.has_terms = true;
+}
+
 void OpQueue::push_op(HostOp op, const uint8_t *flags)
 {
+    if (op.kind == HostOp::DIAG && !flags) terms_of_small_diag(op);
     if (flags) {
         op.mask_row = (int)mask_rows.size();
         mask_rows.emplace_back(flags, flags + batch);

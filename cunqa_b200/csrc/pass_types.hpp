@@ -17,6 +17,9 @@ constexpr int kMaxDiagK = 12;     // diagonal table width (qubits)
 constexpr int kMaxFix = 12;       // targets + in-tile controls of one op
 constexpr int kMatScalars = 2560; // scalars (re/im) of dense-matrix storage per pass (kernel params)
 constexpr int kDiagLut = 192;
+constexpr int kFanMaxCenters = 8;       // centers of a phase fan
+constexpr int kFanMaxLeafBits = 6;      // in-tile leaves of a phase fan (tables of 2^6 entries per center)
+constexpr int kFanMaxChunks = 4;        // out-of-tile leaves, 8 per chunk (256-entry table per chunk and center)
 constexpr int kStabEntries = 1024;      // per-tile store of small diagonal sub-tables (entries; 16 KB of complex128)
 constexpr int kStabMaxBits = 6;        // a diagonal op is staged when at most this many of its qubits are tile qubits
 constexpr uint16_t kNotStaged = 0xFFFF;     // per diagonal op: 64 entries for tile bits 0..5 + 128 for tile bits 6..12
@@ -28,6 +31,11 @@ enum OpKind : uint8_t {
     OP_SWAP = 3,   // swap tbit[0] <-> tbit[1] (controls optional)
     OP_PAIR = 4,   // register block: two dense gates A (k qubits, local bits [0,k)) and B (k2 qubits, local
                    // bits [s,s+k2)) applied back to back to the 2^R amplitudes a thread holds in registers
+    OP_FAN = 5,    // phase fan at the end of a pass: every "center" (a tile bit, k <= 8 of them) carries a phase that is a
+                   // product of one factor per other qubit ("leaf": in-tile non-center bits and out-of-tile qubits); no term
+                   // joins two centers or two leaves.  amplitude *= g * prod_{centers b set} [c_b(tile) * T_b[leaf bits]].
+                   // This is what the controlled-phase ladders of a QFT leave behind once the terms that commute with the
+                   // rest of the pass are pulled out of the per-amplitude tables (planner.cpp: encode_pass).
 };
 
 struct DevOp {
@@ -70,6 +78,13 @@ struct PassParams {
     int32_t n_diag;     // number of OP_DIAG ops; diag_op[slot] = op index of the slot-th one
     int32_t n_stab;     // entries of the shared-memory sub-table store used by this pass (multiple of 8)
     uint8_t diag_op[kMaxOps];
+    // phase fan (at most one per pass, always the last op): DevOp kind OP_FAN with k = #centers, tbit[c] = tile bit of
+    // center c, nfix = #in-tile leaf bits, fixpos[] = their tile bits (ascending), ctrl_in = their tile-bit mask, dsrc[0..3]
+    // = the four centers that are register bits of the sweep, mat_off = first entry of its block in the diagonal-table
+    // buffer: [0] scalar g, then T[c][2^nfix], then X[chunk][c][256] (the out-of-tile leaves, 8 physical qubits per chunk)
+    int32_t fan_op;      // op index, -1 = none
+    int32_t fan_chunks;  // number of out-of-tile leaf chunks
+    uint8_t fan_q[kFanMaxChunks][8];  // physical qubit of every chunk bit (0xFF = unused)
     uint8_t stab_slot[kStabEntries / 8];  // diagonal slot that owns each 8-entry chunk of the store
     uint8_t tile_q[16]; // physical qubit of tile bit j (ascending)
     DevOp ops[kMaxOps];

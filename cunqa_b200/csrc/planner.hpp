@@ -15,6 +15,9 @@
 
 namespace cb200 {
 
+// one factor of a diagonal op: multiply the amplitude by z where qubit a is 1 (and qubit b is 1 when b >= 0); a = b = -1: a scalar
+struct PhaseTerm { int a = -1, b = -1; cplx z = cplx(1, 0); };
+
 struct HostOp {
     enum Kind { DENSE, DIAG, PERMX, SWAP } kind = DENSE;
     std::vector<int> q;     // DENSE/PERMX/SWAP: target qubits; DIAG: table qubits (bit m of the table index <-> q[m])
@@ -22,6 +25,11 @@ struct HostOp {
     std::vector<cplx> m;    // DENSE: 2^k x 2^k row-major; DIAG: 2^k entries
     int mask_row = -1;      // per-state flag row (batched feed-forward), -1 = unconditional
     int n_orig = 1;         // original circuit gates folded into this op
+    // DIAG ops built from 1- and 2-qubit phase gates only (z s t rz p cp cz crz rzz ...): the table is the product of these
+    // terms.  encode_pass uses them to pull the part of a phase ladder that commutes with the rest of its pass out of the
+    // per-amplitude tables (the "fan" at the end of the pass, pass_types.hpp: OP_FAN).
+    std::vector<PhaseTerm> terms;
+    bool has_terms = false;
 
     uint64_t qmask() const;   // all qubits touched
     uint64_t xmask() const;   // qubits acted on non-diagonally
@@ -30,7 +38,8 @@ struct HostOp {
 // encode_pass flags
 constexpr int kEncPairOps = 1;         // register-block adjacent dense gates
 constexpr int kEncDiagFuseAlways = 2;  // always fold a diagonal run into the dense gate that follows it (experiments)
-constexpr int kEncNoStage = 4;         // no per-tile shared-memory staging of diagonal sub-tables (experiments)
+constexpr int kEncNoStage = 4;
+constexpr int kEncFan = 16;            // pull commuting phase-ladder terms into a fan at the end of the pass (TMA kernel, no per-tile conditions)         // no per-tile shared-memory staging of diagonal sub-tables (experiments)
 
 struct PlanOptions {
     int tile_bits = 12;        // t: 2^t amplitudes staged per tile
@@ -48,7 +57,8 @@ struct PlanOptions {
     // per-amplitude sub-tables in shared memory does not (82.6 against 81.6): the pass is bound by its instruction count
     // (258 per amplitude), not by the table loads.  Both stay switchable: CB200_DIAG_FUSE_ALWAYS, CB200_STAGE_DIAG.
     bool diag_fuse_always = true, stage_diag = false;
-    int enc_flags() const { return (pair_ops ? kEncPairOps : 0) | (diag_fuse_always ? kEncDiagFuseAlways : 0) | (stage_diag ? 0 : kEncNoStage); }
+    bool fan = true;           // CB200_FAN: phase fans (OP_FAN) for controlled-phase ladders
+    int enc_flags() const { return (pair_ops ? kEncPairOps : 0) | (diag_fuse_always ? kEncDiagFuseAlways : 0) | (stage_diag ? 0 : kEncNoStage) | (fan ? kEncFan : 0); }
     uint64_t global_mask = 0;  // sharded state: physical qubits that select the rank (never fused into dense blocks)
 };
 
