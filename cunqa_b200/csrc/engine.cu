@@ -54,6 +54,7 @@ void State::init_options(int gbits)
     opt.pair_ops = env_int("CB200_PAIR_OPS", 1) != 0;
     opt.diag_fuse_always = env_int("CB200_DIAG_FUSE_ALWAYS", 1) != 0;
     opt.stage_diag = env_int("CB200_STAGE_DIAG", 0) != 0;
+    opt.fan = env_int("CB200_FAN", 1) != 0;
     if (gbits) opt.global_mask = ((1ull << gbits) - 1ull) << n_local_;
     queue = OpQueue(n, batch, opt);
 }
@@ -381,7 +382,8 @@ void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb, ChunkPipe *pi
         const int stages = tma_stages_;
         size_t smem_tma = (size_t)stages * buf_stride + sizeof(uint64_t) * (stages + 1) + sizeof(uint32_t) * ((((size_t)1 << (p.t - box_bits)) + 3) & ~(size_t)3) +
                           sizeof(T) * (size_t)((p.n_mat + 1) & ~1) + (size_t)((p.n_diag + 1) & ~1) * 8 + (size_t)p.n_stab * sizeof(V) +
-                          (size_t)p.n_diag * (4 + 2 * kDiagLut) + 16 + 1024;
+                          (size_t)p.n_diag * (4 + 2 * kDiagLut) +
+                          (p.fan_op >= 0 ? (((size_t)p.ops[p.fan_op].k << p.ops[p.fan_op].nfix) + (size_t)p.ops[p.fan_op].k * (1 + p.fan_chunks)) * sizeof(V) + 16 : 0) + 16 + 1024;
         int nt = 1 << std::max(5, std::min(8, p.t - kAmpsPerThreadShift));  // 32 / 64 / 128 / 256 threads
         if (tma_threads_ > 0) nt = tma_threads_;
         int ctas = std::max(1, (stages == 3 ? 256 : 384) / nt);
@@ -471,9 +473,17 @@ void State::flush_registers_t()
                regq_[b1].l2p == regq_[b0].l2p)
             b1++;
         cur_reg_ = b0;
+        bool shared = false;
         if (b1 - b0 >= 2) {
-            launch_uniform_t<T>(b0, b1 - b0);
-            uniform_flushes++;
+            // (a layout that depends on the numbers after all -- e.g. a product that happens to be diagonal for one
+            // register only -- is detected before anything is launched: those registers then run one by one)
+            try { launch_uniform_t<T>(b0, b1 - b0); shared = true; uniform_flushes++; }
+            catch (const Unsupported &) { shared = false; }
+        }
+        if (shared) {
+        } else if (b1 - b0 >= 2) {
+            for (int g = b0; g < b1; g++) { cur_reg_ = g; launch_ops_t<T>(regq_[g].ops(), g, 1); }
+            split_flushes++;
         } else {
             launch_ops_t<T>(regq_[b0].ops(), b0, 1);
             split_flushes++;
@@ -559,7 +569,8 @@ void State::launch_uniform_t(int b0, int nb)
         const int stages = tma_stages_;
         const size_t smem_tma = (size_t)stages * buf_stride + sizeof(uint64_t) * (stages + 1) + sizeof(uint32_t) * ((((size_t)1 << (p.t - box_bits)) + 3) & ~(size_t)3) +
                                 sizeof(T) * (size_t)((p.n_mat + 1) & ~1) + (size_t)((p.n_diag + 1) & ~1) * 8 + (size_t)p.n_stab * sizeof(V) +
-                                (size_t)p.n_diag * (4 + 2 * kDiagLut) + 16 + 1024;
+                                (size_t)p.n_diag * (4 + 2 * kDiagLut) +
+                          (p.fan_op >= 0 ? (((size_t)p.ops[p.fan_op].k << p.ops[p.fan_op].nfix) + (size_t)p.ops[p.fan_op].k * (1 + p.fan_chunks)) * sizeof(V) + 16 : 0) + 16 + 1024;
         int nt = 1 << std::max(5, std::min(8, p.t - kAmpsPerThreadShift));
         if (tma_threads_ > 0) nt = tma_threads_;
         int ctas = std::max(1, (stages == 3 ? 256 : 384) / nt);

@@ -1553,6 +1553,7 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
         if (o.contains("lookahead")) opt.lookahead = (int)o.at("lookahead").as_int();
         if (o.contains("lookahead_min_qubits")) opt.lookahead_min_qubits = (int)o.at("lookahead_min_qubits").as_int();
         if (o.contains("fuse")) opt.fuse = o.at("fuse").as_bool();
+        if (o.contains("fan")) opt.fan = o.at("fan").as_bool();
         if (o.contains("world")) world = (int)o.at("world").as_int();
         if (o.contains("rank")) rank = (int)o.at("rank").as_int();
     }
@@ -1606,8 +1607,17 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
             PassParams<double> pp;
             std::vector<cplx> diag;
             std::string err;
-            if (!encode_pass<double>(p, ops, nq, 1, pp, diag, err)) throw std::runtime_error(err);
+            if (!encode_pass<double>(p, ops, nq, 1, pp, diag, err, opt.enc_flags())) throw std::runtime_error(err);
             o.set("diag_entries", Json::integer((long long)diag.size()));
+            o.set("device_ops", Json::integer(pp.n_ops));
+            o.set("diag_tables", Json::integer(pp.n_diag));
+            if (pp.fan_op >= 0) {
+                Json f = Json::object();
+                f.set("centers", Json::integer(pp.ops[pp.fan_op].k));
+                f.set("leaf_bits_in_tile", Json::integer(pp.ops[pp.fan_op].nfix));
+                f.set("leaf_chunks_outside", Json::integer(pp.fan_chunks));
+                o.set("fan", std::move(f));
+            }
             jp.arr.push_back(std::move(o));
         }
         return jp;

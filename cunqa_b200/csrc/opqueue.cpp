@@ -58,16 +58,18 @@ static void terms_of_small_diag(HostOp &d)
     if (k == 0 || k > 2) return;
     for (const cplx &z : d.m) if (std::abs(z) == 0.0) return;
     d.terms.clear();
-    PhaseTerm t;
-    t.z = d.m[0];
-    d.terms.push_back(t);                                   // scalar: the |0..0> entry
-    t.a = d.q[0]; t.z = d.m[1] / d.m[0];
-    d.terms.push_back(t);
+    // (factors that are exactly 1 -- the |0>, |01>, |10> entries of a controlled phase -- are not terms)
+    auto add = [&](int a, int b, cplx z) {
+        if (z == cplx(1, 0)) return;
+        PhaseTerm t;
+        t.a = a; t.b = b; t.z = z;
+        d.terms.push_back(t);
+    };
+    add(-1, -1, d.m[0]);                                    // scalar: the |0..0> entry
+    add(d.q[0], -1, d.m[1] / d.m[0]);
     if (k == 2) {
-        t.a = d.q[1]; t.b = -1; t.z = d.m[2] / d.m[0];
-        d.terms.push_back(t);
-        t.a = d.q[0]; t.b = d.q[1]; t.z = d.m[3] * d.m[0] / (d.m[1] * d.m[2]);
-        d.terms.push_back(t);
+        add(d.q[1], -1, d.m[2] / d.m[0]);
+        add(d.q[0], d.q[1], d.m[3] * d.m[0] / (d.m[1] * d.m[2]));
     }
     d.has_terms = true;
 }

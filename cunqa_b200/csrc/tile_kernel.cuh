@@ -359,6 +359,88 @@ __device__ __noinline__ void op_diag_block(typename Vec2<T>::type *tile, const D
     }
 }
 
+// ---- phase fan (OP_FAN, pass_types.hpp): amplitude *= g * prod over the centers b set in its index of [c_b * T_b[v]],
+// v = the in-tile leaf bits.  A thread owns the 16 settings of four register bits that are not leaves, so v and every
+// center factor are the same for its 16 amplitudes: the four register-bit factors are combined into their 16 subset
+// products (12 complex multiplies) and applied once -- ~44 complex multiplies per thread whatever the number of terms.
+//   fanT: T[c][2^m] (shared memory), fanc: c_b of this tile (shared memory), g: the fan's scalar
+template <typename T, int NT>
+__device__ __noinline__ void op_fan(typename Vec2<T>::type *tile, const DevOp &fo, const typename Vec2<T>::type *fanT,
+                                    const typename Vec2<T>::type *fanc, const typename Vec2<T>::type g, const int tid)
+{
+    using V = typename Vec2<T>::type;
+    constexpr int A = 16;
+    uint32_t bi = tid;
+#pragma unroll
+    for (int f = 0; f < 4; f++) bi = insert0(bi, fo.dsrc[f]);  // ascending register-bit positions
+    uint32_t rbit[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) rbit[b] = 1u << fo.dsrc[b];
+    const int m = fo.nfix, nc = fo.k;
+    uint32_t v = 0;
+    for (int i = 0; i < m; i++) v |= ((bi >> fo.fixpos[i]) & 1u) << i;
+    auto factor = [&](int c) -> V { const V a = fanc[c], b = fanT[(c << m) + v]; return cmul<V, T>(a.x, a.y, b); };
+    uint32_t regc = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) if (fo.dsrc[4 + b] != 0xFF) regc |= 1u << fo.dsrc[4 + b];
+    V s = g;   // the centers that are fixed for this thread
+    for (int c = 0; c < nc; c++)
+        if (!((regc >> c) & 1u) && ((bi >> fo.tbit[c]) & 1u)) { const V f = factor(c); s = cmul<V, T>(s.x, s.y, f); }
+    V f[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        f[b].x = (T)1; f[b].y = (T)0;
+        if (fo.dsrc[4 + b] != 0xFF) f[b] = factor(fo.dsrc[4 + b]);
+    }
+    V g01[4], g23[4];
+    g01[0] = s;
+    g01[1] = cmul<V, T>(s.x, s.y, f[0]);
+    g01[2] = cmul<V, T>(s.x, s.y, f[1]);
+    g01[3] = cmul<V, T>(g01[1].x, g01[1].y, f[1]);
+    g23[1] = f[2];
+    g23[2] = f[3];
+    g23[3] = cmul<V, T>(f[2].x, f[2].y, f[3]);
+#pragma unroll
+    for (int k = 0; k < A; k++) {
+        const uint32_t idx = swz<T>(bi | ((k & 1) ? rbit[0] : 0u) | ((k & 2) ? rbit[1] : 0u) | ((k & 4) ? rbit[2] : 0u) | ((k & 8) ? rbit[3] : 0u));
+        V ph = g01[k & 3];
+        if ((k >> 2) != 0) ph = cmul<V, T>(ph.x, ph.y, g23[k >> 2]);
+        const V a = tile[idx];
+        tile[idx] = cmul<V, T>(ph.x, ph.y, a);
+    }
+}
+
+// the same fan, one amplitude at a time, everything read from the table block in global memory (generic kernel and the
+// kernel variants without the 16-amplitudes-per-thread layout): correctness path, not a fast one
+template <typename T>
+__device__ void op_fan_slow(typename Vec2<T>::type *tile, const DevOp &fo, const uint8_t (*fan_q)[8], const int nch,
+                            const typename Vec2<T>::type *__restrict__ blk, const uint64_t base, const int t, const int tid, const int nt)
+{
+    using V = typename Vec2<T>::type;
+    const int m = fo.nfix, nc = fo.k;
+    uint32_t u[kFanMaxChunks];
+    for (int ch = 0; ch < nch; ch++) {
+        u[ch] = 0;
+        for (int bit = 0; bit < 8; bit++)
+            if (fan_q[ch][bit] != 0xFF) u[ch] |= (uint32_t)((base >> fan_q[ch][bit]) & 1ull) << bit;
+    }
+    const V *Tt = blk + 1, *X = blk + 1 + ((size_t)nc << m);
+    for (uint32_t i = tid; i < (1u << t); i += nt) {
+        uint32_t v = 0;
+        for (int j = 0; j < m; j++) v |= ((i >> fo.fixpos[j]) & 1u) << j;
+        V ph = blk[0];
+        for (int c = 0; c < nc; c++) {
+            if (!((i >> fo.tbit[c]) & 1u)) continue;
+            const V tv = Tt[(c << m) + v];
+            ph = cmul<V, T>(ph.x, ph.y, tv);
+            for (int ch = 0; ch < nch; ch++) { const V x = X[((size_t)ch * nc + c) * 256 + u[ch]]; ph = cmul<V, T>(ph.x, ph.y, x); }
+        }
+        const uint32_t sidx = swz<T>(i);
+        const V a = tile[sidx];
+        tile[sidx] = cmul<V, T>(ph.x, ph.y, a);
+    }
+}
+
 // which ops of the pass act on the tile at `base` of state `b`: unconditional ops always do; ops with
 // controls outside the tile or a per-state mask (rare; listed in cond_mask) are tested individually
 template <typename T>
@@ -394,7 +476,8 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                                           const typename Vec2<T>::type *__restrict__ diag_tabs,
                                           const uint64_t active, const uint64_t base, const int t, const int tid,
                                           const uint16_t *lut = nullptr, const typename Vec2<T>::type *const *tptr = nullptr,
-                                          const int hook_at = 1 << 30, Hook hook = Hook())
+                                          const int hook_at = 1 << 30, Hook hook = Hook(),
+                                          const typename Vec2<T>::type *fanT = nullptr, const typename Vec2<T>::type *fanc = nullptr)
 {
     using V = typename Vec2<T>::type;
     const uint32_t tile_amps = 1u << t;
@@ -461,6 +544,13 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                 }
                 o = oe;
                 __syncthreads();
+                }
+            } else if (op.kind == OP_FAN) {
+                if constexpr (VAR >= 1) {
+                    // fast path: the 16-amplitudes-per-thread layout with the fan's tables in shared memory (TMA kernel)
+                    if (fanT != nullptr && (VAR == 1 || lut != nullptr)) op_fan<T, NT>(tile, op, fanT, fanc, diag_tabs[op.mat_off], tid);
+                    else if constexpr (VAR == 2) op_fan_slow<T>(tile, op, p.fan_q, p.fan_chunks, diag_tabs + op.mat_off, base, t, tid, NT);
+                    __syncthreads();
                 }
             } else {
                 op_perm<T, NT>(tile, op, t, tid);
@@ -627,6 +717,17 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     V *stab = reinterpret_cast<V *>(tptr + ((p.n_diag + 1) & ~1));
     uint32_t *dhi = reinterpret_cast<uint32_t *>(stab + p.n_stab);
     uint16_t *lut = reinterpret_cast<uint16_t *>(dhi + p.n_diag);
+    // phase fan: T[c][2^m] (staged with the matrices), this tile's center factors and their per-chunk parts
+    const int fan_nc = p.fan_op >= 0 ? p.ops[p.fan_op].k : 0, fan_m = p.fan_op >= 0 ? p.ops[p.fan_op].nfix : 0;
+    unsigned char *fan_raw = reinterpret_cast<unsigned char *>(lut + (size_t)p.n_diag * kDiagLut);
+    fan_raw += (16u - (smem_u32(fan_raw) & 15u)) & 15u;
+    V *fanT = reinterpret_cast<V *>(fan_raw);
+    V *fanc = fanT + ((size_t)fan_nc << fan_m);
+    V *fanp = fanc + fan_nc;
+    if (p.fan_op >= 0 && reg_mats == nullptr) {
+        const V *src = diag_tabs + p.ops[p.fan_op].mat_off + 1;
+        for (int e = tid; e < (fan_nc << fan_m); e += NT) fanT[e] = src[e];
+    }
     static_assert(NT >= 32, "one warp at least");
     for (int e = tid; e < p.n_diag * kDiagLut; e += NT) {
         const int sl = e / kDiagLut, r = e - sl * kDiagLut;
@@ -758,14 +859,40 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
             // (mats_s is only read inside apply_ops, and every thread left the previous tile's apply_ops through a barrier)
             const T *src = reg_mats + (size_t)b * reg_mat_stride;
             for (int e = tid; e < p.n_mat; e += NT) mats_s[e] = src[e];
+            if (p.fan_op >= 0) {
+                const V *fsrc = tabs_b + p.ops[p.fan_op].mat_off + 1;
+                for (int e = tid; e < (fan_nc << fan_m); e += NT) fanT[e] = fsrc[e];
+            }
             staged_b = b;
             restaged = true;
         }
+        if (p.fan_op >= 0) {
+            // out-of-tile leaves of the fan: one 256-entry table per (chunk of 8 qubits, center), indexed by the tile base
+            const DevOp &fo = p.ops[p.fan_op];
+            const V *X = tabs_b + fo.mat_off + 1 + ((size_t)fan_nc << fan_m);
+            for (int e = tid; e < fan_nc * p.fan_chunks; e += NT) {
+                const int ch = e / fan_nc;
+                uint32_t u = 0;
+                for (int bit = 0; bit < 8; bit++)
+                    if (p.fan_q[ch][bit] != 0xFF) u |= (uint32_t)((base >> p.fan_q[ch][bit]) & 1ull) << bit;
+                fanp[e] = X[(size_t)e * 256 + u];
+            }
+        }
         mbar_wait(&full[s], parity);
-        if (p.n_diag || restaged) __syncthreads();
+        if (p.n_diag || restaged || p.fan_op >= 0) __syncthreads();
+        if (p.fan_op >= 0) {
+            if (tid < fan_nc) {
+                V c;
+                c.x = (T)1; c.y = (T)0;
+                for (int ch = 0; ch < p.fan_chunks; ch++) { const V x = fanp[ch * fan_nc + tid]; c = cmul<V, T>(c.x, c.y, x); }
+                fanc[tid] = c;
+            }
+            __syncthreads();
+        }
 
         apply_ops<T, NT, COND, VAR>(p, mats_s, tile, tabs_b, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
-                                    (COND || (16 * NT) != (1 << t)) ? nullptr : lut, tptr, refill_after, refill);
+                                    (COND || (16 * NT) != (1 << t)) ? nullptr : lut, tptr, refill_after, refill,
+                                    (COND || (16 * NT) != (1 << t)) ? nullptr : fanT, fanc);
 
         // every thread's generic-proxy writes -> visible to the async proxy; then drain the tile with TMA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
