@@ -135,3 +135,22 @@ def test_lookahead_pass_counts_at_the_headline_sizes(lib_built):
     assert len(cb.plan(qv)["passes"]) <= 66 < 92 <= len(cb.plan(qv, {"lookahead": 0})["passes"])
     hea = C.task(C.hea_ansatz(30, 4, 1, measure=False), 30)
     assert len(cb.plan(hea)["passes"]) <= 6
+
+
+def test_phase_fan_takes_the_commuting_ladder_terms_of_a_qft_pass(lib_built):
+    """encode_pass pulls the controlled-phase terms that commute with the rest of their pass into one fan op: a QFT-30
+    pass then carries a handful of small tables (the ladder terms among its own six qubits) instead of up to 17"""
+    n = 30
+    t = C.task(C.qft(n, C.qft_x(n, seed=7)), n)
+    plain = cb.plan(t, {"fan": False})["passes"]
+    fanned = cb.plan(t, {"fan": True})["passes"]
+    assert len(plain) == len(fanned)
+    assert max(p["diag_tables"] for p in plain) >= 14
+    for p, f in zip(plain, fanned):
+        if p["diag_tables"] >= 5:
+            assert "fan" in f and f["diag_tables"] <= 4
+            assert 1 <= f["fan"]["centers"] <= 8 and f["fan"]["leaf_bits_in_tile"] <= 6 and f["fan"]["leaf_chunks_outside"] <= 4
+        else:
+            assert "fan" not in f
+    # dense-only circuits never get one
+    assert all("fan" not in p for p in cb.plan(C.task(C.quantum_volume(26, depth=4, seed=1), 26), {"fan": True})["passes"])
