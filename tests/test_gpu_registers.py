@@ -138,3 +138,45 @@ def test_config5_as_stated_64_groups_of_24_qubits(backend):
             else:
                 assert O.tvd(res[g]["id_counts"][tid], want[tid]) < 0.5 * math.sqrt(2 ** 11 / shots) + 0.05
     assert st["passes"] <= 64  # not one schedule per group
+
+
+def test_single_precision_and_external_channel_messages_run_alone(backend):
+    """registers are complex128 (the dynamic path's precision, aer_simulator_adapter.cpp:946): a `precision: single` message
+    of a batch runs through the ordinary path and still gets its own answer"""
+    n, shots = 10, 800
+    ins = C.hea_ansatz(n, 2, 3)
+    a = C.task(ins, n, shots=shots, seed=1)
+    b = C.task(ins, n, shots=shots, seed=1, precision="single")
+    ra, rb = backend.execute_many([a, b])
+    assert backend.batch_info()["solo"] == 1
+    assert "ERROR" not in ra and "ERROR" not in rb
+    assert ra["counts"] == backend.execute(a)["counts"] and rb["counts"] == backend.execute(b)["counts"]
+    assert O.tvd(ra["counts"], rb["counts"]) < 0.5 * math.sqrt(2 ** n / shots) + 0.05
+
+
+def test_registers_with_phase_ladders_share_launches(backend):
+    """QFT circuits on different inputs and a parametrised cp / crz / rzz circuit at several angle sets: the phase fans
+    and diagonal tables are per-register rows of one buffer"""
+    n, shots = 13, 3000
+    msgs = [C.task(C.qft(n, x) + C.measure_all(n), n, shots=shots, seed=5) for x in (0, 1, 4097, 8190)]
+    res = backend.execute_many(msgs)
+    assert backend.batch_info()["solo"] == 0
+    for m, r in zip(msgs, res):
+        assert r["counts"] == backend.execute(m)["counts"]
+        assert len(r["counts"]) > 1500          # QFT|x> is uniform in magnitude: nearly every shot a new outcome
+    rng = np.random.default_rng(3)
+    def circ(th):
+        ins = [{"name": "h", "qubits": [q]} for q in range(n)]
+        for q in range(n - 1):
+            ins.append({"name": "cp", "qubits": [q, q + 1], "params": [float(th[q])]})
+            ins.append({"name": "rzz", "qubits": [q, (q + 3) % n], "params": [float(th[q] / 2)]})
+            ins.append({"name": "crz", "qubits": [(q + 5) % n, q], "params": [float(-th[q])]})
+        ins += [{"name": "h", "qubits": [q]} for q in range(0, n, 2)]
+        return ins
+    thetas = [rng.uniform(0, 6.28, n) for _ in range(5)]
+    msgs = [C.task(circ(th) + C.measure_all(n), n, shots=shots, seed=9) for th in thetas]
+    res = backend.execute_many(msgs)
+    assert backend.batch_info() == {"uniform_flushes": 1, "split_flushes": 0, "solo": 0}
+    for g in (0, 2, 4):
+        want = O.run_static(circ(thetas[g]) + C.measure_all(n), n, shots=shots, seed=9, backend="c")[1]
+        assert res[g]["counts"] == want

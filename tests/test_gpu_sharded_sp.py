@@ -132,3 +132,40 @@ def test_backend_execute_on_target_devices(lib_built):
         assert be.last_mode() == (1 if defer else 2)
         assert set(res["counts"]) <= {"000", "101"}          # c0 = c2 = GHZ outcome, c1 = q0 flipped back to 0 when it was 1
     be.close()
+
+
+def test_quantum_communication_group_on_a_sharded_register(lib_built):
+    """two vQPU tasks + communication pair as ONE joint register sharded over the GPUs (the QC executor's message through
+    cb200_backend_execute with a device list): telegate, deferred and per-shot"""
+    devs = _devices()
+    tasks = C.hea_telegate_pair(6, layers=1, seed=2)
+    n_joint = 14
+    be = cb.Backend(devices=devs)
+    for defer, shots in ((True, 2000), (False, 16)):
+        # (per-shot mode: the literal measure-by-measure sequence, so that engine and oracle draw the same stream -- the
+        # terminal inverse-CDF shortcut walks a sharded state in another order than the oracle's)
+        msg = [C.task(t["instructions"], t["num_qubits"], shots=shots, seed=4, task_id=t["id"], is_dynamic=True,
+                      b200_shard_min_qubits=n_joint, b200_defer_measurement=defer, b200_terminal_sampling=False) for t in tasks]
+        res = be.execute(msg)
+        assert "ERROR" not in res, res
+        assert be.last_mode() == (1 if defer else 2)
+        want = O.run_dynamic(tasks, shots, seed=4, defer=defer, terminal_sampling=False)
+        for tid in want:
+            assert sum(res["id_counts"][tid].values()) == shots
+            if not defer:
+                assert res["id_counts"][tid] == want[tid]          # same measurement stream, shot for shot
+            else:
+                assert O.tvd(res["id_counts"][tid], want[tid]) < 0.5 * math.sqrt(2 ** 6 / shots) + 0.05
+    # out-of-band amplitudes and marginals of a sharded register through the wire format
+    n = 13 + len(devs).bit_length() - 1
+    ins = C.quantum_volume(n, depth=2, seed=6)
+    ref, _ = O.run_static(ins, n, backend="c")
+    idx, qs = [0, 3, (1 << n) - 1], [n - 1, 0, 5]
+    r = be.execute(C.task(ins + C.measure_all(n), n, shots=50, seed=1, b200_shard_min_qubits=n, b200_amplitude_indices=idx, b200_marginal_qubits=qs))
+    assert "ERROR" not in r, r
+    assert np.abs(np.array([complex(*z) for z in r["b200_amplitudes"]]) - ref.amplitudes()[idx]).max() < 1e-12
+    p = np.abs(ref.amplitudes()) ** 2
+    i = np.arange(1 << n)
+    j = sum(((i >> q) & 1) << m for m, q in enumerate(qs))
+    assert np.abs(np.array(r["b200_marginal"]) - np.bincount(j, weights=p, minlength=8)).max() < 1e-12
+    be.close()
