@@ -309,8 +309,20 @@ void State::dist_swap_chunked(const std::vector<std::pair<int, int>> &pairs, int
     CB200_CUDA(cudaEventRecord(e0, stream_));
     CB200_CUDA(cudaStreamWaitEvent(xstream_, e0, 0));
     const uint64_t total = (uint64_t)((1u << m) - 1) << (rest_bits - chunk_bits);
-    const int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)num_sms_ * 16);
+    // few CTAs per SM: the exchange has to share the SMs with the tile pass that runs beside it (CB200_SWAP_CTAS_PER_SM)
+    static const int swap_ctas = getenv("CB200_SWAP_CTAS_PER_SM") ? std::max(1, atoi(getenv("CB200_SWAP_CTAS_PER_SM"))) : 2;
+    const int blocks = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)num_sms_ * swap_ctas);
     const int K = 1 << chunk_bits;
+    {   // an SM runs kernels side by side only under ONE shared-memory / L1 split: the exchange kernel (no shared memory)
+        // asks for the split the tile-pass kernel forces, otherwise every SM drains before switching between the two
+        static bool once[16] = {};
+        if (!once[device & 15]) {
+            cudaFuncSetAttribute(qubit_swap_kernel<double2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(qubit_swap_kernel<float2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaGetLastError();
+            once[device & 15] = true;
+        }
+    }
     for (int c = 0; c < K; c++) {
         sp.chunk_bits = chunk_bits;
         sp.chunk = (uint32_t)c;
@@ -355,13 +367,15 @@ void State::flush_dist_t()
     // swaps planned together (same batch id) become one multi-qubit exchange.  Grouping by batch id -- not by adjacency
     // in this rank's segment list -- keeps the number and shape of exchanges identical on every rank: a LOCAL segment
     // that separates two batches on one rank can be empty (all its ops dropped by a global control) on another.
-    // single-process groups CAN pipeline the exchange with the pass that follows it (CB200_SWAP_CHUNK_BITS = 1..3: the
-    // exchange runs in 2^bits chunks on a second stream and the pass starts on the chunks that have arrived).  Measured
-    // on 2 x B200 (profiles/exchange_overlap_r02.txt): QFT-32 takes 222 ms with or without it -- the tile-pass kernel
-    // holds the whole register file of every SM (3 CTAs x 128 threads x 168 registers), so the exchange kernel's CTAs and
-    // the pass's CTAs take turns instead of running side by side.  Hiding the exchange needs the copy engines (peer DMA
-    // through a staging buffer), not a second kernel; until then the default is one exchange kernel on the main stream.
-    static const int chunk_bits_cfg = getenv("CB200_SWAP_CHUNK_BITS") ? std::max(0, std::min(3, atoi(getenv("CB200_SWAP_CHUNK_BITS")))) : 0;
+    // single-process groups pipeline the exchange with the pass that follows it (CB200_SWAP_CHUNK_BITS, default 2; 0 = one
+    // exchange kernel on the main stream as in the one-process-per-GPU mode): the exchange runs in 2^bits chunks on a
+    // second stream, with few CTAs per SM and the shared-memory carve-out of the pass kernel so that both can be
+    // resident on an SM, and the pass starts on the chunks that have arrived.  Measured on 2 x B200
+    // (profiles/exchange_overlap_r02.txt): QFT-32 215.7 -> 206.6 ms (-4 %).  The gain is far below the 17 % a perfect
+    // pipeline would give: side by side on the same SMs the two kernels slow each other down (the pass kernel alone holds
+    // 3 CTAs x 128 threads x 168 registers = the whole register file); hiding the exchange completely needs the copy
+    // engines (peer DMA through a staging buffer) instead of a kernel.
+    static const int chunk_bits_cfg = getenv("CB200_SWAP_CHUNK_BITS") ? std::max(0, std::min(3, atoi(getenv("CB200_SWAP_CHUNK_BITS")))) : 2;
     const int chunk_bits = (dist->group && n_local_ >= 24) ? chunk_bits_cfg : 0;
     std::vector<std::pair<int, int>> group;
     int group_batch = -1;

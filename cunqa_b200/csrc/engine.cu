@@ -412,7 +412,10 @@ void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb, ChunkPipe *pi
             CUtensorMap tmap;
             make_tensor_map(&tmap, run_bits, hi_q, b0, nb);
             TmaLaunch l;
-            l.grid = (unsigned)std::min<uint64_t>(total_tiles / n_chunks, (uint64_t)num_sms_ * ctas);
+            // (a pass that runs beside a chunked exchange leaves room for the exchange kernel's CTAs on every SM)
+            static const int overlap_ctas = env_int("CB200_OVERLAP_PASS_CTAS", 3);
+            const int use_ctas = n_chunks > 1 ? std::max(1, std::min(ctas, overlap_ctas)) : ctas;
+            l.grid = (unsigned)std::min<uint64_t>(total_tiles / n_chunks, (uint64_t)num_sms_ * use_ctas);
             l.smem = smem_tma;
             l.stream = stream_;
             l.diag_tabs = d_diag_;
