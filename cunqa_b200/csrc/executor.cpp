@@ -1610,6 +1610,24 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
             if (!encode_pass<double>(p, ops, nq, 1, pp, diag, err, opt.enc_flags())) throw std::runtime_error(err);
             o.set("diag_entries", Json::integer((long long)diag.size()));
             o.set("device_ops", Json::integer(pp.n_ops));
+            {   // one letter per device op: D dense, T diagonal table, X / S permutations, P register-block pair, F phase fan;
+                // lower case = applied in the same sweep as the op before it (a diagonal run folded into the next dense gate)
+                std::string kinds;
+                for (int q = 0; q < pp.n_ops; q++) {
+                    static const char letter[] = {'D', 'T', 'X', 'S', 'P', 'F'};
+                    kinds += letter[pp.ops[q].kind];
+                    if (pp.ops[q].kind == OP_DIAG) kinds += std::to_string((int)pp.ops[q].k);
+                }
+                o.set("device_kinds", Json::string(kinds));
+                Json sw = Json::array();
+                for (int q = 0; q < pp.n_sweeps; q++) {
+                    Json e = Json::array();
+                    e.arr.push_back(Json::integer(pp.sweeps[q].first));
+                    e.arr.push_back(Json::integer(pp.sweeps[q].len));
+                    sw.arr.push_back(std::move(e));
+                }
+                o.set("sweeps", std::move(sw));   // [first device op, number of ops] of every register sweep
+            }
             o.set("diag_tables", Json::integer(pp.n_diag));
             if (pp.fan_op >= 0) {
                 Json f = Json::object();

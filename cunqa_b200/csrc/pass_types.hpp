@@ -20,6 +20,7 @@ constexpr int kDiagLut = 192;
 constexpr int kFanMaxCenters = 8;       // centers of a phase fan
 constexpr int kFanMaxLeafBits = 6;      // in-tile leaves of a phase fan (tables of 2^6 entries per center)
 constexpr int kFanMaxChunks = 4;        // out-of-tile leaves, 8 per chunk (256-entry table per chunk and center)
+constexpr int kMaxSweeps = 24;          // register sweeps per pass
 constexpr int kStabEntries = 1024;      // per-tile store of small diagonal sub-tables (entries; 16 KB of complex128)
 constexpr int kStabMaxBits = 6;        // a diagonal op is staged when at most this many of its qubits are tile qubits
 constexpr uint16_t kNotStaged = 0xFFFF;     // per diagonal op: 64 entries for tile bits 0..5 + 128 for tile bits 6..12
@@ -82,6 +83,13 @@ struct PassParams {
     // center c, nfix = #in-tile leaf bits, fixpos[] = their tile bits (ascending), ctrl_in = their tile-bit mask, dsrc[0..3]
     // = the four centers that are register bits of the sweep, mat_off = first entry of its block in the diagonal-table
     // buffer: [0] scalar g, then T[c][2^nfix], then X[chunk][c][256] (the out-of-tile leaves, 8 physical qubits per chunk)
+    // register sweeps: consecutive device ops (dense gates of <= 2 qubits, diagonal runs, the fan) that are applied to
+    // the 16 amplitudes a thread holds in registers between ONE load and ONE store of the tile: sweep_at[o] = sweep that
+    // starts at op o (0xFF none); a sweep covers ops [first, first + len) with register bits rb[0..3] (asc: ascending)
+    struct Sweep { uint8_t first, len, rb[4], asc[4]; };
+    int32_t n_sweeps;
+    uint8_t sweep_at[kMaxOps];
+    Sweep sweeps[kMaxSweeps];
     int32_t fan_op;      // op index, -1 = none
     int32_t fan_chunks;  // number of out-of-tile leaf chunks
     uint8_t fan_q[kFanMaxChunks][8];  // physical qubit of every chunk bit (0xFF = unused)

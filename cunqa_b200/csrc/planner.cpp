@@ -572,79 +572,127 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
                 out.needs_full = 2;
         }
     }
-    // Runs of consecutive diagonal ops are applied with 16 amplitudes per thread in registers: the 2^4 settings of
-    // four "register bits" of the tile index (op_diag_block).  A table none of whose qubits is a register bit costs
-    // one lookup per thread instead of one per amplitude, so pick the bits the run's tables depend on least.  When
-    // an uncontrolled dense gate of <= 2 qubits follows the run, its targets are register bits and the gate is
-    // applied in the same sweep (fixpos[0] = its width).  tbit[0..3] = register bits, tbit[4..7] = the same, ascending.
-    if (t >= 4)
-        for (int o = 0; o < nops;) {
-            if (out.ops[o].kind != OP_DIAG) { o++; continue; }
-            int oe = o;
-            while (oe + 1 < nops && out.ops[oe + 1].kind == OP_DIAG) oe++;
-            // register bits for the run: the candidates are ranked by how few of the run's tables depend on them (fewest
-            // dependent tables first; then bits >= 3, so that a warp reads whole 128-byte rows; then high bits).  A table that
-            // depends on a register bit costs 16 lookups + 16 complex multiplies per thread instead of one of each.
-            std::vector<int> users(t, 0);
-            for (int q = o; q <= oe; q++)
-                for (int pos = 0; pos < t; pos++) users[pos] += (out.ops[q].ctrl_in >> pos) & 1u;
-            auto choose = [&](std::vector<int> forced) {
-                std::vector<int> cand;
-                for (int pos = 0; pos < t; pos++)
-                    if (std::find(forced.begin(), forced.end(), pos) == forced.end()) cand.push_back(pos);
-                std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
-                    if (users[a] != users[b]) return users[a] < users[b];
-                    if ((a < 3) != (b < 3)) return b < 3;
-                    return a > b;
-                });
-                for (size_t ci = 0; forced.size() < 4; ci++) forced.push_back(cand[ci]);
-                return forced;
-            };
-            auto dependent_tables = [&](const std::vector<int> &bits) {
-                uint32_t m = 0;
-                for (int b : bits) m |= 1u << b;
-                int cnt = 0;
-                for (int q = o; q <= oe; q++) cnt += (out.ops[q].ctrl_in & m) != 0;
-                return cnt;
-            };
-            std::vector<int> rb = choose({});
-            int fuse_k = 0;
-            if (oe + 1 < nops) {
-                // an uncontrolled dense gate of <= 2 qubits right after the run can be applied in the same sweep (its
-                // targets become register bits: one shared-memory round trip and one barrier saved) -- unless that makes
-                // more of the run's tables depend on register bits, which costs more than the round trip saves
-                const DevOp &dn = out.ops[oe + 1];
-                if (dn.kind == OP_DENSE && dn.k <= 2 && dn.nfix == dn.k && dn.ctrl_out == 0 && !dn.has_mask) {
-                    std::vector<int> forced;
-                    for (int m = 0; m < dn.k; m++) forced.push_back(dn.tbit[m]);
-                    const std::vector<int> with = choose(forced);
-                    if ((flags & kEncDiagFuseAlways) || dependent_tables(with) <= dependent_tables(rb)) {
-                        fuse_k = dn.k;
-                        rb = with;
+    // ---- register sweeps (tile_kernel.cuh: op_sweep).  Consecutive device ops -- uncontrolled dense gates of <= 2 qubits,
+    // runs of diagonal tables, the phase fan -- are applied to the 16 amplitudes a thread holds in registers (the 2^4
+    // settings of four "register bits" of the tile index) between one load and one store of the tile.  A dense gate needs
+    // its targets among the register bits (a 2-qubit gate on bits (0,1) or (2,3), a 1-qubit gate on any); a table none of
+    // whose qubits is a register bit costs one lookup per thread instead of one per amplitude, so the free register bits
+    // are the ones the sweep's tables depend on least; the fan needs register bits that are not leaves.
+    std::memset(out.sweep_at, 0xFF, sizeof(out.sweep_at));
+    out.n_sweeps = 0;
+    if (t >= 4 && (out.n_diag > 0 || out.fan_op >= 0)) {
+        auto sweepable_dense = [&](const DevOp &d) {
+            return d.kind == OP_DENSE && d.k <= 2 && d.nfix == d.k && d.ctrl_out == 0 && !d.has_mask;
+        };
+        for (int o = 0; o < nops && out.n_sweeps < kMaxSweeps;) {
+            const DevOp &first = out.ops[o];
+            if (!(sweepable_dense(first) || (first.kind == OP_DIAG && !first.has_mask) || first.kind == OP_FAN)) { o++; continue; }
+            std::vector<int> rb;           // register bits in register order (tile-bit positions)
+            bool has_fan = false, has_diag = false;
+            int oe = o;                    // one past the last op of the sweep
+            for (; oe < nops; oe++) {
+                DevOp &d = out.ops[oe];
+                if (sweepable_dense(d)) {
+                    if (d.k == 2) {
+                        const auto i0 = std::find(rb.begin(), rb.end(), (int)d.tbit[0]) - rb.begin();
+                        const auto i1 = std::find(rb.begin(), rb.end(), (int)d.tbit[1]) - rb.begin();
+                        if (i0 < (long)rb.size() || i1 < (long)rb.size()) {
+                            // (targets already register bits: only the aligned pairs (0,1) / (2,3) in this order are instantiated)
+                            if (!(i1 == i0 + 1 && (i0 == 0 || i0 == 2) && i1 < (long)rb.size())) break;
+                            d.s = (uint8_t)i0;
+                        } else {
+                            if (rb.size() != 0 && rb.size() != 2) break;
+                            d.s = (uint8_t)rb.size();
+                            rb.push_back(d.tbit[0]);
+                            rb.push_back(d.tbit[1]);
+                        }
+                    } else {
+                        const auto i0 = std::find(rb.begin(), rb.end(), (int)d.tbit[0]) - rb.begin();
+                        if (i0 == (long)rb.size()) {
+                            if (rb.size() >= 4) break;
+                            rb.push_back(d.tbit[0]);
+                        }
+                        d.s = (uint8_t)i0;
                     }
+                } else if (d.kind == OP_DIAG && !d.has_mask) {
+                    has_diag = true;
+                } else if (d.kind == OP_FAN) {
+                    has_fan = true;
+                    oe++;
+                    break;                  // (the fan is the last op of its pass)
+                } else {
+                    break;
                 }
             }
-            std::vector<int> asc = rb;
-            std::sort(asc.begin(), asc.end());
-            // diagonal ops commute: the tables that ignore the register bits go first (fixpos[1] of them)
+            if (oe - o == 1 && out.ops[o].kind == OP_DENSE) { o++; continue; }   // a lone dense gate: the ordinary path
+            // fill up the register bits: fewest dependent tables first; then bits >= 3 (a warp then reads whole 128-byte
+            // rows); then high bits.  Leaves of the fan are excluded (its factors must be thread constants).
+            std::vector<int> users(t, 0);
+            uint32_t fan_leaves = 0;
+            for (int q = o; q < oe; q++) {
+                if (out.ops[q].kind == OP_DIAG)
+                    for (int pos = 0; pos < t; pos++) users[pos] += (out.ops[q].ctrl_in >> pos) & 1u;
+                if (out.ops[q].kind == OP_FAN) fan_leaves = out.ops[q].ctrl_in;
+            }
+            std::vector<int> cand;
+            for (int pos = 0; pos < t; pos++)
+                if (std::find(rb.begin(), rb.end(), pos) == rb.end() && !((fan_leaves >> pos) & 1u)) cand.push_back(pos);
+            std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
+                if (users[a] != users[b]) return users[a] < users[b];
+                if ((a < 3) != (b < 3)) return b < 3;
+                return a > b;
+            });
+            bool ok = true;
+            for (size_t ci = 0; rb.size() < 4; ci++) {
+                if (ci >= cand.size()) { ok = false; break; }
+                rb.push_back(cand[ci]);
+            }
+            for (int b : rb) if ((fan_leaves >> b) & 1u) ok = false;   // (a dense target is never a leaf; belt and braces)
+            if (!ok) { err = "internal: no register bits for a sweep"; return false; }
             uint32_t rmask = 0;
             for (int b : rb) rmask |= 1u << b;
-            std::stable_partition(out.ops + o, out.ops + oe + 1, [&](const DevOp &x) { return (x.ctrl_in & rmask) == 0; });
-            const int slot0 = std::min_element(out.ops + o, out.ops + oe + 1,
-                                               [](const DevOp &a, const DevOp &b) { return a.k2 < b.k2; })->k2;
-            int n_indep = 0;
-            for (int q = o; q <= oe; q++) {
-                out.ops[q].k2 = (uint8_t)(slot0 + (q - o));
-                out.diag_op[slot0 + (q - o)] = (uint8_t)q;
-                n_indep += (out.ops[q].ctrl_in & rmask) == 0;
-                out.ops[q].s = (out.ops[q].ctrl_in & rmask) != 0;  // DIAG: 1 = looked up per amplitude (depends on a register bit)
+            // every run of tables inside the sweep: the tables that ignore the register bits go first (fixpos[1] of them)
+            for (int q = o; q < oe;) {
+                if (out.ops[q].kind != OP_DIAG) { q++; continue; }
+                int qe = q;
+                while (qe + 1 < oe && out.ops[qe + 1].kind == OP_DIAG) qe++;
+                std::stable_partition(out.ops + q, out.ops + qe + 1, [&](const DevOp &x) { return (x.ctrl_in & rmask) == 0; });
+                const int slot0 = std::min_element(out.ops + q, out.ops + qe + 1, [](const DevOp &a, const DevOp &b) { return a.k2 < b.k2; })->k2;
+                int n_indep = 0;
+                for (int r = q; r <= qe; r++) {
+                    out.ops[r].k2 = (uint8_t)(slot0 + (r - q));
+                    out.diag_op[slot0 + (r - q)] = (uint8_t)r;
+                    n_indep += (out.ops[r].ctrl_in & rmask) == 0;
+                    out.ops[r].s = (out.ops[r].ctrl_in & rmask) != 0;  // DIAG: 1 = looked up per amplitude
+                }
+                out.ops[q].fixpos[0] = 0;
+                out.ops[q].fixpos[1] = (uint8_t)n_indep;
+                q = qe + 1;
             }
-            DevOp &run = out.ops[o];
-            for (int b = 0; b < 4; b++) { run.tbit[b] = (uint8_t)rb[b]; run.tbit[4 + b] = (uint8_t)asc[b]; }
-            run.fixpos[0] = (uint8_t)fuse_k;
-            run.fixpos[1] = (uint8_t)n_indep;
-            o = oe + 1;
+            typename PassParams<T>::Sweep &S = out.sweeps[out.n_sweeps];
+            S.first = (uint8_t)o;
+            S.len = (uint8_t)(oe - o);
+            std::vector<int> asc = rb;
+            std::sort(asc.begin(), asc.end());
+            for (int b = 0; b < 4; b++) { S.rb[b] = (uint8_t)rb[b]; S.asc[b] = (uint8_t)asc[b]; }
+            if (has_fan) {   // which center (if any) each register bit of the sweep is
+                DevOp &f = out.ops[oe - 1];
+                for (int b = 0; b < 4; b++) {
+                    f.dsrc[b] = (uint8_t)rb[b];
+                    f.dsrc[4 + b] = 0xFF;
+                    for (int c = 0; c < f.k; c++) if (f.tbit[c] == rb[b]) f.dsrc[4 + b] = (uint8_t)c;
+                }
+            }
+            out.sweep_at[o] = (uint8_t)out.n_sweeps++;
+            (void)has_fan; (void)has_diag;
+            o = oe;
         }
+        // every diagonal run and the fan must sit in a sweep (the lean + diagonal kernel variant has no other path for them)
+        for (int o = 0, covered = -1; o < nops; o++) {
+            if (out.sweep_at[o] != 0xFF) covered = o + out.sweeps[out.sweep_at[o]].len - 1;
+            if ((out.ops[o].kind == OP_DIAG || out.ops[o].kind == OP_FAN) && o > covered && !out.ops[o].has_mask) out.needs_full = 2;
+        }
+    }
     out.cond_mask = 0;
     for (int o = 0; o < nops; o++)
         if (out.ops[o].ctrl_out != 0 || out.ops[o].has_mask) out.cond_mask |= 1ull << o;

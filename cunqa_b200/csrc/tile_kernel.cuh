@@ -260,30 +260,36 @@ __device__ __forceinline__ void op_perm(typename Vec2<T>::type *tile, const DevO
     }
 }
 
-// ---- diagonal runs with the thread's amplitudes resident in registers -----------------------------
-// Each thread owns 16 amplitudes: the 2^4 settings of four "register bits" rb[0..3] of the tile index, chosen per
-// run by the host (encode_pass) among the tile bits the run's tables depend on least.  The in-tile part of a
-// table index is a bit-extract of the tile index, which is additive over disjoint bit sets: index(k) =
-// pext(thread bits) | OR_b pext(1 << rb[b]) for the bits b set in k.  A table none of whose qubits is a register
-// bit therefore costs ONE lookup and one complex multiply per thread (its factor is folded into `acc`, applied to
-// the 16 amplitudes once per run); only tables that do depend on register bits are looked up per amplitude, and
-// then the tables are walked in the outer loop so that the loads of one table are in flight together.  (Not inlined:
-// the block's register allocation must not disturb the dense-gate paths of the kernel.)
-// K > 0: the run is folded into the uncontrolled dense K-qubit gate that follows it (register bits 0..K-1 are the
-// gate's targets): phases applied in registers before the butterfly, one sweep, one barrier.
-template <typename T, int K, int NT>
-__device__ __noinline__ void op_diag_block(typename Vec2<T>::type *tile, const DevOp &run, const T *mat,
-                                              const typename Vec2<T>::type *const *tptr,
-                                              const uint16_t *lut, int s0, int s1, const int tid)
+// ---- register sweeps: dense gates, diagonal runs and the phase fan on the thread's resident amplitudes ------------
+// Each thread owns 16 amplitudes: the 2^4 settings of four "register bits" rb[0..3] of the tile index, chosen per sweep
+// by the host (encode_pass).  Between ONE load and ONE store of the tile the sweep applies a short program:
+//   * dense gates of <= 2 qubits whose targets are register bits (the host places a 2-qubit gate on register bits
+//     (0,1) or (2,3), a 1-qubit gate on any of the four): block_gate on compile-time register indices;
+//   * runs of diagonal tables: the in-tile part of a table index is a bit-extract of the tile index, additive over
+//     disjoint bit sets, so a table none of whose qubits is a register bit costs ONE lookup and one complex multiply per
+//     thread (folded into `acc`, applied once per run); tables that do depend on register bits are looked up per
+//     amplitude, table by table so that the loads of one table are in flight together;
+//   * the phase fan (below).
+// A QFT pass -- H / ladder blocks on six qubits -- is two such sweeps: [dense, tables, dense, tables] and [dense, fan].
+// (Not inlined: the sweep's register allocation must not disturb the dense-gate paths of the kernel.)
+template <typename T> struct FanCtx {
+    const typename Vec2<T>::type *fanT, *fanc;   // T[c][2^m] and this tile's center factors (shared memory)
+};
+
+template <typename T, int NT>
+__device__ __noinline__ void op_sweep(typename Vec2<T>::type *tile, const PassParams<T> &p, const int sw, const T *mats,
+                                      const typename Vec2<T>::type *__restrict__ diag_tabs,
+                                      const typename Vec2<T>::type *const *tptr, const uint16_t *lut, const FanCtx<T> fan, const int tid)
 {
     using V = typename Vec2<T>::type;
     constexpr int A = 16;
+    const typename PassParams<T>::Sweep &S = p.sweeps[sw];
     uint32_t bi = tid;
 #pragma unroll
-    for (int f = 0; f < 4; f++) bi = insert0(bi, run.tbit[4 + f]);  // ascending register-bit positions
+    for (int f = 0; f < 4; f++) bi = insert0(bi, S.asc[f]);
     uint32_t rbit[4];
 #pragma unroll
-    for (int b = 0; b < 4; b++) rbit[b] = 1u << run.tbit[b];
+    for (int b = 0; b < 4; b++) rbit[b] = 1u << S.rb[b];
     V v[A];
     // tile index of amplitude k (k is a compile-time constant wherever this is called: at most three ORs)
     auto ti = [&](int k) -> uint32_t {
@@ -291,125 +297,113 @@ __device__ __noinline__ void op_diag_block(typename Vec2<T>::type *tile, const D
     };
 #pragma unroll
     for (int k = 0; k < A; k++) v[k] = tile[swz<T>(ti(k))];
-    V acc;
-    acc.x = (T)1;
-    acc.y = (T)0;
-    // tables that ignore the register bits come first in the run (host order): one lookup per thread each, four
-    // tables' loads in flight together, their product applied to the 16 amplitudes once
-    int sl = s0;
-    const int s_indep = s0 + run.fixpos[1];
-    // tptr[s]: this tile's sub-table of diagonal op s -- in the shared-memory store when the op is staged, else the slice
-    // of the global table that starts at the op's per-tile base (generic loads serve both)
-    auto index_of = [&](int s) -> uint32_t {
-        const uint16_t *L = lut + s * kDiagLut;
-        return (uint32_t)(L[bi & 63u] | L[64 + (bi >> 6)]);
-    };
-    for (; sl + 4 <= s_indep; sl += 4) {
-        uint32_t ix[4];
-        V q[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) ix[j] = index_of(sl + j);
-#pragma unroll
-        for (int j = 0; j < 4; j++) q[j] = tptr[sl + j][ix[j]];
-        const V q01 = cmul<V, T>(q[0].x, q[0].y, q[1]), q23 = cmul<V, T>(q[2].x, q[2].y, q[3]);
-        acc = cmul<V, T>(acc.x, acc.y, cmul<V, T>(q01.x, q01.y, q23));
-    }
-    for (; sl < s_indep; sl++) {
-        const V q = tptr[sl][index_of(sl)];
-        acc = cmul<V, T>(q.x, q.y, acc);
-    }
-    for (; sl <= s1; sl++) {
-        const uint16_t *L = lut + sl * kDiagLut;
-        const V *tb = tptr[sl] + index_of(sl);
-        uint32_t e[4];
-#pragma unroll
-        for (int b = 0; b < 4; b++) e[b] = L[rbit[b] & 63u] | L[64 + (rbit[b] >> 6)];  // one of the two is entry 0 == 0
-#pragma unroll
-        for (int h = 0; h < A; h += 8) {  // two batches of 8 independent loads (register budget)
-            V q[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int k = h + j;
-                q[j] = tb[((k & 1) ? e[0] : 0u) | ((k & 2) ? e[1] : 0u) | ((k & 4) ? e[2] : 0u) | ((k & 8) ? e[3] : 0u)];
+    const int o_end = S.first + S.len;
+    for (int o = S.first; o < o_end; o++) {
+        const DevOp &op = p.ops[o];
+        if (op.kind == OP_DENSE) {
+            const T *mat = mats + op.mat_off;
+            if (op.k == 2) {
+                if (op.s == 0) block_gate<T, 4, 2, 0>(v, mat);
+                else block_gate<T, 4, 2, 2>(v, mat);
+            } else {
+                switch (op.s) {
+                case 0: block_gate<T, 4, 1, 0>(v, mat); break;
+                case 1: block_gate<T, 4, 1, 1>(v, mat); break;
+                case 2: block_gate<T, 4, 1, 2>(v, mat); break;
+                default: block_gate<T, 4, 1, 3>(v, mat); break;
+                }
             }
+        } else if (op.kind == OP_DIAG) {
+            // the run of consecutive tables that starts here: slots [s0, s1], the first fixpos[1] of them ignore the register bits
+            int oe = o;
+            while (oe + 1 < o_end && p.ops[oe + 1].kind == OP_DIAG) oe++;
+            const int s0 = op.k2, s1 = p.ops[oe].k2, s_indep = s0 + op.fixpos[1];
+            auto index_of = [&](int s) -> uint32_t {
+                const uint16_t *L = lut + s * kDiagLut;
+                return (uint32_t)(L[bi & 63u] | L[64 + (bi >> 6)]);
+            };
+            V acc;
+            acc.x = (T)1;
+            acc.y = (T)0;
+            int sl = s0;
+            for (; sl + 4 <= s_indep; sl += 4) {
+                uint32_t ix[4];
+                V q[4];
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[h + j] = cmul<V, T>(q[j].x, q[j].y, v[h + j]);
+                for (int j = 0; j < 4; j++) ix[j] = index_of(sl + j);
+#pragma unroll
+                for (int j = 0; j < 4; j++) q[j] = tptr[sl + j][ix[j]];
+                const V q01 = cmul<V, T>(q[0].x, q[0].y, q[1]), q23 = cmul<V, T>(q[2].x, q[2].y, q[3]);
+                acc = cmul<V, T>(acc.x, acc.y, cmul<V, T>(q01.x, q01.y, q23));
+            }
+            for (; sl < s_indep; sl++) {
+                const V q = tptr[sl][index_of(sl)];
+                acc = cmul<V, T>(q.x, q.y, acc);
+            }
+            for (; sl <= s1; sl++) {
+                const uint16_t *L = lut + sl * kDiagLut;
+                const V *tb = tptr[sl] + index_of(sl);
+                uint32_t e[4];
+#pragma unroll
+                for (int b = 0; b < 4; b++) e[b] = L[rbit[b] & 63u] | L[64 + (rbit[b] >> 6)];  // one of the two is entry 0 == 0
+#pragma unroll
+                for (int h = 0; h < A; h += 8) {  // two batches of 8 independent loads (register budget)
+                    V q[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int k = h + j;
+                        q[j] = tb[((k & 1) ? e[0] : 0u) | ((k & 2) ? e[1] : 0u) | ((k & 4) ? e[2] : 0u) | ((k & 8) ? e[3] : 0u)];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[h + j] = cmul<V, T>(q[j].x, q[j].y, v[h + j]);
+                }
+            }
+            if (s_indep > s0) {
+#pragma unroll
+                for (int k = 0; k < A; k++) v[k] = cmul<V, T>(acc.x, acc.y, v[k]);
+            }
+            o = oe;
+        } else if (op.kind == OP_FAN) {
+            // amplitude *= g * prod over the centers set in its index of [c_b * T_b[leaf bits]]: the leaf bits and the
+            // centers that are not register bits are thread constants; the four register-bit factors give 16 subset products
+            const int m = op.nfix, nc = op.k;
+            uint32_t lv = 0;
+            for (int i = 0; i < m; i++) lv |= ((bi >> op.fixpos[i]) & 1u) << i;
+            auto factor = [&](int c) -> V { const V a = fan.fanc[c], b = fan.fanT[(c << m) + lv]; return cmul<V, T>(a.x, a.y, b); };
+            // which center (if any) each register bit is (host: dsrc[4..7])
+            int rc[4];
+#pragma unroll
+            for (int b = 0; b < 4; b++) rc[b] = op.dsrc[4 + b] == 0xFF ? -1 : (int)op.dsrc[4 + b];
+            V s = diag_tabs[op.mat_off];
+            for (int c = 0; c < nc; c++)
+                if (c != rc[0] && c != rc[1] && c != rc[2] && c != rc[3] && ((bi >> op.tbit[c]) & 1u)) { const V f = factor(c); s = cmul<V, T>(s.x, s.y, f); }
+            V f[4];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                f[b].x = (T)1; f[b].y = (T)0;
+                if (rc[b] >= 0) f[b] = factor(rc[b]);
+            }
+            V g01[4], g23[4];
+            g01[0] = s;
+            g01[1] = cmul<V, T>(s.x, s.y, f[0]);
+            g01[2] = cmul<V, T>(s.x, s.y, f[1]);
+            g01[3] = cmul<V, T>(g01[1].x, g01[1].y, f[1]);
+            g23[1] = f[2];
+            g23[2] = f[3];
+            g23[3] = cmul<V, T>(f[2].x, f[2].y, f[3]);
+#pragma unroll
+            for (int k = 0; k < A; k++) {
+                V ph = g01[k & 3];
+                if ((k >> 2) != 0) ph = cmul<V, T>(ph.x, ph.y, g23[k >> 2]);
+                v[k] = cmul<V, T>(ph.x, ph.y, v[k]);
+            }
         }
     }
 #pragma unroll
-    for (int k = 0; k < A; k++) v[k] = cmul<V, T>(acc.x, acc.y, v[k]);
-    if constexpr (K == 0) {
-#pragma unroll
-        for (int k = 0; k < A; k++) tile[swz<T>(ti(k))] = v[k];
-    } else {
-        constexpr int D = 1 << K, G = A >> K;
-        T mr[D * D], mi[D * D];
-#pragma unroll
-        for (int e2 = 0; e2 < D * D; e2++) { const V m = reinterpret_cast<const V *>(mat)[e2]; mr[e2] = m.x; mi[e2] = m.y; }
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-#pragma unroll
-            for (int r = 0; r < D; r++) {
-                V o = cmul<V, T>(mr[r * D], mi[r * D], v[g * D]);
-#pragma unroll
-                for (int cc = 1; cc < D; cc++) cfma<V, T>(o, mr[r * D + cc], mi[r * D + cc], v[g * D + cc]);
-                tile[swz<T>(ti(g * D + r))] = o;
-            }
-        }
-    }
+    for (int k = 0; k < A; k++) tile[swz<T>(ti(k))] = v[k];
 }
 
-// ---- phase fan (OP_FAN, pass_types.hpp): amplitude *= g * prod over the centers b set in its index of [c_b * T_b[v]],
-// v = the in-tile leaf bits.  A thread owns the 16 settings of four register bits that are not leaves, so v and every
-// center factor are the same for its 16 amplitudes: the four register-bit factors are combined into their 16 subset
-// products (12 complex multiplies) and applied once -- ~44 complex multiplies per thread whatever the number of terms.
-//   fanT: T[c][2^m] (shared memory), fanc: c_b of this tile (shared memory), g: the fan's scalar
-template <typename T, int NT>
-__device__ __noinline__ void op_fan(typename Vec2<T>::type *tile, const DevOp &fo, const typename Vec2<T>::type *fanT,
-                                    const typename Vec2<T>::type *fanc, const typename Vec2<T>::type g, const int tid)
-{
-    using V = typename Vec2<T>::type;
-    constexpr int A = 16;
-    uint32_t bi = tid;
-#pragma unroll
-    for (int f = 0; f < 4; f++) bi = insert0(bi, fo.dsrc[f]);  // ascending register-bit positions
-    uint32_t rbit[4];
-#pragma unroll
-    for (int b = 0; b < 4; b++) rbit[b] = 1u << fo.dsrc[b];
-    const int m = fo.nfix, nc = fo.k;
-    uint32_t v = 0;
-    for (int i = 0; i < m; i++) v |= ((bi >> fo.fixpos[i]) & 1u) << i;
-    auto factor = [&](int c) -> V { const V a = fanc[c], b = fanT[(c << m) + v]; return cmul<V, T>(a.x, a.y, b); };
-    uint32_t regc = 0;
-#pragma unroll
-    for (int b = 0; b < 4; b++) if (fo.dsrc[4 + b] != 0xFF) regc |= 1u << fo.dsrc[4 + b];
-    V s = g;   // the centers that are fixed for this thread
-    for (int c = 0; c < nc; c++)
-        if (!((regc >> c) & 1u) && ((bi >> fo.tbit[c]) & 1u)) { const V f = factor(c); s = cmul<V, T>(s.x, s.y, f); }
-    V f[4];
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-        f[b].x = (T)1; f[b].y = (T)0;
-        if (fo.dsrc[4 + b] != 0xFF) f[b] = factor(fo.dsrc[4 + b]);
-    }
-    V g01[4], g23[4];
-    g01[0] = s;
-    g01[1] = cmul<V, T>(s.x, s.y, f[0]);
-    g01[2] = cmul<V, T>(s.x, s.y, f[1]);
-    g01[3] = cmul<V, T>(g01[1].x, g01[1].y, f[1]);
-    g23[1] = f[2];
-    g23[2] = f[3];
-    g23[3] = cmul<V, T>(f[2].x, f[2].y, f[3]);
-#pragma unroll
-    for (int k = 0; k < A; k++) {
-        const uint32_t idx = swz<T>(bi | ((k & 1) ? rbit[0] : 0u) | ((k & 2) ? rbit[1] : 0u) | ((k & 4) ? rbit[2] : 0u) | ((k & 8) ? rbit[3] : 0u));
-        V ph = g01[k & 3];
-        if ((k >> 2) != 0) ph = cmul<V, T>(ph.x, ph.y, g23[k >> 2]);
-        const V a = tile[idx];
-        tile[idx] = cmul<V, T>(ph.x, ph.y, a);
-    }
-}
-
+// ---- phase fan (OP_FAN, pass_types.hpp), slow form.  The fast form is part of op_sweep.
 // the same fan, one amplitude at a time, everything read from the table block in global memory (generic kernel and the
 // kernel variants without the 16-amplitudes-per-thread layout): correctness path, not a fast one
 template <typename T>
@@ -486,6 +480,19 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
         if (!hooked && o > hook_at) { hook(); hooked = true; }
             if (COND && !((active >> o) & 1ull)) continue;
             const DevOp &op = p.ops[o];
+            if constexpr (VAR >= 1 && !COND) {
+                // a register sweep starts here (16-amplitudes-per-thread layout, LUT route): several ops, one barrier
+                if (lut != nullptr && p.sweep_at[o] != 0xFF) {
+                    const int sw = p.sweep_at[o];
+                    FanCtx<T> fc;
+                    fc.fanT = fanT;
+                    fc.fanc = fanc;
+                    op_sweep<T, NT>(tile, p, sw, mats, diag_tabs, tptr, lut, fc, tid);
+                    o += p.sweeps[sw].len - 1;
+                    __syncthreads();
+                    continue;
+                }
+            }
             if (op.kind == OP_DENSE) {
                 const T *mat = mats + op.mat_off;
                 if (op.k == 1) op_dense<T, 1, NT>(tile, op, mat, t, tid);
@@ -500,56 +507,33 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                 op_pair_dispatch<T, NT, VAR>(tile, op, mats + op.mat_off, t, tid);
                 __syncthreads();
             } else if (op.kind == OP_DIAG) {
-                if constexpr (VAR >= 1) {  // (passes with diagonal ops never take the lean kernel, see needs_full)
-                // a run of consecutive diagonal ops is applied in ONE sweep of the tile
-                int oe = o;
-                while (oe + 1 < p.n_ops && p.ops[oe + 1].kind == OP_DIAG) oe++;
-                bool done = false;
-                if (VAR == 1 || lut != nullptr) {
-                    // table index = pext(tile index, in-tile mask) through the per-op LUTs, relative to this tile's
-                    // sub-table (tptr, filled once per tile by the caller)
-                    const int s0 = op.k2, s1 = p.ops[oe].k2;
-                    const int fuse_k = op.fixpos[0];  // host: fold the run into the uncontrolled dense gate after it
-                    if (fuse_k != 0) {
-                        const DevOp &dn = p.ops[oe + 1];
-                        const T *mat = mats + dn.mat_off;
-                        if (fuse_k == 1) op_diag_block<T, 1, NT>(tile, op, mat, tptr, lut, s0, s1, tid);
-                        else op_diag_block<T, 2, NT>(tile, op, mat, tptr, lut, s0, s1, tid);
-                        o = oe + 1;
-                        __syncthreads();
-                        continue;
-                    }
-                    op_diag_block<T, 0, NT>(tile, op, nullptr, tptr, lut, s0, s1, tid);
-                    done = true;
-                }
+                // (outside a register sweep: kernels without the 16-amplitudes-per-thread layout, or per-tile conditions)
                 if constexpr (VAR == 2) {
-                    if (!done)
-                        for (uint32_t i = tid; i < tile_amps; i += NT) {
-                            const uint32_t s = swz<T>(i);
-                            V v = tile[s];
-                            for (int q = o; q <= oe; q++) {
-                                if (COND && !((active >> q) & 1ull)) continue;
-                                const DevOp &d = p.ops[q];
-                                uint32_t ti = 0;
-                                for (int m = 0; m < d.k; m++) {
-                                    const uint32_t src = d.dsrc[m];
-                                    const uint32_t bit = src < 64 ? ((i >> src) & 1u) : (uint32_t)((base >> (src - 64)) & 1ull);
-                                    ti |= bit << m;
-                                }
-                                const V ph = diag_tabs[d.mat_off + ti];
-                                v = cmul<V, T>(ph.x, ph.y, v);
+                    int oe = o;
+                    while (oe + 1 < p.n_ops && p.ops[oe + 1].kind == OP_DIAG) oe++;
+                    for (uint32_t i = tid; i < tile_amps; i += NT) {
+                        const uint32_t s = swz<T>(i);
+                        V v = tile[s];
+                        for (int q = o; q <= oe; q++) {
+                            if (COND && !((active >> q) & 1ull)) continue;
+                            const DevOp &d = p.ops[q];
+                            uint32_t ti = 0;
+                            for (int m = 0; m < d.k; m++) {
+                                const uint32_t src = d.dsrc[m];
+                                const uint32_t bit = src < 64 ? ((i >> src) & 1u) : (uint32_t)((base >> (src - 64)) & 1ull);
+                                ti |= bit << m;
                             }
-                            tile[s] = v;
+                            const V ph = diag_tabs[d.mat_off + ti];
+                            v = cmul<V, T>(ph.x, ph.y, v);
                         }
-                }
-                o = oe;
-                __syncthreads();
+                        tile[s] = v;
+                    }
+                    o = oe;
+                    __syncthreads();
                 }
             } else if (op.kind == OP_FAN) {
-                if constexpr (VAR >= 1) {
-                    // fast path: the 16-amplitudes-per-thread layout with the fan's tables in shared memory (TMA kernel)
-                    if (fanT != nullptr && (VAR == 1 || lut != nullptr)) op_fan<T, NT>(tile, op, fanT, fanc, diag_tabs[op.mat_off], tid);
-                    else if constexpr (VAR == 2) op_fan_slow<T>(tile, op, p.fan_q, p.fan_chunks, diag_tabs + op.mat_off, base, t, tid, NT);
+                if constexpr (VAR == 2) {   // (outside a register sweep)
+                    op_fan_slow<T>(tile, op, p.fan_q, p.fan_chunks, diag_tabs + op.mat_off, base, t, tid, NT);
                     __syncthreads();
                 }
             } else {
