@@ -639,11 +639,12 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
                 } else if (d.kind == OP_DIAG && !d.has_mask) {
                     // a long run of tables after a dense gate starts its own sweep: with the gate's targets as register
                     // bits most of its tables would be looked up per amplitude (measured on a QFT without fans: 92 against
-                    // 84 ms); short runs (what a fan leaves behind) stay with the gate
+                    // 84 ms); short runs of small tables (what a fan leaves behind) stay with the gate
                     if (!rb.empty() && (oe == o || out.ops[oe - 1].kind != OP_DIAG)) {
                         int run = 0;
-                        while (oe + run < nops && out.ops[oe + run].kind == OP_DIAG) run++;
-                        if (run > 4) break;
+                        bool small = true;
+                        while (oe + run < nops && out.ops[oe + run].kind == OP_DIAG) { small = small && out.ops[oe + run].k <= 6; run++; }
+                        if (run > 4 || !small) break;
                     }
                     has_diag = true;
                 } else if (d.kind == OP_FAN) {
