@@ -89,6 +89,7 @@ void State::construct(int rank, int world, const uint8_t *nccl_id, ShardGroup *g
     init_options(gbits);
     ctas_per_sm_ = env_int("CB200_CTAS_PER_SM", 0);
     use_tma_ = env_int("CB200_USE_TMA", 1) != 0;
+    const_mats_ = env_int("CB200_CONST_MATS", 1) != 0;
     CB200_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CB200_CUDA(cudaMalloc(&d_state_, state_bytes_));
     CB200_CUDA(cudaMalloc(&d_small_, sizeof(double) * (4 * batch + 64)));
@@ -330,7 +331,7 @@ void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb, ChunkPipe *pi
     std::vector<PassParams<T>> params(passes.size());
     std::string err;
     for (size_t i = 0; i < passes.size(); i++)
-        if (!encode_pass<T>(passes[i], ops, n_local_, vbatch, params[i], diag_host, err, opt.enc_flags())) throw Unsupported(err);
+        if (!encode_pass<T>(passes[i], ops, n_local_, vbatch, params[i], diag_host, err, opt.enc_flags() | (const_mats_ ? 0 : kEncPlainMats))) throw Unsupported(err);
     // diagonal tables and condition flags: staged in pinned memory, copied asynchronously (no stream drain)
     const std::vector<std::vector<uint8_t>> &mask_rows = rq().mask_rows;
     const size_t diag_bytes = diag_host.size() * sizeof(V);
@@ -402,6 +403,12 @@ void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb, ChunkPipe *pi
         if (tma_max_ctas_ > 0) ctas = std::min(ctas, tma_max_ctas_);
         // (a run of one 128-byte row is enough once the three folded qubits make the box 1 KiB = one swizzle atom)
         const bool tma = use_tma_ && p.L >= aprs + (box_bits >= aprs + 3 ? 0 : 1) && view_bytes >= 128 && smem_tma <= max_smem_;
+        if (!tma && p.mat_form != 0) {
+            // the generic kernel reads plain matrix elements: encode this pass again without the three-multiplication form
+            // (such a pass has no diagonal tables: nothing is appended to the table buffer)
+            std::vector<cplx> none;
+            if (!encode_pass<T>(passes[i], ops, n_local_, vbatch, params[i], none, err, opt.enc_flags() | kEncPlainMats)) throw Unsupported(err);
+        }
         for (int c = 0; c < n_chunks; c++) {
         if (n_chunks > 1) {
             pipe->wait_chunk(c);
@@ -511,7 +518,7 @@ void State::launch_uniform_t(int b0, int nb)
     std::vector<cplx> diag0;
     std::string err;
     for (size_t i = 0; i < passes.size(); i++)
-        if (!encode_pass<T>(passes[i], ops0, n_local_, G, params[i], diag0, err, opt.enc_flags())) throw Unsupported(err);
+        if (!encode_pass<T>(passes[i], ops0, n_local_, G, params[i], diag0, err, opt.enc_flags() | kEncPlainMats)) throw Unsupported(err);
     const size_t D = diag0.size();
     std::vector<size_t> mat_off(passes.size() + 1, 0);   // scalar offset of pass i's [G][stride_i] block
     std::vector<uint32_t> mat_stride(passes.size());
@@ -545,7 +552,7 @@ void State::launch_uniform_t(int b0, int nb)
         for (size_t i = 0; i < passes.size(); i++) {
             const PassParams<T> *src = &params[i];
             if (g > 0) {
-                if (!encode_pass<T>(passes[i], ops, n_local_, G, tmp, dg, err, opt.enc_flags())) throw Unsupported(err);
+                if (!encode_pass<T>(passes[i], ops, n_local_, G, tmp, dg, err, opt.enc_flags() | kEncPlainMats)) throw Unsupported(err);
                 if (tmp.n_mat != params[i].n_mat || tmp.n_ops != params[i].n_ops) throw Unsupported("internal: register passes differ in layout");
                 src = &tmp;
             }

@@ -1617,8 +1617,18 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
                     static const char letter[] = {'D', 'T', 'X', 'S', 'P', 'F'};
                     kinds += letter[pp.ops[q].kind];
                     if (pp.ops[q].kind == OP_DIAG) kinds += std::to_string((int)pp.ops[q].k);
+                    if (pp.ops[q].kind == OP_PAIR && !(pp.ops[q].k == 2 && pp.ops[q].k2 == 2 && pp.ops[q].s == 2))   // register block other than the common 4-bit one
+                        kinds += "(" + std::to_string((int)pp.ops[q].k) + std::to_string((int)pp.ops[q].k2) + std::to_string((int)pp.ops[q].s) + ")";
                 }
                 o.set("device_kinds", Json::string(kinds));
+                Json pb = Json::array();   // tile bits of every register block (ascending)
+                for (int q = 0; q < pp.n_ops; q++) {
+                    if (pp.ops[q].kind != OP_PAIR) continue;
+                    Json e = Json::array();
+                    for (int f = 0; f < pp.ops[q].nfix; f++) e.arr.push_back(Json::integer(pp.ops[q].fixpos[f]));
+                    pb.arr.push_back(std::move(e));
+                }
+                o.set("pair_bits", std::move(pb));
                 Json sw = Json::array();
                 for (int q = 0; q < pp.n_sweeps; q++) {
                     Json e = Json::array();

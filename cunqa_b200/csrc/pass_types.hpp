@@ -31,7 +31,9 @@ enum OpKind : uint8_t {
     OP_PERMX = 2,  // X on tbit[0] (controls optional): pure pair swap, no flops
     OP_SWAP = 3,   // swap tbit[0] <-> tbit[1] (controls optional)
     OP_PAIR = 4,   // register block: two dense gates A (k qubits, local bits [0,k)) and B (k2 qubits, local
-                   // bits [s,s+k2)) applied back to back to the 2^R amplitudes a thread holds in registers
+                   // bits [s,s+k2); k2 = 0: A alone) applied back to back to the 2^nfix amplitudes a thread holds in
+                   // registers; nfix = 4 local bits (tbit[0..3], the gates' bits first, then spectator bits no gate
+                   // touches) whenever the tile has four bits
     OP_FAN = 5,    // phase fan at the end of a pass: every "center" (a tile bit, k <= 8 of them) carries a phase that is a
                    // product of one factor per other qubit ("leaf": in-tile non-center bits and out-of-tile qubits); no term
                    // joins two centers or two leaves.  amplitude *= g * prod_{centers b set} [c_b(tile) * T_b[leaf bits]].
@@ -54,7 +56,9 @@ struct DevOp {
     uint32_t mat_off;   // DENSE: scalar offset into PassParams::mats; DIAG: element offset into the diag-table buffer
     uint64_t ctrl_out;  // physical-qubit mask of controls outside the tile (tested on the tile base)
     int32_t mask_row;   // row of the per-state flag matrix (batched feed-forward) when has_mask
-    uint8_t k2, s;      // PAIR: #targets of gate B and its first local bit; B's matrix follows A's in mats
+    uint8_t k2, s;      // DENSE: k2 = 1: plain (re, im) elements even in a pass with mat_form = 1 (unused by encode_pass today: such
+                        // passes have no sweeps); s = the gate's first register bit in its sweep
+                        // PAIR: #targets of gate B and its first local bit; B's matrix follows A's in mats
                         // DIAG: k2 = slot of this op among the pass's diagonal ops (index of its pext tables); s = 1 when the
                         // table depends on a register bit of its run (looked up per amplitude)
     uint16_t stage_off;  // DIAG: entry offset of this op's per-tile sub-table in the shared-memory table store; kNotStaged = read from global memory
@@ -68,7 +72,8 @@ struct PassParams {
     int32_t L;        // low tile bits that are physical qubits 0..L-1 (contiguous run = 2^L amps)
     int32_t n_ops;
     int32_t batch;    // independent states
-    int32_t pad_;
+    int32_t mat_form; // 0: <= 2-qubit matrices as plain (re, im) pairs; 1: three-multiplication form (tile_kernel.cuh), read from
+                      // the kernel parameters by the CM kernel variant
     uint64_t tiles_per_state;
     uint64_t cond_mask; // ops whose activity depends on the tile (controls outside the tile / per-state mask)
     uint64_t chunk_mask, chunk_val;  // only tiles whose base satisfies (base & chunk_mask) == chunk_val are processed
@@ -96,7 +101,8 @@ struct PassParams {
     uint8_t stab_slot[kStabEntries / 8];  // diagonal slot that owns each 8-entry chunk of the store
     uint8_t tile_q[16]; // physical qubit of tile bit j (ascending)
     DevOp ops[kMaxOps];
-    alignas(16) T mats[kMatScalars];  // (re, im) pairs, read as one 16-byte element
+    alignas(16) T mats[kMatScalars];  // dense matrices: <= 2 qubits in the three-multiplication form of tile_kernel.cuh (3 scalars per
+                                      // element), wider blocks and the gates of register sweeps as (re, im) pairs
 };
 
 // dim3 / smem sizing helpers shared with the host

@@ -168,6 +168,29 @@ void Fuser::push(HostOp op)
     ops.push_back(std::move(op));
 }
 
+// scalars of kernel-parameter storage a dense k-qubit matrix takes (pass_types.hpp: 3 per element up to two qubits)
+static int dense_scalars(int k) { return (k <= 2 ? 3 : 2) * (1 << (2 * k)); }
+
+// Dense matrices are written as plain (re, im) pairs while a pass is encoded; a pass that qualifies (encode_pass, end)
+// then has its <= 2-qubit matrices rewritten in place into the three-multiplication form of tile_kernel.cuh: element
+// e = c + i d becomes m[2e] = c, m[2e+1] = -(c+d), m[2E+e] = d-c (E = 4^k; the slot holds 3E scalars in either form).
+template <typename T>
+static void pack_dense(T *dst, const cplx *m, int k)
+{
+    const int E = 1 << (2 * k);
+    for (int e = 0; e < E; e++) { dst[2 * e] = (T)m[e].real(); dst[2 * e + 1] = (T)m[e].imag(); }
+}
+template <typename T>
+static void to_mul3(T *m, int k)
+{
+    const int E = 1 << (2 * k);
+    for (int e = 0; e < E; e++) {
+        const T c = m[2 * e], d = m[2 * e + 1];
+        m[2 * e + 1] = -(c + d);
+        m[2 * E + e] = d - c;
+    }
+}
+
 static int dense_cost(const HostOp &op)
 {
     switch (op.kind) {
@@ -200,7 +223,7 @@ std::vector<int> admit(const std::vector<HostOp> &ops, const std::vector<char> &
         if (can) {
             const uint64_t newQ = Q | qx;
             const int c = dense_cost(op);
-            const int ms = op.kind == HostOp::DENSE ? 2 * (1 << (2 * op.q.size())) : 0;
+            const int ms = op.kind == HostOp::DENSE ? dense_scalars((int)op.q.size()) : 0;
             bool fits = (grow ? popcount64(newQ) <= t : newQ == Q) && (int)sel.size() < kMaxOps && mat_scalars + ms <= kMatScalars;
             if (fits && opt.max_pass_cost > 0 && !sel.empty() && cost + c > opt.max_pass_cost) fits = false;
             if (fits) {
@@ -299,6 +322,28 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
         return -1;
     };
     int nops = 0, mat_used = 0;
+    // local bits of a register block (OP_PAIR): the gates' tile bits; widen: filled up to four with spectator bits -- free
+    // tile bits, highest first, so that the lanes of a warp keep the low tile bits (distinct shared-memory banks): a thread
+    // then holds 16 amplitudes whatever the gates' widths (tile_kernel.cuh: op_pair, RW = 4)
+    auto set_block_bits = [&](DevOp &d, std::vector<int> lpos, bool widen) {
+        for (int pos = t - 1; pos >= 0 && lpos.size() < 4 && widen; pos--)
+            if (std::find(lpos.begin(), lpos.end(), pos) == lpos.end()) lpos.push_back(pos);
+        const int R = (int)lpos.size();
+        if (R < 1 || R > 4) return false;
+        for (int m = 0; m < R; m++) d.tbit[m] = (uint8_t)lpos[m];
+        std::vector<int> fix = lpos;
+        std::sort(fix.begin(), fix.end());
+        d.nfix = (uint8_t)R;
+        for (int f = 0; f < R; f++) d.fixpos[f] = (uint8_t)fix[f];
+        // segment masks of the group index: bits between consecutive fixed positions move up together
+        for (int k = 0; k <= R; k++) {
+            const int lo = k == 0 ? 0 : fix[k - 1] - (k - 1);
+            const int hi = k == R ? 16 : fix[k] - k;
+            d.seg[k] = (uint16_t)(hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u);
+        }
+        for (int k = R + 1; k < 6; k++) d.seg[k] = 0;
+        return true;
+    };
     auto pairable = [&](const HostOp &o) {
         return o.kind == HostOp::DENSE && o.q.size() <= 2 && o.ctrl.empty() && o.mask_row < 0;
     };
@@ -426,32 +471,24 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
             local.insert(local.end(), shared.begin(), shared.end());
             local.insert(local.end(), b_only.begin(), b_only.end());
             const int K1 = (int)A.q.size(), K2 = (int)B.q.size(), S = K1 - (int)shared.size(), R = (int)local.size();
-            const int sc = 2 * ((1 << (2 * K1)) + (1 << (2 * K2)));
+            const int sc = dense_scalars(K1) + dense_scalars(K2);
             if (R <= 4 && mat_used + sc <= kMatScalars) {
                 d.kind = OP_PAIR;
                 d.k = (uint8_t)K1;
                 d.k2 = (uint8_t)K2;
                 d.s = (uint8_t)S;
-                std::vector<int> fix;
+                std::vector<int> lpos;
                 for (int m = 0; m < R; m++) {
                     const int p = tile_pos(local[m]);
                     if (p < 0) { err = "internal: target outside tile"; return false; }
-                    d.tbit[m] = (uint8_t)p;
-                    fix.push_back(p);
+                    lpos.push_back(p);
                 }
-                std::sort(fix.begin(), fix.end());
-                d.nfix = (uint8_t)R;
-                for (int f = 0; f < R; f++) d.fixpos[f] = (uint8_t)fix[f];
-                // segment masks of the group index: bits between consecutive fixed positions move up together
-                for (int k = 0; k <= R; k++) {
-                    const int lo = k == 0 ? 0 : fix[k - 1] - (k - 1);
-                    const int hi = k == R ? 16 : fix[k] - k;
-                    d.seg[k] = (uint16_t)(hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u);
-                }
+                if (!set_block_bits(d, lpos, false)) { err = "internal: register block without local bits"; return false; }
                 d.mat_off = (uint32_t)mat_used;
                 const std::vector<cplx> MA = embed_dense(A, la), MB = embed_dense(B, lb);
-                for (const std::vector<cplx> *M : {&MA, &MB})
-                    for (const cplx &z : *M) { out.mats[mat_used++] = (T)z.real(); out.mats[mat_used++] = (T)z.imag(); }
+                pack_dense(out.mats + mat_used, MA.data(), K1);
+                pack_dense(out.mats + mat_used + dense_scalars(K1), MB.data(), K2);
+                mat_used += sc;
                 pi++;  // B consumed
                 continue;
             }
@@ -509,13 +546,10 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
         d.nfix = (uint8_t)fix.size();
         for (int f = 0; f < d.nfix && f < kMaxFix; f++) d.fixpos[f] = (uint8_t)fix[f];
         if (op.kind == HostOp::DENSE) {
-            const int sc = 2 * (1 << (2 * d.k));
+            const int sc = dense_scalars(d.k);
             if (mat_used + sc > kMatScalars) { err = "pass matrix storage exhausted"; return false; }
             d.mat_off = (uint32_t)mat_used;
-            for (size_t e = 0; e < op.m.size(); e++) {
-                out.mats[mat_used + 2 * e] = (T)op.m[e].real();
-                out.mats[mat_used + 2 * e + 1] = (T)op.m[e].imag();
-            }
+            pack_dense(out.mats + mat_used, op.m.data(), d.k);
             mat_used += sc;
         }
     }
@@ -727,6 +761,35 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
     out.cond_mask = 0;
     for (int o = 0; o < nops; o++)
         if (out.ops[o].ctrl_out != 0 || out.ops[o].has_mask) out.cond_mask |= 1ull << o;
+    // Passes that the lean kernel variant serves without per-tile conditions (register blocks and <= 2-qubit gates only:
+    // the FP64-pipe-bound passes of dense circuits) get the fast forms of tile_kernel.cuh: every register block is widened
+    // to four local bits, a lone uncontrolled 2-qubit gate becomes a block of one gate, and in FP64 the matrices are kept
+    // in the three-multiplication form, which the kernel reads from its parameters through the uniform datapath
+    // (mat_form 1; FP32: plain elements, mat_form 2).  Per-register matrices (kEncPlainMats: they live in global memory) and
+    // every other pass keep natural blocks and plain elements (mat_form 0).
+    out.mat_form = 0;
+    if (pair_ops && !(flags & kEncPlainMats) && out.cond_mask == 0 && out.needs_full == 0 && t >= 4) {
+        out.mat_form = sizeof(T) == 8 ? 1 : 2;
+        for (int o = 0; o < nops; o++) {
+            DevOp &d = out.ops[o];
+            if (d.kind == OP_DENSE && d.k == 2 && d.nfix == 2) {
+                d.kind = OP_PAIR;
+                d.k2 = 0;
+                d.s = 0;
+            }
+            if (d.kind == OP_PAIR) {
+                const int R = std::max<int>(d.k, d.s + d.k2);
+                std::vector<int> lpos(d.tbit, d.tbit + R);
+                if (!set_block_bits(d, lpos, true)) { err = "internal: register block without local bits"; return false; }
+            }
+            if (out.mat_form != 1) continue;
+            if (d.kind == OP_DENSE && d.k <= 2) to_mul3(out.mats + d.mat_off, d.k);
+            if (d.kind == OP_PAIR) {
+                to_mul3(out.mats + d.mat_off, d.k);
+                if (d.k2) to_mul3(out.mats + d.mat_off + dense_scalars(d.k), d.k2);
+            }
+        }
+    }
     // Per-tile staging of small diagonal sub-tables.  For a given tile the table-index bits that come from qubits outside
     // the tile are constants, so the op only ever reads the 2^nfix consecutive entries that start at its per-tile base
     // (in-tile qubits are the low index bits, see above).  Ops with few in-tile qubits -- the CP ladders of a QFT are

@@ -39,6 +39,7 @@ struct HostOp {
 constexpr int kEncPairOps = 1;         // register-block adjacent dense gates
 constexpr int kEncDiagFuseAlways = 2;  // always fold a diagonal run into the dense gate that follows it (experiments)
 constexpr int kEncNoStage = 4;
+constexpr int kEncPlainMats = 32;      // never the three-multiplication matrix form (per-register matrices, A/B experiments)
 constexpr int kEncFan = 16;            // pull commuting phase-ladder terms into a fan at the end of the pass (TMA kernel, no per-tile conditions)         // no per-tile shared-memory staging of diagonal sub-tables (experiments)
 
 struct PlanOptions {

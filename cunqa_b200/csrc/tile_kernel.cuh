@@ -62,10 +62,49 @@ __device__ __forceinline__ void cfma(V &acc, const T mr, const T mi, const V a)
     acc.y = fma(mi, a.x, acc.y);
 }
 
+// ---- dense gates of <= 2 qubits: complex products with three multiplications --------------------
+// Matrix element e = c + i d of such a gate is stored as  mat[2e] = c,  mat[2e+1] = -(c+d),  mat[2E+e] = d-c  (E = 4^K
+// elements; planner.cpp: pack_dense).  With s_j = re_j + im_j shared by all rows of the gate,
+//     re_i = sum_j c_ij s_j + sum_j [-(c+d)_ij] im_j        im_i = sum_j c_ij s_j + sum_j (d-c)_ij re_j
+// i.e. 13 FP64 instructions per amplitude of a 2-qubit gate instead of 16 (the kernel is FP64-pipe bound on these).  Two
+// rows of the matrix are live at a time (24 values): read from the kernel parameters they stay in uniform registers
+// (LDCU -> UR operands of DFMA: no vector registers, no shared-memory wavefronts), read from shared memory (per-register
+// matrices, conditioned passes) they cost 12 128-bit loads per row pair.
+template <typename T, int K>
+__device__ __forceinline__ void rows2_mul3(const T *mat, const int r0, const typename Vec2<T>::type (&in)[1 << K], const T (&s)[1 << K],
+                                           typename Vec2<T>::type (&out)[2])
+{
+    using V = typename Vec2<T>::type;
+    constexpr int D = 1 << K, E = D * D;
+    const V *mv = reinterpret_cast<const V *>(mat);   // (c, -(c+d)) pairs, then the (d-c) values two by two
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const int r = r0 + rr;
+        V cn[D], dm[D / 2];
+#pragma unroll
+        for (int c = 0; c < D; c++) cn[c] = mv[r * D + c];
+#pragma unroll
+        for (int c = 0; c < D / 2; c++) dm[c] = mv[E + (r * D) / 2 + c];
+        T tt = cn[0].x * s[0];
+#pragma unroll
+        for (int c = 1; c < D; c++) tt = fma(cn[c].x, s[c], tt);
+        T re = tt, im = tt;
+#pragma unroll
+        for (int c = 0; c < D; c++) {
+            re = fma(cn[c].y, in[c].y, re);
+            im = fma((c & 1) ? dm[c / 2].y : dm[c / 2].x, in[c].x, im);
+        }
+        out[rr].x = re;
+        out[rr].y = im;
+    }
+}
+
 // ---- dense k-qubit block on the tile -----------------------------------------------------------
-// K <= 2: the matrix is hoisted into registers (16 complex elements, one 128-bit load each);
-// K >= 3: matrix elements stream in inside the row loop.
-template <typename T, int K, int NT>
+// K <= 2: three-multiplication form when the pass stores its matrices that way (M3: PassParams::mat_form, FP64 passes
+// served by the lean kernel, matrices read from the kernel parameters) and the gate does not belong to a register sweep
+// (DevOp::k2); otherwise plain (re, im) elements hoisted into registers, one 128-bit load each.  K >= 3: plain matrix
+// elements streamed in inside the row loop.
+template <typename T, int K, int NT, bool M3>
 __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
                                          const int t, const int tid)
 {
@@ -82,6 +121,30 @@ __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const Dev
     }
     const int nfix = op.nfix;
     const uint32_t ngroups = 1u << (t - nfix);
+    if constexpr (K <= 2 && M3) {
+        if (!op.k2) {
+            for (uint32_t g = tid; g < ngroups; g += NT) {
+                uint32_t idx = g;
+                for (int f = 0; f < nfix; f++) idx = insert0(idx, op.fixpos[f]);
+                idx |= op.ctrl_in;
+                V in[D];
+                T s[D];
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    in[j] = tile[swz<T>(idx | off[j])];
+                    s[j] = in[j].x + in[j].y;
+                }
+#pragma unroll
+                for (int r0 = 0; r0 < D; r0 += 2) {
+                    V out[2];
+                    rows2_mul3<T, K>(mat, r0, in, s, out);
+                    tile[swz<T>(idx | off[r0])] = out[0];
+                    tile[swz<T>(idx | off[r0 + 1])] = out[1];
+                }
+            }
+            return;
+        }
+    }
     if constexpr (K <= 2) {
         T mr[D * D], mi[D * D];
 #pragma unroll
@@ -92,9 +155,7 @@ __device__ __forceinline__ void op_dense(typename Vec2<T>::type *tile, const Dev
             idx |= op.ctrl_in;
             V in[D];
 #pragma unroll
-            for (int j = 0; j < D; j++) {
-                in[j] = tile[swz<T>(idx | off[j])];
-            }
+            for (int j = 0; j < D; j++) in[j] = tile[swz<T>(idx | off[j])];
 #pragma unroll
             for (int r = 0; r < D; r++) {
                 V acc = cmul<V, T>(mr[r * D], mi[r * D], in[0]);
@@ -153,8 +214,10 @@ __device__ __forceinline__ void sts_amp(uint32_t addr, float2 v)
 // ---- register block: two dense gates per shared-memory round trip ---------------------------------
 // The thread holds the 2^R amplitudes spanned by the block's R local bits in registers; gate A acts on
 // local bits [0,K1), gate B on local bits [S,S+K2).  All register indices are compile-time.
+// the same on plain (re, im) matrix elements hoisted into registers: the dense gates of a register sweep (op_sweep), whose
+// matrices come from shared memory and whose register budget is spent on the tables of the sweep
 template <typename T, int R, int K, int S>
-__device__ __forceinline__ void block_gate(typename Vec2<T>::type (&a)[1 << R], const T *mat)
+__device__ __forceinline__ void block_gate_plain(typename Vec2<T>::type (&a)[1 << R], const T *mat)
 {
     using V = typename Vec2<T>::type;
     constexpr int D = 1 << K;
@@ -178,12 +241,45 @@ __device__ __forceinline__ void block_gate(typename Vec2<T>::type (&a)[1 << R], 
     }
 }
 
-template <typename T, int K1, int K2, int S, int NT>
+template <typename T, int R, int K, int S>
+__device__ __forceinline__ void block_gate(typename Vec2<T>::type (&a)[1 << R], const T *mat)
+{
+    using V = typename Vec2<T>::type;
+    constexpr int D = 1 << K, G = 1 << (R - K), NCH = D / 2;
+    static_assert(K == 1 || K == 2, "register blocks hold 1- and 2-qubit gates");
+    // two matrix rows at a time over all groups: rows 0,1 of a 2-qubit gate wait in `keep` until rows 2,3 are known
+    V keep[NCH > 1 ? G : 1][2];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch++) {
+#pragma unroll
+        for (int rest = 0; rest < G; rest++) {
+            const int lo = rest & ((1 << S) - 1), hi = rest >> S;
+            const int base = (hi << (S + K)) | lo;
+            V in[D];
+            T s[D];
+#pragma unroll
+            for (int j = 0; j < D; j++) { in[j] = a[base | (j << S)]; s[j] = in[j].x + in[j].y; }
+            V out[2];
+            rows2_mul3<T, K>(mat, 2 * ch, in, s, out);
+            if (ch + 1 < NCH) { keep[rest][0] = out[0]; keep[rest][1] = out[1]; }
+            else {
+                a[base | ((2 * ch) << S)] = out[0];
+                a[base | ((2 * ch + 1) << S)] = out[1];
+                if (NCH > 1) { a[base] = keep[rest][0]; a[base | (1 << S)] = keep[rest][1]; }
+            }
+        }
+    }
+}
+
+// RW = 4: the block is widened to four local bits with spectator bits (local bits the gates do not touch; the host picks
+// free tile bits): every thread then holds 16 amplitudes and makes one trip whatever the gates' widths, and K2 = 0 is a
+// single gate.
+template <typename T, int K1, int K2, int S, int NT, bool M3, int RW = 0>
 __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
                                         const int t, const int tid)
 {
     using V = typename Vec2<T>::type;
-    constexpr int R = (K1 > S + K2) ? K1 : (S + K2);
+    constexpr int R = RW ? RW : ((K1 > S + K2) ? K1 : (S + K2));
     constexpr int D = 1 << R;
     // the swizzle is XOR-linear and the block bits are disjoint from the group bits, so
     // swz(idx | off_j) = swz(idx) ^ swz(off_j): one XOR per amplitude instead of re-swizzling
@@ -212,29 +308,47 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
         V a[D];
 #pragma unroll
         for (int j = 0; j < D; j++) { addr[j] = tile_s + (bidx ^ boff[j]); a[j] = lds_amp(addr[j], V()); }
-        block_gate<T, R, K1, 0>(a, mat);
-        block_gate<T, R, K2, S>(a, mat + 2 * (1 << (2 * K1)));
+        // (gate B's matrix sits 3 * 4^K1 scalars after gate A's in either form: planner.cpp, dense_scalars)
+        if constexpr (M3) {
+            block_gate<T, R, K1, 0>(a, mat);
+            if constexpr (K2 > 0) block_gate<T, R, K2, S>(a, mat + 3 * (1 << (2 * K1)));
+        } else {
+            block_gate_plain<T, R, K1, 0>(a, mat);
+            if constexpr (K2 > 0) block_gate_plain<T, R, K2, S>(a, mat + 3 * (1 << (2 * K1)));
+        }
 #pragma unroll
         for (int j = 0; j < D; j++) sts_amp(addr[j], a[j]);
     }
 }
 
-template <typename T, int NT, int VAR>
+// FORM (PassParams::mat_form): 0 = blocks at their natural width, plain matrices (every kernel variant; what per-register
+// matrices, conditioned passes and the full variant use); 1 / 2 = lean passes without per-tile conditions: blocks
+// widened to four local bits, matrices in the three-multiplication form read from the kernel parameters (1, FP64) or plain
+// from shared memory (2, FP32).
+template <typename T, int NT, int VAR, int FORM>
 __device__ __forceinline__ void op_pair_dispatch(typename Vec2<T>::type *tile, const DevOp &op, const T *mat,
                                                  const int t, const int tid)
 {
     const int code = (op.k << 4) | (op.k2 << 2) | op.s;
-    if (code == ((2 << 4) | (2 << 2) | 2)) { op_pair<T, 2, 2, 2, NT>(tile, op, mat, t, tid); return; }
-    if (code == ((2 << 4) | (2 << 2) | 1)) { op_pair<T, 2, 2, 1, NT>(tile, op, mat, t, tid); return; }
-    if (code == ((1 << 4) | (1 << 2) | 1)) { op_pair<T, 1, 1, 1, NT>(tile, op, mat, t, tid); return; }
-    if constexpr (VAR == 2) {
-        switch (code) {
-        case (1 << 4) | (1 << 2) | 0: op_pair<T, 1, 1, 0, NT>(tile, op, mat, t, tid); break;
-        case (1 << 4) | (2 << 2) | 1: op_pair<T, 1, 2, 1, NT>(tile, op, mat, t, tid); break;
-        case (1 << 4) | (2 << 2) | 0: op_pair<T, 1, 2, 0, NT>(tile, op, mat, t, tid); break;
-        case (2 << 4) | (1 << 2) | 2: op_pair<T, 2, 1, 2, NT>(tile, op, mat, t, tid); break;
-        case (2 << 4) | (1 << 2) | 1: op_pair<T, 2, 1, 1, NT>(tile, op, mat, t, tid); break;
-        default: op_pair<T, 2, 2, 0, NT>(tile, op, mat, t, tid); break;
+    if constexpr (FORM != 0) {
+        constexpr bool M3 = FORM == 1;
+        if (code == ((2 << 4) | (2 << 2) | 2)) { op_pair<T, 2, 2, 2, NT, M3, 4>(tile, op, mat, t, tid); return; }
+        if (code == ((2 << 4) | (2 << 2) | 1)) { op_pair<T, 2, 2, 1, NT, M3, 4>(tile, op, mat, t, tid); return; }
+        if (code == ((2 << 4) | (0 << 2) | 0)) { op_pair<T, 2, 0, 0, NT, M3, 4>(tile, op, mat, t, tid); return; }
+        op_pair<T, 1, 1, 1, NT, M3, 4>(tile, op, mat, t, tid);
+    } else {
+        if (code == ((2 << 4) | (2 << 2) | 2)) { op_pair<T, 2, 2, 2, NT, false>(tile, op, mat, t, tid); return; }
+        if (code == ((2 << 4) | (2 << 2) | 1)) { op_pair<T, 2, 2, 1, NT, false>(tile, op, mat, t, tid); return; }
+        if (code == ((1 << 4) | (1 << 2) | 1)) { op_pair<T, 1, 1, 1, NT, false>(tile, op, mat, t, tid); return; }
+        if constexpr (VAR == 2) {
+            switch (code) {
+            case (1 << 4) | (1 << 2) | 0: op_pair<T, 1, 1, 0, NT, false>(tile, op, mat, t, tid); break;
+            case (1 << 4) | (2 << 2) | 1: op_pair<T, 1, 2, 1, NT, false>(tile, op, mat, t, tid); break;
+            case (1 << 4) | (2 << 2) | 0: op_pair<T, 1, 2, 0, NT, false>(tile, op, mat, t, tid); break;
+            case (2 << 4) | (1 << 2) | 2: op_pair<T, 2, 1, 2, NT, false>(tile, op, mat, t, tid); break;
+            case (2 << 4) | (1 << 2) | 1: op_pair<T, 2, 1, 1, NT, false>(tile, op, mat, t, tid); break;
+            default: op_pair<T, 2, 2, 0, NT, false>(tile, op, mat, t, tid); break;
+            }
         }
     }
 }
@@ -303,14 +417,14 @@ __device__ __noinline__ void op_sweep(typename Vec2<T>::type *tile, const PassPa
         if (op.kind == OP_DENSE) {
             const T *mat = mats + op.mat_off;
             if (op.k == 2) {
-                if (op.s == 0) block_gate<T, 4, 2, 0>(v, mat);
-                else block_gate<T, 4, 2, 2>(v, mat);
+                if (op.s == 0) block_gate_plain<T, 4, 2, 0>(v, mat);
+                else block_gate_plain<T, 4, 2, 2>(v, mat);
             } else {
                 switch (op.s) {
-                case 0: block_gate<T, 4, 1, 0>(v, mat); break;
-                case 1: block_gate<T, 4, 1, 1>(v, mat); break;
-                case 2: block_gate<T, 4, 1, 2>(v, mat); break;
-                default: block_gate<T, 4, 1, 3>(v, mat); break;
+                case 0: block_gate_plain<T, 4, 1, 0>(v, mat); break;
+                case 1: block_gate_plain<T, 4, 1, 1>(v, mat); break;
+                case 2: block_gate_plain<T, 4, 1, 2>(v, mat); break;
+                default: block_gate_plain<T, 4, 1, 3>(v, mat); break;
                 }
             }
         } else if (op.kind == OP_DIAG) {
@@ -465,13 +579,14 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 // remaining ops still run.
 // VAR: 0 = lean (1-2 qubit dense gates, the common register blocks, permutations), 1 = lean + diagonal runs through the
 // LUT / register-block path, 2 = everything (dense k >= 3, all register blocks, the generic per-bit diagonal gather)
-template <typename T, int NT, bool COND, int VAR, typename Hook = NoHook>
+template <typename T, int NT, bool COND, int VAR, typename Hook = NoHook, int FORM = 0>
 __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats, typename Vec2<T>::type *tile,
                                           const typename Vec2<T>::type *__restrict__ diag_tabs,
                                           const uint64_t active, const uint64_t base, const int t, const int tid,
                                           const uint16_t *lut = nullptr, const typename Vec2<T>::type *const *tptr = nullptr,
                                           const int hook_at = 1 << 30, Hook hook = Hook(),
-                                          const typename Vec2<T>::type *fanT = nullptr, const typename Vec2<T>::type *fanc = nullptr)
+                                          const typename Vec2<T>::type *fanT = nullptr, const typename Vec2<T>::type *fanc = nullptr,
+                                          const T *mats_sweep = nullptr)
 {
     using V = typename Vec2<T>::type;
     const uint32_t tile_amps = 1u << t;
@@ -487,7 +602,7 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                     FanCtx<T> fc;
                     fc.fanT = fanT;
                     fc.fanc = fanc;
-                    op_sweep<T, NT>(tile, p, sw, mats, diag_tabs, tptr, lut, fc, tid);
+                    op_sweep<T, NT>(tile, p, sw, mats_sweep, diag_tabs, tptr, lut, fc, tid);   // (not inlined: matrices from shared memory)
                     o += p.sweeps[sw].len - 1;
                     __syncthreads();
                     continue;
@@ -495,16 +610,16 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
             }
             if (op.kind == OP_DENSE) {
                 const T *mat = mats + op.mat_off;
-                if (op.k == 1) op_dense<T, 1, NT>(tile, op, mat, t, tid);
-                else if (op.k == 2) op_dense<T, 2, NT>(tile, op, mat, t, tid);
+                if (op.k == 1) op_dense<T, 1, NT, FORM == 1>(tile, op, mat, t, tid);
+                else if (op.k == 2) op_dense<T, 2, NT, FORM == 1>(tile, op, mat, t, tid);
                 else if constexpr (VAR == 2) {
-                    if (op.k == 3) op_dense<T, 3, NT>(tile, op, mat, t, tid);
-                    else if (op.k == 4) op_dense<T, 4, NT>(tile, op, mat, t, tid);
-                    else op_dense<T, 5, NT>(tile, op, mat, t, tid);
+                    if (op.k == 3) op_dense<T, 3, NT, false>(tile, op, mat, t, tid);
+                    else if (op.k == 4) op_dense<T, 4, NT, false>(tile, op, mat, t, tid);
+                    else op_dense<T, 5, NT, false>(tile, op, mat, t, tid);
                 }
                 __syncthreads();
             } else if (op.kind == OP_PAIR) {
-                op_pair_dispatch<T, NT, VAR>(tile, op, mats + op.mat_off, t, tid);
+                op_pair_dispatch<T, NT, VAR, FORM>(tile, op, mats + op.mat_off, t, tid);
                 __syncthreads();
             } else if (op.kind == OP_DIAG) {
                 // (outside a register sweep: kernels without the 16-amplitudes-per-thread layout, or per-tile conditions)
@@ -661,7 +776,9 @@ __device__ __forceinline__ void tma_store_row(const CUtensorMap *map, const void
 // tiles, so the load / math / store / barrier phases of different CTAs interleave on an SM.
 // kStages tile buffers per CTA: 3 = the CTA overlaps its own load / math / store; 2 = one more CTA fits per
 // SM and the overlap comes from the other resident CTAs.
-template <typename T, int NT, bool COND, int VAR, int kStages>
+// FORM = PassParams::mat_form (op_pair_dispatch).  FORM 1: the dense matrices of the register blocks and dense gates are
+// read straight from the kernel parameters (uniform datapath) instead of the shared-memory copy.
+template <typename T, int NT, bool COND, int VAR, int kStages, int FORM = 0>
 __global__ void __launch_bounds__(NT, (kStages == 3 ? 256 : 384) / NT)
 tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_constant__ CUtensorMap tmap,
                      const typename Vec2<T>::type *__restrict__ diag_tabs, const uint8_t *__restrict__ flags,
@@ -874,9 +991,9 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
             __syncthreads();
         }
 
-        apply_ops<T, NT, COND, VAR>(p, mats_s, tile, tabs_b, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
+        apply_ops<T, NT, COND, VAR, decltype(refill), FORM>(p, FORM == 1 ? p.mats : mats_s, tile, tabs_b, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
                                     (COND || (16 * NT) != (1 << t)) ? nullptr : lut, tptr, refill_after, refill,
-                                    (COND || (16 * NT) != (1 << t)) ? nullptr : fanT, fanc);
+                                    (COND || (16 * NT) != (1 << t)) ? nullptr : fanT, fanc, mats_s);
 
         // every thread's generic-proxy writes -> visible to the async proxy; then drain the tile with TMA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

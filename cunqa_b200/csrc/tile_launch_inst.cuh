@@ -23,7 +23,7 @@ cudaError_t launch_tile_pass_tma<CB200_T, CB200_NT>(const PassParams<CB200_T> &p
     using T = CB200_T;
     using V = typename Vec2<T>::type;
     constexpr int N = CB200_NT;
-    static size_t seen_all[kMaxDevices][8] = {};
+    static size_t seen_all[kMaxDevices][12] = {};
     size_t *seen = seen_all[l.device & (kMaxDevices - 1)];
     const bool cnd = p.cond_mask != 0;
     // kernel variant: 0 lean, 1 lean + diagonal runs, 2 full.  The diagonal-run path needs the LUT route (no per-tile
@@ -42,6 +42,11 @@ cudaError_t launch_tile_pass_tma<CB200_T, CB200_NT>(const PassParams<CB200_T> &p
         return go(tile_pass_tma_kernel<T, N, false, 2, 3>, seen[1]);   // (three stages: experiments only, full variant)
     }
     if (cnd) return go(tile_pass_tma_kernel<T, N, true, 2, 2>, seen[2]);
+    if (p.mat_form != 0) {   // lean pass with widened register blocks (encode_pass): FP64 -> form 1, FP32 -> form 2
+        constexpr int kForm = sizeof(T) == 8 ? 1 : 2;
+        if (l.reg_mats != nullptr || var != 0 || p.mat_form != kForm) return cudaErrorInvalidValue;
+        return go(tile_pass_tma_kernel<T, N, false, 0, 2, kForm>, seen[6]);
+    }
     if (var == 0) return go(tile_pass_tma_kernel<T, N, false, 0, 2>, seen[3]);
     if (var == 1) return go(tile_pass_tma_kernel<T, N, false, 1, 2>, seen[4]);
     return go(tile_pass_tma_kernel<T, N, false, 2, 2>, seen[5]);
