@@ -1625,7 +1625,9 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
                 for (int q = 0; q < pp.n_ops; q++) {
                     if (pp.ops[q].kind != OP_PAIR) continue;
                     Json e = Json::array();
-                    for (int f = 0; f < pp.ops[q].nfix; f++) e.arr.push_back(Json::integer(pp.ops[q].fixpos[f]));
+                    std::vector<int> bits(pp.ops[q].tbit, pp.ops[q].tbit + pp.ops[q].nfix);
+                    std::sort(bits.begin(), bits.end());
+                    for (int b : bits) e.arr.push_back(Json::integer(b));
                     pb.arr.push_back(std::move(e));
                 }
                 o.set("pair_bits", std::move(pb));

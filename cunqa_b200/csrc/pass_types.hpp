@@ -47,7 +47,10 @@ struct DevOp {
     uint8_t nfix;    // DENSE/PERM/PAIR: number of entries in fixpos (targets + in-tile controls)
     uint8_t has_mask;
     uint8_t tbit[8];        // DENSE/PERM: tile-bit position of target m
-    uint8_t fixpos[kMaxFix]; // ascending tile-bit positions where a bit is inserted into the group index
+    union {
+        uint8_t fixpos[kMaxFix]; // ascending tile-bit positions where a bit is inserted into the group index
+        uint16_t sboff[4];       // PAIR: swizzled tile index of local bit m, swz(1 << tbit[m])
+    };
     union {
         uint8_t dsrc[kMaxDiagK]; // DIAG: source of table-index bit m: <64 tile bit, >=64 physical qubit (v-64) outside the tile
         uint16_t seg[6];         // PAIR: group index -> tile index deposit, idx = sum_k (g & seg[k]) << k  (k <= nfix)
@@ -100,6 +103,8 @@ struct PassParams {
     uint8_t fan_q[kFanMaxChunks][8];  // physical qubit of every chunk bit (0xFF = unused)
     uint8_t stab_slot[kStabEntries / 8];  // diagonal slot that owns each 8-entry chunk of the store
     uint8_t tile_q[16]; // physical qubit of tile bit j (ascending)
+    uint32_t tile_seg[kMaxTileBits + 1];  // tile number -> (tile base >> L): sum_k (x & tile_seg[k]) << k, k <= t - L (the bits of the
+                                          // tile number between two high tile qubits move up together)
     DevOp ops[kMaxOps];
     alignas(16) T mats[kMatScalars];  // dense matrices: <= 2 qubits in the three-multiplication form of tile_kernel.cuh (3 scalars per
                                       // element), wider blocks and the gates of register sweeps as (re, im) pairs

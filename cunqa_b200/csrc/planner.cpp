@@ -317,6 +317,11 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
     out.batch = batch;
     out.tiles_per_state = 1ull << (n - t);
     for (int j = 0; j < t; j++) out.tile_q[j] = (uint8_t)pass.tile_q[j];
+    for (int k = 0, lo = 0; k <= t - pass.L; k++) {   // segment masks of the tile number (tile_kernel.cuh: tile_dep)
+        const int hi = k == t - pass.L ? 32 : std::max(lo, pass.tile_q[pass.L + k] - pass.L - k);
+        out.tile_seg[k] = (uint32_t)((hi >= 32 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull));
+        lo = hi;
+    }
     auto tile_pos = [&](int qubit) {
         for (int j = 0; j < t; j++) if (pass.tile_q[j] == qubit) return j;
         return -1;
@@ -334,7 +339,11 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
         std::vector<int> fix = lpos;
         std::sort(fix.begin(), fix.end());
         d.nfix = (uint8_t)R;
-        for (int f = 0; f < R; f++) d.fixpos[f] = (uint8_t)fix[f];
+        for (int m = 0; m < 4; m++) {   // swizzled tile index of every local bit (tile_kernel.cuh: swz)
+            const uint32_t i = m < R ? 1u << lpos[m] : 0u;
+            const uint32_t sw = sizeof(T) == 8 ? (i ^ ((i >> 3) & 7u)) : (i ^ (((i >> 4) & 7u) << 1));
+            d.sboff[m] = (uint16_t)sw;
+        }
         // segment masks of the group index: bits between consecutive fixed positions move up together
         for (int k = 0; k <= R; k++) {
             const int lo = k == 0 ? 0 : fix[k - 1] - (k - 1);

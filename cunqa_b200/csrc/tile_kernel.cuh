@@ -287,7 +287,7 @@ __device__ __forceinline__ void op_pair(typename Vec2<T>::type *tile, const DevO
     const uint32_t tile_s = smem_u32(tile);
     uint32_t sb[R], seg[R + 1];
 #pragma unroll
-    for (int m = 0; m < R; m++) sb[m] = swz<T>(1u << op.tbit[m]) << kShift;
+    for (int m = 0; m < R; m++) sb[m] = (uint32_t)op.sboff[m] << kShift;   // sboff[m] = swz<T>(1u << op.tbit[m]) (encode_pass)
 #pragma unroll
     for (int m = 0; m <= R; m++) seg[m] = op.seg[m];
     uint32_t boff[D];  // byte offset of block element j relative to the group's element 0 (XOR-combined)
@@ -809,7 +809,7 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     // reg_mats != nullptr: many independent registers batched in one launch (same pass structure, each state of the
     // batch with its own matrices and diagonal tables): the matrices are (re)staged whenever the CTA moves on to a tile
     // of another state -- tiles are numbered state-major, so that happens once per 2^(n-t)/gridDim tiles
-    if (reg_mats == nullptr)
+    if (FORM != 1 && reg_mats == nullptr)
         for (int e = tid; e < p.n_mat; e += NT) mats_s[e] = p.mats[e];
     uint64_t staged_b = ~0ull;
     // per diagonal op: this tile's sub-table pointer, the per-tile index part that comes from qubits outside the tile,
@@ -825,12 +825,12 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     V *fanT = reinterpret_cast<V *>(fan_raw);
     V *fanc = fanT + ((size_t)fan_nc << fan_m);
     V *fanp = fanc + fan_nc;
-    if (p.fan_op >= 0 && reg_mats == nullptr) {
+    if (VAR >= 1 && p.fan_op >= 0 && reg_mats == nullptr) {
         const V *src = diag_tabs + p.ops[p.fan_op].mat_off + 1;
         for (int e = tid; e < (fan_nc << fan_m); e += NT) fanT[e] = src[e];
     }
     static_assert(NT >= 32, "one warp at least");
-    for (int e = tid; e < p.n_diag * kDiagLut; e += NT) {
+    for (int e = tid; VAR >= 1 && e < p.n_diag * kDiagLut; e += NT) {
         const int sl = e / kDiagLut, r = e - sl * kDiagLut;
         const uint32_t mask = p.ops[p.diag_op[sl]].ctrl_in;
         const uint32_t val = r < 64 ? (uint32_t)r : (uint32_t)(r - 64) << 6;
@@ -858,13 +858,23 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
 
     const uint64_t total_tiles = p.tiles_per_state * (uint64_t)p.batch;
     const int tps_shift = n - t;  // tiles_per_state = 2^(n-t)
-    // tile number -> amplitude offset of the tile inside the whole buffer (state b, base within the state)
-    auto tile_base = [&](uint64_t tileno, uint64_t &b) -> uint64_t {
+    // tile number -> amplitude offset of the tile inside the whole buffer (state b, base within the state): the bits of the
+    // tile number move up past the high tile qubits segment by segment (PassParams::tile_seg, 32-bit arithmetic: the
+    // deposited number is base >> L < 2^(n-L))
+    const int nseg = t - L + 1;
+    auto tile_dep = [&](uint64_t tileno, uint64_t &b) -> uint32_t {
         b = tileno >> tps_shift;
-        uint64_t x = tileno & (p.tiles_per_state - 1ull);
-        for (int j = L; j < t; j++) x = insert0_64(x, p.tile_q[j] - L);
-        return x << L;
+        const uint32_t x = (uint32_t)(tileno & (p.tiles_per_state - 1ull));
+        uint32_t dep = 0;   // (masks past the last segment are zero: static indices, the masks are constant-bank operands)
+#pragma unroll
+        for (int k = 0; k < 8; k++) dep |= (x & p.tile_seg[k]) << k;
+        if (nseg > 8) {
+#pragma unroll
+            for (int k = 8; k <= kMaxTileBits; k++) dep |= (x & p.tile_seg[k]) << k;
+        }
+        return dep;
     };
+    auto tile_base = [&](uint64_t tileno, uint64_t &b) -> uint64_t { return (uint64_t)tile_dep(tileno, b) << L; };
     // next tile of this CTA (stride gridDim.x) that some op acts on; ~0 = none.  Evaluated identically by
     // every thread, so the tile sequence lives in registers and needs no shared bookkeeping.
     auto next_active = [&](uint64_t from) -> uint64_t {
@@ -890,8 +900,8 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
     // first 128-byte row of a tile in the whole buffer
     auto tile_row = [&](uint64_t tileno) -> uint32_t {
         uint64_t b;
-        const uint64_t base = tile_base(tileno, b);
-        return (uint32_t)(((b << n) + base) >> kAmpsPerRowShift);
+        const uint32_t dep = tile_dep(tileno, b);
+        return (uint32_t)(b << (n - kAmpsPerRowShift)) + (dep << (L - kAmpsPerRowShift));   // (the TMA path has L >= the row shift)
     };
     auto issue_load = [&](int s, uint32_t row0) {
         if (tid == 0) mbar_arrive_expect_tx(&full[s], tile_bytes);
@@ -938,6 +948,7 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
         V *tile = reinterpret_cast<V *>(smem_raw + (size_t)s * buf_stride);
         // per-tile base of every diagonal table (the index bits that come from qubits outside the tile)
         const V *tabs_b = diag_tabs + (size_t)b * reg_diag_stride;
+        if constexpr (VAR >= 1) {   // (the lean variant runs passes without diagonal tables and fans)
         for (int sl = tid; sl < p.n_diag; sl += NT) {
             const DevOp &d = p.ops[p.diag_op[sl]];
             uint32_t hi = 0;
@@ -955,8 +966,9 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
                 if (e < (1u << d.nfix)) stab[x] = tabs_b[dhi[sl] + e];
             }
         }
+        }
         bool restaged = false;
-        if (reg_mats != nullptr && b != staged_b) {
+        if (FORM == 0 && reg_mats != nullptr && b != staged_b) {
             // (mats_s is only read inside apply_ops, and every thread left the previous tile's apply_ops through a barrier)
             const T *src = reg_mats + (size_t)b * reg_mat_stride;
             for (int e = tid; e < p.n_mat; e += NT) mats_s[e] = src[e];
@@ -967,7 +979,7 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
             staged_b = b;
             restaged = true;
         }
-        if (p.fan_op >= 0) {
+        if (VAR >= 1 && p.fan_op >= 0) {
             // out-of-tile leaves of the fan: one 256-entry table per (chunk of 8 qubits, center), indexed by the tile base
             const DevOp &fo = p.ops[p.fan_op];
             const V *X = tabs_b + fo.mat_off + 1 + ((size_t)fan_nc << fan_m);
@@ -980,8 +992,8 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
             }
         }
         mbar_wait(&full[s], parity);
-        if (p.n_diag || restaged || p.fan_op >= 0) __syncthreads();
-        if (p.fan_op >= 0) {
+        if ((VAR >= 1 && (p.n_diag || p.fan_op >= 0)) || restaged) __syncthreads();
+        if (VAR >= 1 && p.fan_op >= 0) {
             if (tid < fan_nc) {
                 V c;
                 c.x = (T)1; c.y = (T)0;

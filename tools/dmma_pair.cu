@@ -82,13 +82,13 @@ __global__ void __launch_bounds__(128, 3) k_dfma(const __grid_constant__ DevOp o
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     double2 *tile = reinterpret_cast<double2 *>(smem);
-    double *mats = reinterpret_cast<double *>(smem + 2048 * 16);
+    double *mats = reinterpret_cast<double *>(smem + 2048 * 16);   // gate A in a slot of 48 scalars, gate B after it (production layout)
     const int tid = threadIdx.x;
     for (int i = tid; i < 2048; i += 128) tile[swz<double>(i)] = make_double2(1.0 / (1 + i), 0.5 / (1 + i));
-    if (tid < 64) mats[tid] = mats_g[tid];
+    if (tid < 64) mats[tid < 32 ? tid : tid + 16] = mats_g[tid];
     __syncthreads();
     for (int it = 0; it < iters; it++) {
-        op_pair<double, 2, 2, 2, 128>(tile, op, mats, 11, tid);
+        op_pair<double, 2, 2, 2, 128, false>(tile, op, mats, 11, tid);
         __syncthreads();
     }
     if (out) for (int i = tid; i < 2048; i += 128) out[(size_t)blockIdx.x * 2048 + i] = tile[swz<double>(i)];
@@ -156,6 +156,7 @@ int main(int argc, char **argv)
         // production op: local bits [0,2) = gate A, [2,4) = gate B; seg masks as encode_pass builds them
         DevOp d{};
         d.kind = OP_PAIR; d.k = 2; d.k2 = 2; d.s = 2; d.nfix = 4;
+        for (int m = 0; m < 4; m++) d.sboff[m] = (uint16_t)(((1u << cs.bits[m]) ^ (((1u << cs.bits[m]) >> 3) & 7u)));
         std::vector<int> fix(cs.bits, cs.bits + 4);
         for (int m = 0; m < 4; m++) d.tbit[m] = (uint8_t)cs.bits[m];
         std::sort(fix.begin(), fix.end());

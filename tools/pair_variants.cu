@@ -25,7 +25,7 @@ using namespace cb200;
 struct CP {
     DevOp op[2];
     int off[2];
-    alignas(16) double mats[2 * 64];     // per op: gate A (re, im) x 16, gate B (re, im) x 16
+    alignas(16) double mats[2 * 96];     // per op: gate A (re, im) x 16 in a slot of 48 scalars, gate B likewise (production layout)
     alignas(16) double mats3[2 * 96];    // per op: gate A (c, -(c+d), d-c) x 16, gate B likewise
 };
 
@@ -116,7 +116,7 @@ __device__ __forceinline__ void pair_block(double2 *tile, const DevOp &op, const
         addr[j] = tile_s + (bidx ^ o);
         a[j] = lds_amp(addr[j], double2());
     }
-    if (MODE == 1) { gate_const<4, 2, 0>(a, mat); gate_const<4, 2, 2>(a, mat + 32); }
+    if (MODE == 1) { gate_const<4, 2, 0>(a, mat); gate_const<4, 2, 2>(a, mat + 48); }
     else { gate_mul3<4, 2, 0>(a, mat); gate_mul3<4, 2, 2>(a, mat + 48); }
 #pragma unroll
     for (int j = 0; j < D; j++) sts_amp(addr[j], a[j]);
@@ -127,16 +127,16 @@ __global__ void __launch_bounds__(128, CTAS) k_pair(const __grid_constant__ CP p
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     double2 *tile = reinterpret_cast<double2 *>(smem);
-    double *mats = reinterpret_cast<double *>(smem + 2048 * 16);
+    double *mats = reinterpret_cast<double *>(smem + 2048 * 16);   // (192 doubles)
     const int tid = threadIdx.x;
     for (int i = tid; i < 2048; i += 128) tile[swz<double>(i)] = make_double2(1.0 / (1 + i), 0.5 / (1 + i));
-    if (tid < 128) mats[tid] = mats_g[tid];
+    for (int e = tid; e < 192; e += 128) mats[e] = mats_g[e];
     __syncthreads();
     for (int it = 0; it < iters; it++) {
         const int o = it & 1;   // two ops alternate: the op index is a run-time (uniform) value, as in the pass kernel
-        if (MODE == 0) op_pair<double, 2, 2, 2, 128>(tile, p.op[o], mats + p.off[o], 11, tid);
+        if (MODE == 0) op_pair<double, 2, 2, 2, 128, false>(tile, p.op[o], mats + p.off[o], 11, tid);
         else if (MODE == 1) pair_block<1>(tile, p.op[o], p.mats + p.off[o], tid);
-        else pair_block<2>(tile, p.op[o], p.mats3 + (p.off[o] >> 1) * 3, tid);
+        else pair_block<2>(tile, p.op[o], p.mats3 + p.off[o], tid);
         __syncthreads();
     }
     if (out) for (int i = tid; i < 2048; i += 128) out[(size_t)blockIdx.x * 2048 + i] = tile[swz<double>(i)];
@@ -166,6 +166,7 @@ static void fill_op(DevOp &d, const int bits[4])
 {
     d = DevOp{};
     d.kind = OP_PAIR; d.k = 2; d.k2 = 2; d.s = 2; d.nfix = 4;
+    for (int m = 0; m < 4; m++) d.sboff[m] = (uint16_t)(((1u << bits[m]) ^ (((1u << bits[m]) >> 3) & 7u)));
     std::vector<int> fix(bits, bits + 4);
     for (int m = 0; m < 4; m++) d.tbit[m] = (uint8_t)bits[m];
     std::sort(fix.begin(), fix.end());
@@ -219,20 +220,20 @@ int main(int argc, char **argv)
     double2 *d_out = nullptr;
     cudaMalloc(&d_out, (size_t)2048 * sizeof(double2));
     double *d_m = nullptr;
-    cudaMalloc(&d_m, 128 * sizeof(double));
+    cudaMalloc(&d_m, 192 * sizeof(double));
     const size_t smem3 = 66 * 1024, smem4 = 2048 * 16 + 2048;   // 3 CTAs per SM as in the pass kernel (two 32 KB stages); 4-5 if the tile were single-buffered
     printf("%-40s %10s %10s %10s %10s %10s %10s\n", "bit placement (op 0 / op 1)", "smem x3", "const x3", "mul3 x3", "const x4", "mul3 x4", "mul3 x5");
     for (const Case &cs : cases) {
         CP p{};
         fill_op(p.op[0], cs.b0);
         fill_op(p.op[1], cs.b1);
-        p.off[0] = 0; p.off[1] = 64;
-        for (int g = 0; g < 4; g++) haar4(rng, p.mats + 32 * g);
+        p.off[0] = 0; p.off[1] = 96;
+        for (int g = 0; g < 4; g++) haar4(rng, p.mats + 48 * g);
         for (int e = 0; e < 64; e++) {
-            const double c = p.mats[2 * e], d = p.mats[2 * e + 1];
+            const double c = p.mats[48 * (e / 16) + 2 * (e % 16)], d = p.mats[48 * (e / 16) + 2 * (e % 16) + 1];
             p.mats3[3 * e] = c; p.mats3[3 * e + 1] = -(c + d); p.mats3[3 * e + 2] = d - c;
         }
-        cudaMemcpy(d_m, p.mats, 128 * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(d_m, p.mats, 192 * sizeof(double), cudaMemcpyHostToDevice);
         std::vector<double2> r0, r1, r2;
         const double t0 = run<0, 3>(p, d_m, 3, sms, iters, smem3, d_out, &r0);
         const double t1 = run<1, 3>(p, d_m, 3, sms, iters, smem3, d_out, &r1);
