@@ -442,16 +442,17 @@ def main():
     # two 2-qubit gates per pass (CB200_MAX_PASS_COST=8): few flops per byte, so the pass streams at the memory roofline.
     regimes = {}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # cost = sum over a pass's dense ops of 2^k: 8 = two 2-qubit gates per pass (memory IS the bound), 12 = three (the
-        # balance point asked for by the north star: HBM fraction >= 0.70 with the kernel still doing useful flops)
-        for cost, key in ((8, "hbm_bound_regime"), (12, "balanced_regime")):
+        # cost = sum over a pass's dense ops of 2^k: 8 = two 2-qubit gates per pass, two layers of the circuit (memory IS the
+        # bound); 16 = four gates per pass, the WHOLE circuit (the balance point asked for by the north star: HBM fraction
+        # >= 0.70 with the kernel doing useful flops)
+        for cost, key, rdepth in ((8, "hbm_bound_regime", 2), (16, "balanced_regime", depth)):
             os.environ["CB200_MAX_PASS_COST"] = str(cost)
             try:
                 sv2 = cb.StateVector(n, "double", device=local_rank)
                 st2 = torch.cuda.ExternalStream(sv2.stream(), device=torch.device("cuda", local_rank))
-                short = C.quantum_volume(n, depth=2, seed=SEED)
+                short = C.quantum_volume(n, depth=rdepth, seed=SEED)
                 best = None
-                for rep in range(3):
+                for rep in range(3 if rdepth <= 2 else 1):
                     sv2.reset(); sv2.run(short[:1]); sv2.flush(); sv2.sync()      # state initialised, first gate done
                     a0 = sv2.stats()
                     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -465,7 +466,7 @@ def main():
                 np2 = a1["passes"] - a0["passes"]
                 peak2, _ = load_peaks()
                 gbs = 2.0 * S * np2 / (best / 1e3) / 1e9
-                regimes[key] = {"workload": f"QV-{n} depth 2 ({len(short) - 1} gates), planner capped at {cost // 4} two-qubit gates per pass",
+                regimes[key] = {"workload": f"QV-{n} depth {rdepth} ({len(short) - 1} gates), planner capped at {cost // 4} two-qubit gates per pass",
                                 "tile_passes": np2, "gates_per_pass": (len(short) - 1) / np2, "ms": best, "achieved": gbs, "peak": peak2,
                                 "unit": "GB/s", "frac": gbs / peak2, "gates_per_s": (len(short) - 1) / (best / 1e3)}
                 sv2.close()
@@ -533,10 +534,14 @@ def main():
                          "algorithmic_bytes_per_launch": 2 * S,
                          "note": "the step is fp64-pipe bound (see fp64_pipe): fuller passes raise gates/s and lower this fraction; "
                                  "with one op per pass the same kernel streams at 0.93-1.0 of the peak (DESIGN.md section 6)"},
-            # explanatory: the co-bound.  A Haar SU(4) gate costs 16 FMA (32 flop) per amplitude; the peak is the DFMA
-            # rate measured with tools/fp64_pipes.cu on this pool's B200 (profiles/fp64_pipes_r01.txt)
-            "fp64_pipe": {"achieved": gates * float(2 ** n) * 32.0 / (ms_per_step / 1e3) / 1e12, "peak": 33.1,
-                          "unit": "TFLOP/s", "frac": gates * float(2 ** n) * 32.0 / (ms_per_step / 1e3) / 1e12 / 33.1,
+            # explanatory: the co-bound.  A Haar SU(4) gate is 16 complex multiply-adds = 32 flop per amplitude in the textbook
+            # count ("useful"); the kernel executes it with 3-multiplication complex products: 12 FMA + 1 ADD = 13 FP64
+            # instructions per amplitude (tile_kernel.cuh: rows2_mul3).  frac = FP64 instruction slots used / the DFMA
+            # issue rate measured with tools/fp64_pipes.cu on this pool's B200 (33.1 TFLOP/s = 16.55 T instr/s).
+            "fp64_pipe": {"achieved": gates * float(2 ** n) * 13.0 * 2.0 / (ms_per_step / 1e3) / 1e12, "peak": 33.1,
+                          "unit": "TFLOP/s", "frac": gates * float(2 ** n) * 13.0 * 2.0 / (ms_per_step / 1e3) / 1e12 / 33.1,
+                          "useful_tflops_at_32_flop_per_amplitude_gate": gates * float(2 ** n) * 32.0 / (ms_per_step / 1e3) / 1e12,
+                          "fp64_instructions_per_amplitude_gate": 13,
                           "peak_source": "measured DFMA rate, profiles/fp64_pipes_r01.txt"},
             "e2e": {"value": gates * world / e2e_s, "unit": "gates/s", "h2d_bytes_per_step": est["h2d_bytes"] + len(task_text),
                     "d2h_bytes_per_step": est["d2h_bytes"], "ms_per_step": e2e_s * 1e3, "shots": SHOTS,

@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ, src.rsplit(".", 1)[0] + ".o")
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr):
-            cmd = [_nvcc(), *NVCC_FLAGS, "-x", "cu", "-c", s, "-o", o]
+            cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("CB200_NVCC_EXTRA", "").split(), "-x", "cu", "-c", s, "-o", o]   # (extra flags: experiments)
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), file=sys.stderr)

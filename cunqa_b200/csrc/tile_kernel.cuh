@@ -386,12 +386,15 @@ __device__ __forceinline__ void op_perm(typename Vec2<T>::type *tile, const DevO
 //   * the phase fan (below).
 // A QFT pass -- H / ladder blocks on six qubits -- is two such sweeps: [dense, tables, dense, tables] and [dense, fan].
 // (Not inlined: the sweep's register allocation must not disturb the dense-gate paths of the kernel.)
+#ifndef CB200_SWEEP_INLINE
+#define CB200_SWEEP_INLINE __noinline__
+#endif
 template <typename T> struct FanCtx {
     const typename Vec2<T>::type *fanT, *fanc;   // T[c][2^m] and this tile's center factors (shared memory)
 };
 
 template <typename T, int NT>
-__device__ __noinline__ void op_sweep(typename Vec2<T>::type *tile, const PassParams<T> &p, const int sw, const T *mats,
+__device__ CB200_SWEEP_INLINE void op_sweep(typename Vec2<T>::type *tile, const PassParams<T> &p, const int sw, const T *mats,
                                       const typename Vec2<T>::type *__restrict__ diag_tabs,
                                       const typename Vec2<T>::type *const *tptr, const uint16_t *lut, const FanCtx<T> fan, const int tid)
 {
