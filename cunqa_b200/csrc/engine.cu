@@ -55,6 +55,7 @@ void State::init_options(int gbits)
     opt.diag_fuse_always = env_int("CB200_DIAG_FUSE_ALWAYS", 1) != 0;
     opt.stage_diag = env_int("CB200_STAGE_DIAG", 0) != 0;
     opt.fan = env_int("CB200_FAN", 1) != 0;
+    opt.lin_perm = env_int("CB200_LIN_PERM", 1) != 0;
     if (gbits) opt.global_mask = ((1ull << gbits) - 1ull) << n_local_;
     queue = OpQueue(n, batch, opt);
 }

@@ -1610,13 +1610,13 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
             if (!encode_pass<double>(p, ops, nq, 1, pp, diag, err, opt.enc_flags())) throw std::runtime_error(err);
             o.set("diag_entries", Json::integer((long long)diag.size()));
             o.set("device_ops", Json::integer(pp.n_ops));
-            {   // one letter per device op: D dense, T diagonal table, X / S permutations, P register-block pair, F phase fan;
+            {   // one letter per device op: D dense, T diagonal table, X / S permutations, P register-block pair, F phase fan, L linear permutation (a run of X / CX / SWAP);
                 // lower case = applied in the same sweep as the op before it (a diagonal run folded into the next dense gate)
                 std::string kinds;
                 for (int q = 0; q < pp.n_ops; q++) {
-                    static const char letter[] = {'D', 'T', 'X', 'S', 'P', 'F'};
+                    static const char letter[] = {'D', 'T', 'X', 'S', 'P', 'F', 'L'};
                     kinds += letter[pp.ops[q].kind];
-                    if (pp.ops[q].kind == OP_DIAG) kinds += std::to_string((int)pp.ops[q].k);
+                    if (pp.ops[q].kind == OP_DIAG || pp.ops[q].kind == OP_LINPERM) kinds += std::to_string((int)pp.ops[q].k);   // table width / gates in the run
                     if (pp.ops[q].kind == OP_PAIR && !(pp.ops[q].k == 2 && pp.ops[q].k2 == 2 && pp.ops[q].s == 2))   // register block other than the common 4-bit one
                         kinds += "(" + std::to_string((int)pp.ops[q].k) + std::to_string((int)pp.ops[q].k2) + std::to_string((int)pp.ops[q].s) + ")";
                 }

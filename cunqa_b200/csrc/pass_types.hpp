@@ -39,21 +39,32 @@ enum OpKind : uint8_t {
                    // joins two centers or two leaves.  amplitude *= g * prod_{centers b set} [c_b(tile) * T_b[leaf bits]].
                    // This is what the controlled-phase ladders of a QFT leave behind once the terms that commute with the
                    // rest of the pass are pulled out of the per-amplitude tables (planner.cpp: encode_pass).
+    OP_LINPERM = 6, // a run of unconditioned X / CX / SWAP gates as ONE permutation of the tile: X, CX and SWAP map index
+                    // bits linearly over GF(2), so a run of them moves the amplitude at tile index s(d) = c ^ M d to d.  The
+                    // shared-memory swizzle is linear too and is folded in: lin[i] (uint16 view of bytes 4..35 of the
+                    // descriptor, DevOp::lin) = swz(column i of M) for tile bit i, lin[15] = swz(c): the slot of the source
+                    // of d is the XOR of lin[15] and the lin[i] of the bits set in d.  One load + one store per amplitude
+                    // and two barriers whatever the length of the run (a CX ladder of an ansatz layer: 6-9 gates).
 };
 
 struct DevOp {
     uint8_t kind;
-    uint8_t k;       // DENSE: #targets; DIAG: #qubits of the table; PAIR: #targets of gate A
+    uint8_t k;       // DENSE: #targets; DIAG: #qubits of the table; PAIR: #targets of gate A; LINPERM: #gates of the run
     uint8_t nfix;    // DENSE/PERM/PAIR: number of entries in fixpos (targets + in-tile controls)
     uint8_t has_mask;
-    uint8_t tbit[8];        // DENSE/PERM: tile-bit position of target m
     union {
-        uint8_t fixpos[kMaxFix]; // ascending tile-bit positions where a bit is inserted into the group index
-        uint16_t sboff[4];       // PAIR: swizzled tile index of local bit m, swz(1 << tbit[m])
-    };
-    union {
-        uint8_t dsrc[kMaxDiagK]; // DIAG: source of table-index bit m: <64 tile bit, >=64 physical qubit (v-64) outside the tile
-        uint16_t seg[6];         // PAIR: group index -> tile index deposit, idx = sum_k (g & seg[k]) << k  (k <= nfix)
+        struct {
+            uint8_t tbit[8];        // DENSE/PERM: tile-bit position of target m
+            union {
+                uint8_t fixpos[kMaxFix]; // ascending tile-bit positions where a bit is inserted into the group index
+                uint16_t sboff[4];       // PAIR: swizzled tile index of local bit m, swz(1 << tbit[m])
+            };
+            union {
+                uint8_t dsrc[kMaxDiagK]; // DIAG: source of table-index bit m: <64 tile bit, >=64 physical qubit (v-64) outside the tile
+                uint16_t seg[6];         // PAIR: group index -> tile index deposit, idx = sum_k (g & seg[k]) << k  (k <= nfix)
+            };
+        };
+        uint16_t lin[16];           // LINPERM: swizzled columns of the index map, [15] = swizzled constant
     };
     uint32_t ctrl_in;   // in-tile control bits (OR-ed into the tile index; those bits are in fixpos)
     uint32_t mat_off;   // DENSE: scalar offset into PassParams::mats; DIAG: element offset into the diag-table buffer

@@ -625,6 +625,54 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
             }
         }
     }
+    // ---- runs of unconditioned X / CX / SWAP gates collapse into one linear permutation of the tile (OP_LINPERM) -----
+    if ((flags & kEncLinPerm) && t >= 4 && t <= (sizeof(T) == 8 ? 12 : 13)) {
+        auto lin_ok = [&](const DevOp &d) {
+            if (d.has_mask || d.ctrl_out != 0) return false;
+            if (d.kind == OP_PERMX) return popcount64(d.ctrl_in) <= 1;
+            return d.kind == OP_SWAP && d.ctrl_in == 0;
+        };
+        int remap[kMaxOps + 1];
+        int w = 0;
+        for (int o = 0; o < nops;) {
+            int e = o;
+            while (e < nops && lin_ok(out.ops[e])) e++;
+            if (e - o < 2) { remap[o] = w; if (w != o) out.ops[w] = out.ops[o]; w++; o++; continue; }
+            // state_after[d] = state_before[s(d)] with s = f_o . f_(o+1) . ... . f_(e-1) (every gate is its own inverse):
+            // evaluate s on 0 and on the unit vectors -- it is affine over GF(2)
+            auto src = [&](uint32_t idx) {
+                for (int q = e - 1; q >= o; q--) {
+                    const DevOp &g = out.ops[q];
+                    if (g.kind == OP_PERMX) {
+                        if ((idx & g.ctrl_in) == g.ctrl_in) idx ^= 1u << g.tbit[0];
+                    } else {
+                        const uint32_t a = (idx >> g.tbit[0]) & 1u, b = (idx >> g.tbit[1]) & 1u;
+                        if (a != b) idx ^= (1u << g.tbit[0]) | (1u << g.tbit[1]);
+                    }
+                }
+                return idx;
+            };
+            auto swz_t = [&](uint32_t i) { return sizeof(T) == 8 ? (i ^ ((i >> 3) & 7u)) : (i ^ (((i >> 4) & 7u) << 1)); };
+            DevOp L;
+            std::memset(&L, 0, sizeof(L));
+            L.kind = OP_LINPERM;
+            L.k = (uint8_t)std::min(255, e - o);
+            L.mask_row = -1;
+            const uint32_t c0 = src(0);
+            for (int i = 0; i < t; i++) L.lin[i] = (uint16_t)swz_t(src(1u << i) ^ c0);
+            L.lin[15] = (uint16_t)swz_t(c0);
+            for (int q = o; q < e; q++) remap[q] = w;
+            out.ops[w++] = L;
+            o = e;
+        }
+        remap[nops] = w;
+        if (w != nops) {
+            for (int sl = 0; sl < out.n_diag; sl++) out.diag_op[sl] = (uint8_t)remap[out.diag_op[sl]];
+            if (out.fan_op >= 0) out.fan_op = remap[out.fan_op];
+            for (int o = w; o < nops; o++) std::memset(&out.ops[o], 0, sizeof(DevOp));
+            nops = w;
+        }
+    }
     out.n_ops = nops;
     out.n_mat = mat_used;
     out.needs_full = (out.n_diag > 0 || out.fan_op >= 0) ? 1 : 0;  // the lean kernel variant carries no diagonal-run / fan code

@@ -39,6 +39,7 @@ struct HostOp {
 constexpr int kEncPairOps = 1;         // register-block adjacent dense gates
 constexpr int kEncDiagFuseAlways = 2;  // always fold a diagonal run into the dense gate that follows it (experiments)
 constexpr int kEncNoStage = 4;
+constexpr int kEncLinPerm = 64;        // runs of unconditioned X / CX / SWAP gates as one linear permutation of the tile (OP_LINPERM)
 constexpr int kEncPlainMats = 32;      // never the three-multiplication matrix form (per-register matrices, A/B experiments)
 constexpr int kEncFan = 16;            // pull commuting phase-ladder terms into a fan at the end of the pass (TMA kernel, no per-tile conditions)         // no per-tile shared-memory staging of diagonal sub-tables (experiments)
 
@@ -59,7 +60,8 @@ struct PlanOptions {
     // (258 per amplitude), not by the table loads.  Both stay switchable: CB200_DIAG_FUSE_ALWAYS, CB200_STAGE_DIAG.
     bool diag_fuse_always = true, stage_diag = false;
     bool fan = true;           // CB200_FAN: phase fans (OP_FAN) for controlled-phase ladders
-    int enc_flags() const { return (pair_ops ? kEncPairOps : 0) | (diag_fuse_always ? kEncDiagFuseAlways : 0) | (stage_diag ? 0 : kEncNoStage) | (fan ? kEncFan : 0); }
+    bool lin_perm = true;      // CB200_LIN_PERM: runs of X / CX / SWAP gates as one permutation of the tile (OP_LINPERM)
+    int enc_flags() const { return (pair_ops ? kEncPairOps : 0) | (diag_fuse_always ? kEncDiagFuseAlways : 0) | (stage_diag ? 0 : kEncNoStage) | (fan ? kEncFan : 0) | (lin_perm ? kEncLinPerm : 0); }
     uint64_t global_mask = 0;  // sharded state: physical qubits that select the rank (never fused into dense blocks)
 };
 

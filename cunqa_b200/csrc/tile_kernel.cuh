@@ -374,6 +374,44 @@ __device__ __forceinline__ void op_perm(typename Vec2<T>::type *tile, const DevO
     }
 }
 
+// ---- a run of X / CX / SWAP gates as one permutation of the tile (OP_LINPERM, pass_types.hpp) ----------------------
+// Thread g owns the destinations d = g | j << (t-4), j < 16 (lanes on the low tile bits: the stores of a warp hit distinct
+// banks); the slot of the source of d is lin[15] ^ XOR of lin[i] over the bits i set in d.  All loads, a barrier, all
+// stores.  A thread holds 16 amplitudes per trip; FP32 tiles of 2^13 amplitudes take two trips' worth of registers.
+template <typename T, int NT>
+__device__ __forceinline__ void op_linperm(typename Vec2<T>::type *tile, const DevOp &op, const int t, const int tid)
+{
+    using V = typename Vec2<T>::type;
+    constexpr int TRIPS = sizeof(T) == 4 ? 2 : 1;
+    const int hb = t - 4;                       // tile bits [hb, t) count the thread's 16 amplitudes
+    const uint32_t ngroups = 1u << hb;
+    uint32_t jc[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+        jc[j] = ((j & 1) ? (uint32_t)op.lin[hb] : 0u) ^ ((j & 2) ? (uint32_t)op.lin[hb + 1] : 0u) ^ ((j & 4) ? (uint32_t)op.lin[hb + 2] : 0u) ^
+                ((j & 8) ? (uint32_t)op.lin[hb + 3] : 0u);
+    V v[TRIPS][16];
+#pragma unroll
+    for (int tr = 0; tr < TRIPS; tr++) {
+        const uint32_t g = (uint32_t)tid + (uint32_t)tr * NT;
+        if (g < ngroups) {
+            uint32_t sb = op.lin[15];
+            for (int i = 0; i < hb; i++) sb ^= ((g >> i) & 1u) ? (uint32_t)op.lin[i] : 0u;
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[tr][j] = tile[sb ^ jc[j]];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int tr = 0; tr < TRIPS; tr++) {
+        const uint32_t g = (uint32_t)tid + (uint32_t)tr * NT;
+        if (g < ngroups) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) tile[swz<T>(g | ((uint32_t)j << hb))] = v[tr][j];
+        }
+    }
+}
+
 // ---- register sweeps: dense gates, diagonal runs and the phase fan on the thread's resident amplitudes ------------
 // Each thread owns 16 amplitudes: the 2^4 settings of four "register bits" rb[0..3] of the tile index, chosen per sweep
 // by the host (encode_pass).  Between ONE load and ONE store of the tile the sweep applies a short program:
@@ -654,6 +692,9 @@ __device__ __forceinline__ void apply_ops(const PassParams<T> &p, const T *mats,
                     op_fan_slow<T>(tile, op, p.fan_q, p.fan_chunks, diag_tabs + op.mat_off, base, t, tid, NT);
                     __syncthreads();
                 }
+            } else if (op.kind == OP_LINPERM) {
+                op_linperm<T, NT>(tile, op, t, tid);
+                __syncthreads();
             } else {
                 op_perm<T, NT>(tile, op, t, tid);
                 __syncthreads();
