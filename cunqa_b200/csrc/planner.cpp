@@ -818,18 +818,18 @@ bool encode_pass(const Pass &pass, const std::vector<HostOp> &ops, int n, int ba
     out.cond_mask = 0;
     for (int o = 0; o < nops; o++)
         if (out.ops[o].ctrl_out != 0 || out.ops[o].has_mask) out.cond_mask |= 1ull << o;
-    // Passes that the lean kernel variant serves without per-tile conditions (register blocks and <= 2-qubit gates only:
+    // Passes that the lean kernel variant serves (register blocks, <= 2-qubit gates and permutations only:
     // the FP64-pipe-bound passes of dense circuits) get the fast forms of tile_kernel.cuh: every register block is widened
     // to four local bits, a lone uncontrolled 2-qubit gate becomes a block of one gate, and in FP64 the matrices are kept
     // in the three-multiplication form, which the kernel reads from its parameters through the uniform datapath
     // (mat_form 1; FP32: plain elements, mat_form 2).  Per-register matrices (kEncPlainMats: they live in global memory) and
     // every other pass keep natural blocks and plain elements (mat_form 0).
     out.mat_form = 0;
-    if (pair_ops && !(flags & kEncPlainMats) && out.cond_mask == 0 && out.needs_full == 0 && t >= 4) {
+    if (pair_ops && !(flags & kEncPlainMats) && out.needs_full == 0 && t >= 4) {
         out.mat_form = sizeof(T) == 8 ? 1 : 2;
         for (int o = 0; o < nops; o++) {
             DevOp &d = out.ops[o];
-            if (d.kind == OP_DENSE && d.k == 2 && d.nfix == 2) {
+            if (d.kind == OP_DENSE && d.k == 2 && d.nfix == 2 && d.ctrl_out == 0 && !d.has_mask) {
                 d.kind = OP_PAIR;
                 d.k2 = 0;
                 d.s = 0;

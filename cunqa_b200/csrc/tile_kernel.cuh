@@ -390,25 +390,23 @@ __device__ __forceinline__ void op_linperm(typename Vec2<T>::type *tile, const D
     for (int j = 0; j < 16; j++)
         jc[j] = ((j & 1) ? (uint32_t)op.lin[hb] : 0u) ^ ((j & 2) ? (uint32_t)op.lin[hb + 1] : 0u) ^ ((j & 4) ? (uint32_t)op.lin[hb + 2] : 0u) ^
                 ((j & 8) ? (uint32_t)op.lin[hb + 3] : 0u);
+    // (threads past the last group repeat it: they load and store the same values as its owner, so the amplitudes stay in
+    // registers without a guard around the barrier)
     V v[TRIPS][16];
 #pragma unroll
     for (int tr = 0; tr < TRIPS; tr++) {
-        const uint32_t g = (uint32_t)tid + (uint32_t)tr * NT;
-        if (g < ngroups) {
-            uint32_t sb = op.lin[15];
-            for (int i = 0; i < hb; i++) sb ^= ((g >> i) & 1u) ? (uint32_t)op.lin[i] : 0u;
+        const uint32_t g = min((uint32_t)tid + (uint32_t)tr * NT, ngroups - 1u);
+        uint32_t sb = op.lin[15];
+        for (int i = 0; i < hb; i++) sb ^= ((g >> i) & 1u) ? (uint32_t)op.lin[i] : 0u;
 #pragma unroll
-            for (int j = 0; j < 16; j++) v[tr][j] = tile[sb ^ jc[j]];
-        }
+        for (int j = 0; j < 16; j++) v[tr][j] = tile[sb ^ jc[j]];
     }
     __syncthreads();
 #pragma unroll
     for (int tr = 0; tr < TRIPS; tr++) {
-        const uint32_t g = (uint32_t)tid + (uint32_t)tr * NT;
-        if (g < ngroups) {
+        const uint32_t g = min((uint32_t)tid + (uint32_t)tr * NT, ngroups - 1u);
 #pragma unroll
-            for (int j = 0; j < 16; j++) tile[swz<T>(g | ((uint32_t)j << hb))] = v[tr][j];
-        }
+        for (int j = 0; j < 16; j++) tile[swz<T>(g | ((uint32_t)j << hb))] = v[tr][j];
     }
 }
 

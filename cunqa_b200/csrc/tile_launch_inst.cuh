@@ -37,16 +37,17 @@ cudaError_t launch_tile_pass_tma<CB200_T, CB200_NT>(const PassParams<CB200_T> &p
                                                 (const T *)l.reg_mats, l.reg_mat_stride, l.reg_diag_stride);
         return cudaGetLastError();
     };
+    if (p.mat_form != 0) {   // lean pass with widened register blocks (encode_pass): FP64 -> form 1, FP32 -> form 2
+        constexpr int kForm = sizeof(T) == 8 ? 1 : 2;
+        if (l.reg_mats != nullptr || p.needs_full != 0 || p.mat_form != kForm) return cudaErrorInvalidValue;   // (always two stages)
+        if (cnd) return go(tile_pass_tma_kernel<T, N, true, 0, 2, kForm>, seen[7]);
+        return go(tile_pass_tma_kernel<T, N, false, 0, 2, kForm>, seen[6]);
+    }
     if (l.stages == 3) {
         if (cnd) return go(tile_pass_tma_kernel<T, N, true, 2, 3>, seen[0]);
         return go(tile_pass_tma_kernel<T, N, false, 2, 3>, seen[1]);   // (three stages: experiments only, full variant)
     }
     if (cnd) return go(tile_pass_tma_kernel<T, N, true, 2, 2>, seen[2]);
-    if (p.mat_form != 0) {   // lean pass with widened register blocks (encode_pass): FP64 -> form 1, FP32 -> form 2
-        constexpr int kForm = sizeof(T) == 8 ? 1 : 2;
-        if (l.reg_mats != nullptr || var != 0 || p.mat_form != kForm) return cudaErrorInvalidValue;
-        return go(tile_pass_tma_kernel<T, N, false, 0, 2, kForm>, seen[6]);
-    }
     if (var == 0) return go(tile_pass_tma_kernel<T, N, false, 0, 2>, seen[3]);
     if (var == 1) return go(tile_pass_tma_kernel<T, N, false, 1, 2>, seen[4]);
     return go(tile_pass_tma_kernel<T, N, false, 2, 2>, seen[5]);
