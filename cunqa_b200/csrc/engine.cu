@@ -485,7 +485,8 @@ void State::flush_registers_t()
             b1++;
         cur_reg_ = b0;
         bool shared = false;
-        if (b1 - b0 >= 2) {
+        static const bool uniform_ok = env_int("CB200_REG_UNIFORM", 1) != 0;   // (0: every register by itself -- A/B switch)
+        if (b1 - b0 >= 2 && uniform_ok) {
             // (a layout that depends on the numbers after all -- e.g. a product that happens to be diagonal for one
             // register only -- is detected before anything is launched: those registers then run one by one)
             try { launch_uniform_t<T>(b0, b1 - b0); shared = true; uniform_flushes++; }
@@ -518,14 +519,28 @@ void State::launch_uniform_t(int b0, int nb)
     std::vector<PassParams<T>> params(passes.size());
     std::vector<cplx> diag0;
     std::string err;
-    for (size_t i = 0; i < passes.size(); i++)
-        if (!encode_pass<T>(passes[i], ops0, n_local_, G, params[i], diag0, err, opt.enc_flags() | kEncPlainMats)) throw Unsupported(err);
+    // A pass that the lean FP64 kernel variant serves keeps the fast forms of its matrices (encode_pass: mat_form 1), which
+    // the kernel reads from its parameters: such a pass is launched over as many registers at a time as their matrices fit
+    // into one parameter block (state b reads mats + b * reg_stride); every other pass reads row b of a matrix buffer in
+    // global memory (reg_mats).
+    std::vector<int> pflags(passes.size(), opt.enc_flags() | kEncPlainMats);
+    for (size_t i = 0; i < passes.size(); i++) {
+        if (sizeof(T) == 8 && const_mats_ && use_tma_) {
+            std::vector<cplx> none;
+            if (!encode_pass<T>(passes[i], ops0, n_local_, G, params[i], none, err, opt.enc_flags())) throw Unsupported(err);
+            if (params[i].mat_form == 1 && params[i].n_mat > 0) pflags[i] = opt.enc_flags();
+        }
+        if (!encode_pass<T>(passes[i], ops0, n_local_, G, params[i], diag0, err, pflags[i])) throw Unsupported(err);
+    }
+    auto fast = [&](size_t i) { return !(pflags[i] & kEncPlainMats); };
+    std::vector<std::vector<T>> fast_mats(passes.size());   // [pass][register * stride]: matrices of the fast passes
     const size_t D = diag0.size();
     std::vector<size_t> mat_off(passes.size() + 1, 0);   // scalar offset of pass i's [G][stride_i] block
     std::vector<uint32_t> mat_stride(passes.size());
     for (size_t i = 0; i < passes.size(); i++) {
         mat_stride[i] = (uint32_t)((params[i].n_mat + 1) & ~1);
-        mat_off[i + 1] = mat_off[i] + (size_t)mat_stride[i] * G;
+        mat_off[i + 1] = mat_off[i] + (fast(i) ? 0 : (size_t)mat_stride[i] * G);
+        if (fast(i)) fast_mats[i].assign((size_t)mat_stride[i] * G, (T)0);
     }
     const size_t mats_bytes = mat_off.back() * sizeof(T), diag_bytes = (size_t)G * D * sizeof(V);
     if (mats_bytes > regmats_cap_) {
@@ -553,11 +568,13 @@ void State::launch_uniform_t(int b0, int nb)
         for (size_t i = 0; i < passes.size(); i++) {
             const PassParams<T> *src = &params[i];
             if (g > 0) {
-                if (!encode_pass<T>(passes[i], ops, n_local_, G, tmp, dg, err, opt.enc_flags() | kEncPlainMats)) throw Unsupported(err);
-                if (tmp.n_mat != params[i].n_mat || tmp.n_ops != params[i].n_ops) throw Unsupported("internal: register passes differ in layout");
+                if (!encode_pass<T>(passes[i], ops, n_local_, G, tmp, dg, err, pflags[i])) throw Unsupported(err);
+                if (tmp.n_mat != params[i].n_mat || tmp.n_ops != params[i].n_ops || tmp.mat_form != params[i].mat_form)
+                    throw Unsupported("internal: register passes differ in layout");
                 src = &tmp;
             }
-            std::memcpy(hm + mat_off[i] + (size_t)g * mat_stride[i], src->mats, sizeof(T) * (size_t)src->n_mat);
+            T *dst = fast(i) ? fast_mats[i].data() + (size_t)g * mat_stride[i] : hm + mat_off[i] + (size_t)g * mat_stride[i];
+            std::memcpy(dst, src->mats, sizeof(T) * (size_t)src->n_mat);
         }
         const std::vector<cplx> &d = g == 0 ? diag0 : dg;
         if (d.size() != D) throw Unsupported("internal: register diagonal tables differ in layout");
@@ -589,6 +606,43 @@ void State::launch_uniform_t(int b0, int nb)
         if (tma_max_ctas_ > 0) ctas = std::min(ctas, tma_max_ctas_);
         const bool tma = use_tma_ && p.L >= aprs + (box_bits >= aprs + 3 ? 0 : 1) && view_bytes >= 128 && smem_tma <= max_smem_;
         const T *rm = reinterpret_cast<const T *>(d_regmats_) + mat_off[i];
+        if (fast(i) && tma) {
+            // registers per launch: as many as fit into the parameter block's matrix storage
+            const int K = std::max(1, std::min<int>(G, kMatScalars / (int)mat_stride[i]));
+            for (int c0 = 0; c0 < G; c0 += K) {
+                const int kc = std::min(K, G - c0);
+                PassParams<T> pc = p;
+                pc.batch = kc;
+                pc.reg_stride = kc > 1 ? (int32_t)mat_stride[i] : 0;
+                std::memcpy(pc.mats, fast_mats[i].data() + (size_t)c0 * mat_stride[i], sizeof(T) * (size_t)mat_stride[i] * kc);
+                CUtensorMap tmap;
+                make_tensor_map(&tmap, run_bits, hi_q, b0 + c0, kc);
+                TmaLaunch l;
+                l.grid = (unsigned)std::min<uint64_t>(p.tiles_per_state * (uint64_t)kc, (uint64_t)num_sms_ * ctas);
+                l.smem = smem_tma;
+                l.stream = stream_;
+                l.diag_tabs = d_diag_;
+                l.flags = d_flags_;
+                l.box_bits = box_bits;
+                l.buf_stride = buf_stride;
+                l.refill_after = tma_refill_after_;
+                l.stages = stages;
+                l.device = device;
+                cudaError_t e;
+                if (nt == 256) e = launch_tile_pass_tma<T, 256>(pc, tmap, l);
+                else if (nt == 128) e = launch_tile_pass_tma<T, 128>(pc, tmap, l);
+                else if (nt == 64) e = launch_tile_pass_tma<T, 64>(pc, tmap, l);
+                else e = launch_tile_pass_tma<T, 32>(pc, tmap, l);
+                CB200_CUDA(e);
+                stats.launches++;
+                stats.h2d_bytes += sizeof(PassParams<T>) + sizeof(CUtensorMap);
+            }
+            stats.passes++;
+            stats.bytes += 2ull * view_bytes;
+            stats.fused_ops += (uint64_t)p.n_ops * (uint64_t)G;
+            continue;
+        }
+        if (fast(i)) throw Unsupported("internal: fast register pass without the TMA path");
         if (tma) {
             CUtensorMap tmap;
             make_tensor_map(&tmap, run_bits, hi_q, b0, nb);

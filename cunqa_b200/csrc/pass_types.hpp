@@ -93,6 +93,8 @@ struct PassParams {
     uint64_t chunk_mask, chunk_val;  // only tiles whose base satisfies (base & chunk_mask) == chunk_val are processed
                                      // (a sharded pass pipelined behind a chunked qubit exchange); 0 / 0 = every tile
     int32_t n_mat;      // scalars used in mats (staged into shared memory once per CTA)
+    int32_t reg_stride; // mat_form 1 with several registers in one launch: state b of the launch reads its matrices at
+                        // mats + b * reg_stride (0 = one set for all states)
     int32_t needs_full; // kernel variant: 0 = lean (1-2 qubit dense gates, common register blocks, permutations), 1 = lean +
                         // diagonal runs, 2 = full (dense k>=3, unusual register blocks, generic diagonal path)
     int32_t n_diag;     // number of OP_DIAG ops; diag_op[slot] = op index of the slot-th one

@@ -1045,7 +1045,7 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
             __syncthreads();
         }
 
-        apply_ops<T, NT, COND, VAR, decltype(refill), FORM>(p, FORM == 1 ? p.mats : mats_s, tile, tabs_b, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
+        apply_ops<T, NT, COND, VAR, decltype(refill), FORM>(p, FORM == 1 ? p.mats + (uint32_t)b * (uint32_t)p.reg_stride : mats_s, tile, tabs_b, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
                                     (COND || (16 * NT) != (1 << t)) ? nullptr : lut, tptr, refill_after, refill,
                                     (COND || (16 * NT) != (1 << t)) ? nullptr : fanT, fanc, mats_s);
 
