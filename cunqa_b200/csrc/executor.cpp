@@ -3,6 +3,7 @@
 #include "dist_plan.hpp"
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -419,12 +420,25 @@ Json Backend::run_static_parsed(const void *parsed_task)
     std::string key((size_t)c.num_clbits, '0');
     if (c.num_clbits <= 64) {
         // classical register of every shot as an integer, sorted: equal outcomes are adjacent, one string each
-        for (uint64_t &s : samples) {
-            uint64_t r = 0;
-            for (auto &qc : meas) r = (r & ~(1ull << qc.second)) | (((s >> qc.first) & 1ull) << qc.second);
-            s = r;
+        bool identity = (int)meas.size() == c.num_clbits;   // measure q -> c with q == c for every classical bit, each once
+        for (size_t i = 0; i < meas.size() && identity; i++) identity = meas[i].first == (int)i && meas[i].second == (int)i;
+        if (!identity) {
+            for (uint64_t &s : samples) {
+                uint64_t r = 0;
+                for (auto &qc : meas) r = (r & ~(1ull << qc.second)) | (((s >> qc.first) & 1ull) << qc.second);
+                s = r;
+            }
+        } else if (c.num_clbits < 64) {
+            const uint64_t keep = (1ull << c.num_clbits) - 1ull;
+            for (uint64_t &s : samples) s &= keep;
         }
         std::sort(samples.begin(), samples.end());
+        static const std::array<std::array<char, 8>, 256> kByteBits = [] {   // "00000000" .. "11111111", most significant bit first
+            std::array<std::array<char, 8>, 256> tb{};
+            for (int v = 0; v < 256; v++)
+                for (int b = 0; b < 8; b++) tb[v][7 - b] = ((v >> b) & 1) ? '1' : '0';
+            return tb;
+        }();
         // the counts object is rendered straight into JSON text: {"<bits>":n,...} (a 16-qubit ansatz at 1024 shots has
         // about a thousand distinct outcomes; building and dumping a node per outcome was a quarter of the evaluation)
         std::string text;
@@ -434,7 +448,11 @@ Json Backend::run_static_parsed(const void *parsed_task)
         for (size_t i = 0; i < samples.size();) {
             size_t j = i;
             while (j < samples.size() && samples[j] == samples[i]) j++;
-            for (int b = 0; b < c.num_clbits; b++) key[c.num_clbits - 1 - b] = ((samples[i] >> b) & 1ull) ? '1' : '0';
+            {   // classical bit 0 is the rightmost character: whole bytes from the table, the leading bits one by one
+                int b = 0;
+                for (; b + 8 <= c.num_clbits; b += 8) std::memcpy(&key[c.num_clbits - 8 - b], kByteBits[(samples[i] >> b) & 0xFFull].data(), 8);
+                for (; b < c.num_clbits; b++) key[c.num_clbits - 1 - b] = ((samples[i] >> b) & 1ull) ? '1' : '0';
+            }
             if (i) text += ',';
             text += '"';
             text += key;
