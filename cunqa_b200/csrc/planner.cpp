@@ -153,19 +153,29 @@ bool Fuser::try_merge(HostOp &prev, const HostOp &nw)
 void Fuser::push(HostOp op)
 {
     if (!opt.fuse || op.mask_row >= 0) { ops.push_back(std::move(op)); return; }
-    const uint64_t qm = op.qmask(), xm = op.xmask();
+    // `self`: where the op lives once it has merged with an earlier one.  A merge that widened the earlier op (a 1-qubit
+    // gate swallowed by the 2-qubit gate that follows it) goes on looking further back from there: the block may now
+    // contain other earlier gates too (ry(a), ry(b), cx(a,b): both rotations end up in the block, not one of them)
+    int self = -1;
     int steps = 0;
     for (int i = (int)ops.size() - 1; i >= 0 && steps < 64; --i, ++steps) {
+        const HostOp &cur = self >= 0 ? ops[self] : op;
+        const uint64_t qm = cur.qmask(), xm = cur.xmask();
         HostOp &prev = ops[i];
         const uint64_t pm = prev.qmask();
         if (!(pm & qm)) continue;      // disjoint: commutes
         if (prev.mask_row >= 0) break; // conditioned op: ordering barrier
-        if (try_merge(prev, op)) return;
+        if (try_merge(prev, cur)) {
+            if (self >= 0) ops.erase(ops.begin() + self);
+            if (ops[i].qmask() == pm || ops[i].kind != HostOp::DENSE) return;   // the earlier op kept its width: nothing new in reach
+            self = i;
+            continue;
+        }
         const bool commute = ((prev.xmask() & qm) == 0) && ((xm & pm) == 0);
         if (commute) continue;         // both act diagonally on the shared qubits
         break;
     }
-    ops.push_back(std::move(op));
+    if (self < 0) ops.push_back(std::move(op));
 }
 
 // scalars of kernel-parameter storage a dense k-qubit matrix takes (pass_types.hpp: 3 per element up to two qubits)
