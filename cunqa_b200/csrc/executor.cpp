@@ -1572,6 +1572,8 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
         if (o.contains("lookahead_min_qubits")) opt.lookahead_min_qubits = (int)o.at("lookahead_min_qubits").as_int();
         if (o.contains("fuse")) opt.fuse = o.at("fuse").as_bool();
         if (o.contains("fan")) opt.fan = o.at("fan").as_bool();
+        if (o.contains("lin_perm")) opt.lin_perm = o.at("lin_perm").as_bool();
+        if (o.contains("pair_ops")) opt.pair_ops = o.at("pair_ops").as_bool();
         if (o.contains("world")) world = (int)o.at("world").as_int();
         if (o.contains("rank")) rank = (int)o.at("rank").as_int();
     }

@@ -255,3 +255,64 @@ def test_batched_states_and_masked_gates(lib_built):
         assert list(bits) == [1, 0, 1, 0, 1]
         assert np.allclose(sv.norm(), 1.0, atol=1e-12)
         assert np.allclose(sv.prob1(5), [1, 0, 1, 0, 1], atol=1e-12)
+
+
+# ---- round 2: fast forms of the lean passes, linear permutations -----------------------------------------------------
+def _permutation_heavy(n, n_gates, seed):
+    """X / CX / SWAP runs between Haar blocks: what OP_LINPERM composes"""
+    rng = np.random.default_rng(seed)
+    ins = []
+    for g in range(n_gates):
+        q = list(map(int, rng.permutation(n)[:2]))
+        r = int(rng.integers(0, 8))
+        if r == 0:
+            ins.append(C.unitary_inst(C.haar_unitary(rng, 4), q))
+        elif r == 1:
+            ins.append({"name": "x", "qubits": q[:1]})
+        elif r == 2:
+            ins.append({"name": "h", "qubits": q[:1]})
+        elif r == 3:
+            ins.append({"name": "ccx", "qubits": q + [int(next(x for x in rng.permutation(n) if x not in q))]})
+        else:
+            ins.append({"name": "cx", "qubits": q})
+    return ins
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+@pytest.mark.parametrize("tile_bits", [6, 9, 11, 13])
+def test_linear_permutation_runs_match_oracle(lib_built, monkeypatch, tile_bits, precision):
+    """runs of X / CX gates applied as one GF(2)-linear permutation of the tile (OP_LINPERM): against the oracle at several
+    tile sizes (generic kernel, TMA kernels of 32 ... 256 threads, FP32 tiles of 2^13 amplitudes = two trips per thread),
+    and identical to the gate-by-gate permutations with the switch off"""
+    n = 15
+    monkeypatch.setenv("CB200_TILE_BITS", str(tile_bits))
+    ins = _permutation_heavy(n, 260, 40 + tile_bits)
+    ref, _ = O.run_static(ins, n, backend="c")
+    got, _ = run_gpu(ins, n, precision)
+    assert np.abs(got - ref.amplitudes()).max() < TOL[precision]
+    monkeypatch.setenv("CB200_LIN_PERM", "0")
+    plain, _ = run_gpu(ins, n, precision)
+    assert np.abs(got - plain).max() < (1e-14 if precision == "double" else 1e-6)   # a permutation moves amplitudes, it does no arithmetic
+
+
+def test_fast_forms_equal_plain_forms(lib_built, monkeypatch):
+    """QV-18 through the lean FP64 kernel in its fast forms (3-multiplication products, matrices from the kernel
+    parameters, widened blocks) and with plain matrices from shared memory (CB200_CONST_MATS=0): same state to rounding,
+    both equal to the oracle; the fast forms really ran (conditions inside the tile included: cx / ccx between the blocks)"""
+    n = 18
+    rng = np.random.default_rng(5)
+    ins = []
+    for layer in range(8):
+        perm = rng.permutation(n)
+        for k in range(n // 2):
+            ins.append(C.unitary_inst(C.haar_unitary(rng, 4), [int(perm[2 * k]), int(perm[2 * k + 1])]))
+        ins.append({"name": "cx", "qubits": [int(perm[0]), int(perm[3])]})
+        ins.append({"name": "ry", "qubits": [int(perm[5])], "params": [0.1 * layer + 0.05]})
+    ref, _ = O.run_static(ins, n, backend="c")
+    fast, st = run_gpu(ins, n)
+    monkeypatch.setenv("CB200_CONST_MATS", "0")
+    plain, _ = run_gpu(ins, n)
+    assert np.abs(fast - ref.amplitudes()).max() < 1e-12
+    assert np.abs(plain - ref.amplitudes()).max() < 1e-12
+    assert np.abs(fast - plain).max() < 1e-13
+    assert fidelity(fast, ref.amplitudes()) >= 1 - 1e-12

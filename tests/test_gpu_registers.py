@@ -180,3 +180,27 @@ def test_registers_with_phase_ladders_share_launches(backend):
     for g in (0, 2, 4):
         want = O.run_static(circ(thetas[g]) + C.measure_all(n), n, shots=shots, seed=9, backend="c")[1]
         assert res[g]["counts"] == want
+
+
+def test_fast_register_passes_equal_per_register_rows(lib_built, monkeypatch):
+    """register mode, FP64: lean passes keep their matrices in the kernel parameters, several registers per launch
+    (PassParams::reg_stride); CB200_CONST_MATS=0 sends every pass through the per-register matrix rows in global memory.
+    Same counts for the same seeds, and equal to the registers run one by one."""
+    n, G = 12, 9     # 9 registers: the last parameter block of a pass is not full
+    msgs = [C.task(C.hea_ansatz(n, 2, seed=11 + g), n, shots=300, seed=70 + g) for g in range(G)]
+    be = cb.Backend(0)
+    fast = be.execute_many(msgs)
+    info = be.batch_info()
+    be.close()
+    monkeypatch.setenv("CB200_CONST_MATS", "0")
+    be = cb.Backend(0)
+    rows = be.execute_many(msgs)
+    be.close()
+    monkeypatch.delenv("CB200_CONST_MATS")
+    be = cb.Backend(0)
+    solo = [be.execute(m) for m in msgs]
+    be.close()
+    assert info["uniform_flushes"] >= 1
+    for f, r, s in zip(fast, rows, solo):
+        assert "ERROR" not in f, f
+        assert f["counts"] == r["counts"] == s["counts"]

@@ -154,3 +154,34 @@ def test_phase_fan_takes_the_commuting_ladder_terms_of_a_qft_pass(lib_built):
             assert "fan" not in f
     # dense-only circuits never get one
     assert all("fan" not in p for p in cb.plan(C.task(C.quantum_volume(26, depth=4, seed=1), 26), {"fan": True})["passes"])
+
+
+def test_fuser_absorbs_both_rotations_into_the_entangler(lib_built):
+    """ry(a), ry(b), cx(a, b): the entangler swallows the rotation next to it and, widened, goes on to the other one
+    (round 2: a merge that widens the earlier op keeps looking further back)"""
+    ins = [{"name": "ry", "qubits": [0], "params": [0.3]}, {"name": "ry", "qubits": [1], "params": [1.1]},
+           {"name": "h", "qubits": [2]}, {"name": "cx", "qubits": [0, 1]}]
+    plan = cb.plan(C.task(ins, 3))
+    assert len(plan["ops"]) == 2                       # the block on (0, 1) and the h on 2
+    ref, _ = O.run_static(ins, 3, backend="numpy")
+    assert np.abs(replay_plan(plan, 3) - ref.amplitudes()).max() < 1e-12
+    # a gate in between that does not commute stops the search
+    ins2 = [{"name": "ry", "qubits": [0], "params": [0.3]}, {"name": "cx", "qubits": [0, 2]}, {"name": "ry", "qubits": [1], "params": [1.1]},
+            {"name": "cx", "qubits": [0, 1]}]
+    plan2 = cb.plan(C.task(ins2, 3))
+    ref2, _ = O.run_static(ins2, 3, backend="numpy")
+    assert np.abs(replay_plan(plan2, 3) - ref2.amplitudes()).max() < 1e-12
+
+
+def test_permutation_runs_and_block_forms_in_the_plan(lib_built):
+    """device-op letters of the plan: a run of CX gates is one linear permutation (L<gates>), the register blocks of a lean
+    pass are widened (P = two 2-qubit gates on four bits, P(221) / P(200) with spectator bits)"""
+    n = 20
+    kinds = [p["device_kinds"] for p in cb.plan(C.task(C.ghz(n, measure=False), n))["passes"]]
+    assert any("L" in k for k in kinds), kinds
+    off = [p["device_kinds"] for p in cb.plan(C.task(C.ghz(n, measure=False), n), {"lin_perm": False})["passes"]]
+    assert not any("L" in k for k in off) and sum(k.count("X") for k in off) > sum(k.count("X") for k in kinds)
+    qv = cb.plan(C.task(C.quantum_volume(16, seed=3), 16))
+    for p in qv["passes"]:
+        assert set(p["device_kinds"]) <= set("P(0123456789)"), p["device_kinds"]   # every op of a QV pass is a register block
+        assert all(len(bits) == 4 for bits in p["pair_bits"])                       # ... on four local bits
