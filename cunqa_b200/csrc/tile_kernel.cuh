@@ -821,7 +821,7 @@ __device__ __forceinline__ void tma_store_row(const CUtensorMap *map, const void
 // FORM = PassParams::mat_form (op_pair_dispatch).  FORM 1: the dense matrices of the register blocks and dense gates are
 // read straight from the kernel parameters (uniform datapath) instead of the shared-memory copy.
 template <typename T, int NT, bool COND, int VAR, int kStages, int FORM = 0>
-__global__ void __launch_bounds__(NT, (kStages == 3 ? 256 : 384) / NT)
+__global__ void __launch_bounds__(NT, (kStages == 3 ? 256 : kStages == 2 ? 384 : 512) / NT)
 tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_constant__ CUtensorMap tmap,
                      const typename Vec2<T>::type *__restrict__ diag_tabs, const uint8_t *__restrict__ flags,
                      const int box_bits, const uint32_t buf_stride, const int refill_after,
@@ -985,6 +985,7 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
             if (tq[kStages - 1] != ~0ull) issue_load(s2, trow[kStages - 1]);
         };
 
+        if constexpr (kStages == 1) refill();   // single buffer: drain the previous tile's stores, then load this tile
         uint64_t b;
         const uint64_t base = tile_base(tq[0], b);
         V *tile = reinterpret_cast<V *>(smem_raw + (size_t)s * buf_stride);
@@ -1045,9 +1046,16 @@ tile_pass_tma_kernel(const __grid_constant__ PassParams<T> p, const __grid_const
             __syncthreads();
         }
 
+        if constexpr (kStages == 1) {
+            // (one buffer: the tile's own load was issued at the top of the iteration, nothing to recycle during the ops)
+            apply_ops<T, NT, COND, VAR, NoHook, FORM>(p, FORM == 1 ? p.mats + (uint32_t)b * (uint32_t)p.reg_stride : mats_s, tile, tabs_b, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
+                                        (COND || (16 * NT) != (1 << t)) ? nullptr : lut, tptr, 1 << 30, NoHook(),
+                                        (COND || (16 * NT) != (1 << t)) ? nullptr : fanT, fanc, mats_s);
+        } else {
         apply_ops<T, NT, COND, VAR, decltype(refill), FORM>(p, FORM == 1 ? p.mats + (uint32_t)b * (uint32_t)p.reg_stride : mats_s, tile, tabs_b, COND ? active_ops(p, flags, b, base) : ~0ull, base, t, tid,
                                     (COND || (16 * NT) != (1 << t)) ? nullptr : lut, tptr, refill_after, refill,
                                     (COND || (16 * NT) != (1 << t)) ? nullptr : fanT, fanc, mats_s);
+        }
 
         // every thread's generic-proxy writes -> visible to the async proxy; then drain the tile with TMA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -41,6 +41,7 @@ cudaError_t launch_tile_pass_tma<CB200_T, CB200_NT>(const PassParams<CB200_T> &p
         constexpr int kForm = sizeof(T) == 8 ? 1 : 2;
         if (l.reg_mats != nullptr || p.needs_full != 0 || p.mat_form != kForm) return cudaErrorInvalidValue;   // (always two stages)
         if (cnd) return go(tile_pass_tma_kernel<T, N, true, 0, 2, kForm>, seen[7]);
+        if (l.stages == 1) return go(tile_pass_tma_kernel<T, N, false, 0, 1, kForm>, seen[8]);   // (experiment: one buffer, more CTAs per SM)
         return go(tile_pass_tma_kernel<T, N, false, 0, 2, kForm>, seen[6]);
     }
     if (l.stages == 3) {
