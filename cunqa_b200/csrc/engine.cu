@@ -87,6 +87,7 @@ void State::construct(int rank, int world, const uint8_t *nccl_id, ShardGroup *g
     tma_refill_after_ = env_int("CB200_TMA_REFILL_AFTER", 0);
     tma_max_ctas_ = env_int("CB200_TMA_MAX_CTAS", 0);
     tma_stages_ = std::max(1, std::min(3, env_int("CB200_TMA_STAGES", 2)));
+    diag_stages_ = std::max(1, std::min(2, env_int("CB200_DIAG_STAGES", 1)));
     init_options(gbits);
     ctas_per_sm_ = env_int("CB200_CTAS_PER_SM", 0);
     use_tma_ = env_int("CB200_USE_TMA", 1) != 0;
@@ -381,13 +382,21 @@ void State::launch_ops_t(std::vector<HostOp> &ops, int b0, int nb, ChunkPipe *pi
         if (run_bits == p.L && tma_fold_dims_)
             for (int d = 0; d < 3 && p.L + d < p.t; d++) { hi_q[d] = p.tile_q[p.L + d]; box_bits++; }
         const uint32_t buf_stride = (uint32_t)std::max<size_t>(1024, sizeof(V) << p.t);
-        const int stages = (tma_stages_ == 1 && !(p.mat_form != 0 && p.cond_mask == 0)) ? 2 : tma_stages_;   // (one stage: lean fast passes only)
+        int nt = 1 << std::max(5, std::min(8, p.t - kAmpsPerThreadShift));  // 32 / 64 / 128 / 256 threads
+        if (tma_threads_ > 0) nt = tma_threads_;
+        // Tile buffers per CTA.  Two: the CTA overlaps its own load / math / store (three CTAs of 128 threads per SM).
+        // Passes made of register sweeps (diagonal runs, fans: QFT) are latency bound, not FP64 bound: ONE buffer and four
+        // CTAs per SM serve them better on big states (QFT-33 500 against 533 ms; QFT-30 unchanged); the FP64-bound lean
+        // passes lose with one buffer (QV-30 615 against 578 ms) and take it only on request (CB200_TMA_STAGES=1).
+        int stages = std::max(2, tma_stages_);
+        if (p.cond_mask == 0 && 16 * nt == (1 << p.t)) {
+            if (p.needs_full == 1) stages = diag_stages_;
+            else if (p.mat_form != 0 && tma_stages_ == 1) stages = 1;
+        }
         size_t smem_tma = (size_t)stages * buf_stride + sizeof(uint64_t) * (stages + 1) + sizeof(uint32_t) * ((((size_t)1 << (p.t - box_bits)) + 3) & ~(size_t)3) +
                           sizeof(T) * (size_t)((p.n_mat + 1) & ~1) + (size_t)((p.n_diag + 1) & ~1) * 8 + (size_t)p.n_stab * sizeof(V) +
                           (size_t)p.n_diag * (4 + 2 * kDiagLut) +
                           (p.fan_op >= 0 ? (((size_t)p.ops[p.fan_op].k << p.ops[p.fan_op].nfix) + (size_t)p.ops[p.fan_op].k * (1 + p.fan_chunks)) * sizeof(V) + 16 : 0) + 16 + 1024;
-        int nt = 1 << std::max(5, std::min(8, p.t - kAmpsPerThreadShift));  // 32 / 64 / 128 / 256 threads
-        if (tma_threads_ > 0) nt = tma_threads_;
         int ctas = std::max(1, (stages == 3 ? 256 : stages == 2 ? 384 : 512) / nt);
         {   // staged diagonal sub-tables must not cost a resident CTA: drop them when they would
             const size_t without = smem_tma - (size_t)p.n_stab * sizeof(V);

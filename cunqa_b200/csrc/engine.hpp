@@ -185,6 +185,7 @@ private:
     int tma_threads_ = 0;
     int ctas_per_sm_ = 0;  // 0 = occupancy query (generic kernel only)
     bool use_tma_ = true;
+    int diag_stages_ = 1;      // tile buffers per CTA for passes made of register sweeps (engine.cu: launch_ops_t)
     bool const_mats_ = true;   // dense matrices read from the kernel parameters (uniform datapath) where one set serves the launch
     void make_tensor_map(CUtensorMap *out, int run_bits, const int hi_qubits[3], int b0 = 0, int nb = -1);
     bool tma_fold_dims_ = true;

@@ -50,6 +50,7 @@ cudaError_t launch_tile_pass_tma<CB200_T, CB200_NT>(const PassParams<CB200_T> &p
     }
     if (cnd) return go(tile_pass_tma_kernel<T, N, true, 2, 2>, seen[2]);
     if (var == 0) return go(tile_pass_tma_kernel<T, N, false, 0, 2>, seen[3]);
+    if (var == 1 && l.stages == 1) return go(tile_pass_tma_kernel<T, N, false, 1, 1>, seen[9]);   // (experiment: one buffer, more CTAs per SM)
     if (var == 1) return go(tile_pass_tma_kernel<T, N, false, 1, 2>, seen[4]);
     return go(tile_pass_tma_kernel<T, N, false, 2, 2>, seen[5]);
 }
