@@ -367,7 +367,7 @@ void State::flush_dist_t()
     // swaps planned together (same batch id) become one multi-qubit exchange.  Grouping by batch id -- not by adjacency
     // in this rank's segment list -- keeps the number and shape of exchanges identical on every rank: a LOCAL segment
     // that separates two batches on one rank can be empty (all its ops dropped by a global control) on another.
-    // single-process groups pipeline the exchange with the pass that follows it (CB200_SWAP_CHUNK_BITS, default 2; 0 = one
+    // single-process groups pipeline the exchange with the pass that follows it (CB200_SWAP_CHUNK_BITS; 0 = one
     // exchange kernel on the main stream as in the one-process-per-GPU mode): the exchange runs in 2^bits chunks on a
     // second stream, with few CTAs per SM and the shared-memory carve-out of the pass kernel so that both can be
     // resident on an SM, and the pass starts on the chunks that have arrived.  Measured on 2 x B200
@@ -375,14 +375,19 @@ void State::flush_dist_t()
     // pipeline would give: side by side on the same SMs the two kernels slow each other down (the pass kernel alone holds
     // 3 CTAs x 128 threads x 168 registers = the whole register file); hiding the exchange completely needs the copy
     // engines (peer DMA through a staging buffer) instead of a kernel.
-    static const int chunk_bits_cfg = getenv("CB200_SWAP_CHUNK_BITS") ? std::max(0, std::min(3, atoi(getenv("CB200_SWAP_CHUNK_BITS")))) : 2;
-    const int chunk_bits = (dist->group && n_local_ >= 24) ? chunk_bits_cfg : 0;
+    // Chunks per exchange, re-measured with the round-2 kernels (wall clock of QFT-(33+g), best of 3): an exchange of ONE
+    // qubit pair (2 GPUs) is best in 4 chunks (671 against 697 ms in 2 and 724 unchunked), exchanges of two and three pairs
+    // (every rank talks to 3 / 7 partners per chunk) in 2 (4 GPUs: 819 against 854 ms; 8 GPUs: 887 against 935 and 938
+    // unchunked).  CB200_SWAP_CHUNK_BITS overrides both.
+    static const int chunk_bits_cfg = getenv("CB200_SWAP_CHUNK_BITS") ? std::max(0, std::min(3, atoi(getenv("CB200_SWAP_CHUNK_BITS")))) : -1;
+    const bool may_chunk = dist->group && n_local_ >= 24;
     std::vector<std::pair<int, int>> group;
     int group_batch = -1;
     ChunkPipe pipe;   // the exchange in flight, if any
     auto exchange = [&](const DistSegment *next_local) {
         if (!group.empty()) {
             if (pipe.wait_all) { pipe.wait_all(); pipe = ChunkPipe(); }   // two exchanges back to back: the first one completes first
+            const int chunk_bits = !may_chunk ? 0 : chunk_bits_cfg >= 0 ? chunk_bits_cfg : (group.size() >= 2 ? 1 : 2);
             if (chunk_bits > 0) {
                 // (chunked or not is decided by rank-independent facts only: every rank takes the same path)
                 // the tile qubits of the pass that will follow the exchange on this rank (same schedule launch_ops_t derives)
