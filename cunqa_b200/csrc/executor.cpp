@@ -1651,6 +1651,14 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
                     pb.arr.push_back(std::move(e));
                 }
                 o.set("pair_bits", std::move(pb));
+                Json lp = Json::array();   // every linear permutation (OP_LINPERM): its swizzled index-map columns, [15] = constant
+                for (int q = 0; q < pp.n_ops; q++) {
+                    if (pp.ops[q].kind != OP_LINPERM) continue;
+                    Json e = Json::array();
+                    for (int i = 0; i < 16; i++) e.arr.push_back(Json::integer(pp.ops[q].lin[i]));
+                    lp.arr.push_back(std::move(e));
+                }
+                o.set("lin_perms", std::move(lp));
                 Json sw = Json::array();
                 for (int q = 0; q < pp.n_sweeps; q++) {
                     Json e = Json::array();

@@ -185,3 +185,59 @@ def test_permutation_runs_and_block_forms_in_the_plan(lib_built):
     for p in qv["passes"]:
         assert set(p["device_kinds"]) <= set("P(0123456789)"), p["device_kinds"]   # every op of a QV pass is a register block
         assert all(len(bits) == 4 for bits in p["pair_bits"])                       # ... on four local bits
+
+
+def test_linear_permutation_tables_equal_the_gates_applied_one_by_one(lib_built):
+    """OP_LINPERM (round 2): the host composes a run of X / CX / SWAP gates into one GF(2)-affine map of the tile index and
+    folds the shared-memory swizzle into its columns.  Bit-exact check on the CPU: for every destination index of the tile
+    the table's source equals the index obtained by undoing the gates of the run one by one."""
+    import re
+    rng = np.random.default_rng(3)
+    n = 9                                            # one tile holds the whole register: tile bit = qubit
+    ins = [{"name": "h", "qubits": [0]}]
+    for _ in range(40):
+        a, b = map(int, rng.permutation(n)[:2])
+        r = int(rng.integers(0, 4))
+        # (uncontrolled swaps are relabelled away by the queue and never reach a pass: cswap would not be linear)
+        ins.append({"name": "x", "qubits": [a]} if r == 0 else {"name": "cx", "qubits": [a, b]})
+    ins.append({"name": "h", "qubits": [1]})
+    plan = cb.plan(C.task(ins, n), {"fuse": False, "tile_bits": n, "min_run_bits": 0})
+    assert plan["l2p"] == list(range(n))
+    checked = 0
+    for p in plan["passes"]:
+        assert p["tile_q"] == list(range(n))
+        host = [plan["ops"][i] for i in p["ops"]]
+        tokens = re.findall(r"L\d+|P\(\d+\)|P|[DXSTF]\d*", p["device_kinds"])
+        pos, tables = 0, iter(p["lin_perms"])
+        for tok in tokens:
+            if tok.startswith("L"):
+                k = int(tok[1:])
+                run = host[pos:pos + k]
+                lin = next(tables)
+                swz = lambda i: i ^ ((i >> 3) & 7)   # fp64 tiles; an involution
+                for d in range(1 << n):
+                    slot = lin[15]
+                    for i in range(n):
+                        if (d >> i) & 1:
+                            slot ^= lin[i]
+                    src = d                          # undo the run: last gate first (every gate is its own inverse)
+                    for g in reversed(run):
+                        assert g["kind"] in ("permx", "swap"), g
+                        if g["kind"] == "permx":
+                            if all((src >> c) & 1 for c in g["ctrl"]):
+                                src ^= 1 << g["q"][0]
+                        else:
+                            x, y = g["q"]
+                            if ((src >> x) & 1) != ((src >> y) & 1):
+                                src ^= (1 << x) | (1 << y)
+                    assert swz(slot) == src, (d, slot, src)
+                pos += k
+                checked += 1
+            elif tok.startswith("P("):
+                pos += 1 if tok[2:5].endswith("00") else 2
+            elif tok == "P":
+                pos += 2
+            else:
+                pos += 1
+        assert pos == len(host)
+    assert checked >= 1
