@@ -1651,6 +1651,18 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
                     pb.arr.push_back(std::move(e));
                 }
                 o.set("pair_bits", std::move(pb));
+                Json pd = Json::array();   // ... and its descriptor: local bits in block order, group-index segment masks, swizzled offsets
+                for (int q = 0; q < pp.n_ops; q++) {
+                    if (pp.ops[q].kind != OP_PAIR) continue;
+                    Json e = Json::object(), tb = Json::array(), sg = Json::array(), so = Json::array();
+                    for (int m = 0; m < pp.ops[q].nfix; m++) { tb.arr.push_back(Json::integer(pp.ops[q].tbit[m])); so.arr.push_back(Json::integer(pp.ops[q].sboff[m])); }
+                    for (int m = 0; m <= pp.ops[q].nfix; m++) sg.arr.push_back(Json::integer(pp.ops[q].seg[m]));
+                    e.set("tbit", std::move(tb));
+                    e.set("seg", std::move(sg));
+                    e.set("sboff", std::move(so));
+                    pd.arr.push_back(std::move(e));
+                }
+                o.set("pair_desc", std::move(pd));
                 Json lp = Json::array();   // every linear permutation (OP_LINPERM): its swizzled index-map columns, [15] = constant
                 for (int q = 0; q < pp.n_ops; q++) {
                     if (pp.ops[q].kind != OP_LINPERM) continue;
@@ -1659,6 +1671,9 @@ std::string plan_task_json(const std::string &task_json, const std::string &opti
                     lp.arr.push_back(std::move(e));
                 }
                 o.set("lin_perms", std::move(lp));
+                Json ts = Json::array();   // tile number -> (tile base >> L) segment masks (PassParams::tile_seg)
+                for (int k = 0; k <= pp.t - pp.L; k++) ts.arr.push_back(Json::integer((long long)pp.tile_seg[k]));
+                o.set("tile_seg", std::move(ts));
                 Json sw = Json::array();
                 for (int q = 0; q < pp.n_sweeps; q++) {
                     Json e = Json::array();

@@ -241,3 +241,52 @@ def test_linear_permutation_tables_equal_the_gates_applied_one_by_one(lib_built)
                 pos += 1
         assert pos == len(host)
     assert checked >= 1
+
+
+def test_tile_number_to_base_segment_masks(lib_built):
+    """PassParams::tile_seg (round 2): the kernel turns a tile number into the tile's base address with
+    sum_k (x & seg[k]) << k; it must equal inserting a zero bit at every high tile qubit, lowest first"""
+    rng = np.random.default_rng(11)
+    for n, ins, opts in ((22, C.quantum_volume(22, depth=3, seed=1), None), (20, C.qft(20, 5), {"tile_bits": 9, "min_run_bits": 3}),
+                         (17, C.quantum_volume(17, depth=2, seed=2), {"tile_bits": 6, "min_run_bits": 0})):
+        for p in cb.plan(C.task(ins, n), opts)["passes"]:
+            tq, L, seg = p["tile_q"], p["L"], p["tile_seg"]
+            t = len(tq)
+            assert len(seg) == t - L + 1 and tq[:L] == list(range(L))
+            for x in [0, (1 << (n - t)) - 1] + [int(v) for v in rng.integers(0, 1 << (n - t), 50)]:
+                want = x
+                for q in tq[L:]:                      # ascending: insert a zero at bit (q - L)
+                    pos = q - L
+                    want = ((want >> pos) << (pos + 1)) | (want & ((1 << pos) - 1))
+                got = 0
+                for k, m in enumerate(seg):
+                    got |= (x & m) << k
+                assert got == want, (tq, L, x)
+                base = got << L
+                assert all(not (base >> q) & 1 for q in tq)   # the tile's own qubits are zero in its base
+
+
+def test_register_block_descriptors(lib_built):
+    """OP_PAIR descriptors as the kernel reads them: the group index g of a thread is deposited around the block's local
+    bits by sum_m (g & seg[m]) << m -- a bijection onto the tile indices whose local bits are zero -- and sboff[m] is the
+    swizzled tile index of local bit m; lean passes hold four local bits (spectators included)"""
+    swz = lambda i: i ^ ((i >> 3) & 7)
+    seen = 0
+    for n, ins in ((16, C.quantum_volume(16, seed=4)), (14, C.hea_ansatz(14, 3, measure=False))):
+        for p in cb.plan(C.task(ins, n))["passes"]:
+            t = len(p["tile_q"])
+            for d in p["pair_desc"]:
+                bits, R = d["tbit"], len(d["tbit"])
+                assert R == 4 and len(set(bits)) == R and all(0 <= b < t for b in bits)
+                assert d["sboff"] == [swz(1 << b) for b in bits]
+                mask = sum(1 << b for b in bits)
+                idx = set()
+                for g in range(1 << (t - R)):
+                    i = 0
+                    for m, sm in enumerate(d["seg"]):
+                        i |= (g & sm) << m
+                    assert i & mask == 0 and i < (1 << t)
+                    idx.add(i)
+                assert len(idx) == 1 << (t - R)
+                seen += 1
+    assert seen > 10
